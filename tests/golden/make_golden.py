@@ -1,0 +1,245 @@
+"""
+Generates tests/golden/*.npz by EXECUTING THE REFERENCE ITSELF (build container only).
+
+The reference (/root/reference, read-only) is imported unmodified.  Its three C++
+extensions are the ones oracle/Makefile compiles into oracle/_ref from the
+reference's own sources.  Dependencies that are not installed here and are not
+on the chunk_ccs / chunk_overlaps / merge_ccs path are replaced by MagicMock;
+two that ARE on the path are absent too and get minimal stand-ins:
+
+* cc3d.connected_components  -> scipy.ndimage.label (same partition; same 1..N
+  raster-first numbering -- see oracle/oracle.py header)
+* igraph.Graph               -> scipy.sparse.csgraph.connected_components
+  (proc/utils.py:39-74 only needs Graph(n), .vs["ids"], len(.vs), .add_edges,
+  .components(); the result is order-free because make_id_map maps to min())
+
+Run:  python tests/golden/make_golden.py      (writes next to this file)
+The fixtures travel to the GPU box; this script and /root/reference do not need to.
+"""
+import importlib.util
+import io
+import os
+import sys
+import types
+from contextlib import redirect_stdout
+from unittest import mock
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+
+def _install_reference():
+    from scipy import ndimage
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components as cg_cc
+
+    for name in ["h5py", "cloudvolume", "taskqueue", "sqlalchemy", "sqlalchemy.sql", "psycopg2", "boto3",
+                 "fastremap", "zstandard", "future", "future.standard_library", "builtins_stub"]:
+        sys.modules.setdefault(name, mock.MagicMock())
+    import google.cloud  # namespace package exists in this image
+    storage = mock.MagicMock()
+    sys.modules["google.cloud.storage"] = storage
+    google.cloud.storage = storage
+
+    cc3d = types.ModuleType("cc3d")
+
+    def connected_components(arr, connectivity=26, **kw):
+        rank = {6: 1, 18: 2, 26: 3}[connectivity]
+        struct = ndimage.generate_binary_structure(3, rank)
+        arr = np.asarray(arr)
+        if arr.dtype == bool:
+            return ndimage.label(arr, structure=struct)[0].astype(np.uint32)
+        # multi-label: components of equal nonzero value, numbered by first voxel
+        out = np.zeros(arr.shape, dtype=np.int64)
+        firsts = []
+        for v in np.unique(arr):
+            if v == 0:
+                continue
+            lab, n = ndimage.label(arr == v, structure=struct)
+            for k in range(1, n + 1):
+                firsts.append((np.flatnonzero(lab.ravel() == k)[0], v, k))
+            out[lab > 0] = -1
+        firsts.sort()
+        out[:] = 0
+        cache = {}
+        for (new, (_, v, k)) in enumerate(firsts, start=1):
+            if v not in cache:
+                cache[v] = ndimage.label(arr == v, structure=struct)[0]
+            out[cache[v] == k] = new
+        return out.astype(np.uint32)
+
+    cc3d.connected_components = connected_components
+    sys.modules["cc3d"] = cc3d
+
+    igraph = types.ModuleType("igraph")
+
+    class _VS(dict):
+        def __init__(self, n):
+            super().__init__()
+            self._n = n
+
+        def __len__(self):
+            return self._n
+
+    class Graph:
+        def __init__(self, n):
+            self.n = n
+            self.vs = _VS(n)
+            self.edges = []
+
+        def add_edges(self, es):
+            self.edges.extend(list(es))
+
+        def components(self):
+            if self.n == 0:
+                return []
+            if self.edges:
+                e = np.array(self.edges, dtype=np.int64)
+                m = coo_matrix((np.ones(len(e)), (e[:, 0], e[:, 1])), shape=(self.n, self.n))
+            else:
+                m = coo_matrix((self.n, self.n))
+            _, lab = cg_cc(m, directed=False)
+            out = {}
+            for (i, l) in enumerate(lab.tolist()):
+                out.setdefault(l, []).append(i)
+            return list(out.values())
+
+    igraph.Graph = Graph
+    sys.modules["igraph"] = igraph
+
+    # the reference's own extensions, compiled from its sources into oracle/_ref
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    for name in ["_describe", "_relabel", "_seg_utils"]:
+        f = [x for x in os.listdir(refdir) if x.startswith(name + ".")][0]
+        full = "synaptor.seg_utils." + name
+        spec = importlib.util.spec_from_file_location(full, os.path.join(refdir, f))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        sys.modules[full] = mod
+
+    sys.path.insert(0, REF)
+    import synaptor  # noqa
+    return synaptor
+
+
+def quiet(fn, *a, **k):
+    with redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def flatten_conts(conts):
+    """{Face: [Continuation]} -> arrays (face_axis, face_hi, segid, n) + concatenated coords."""
+    meta, coords = [], []
+    for (face, lst) in conts.items():
+        for c in lst:
+            meta.append((face.axis, int(face.hi_index), int(c.segid), len(c.face_coords)))
+            coords.append(np.asarray(c.face_coords, dtype=np.int64).reshape(-1, 2))
+    meta = np.array(meta, dtype=np.int64).reshape(-1, 4)
+    coords = np.concatenate(coords) if coords else np.zeros((0, 2), dtype=np.int64)
+    return meta, coords
+
+
+def df_to_arrays(df):
+    return np.asarray(df.index, dtype=np.float64), df.to_numpy(dtype=np.float64)
+
+
+def main():
+    syn = _install_reference()
+    from oracle import oracle as orc
+    tasks = syn.proc.tasks
+    out = {}
+
+    # ---- G1: cc_task, ragged shape, offset, dust ---------------------------------
+    pred = orc.synth_pred((48, 40, 36), seed=3, sigma=1.5, fg=0.08)
+    ccs, conts, info = quiet(tasks.cc_task, pred, 0.5, 20, offset=(100, 200, 300))
+    meta, coords = flatten_conts(conts)
+    idx, tab = df_to_arrays(info)
+    np.savez_compressed(os.path.join(HERE, "g1_cc_task.npz"), pred=pred, thresh=0.5, dust=20,
+                        offset=np.array([100, 200, 300]), ccs=ccs, cont_meta=meta, cont_coords=coords,
+                        info_index=idx, info_table=tab, info_columns=np.array(list(info.columns)))
+    out["g1"] = (int(ccs.max()), len(info))
+
+    # ---- G2: overlap_task vs uint64 base with ids > 2**32 -------------------------
+    base = orc.synth_base((48, 40, 36), seed=5, block=8, bg=0.1)
+    ov = quiet(tasks.overlap_task, ccs, base)
+    np.savez_compressed(os.path.join(HERE, "g2_overlap_task.npz"), ccs=ccs, base=base,
+                        row=np.asarray(ov.row, dtype=np.int64), col=np.asarray(ov.col, dtype=np.int64),
+                        data=np.asarray(ov.data, dtype=np.int64), shape=np.array(ov.shape, dtype=np.int64))
+    mo = syn.proc.overlap.find_max_overlaps(ov)
+    np.savez_compressed(os.path.join(HERE, "g2_max_overlaps.npz"), row=np.asarray(mo.row, dtype=np.int64),
+                        col=np.asarray(mo.col, dtype=np.int64), data=np.asarray(mo.data, dtype=np.int64))
+    out["g2"] = ov.nnz
+    # empty cases
+    e1 = quiet(tasks.overlap_task, np.zeros((4, 4, 4), np.uint32), base[:4, :4, :4])
+    assert e1.shape == (0, 0)
+
+    # ---- G3: dilated_components ---------------------------------------------------
+    pred3 = orc.synth_pred((12, 40, 44), seed=7, sigma=1.2, fg=0.06)
+    d = {"pred": pred3, "thresh": 0.5}
+    for k in (1, 2, 5):
+        d[f"ccs_k{k}"] = syn.proc.seg.dilated_components(pred3, k, 0.5)
+        mask = pred3 > 0.5
+        d[f"dil_k{k}"] = syn.seg_utils.dilate_by_k(mask, k)
+    np.savez_compressed(os.path.join(HERE, "g3_dilated.npz"), **d)
+    out["g3"] = [int(d[f"ccs_k{k}"].max()) for k in (1, 2, 5)]
+
+    # ---- G4: chunked cc_task -> merge_ccs_task -> remap_ids_task -------------------
+    vol = orc.synth_pred((40, 36, 32), seed=11, sigma=2.0, fg=0.10)
+    from synaptor.types.bbox import chunk_bboxes
+    cshape = (20, 18, 16)
+    boxes = chunk_bboxes(vol.shape, cshape)
+    grid = (2, 2, 2)
+    cont_arr = np.empty(grid, dtype=object)
+    info_arr = np.empty(grid, dtype=object)
+    seg_arr = np.empty(grid, dtype=object)
+    for (gi, bb) in zip(np.ndindex(grid), boxes):
+        sl = bb.index()
+        c, ct, inf = quiet(tasks.cc_task, np.ascontiguousarray(vol[sl]), 0.5, 10, offset=tuple(bb.min()))
+        cont_arr[gi], info_arr[gi], seg_arr[gi] = ct, inf, c
+    chunk_tables = {f"chunk_table_{i}": np.concatenate(
+        [np.asarray(info_arr[gi].index, dtype=np.int64)[:, None], info_arr[gi].to_numpy(dtype=np.int64)], axis=1)
+        for (i, gi) in enumerate(np.ndindex(grid))}
+    chunk_segs = {f"chunk_seg_{i}": seg_arr[gi] for (i, gi) in enumerate(np.ndindex(grid))}
+    merged, id_maps = quiet(tasks.merge_ccs_task, cont_arr, info_arr, 15, (20, 18))
+    final = np.zeros(vol.shape, dtype=np.uint32)
+    for (gi, bb) in zip(np.ndindex(grid), boxes):
+        final[bb.index()] = quiet(tasks.remap_ids_task, seg_arr[gi].copy(), id_maps[gi], copy=False)
+    midx, mtab = df_to_arrays(merged)
+    maps = {f"id_map_{i}": np.array(sorted(id_maps[gi].items()), dtype=np.int64).reshape(-1, 2)
+            for (i, gi) in enumerate(np.ndindex(grid))}
+    np.savez_compressed(os.path.join(HERE, "g4_merge_ccs.npz"), vol=vol, thresh=0.5, dust=10, size_thr=15,
+                        chunk_shape=np.array(cshape), max_face_shape=np.array([20, 18]),
+                        merged_index=midx, merged_table=mtab, merged_columns=np.array(list(merged.columns)),
+                        final=final, **maps, **chunk_tables, **chunk_segs)
+    out["g4"] = (len(merged), int(final.max()))
+
+    # ---- G5: centers_of_mass rounding / float32 path ------------------------------
+    seg = np.zeros((6, 5, 700), dtype=np.uint32)
+    seg[0, 0, 0:2] = 1           # mean z = 0.5 -> rounds away to 1
+    seg[1:4, 1, 3] = 2           # x mean 2
+    seg[0:2, 2, 7] = 3           # x mean 0.5 -> 1
+    seg[5, 4, :] = 4             # sum z = 244650
+    seg[2, 0:4, 10:12] = 5
+    big = np.ones((300, 300, 300), dtype=np.uint32)  # sums > 2**24: float32 rounding of the sums
+    c_small = syn.seg_utils.centers_of_mass(seg)
+    c_big = syn.seg_utils.centers_of_mass(big)
+    assert c_big[1] == (150, 150, 150), c_big
+    np.savez_compressed(os.path.join(HERE, "g5_centroids.npz"), seg=seg,
+                        ids=np.array(sorted(c_small), dtype=np.int64),
+                        cents=np.array([c_small[i] for i in sorted(c_small)], dtype=np.int64),
+                        big_shape=np.array(big.shape), big_cent=np.array(c_big[1], dtype=np.int64))
+
+    # ---- G6: threshold semantics (float32 compare, NaN) ---------------------------
+    t = np.array([0.3, np.float32(0.3), np.nextafter(np.float32(0.3), np.float32(1)), np.nan, 0.5, -0.0, 1.0],
+                 dtype=np.float32).reshape(1, 1, -1)
+    np.savez_compressed(os.path.join(HERE, "g6_threshold.npz"), d=t, thresh=0.3,
+                        ccs=syn.proc.seg.connected_components(t, 0.3))
+    print("golden written:", out)
+
+
+if __name__ == "__main__":
+    main()
