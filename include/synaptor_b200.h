@@ -1,0 +1,193 @@
+/*
+ * synaptor_b200.h -- C ABI of libsynaptor_b200.so (sm_100a).
+ *
+ * Drop-in boundary for Synaptor's chunk_ccs / chunk_overlaps / merge_ccs /
+ * remap_ids hot path.  Every entry point replaces one native or Python-level
+ * call of the reference (cited per function, paths relative to the reference
+ * tree).  Conventions:
+ *
+ *   - all volume pointers are CALLER-OWNED DEVICE pointers (e.g.
+ *     torch.Tensor.data_ptr()), C-contiguous [x][y][z], z fastest -- the layout
+ *     the reference has after np.ascontiguousarray (proc/seg/conncomps.py:21);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success or a negative SYN_ERR_* code and never
+ *     throws; syn_last_error() gives the message for the calling thread;
+ *   - variable-length results use caller-provided capacity; the true sizes come
+ *     back in the `counts` array, and SYN_ERR_CAPACITY says "retry larger";
+ *   - no hidden host synchronisation unless `counts_host` is non-NULL (then the
+ *     call ends with one D2H copy of the counts + a stream synchronise).
+ */
+#ifndef SYNAPTOR_B200_H
+#define SYNAPTOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SYN_API __attribute__((visibility("default")))
+#else
+#define SYN_API
+#endif
+
+#define SYN_OK 0
+#define SYN_ERR_INVALID (-1)   /* bad argument (shape, connectivity, null pointer, ...) */
+#define SYN_ERR_CUDA (-2)      /* a CUDA runtime call or launch failed */
+#define SYN_ERR_CAPACITY (-3)  /* max_runs / max_segs / max_pairs too small: see counts */
+#define SYN_ERR_WORKSPACE (-4) /* workspace_bytes smaller than syn_ccs_workspace_bytes() */
+
+/* indices into the int64 counts[SYN_NCOUNTS] array (device copy lives at the
+ * start of the workspace; host copy is filled when counts_host != NULL) */
+enum {
+    SYN_CNT_RUNS = 0,        /* z-runs of the labelled mask (needed max_runs) */
+    SYN_CNT_COMPONENTS = 1,  /* raw connected components before the dust filter */
+    SYN_CNT_KEPT = 2,        /* rows of the segment table (needed max_segs) */
+    SYN_CNT_PAIRS = 3,       /* distinct (label, base id) overlap pairs (needed max_pairs) */
+    SYN_CNT_MAX_BASE = 4,    /* max over the whole base volume (bit pattern of a uint64) */
+    SYN_CNT_MAX_LABEL = 5,   /* largest label written to the label volume */
+    SYN_CNT_ERRFLAGS = 6,    /* bit 0 runs overflow, bit 1 segs overflow, bit 2 pair table overflow,
+                                bit 3 pair output overflow */
+    SYN_CNT_FG_VOXELS = 7,   /* voxels above threshold */
+    SYN_CNT_TABLE_SLOTS = 8, /* occupied slots in the pair hash table */
+    SYN_NCOUNTS = 16
+};
+
+/* columns of one segment-table row (int64 each), in the order of the reference's
+ * DataFrame (proc/seg/misc.py:14-37, proc/colnames.py:6-24) preceded by the id */
+enum {
+    SYN_SEG_ID = 0, SYN_SEG_SIZE = 1, SYN_SEG_CX = 2, SYN_SEG_CY = 3, SYN_SEG_CZ = 4,
+    SYN_SEG_BX = 5, SYN_SEG_BY = 6, SYN_SEG_BZ = 7, SYN_SEG_EX = 8, SYN_SEG_EY = 9, SYN_SEG_EZ = 10,
+    SYN_SEG_NCOLS = 11
+};
+
+SYN_API int syn_version(void);
+SYN_API const char *syn_last_error(void);
+
+/* Bytes of device workspace syn_chunk_ccs needs for this shape.
+ * max_runs  : capacity for z-runs (worst case nx*ny*ceil(nz/2));
+ * max_pairs : capacity of the overlap pair table (0 when base_seg is NULL). */
+SYN_API int64_t syn_ccs_workspace_bytes(int64_t nx, int64_t ny, int64_t nz, int64_t max_runs, int64_t max_pairs);
+
+/*
+ * syn_chunk_ccs -- the whole of proc.tasks.cc_task's array work
+ * (synaptor/proc/tasks.py:26-69) and, when base_seg != NULL, of
+ * proc.tasks.overlap_task (tasks.py:290-297) fused into the same pass:
+ *
+ *   mask = pred > thresh                         proc/seg/conncomps.py:17
+ *   [dil_k > 0: 2-D L1 dilation over axes 1,2]   conncomps.py:32-52 -> seg_utils/_seg_utils.cpp:25-82,180-200
+ *   3-D connected components, labels 1..N in     conncomps.py:22 -> cc3d.connected_components(connectivity=6)
+ *     raster order of first voxel
+ *   ids touching any chunk face are exempt       proc/seg/continuation.py:87-114, tasks.py:45-51
+ *   ids with size < dust_thresh removed (-> 0)   seg_utils/filtering.py:7-40 -> _relabel.cpp:19-38
+ *   size / centroid / bbox per surviving id      seg_utils/describe.py:14-80, _describe.cpp:23-64,
+ *                                                scipy.ndimage.find_objects (half-open boxes)
+ *   (label, base id) pair counts, first-         seg_utils/overlap.py:10-61 (collections.Counter order)
+ *     occurrence raster order, + max(base)
+ *
+ * connectivity: 6 (the reference), 18 or 26 (extensions).
+ * labels_out  : uint32 [nx][ny][nz].
+ * seg_table   : int64 [max_segs][SYN_SEG_NCOLS], rows in ascending id; centroid
+ *               and bbox already shifted by offset_xyz (describe.py:28,55-59).
+ * pair_*      : device arrays of capacity max_pairs (ignored when base_seg == NULL).
+ * counts_host : optional int64[SYN_NCOUNTS]; when given the call synchronises and
+ *               returns SYN_ERR_CAPACITY if any capacity was exceeded.
+ */
+SYN_API int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz,
+                  float thresh, int connectivity, int dil_k, int64_t dust_thresh,
+                  const int64_t *offset_xyz /* host int64[3] or NULL */,
+                  uint32_t *labels_out,
+                  int64_t *seg_table, int64_t max_segs,
+                  const uint64_t *base_seg,
+                  uint32_t *pair_rows, uint64_t *pair_cols, int64_t *pair_counts, int64_t max_pairs,
+                  void *workspace, int64_t workspace_bytes, int64_t max_runs,
+                  int64_t *counts_host, void *stream);
+
+/* Copies the device counts at the head of `workspace` to host and synchronises. */
+SYN_API int syn_read_counts(const void *workspace, int64_t *counts_host, void *stream);
+
+/*
+ * syn_count_overlaps -- seg_utils.count_overlaps(seg1, seg2, orig_ids=True)
+ * (synaptor/seg_utils/overlap.py:10-61) on arbitrary uint32 / uint64 volumes.
+ * Fills pair_* in first-occurrence raster order; counts[SYN_CNT_PAIRS],
+ * counts[SYN_CNT_MAX_LABEL] = max(seg1), counts[SYN_CNT_MAX_BASE] = max(seg2).
+ * Workspace: syn_overlap_workspace_bytes(n_voxels, max_pairs).
+ */
+SYN_API int64_t syn_overlap_workspace_bytes(int64_t nx, int64_t ny, int64_t nz, int64_t max_pairs);
+SYN_API int syn_count_overlaps(const uint32_t *seg1, const uint64_t *seg2, int64_t nx, int64_t ny, int64_t nz,
+                       uint32_t *pair_rows, uint64_t *pair_cols, int64_t *pair_counts, int64_t max_pairs,
+                       void *workspace, int64_t workspace_bytes,
+                       int64_t *counts_host, void *stream);
+
+/*
+ * syn_extract_faces -- the six np.take(seg, -1|0, axis) slices of
+ * proc/seg/continuation.py:52-55, in Face.all_faces() order
+ * (axis0 hi, axis0 lo, axis1 hi, axis1 lo, axis2 hi, axis2 lo), written back to
+ * back into faces_out (uint32, 2*(ny*nz + nx*nz + nx*ny) elements).
+ */
+SYN_API int syn_extract_faces(const uint32_t *labels, int64_t nx, int64_t ny, int64_t nz,
+                      uint32_t *faces_out, void *stream);
+
+/*
+ * syn_relabel_lut -- seg_utils.relabel_data (seg_utils/relabel.py:7-27 ->
+ * _relabel.cpp:19-38) with the dict given as a dense table: values v < lut_len
+ * become lut[v] (identity entries for non-keys), others stay.  In place.
+ */
+SYN_API int syn_relabel_lut(uint32_t *labels, int64_t n, const uint32_t *lut, int64_t lut_len, void *stream);
+
+/*
+ * syn_segment_stats -- seg_utils.segment_sizes / centers_of_mass /
+ * bounding_boxes (seg_utils/describe.py:14-80, _describe.cpp:23-64) of a label
+ * volume whose ids are <= max_id.  stats: int64 [max_id+1][SYN_SEG_NCOLS]
+ * (row i = id i; size 0 for absent ids; no offset applied).
+ */
+SYN_API int syn_segment_stats(const uint32_t *labels, int64_t nx, int64_t ny, int64_t nz,
+                      int64_t max_id, int64_t *stats, void *stream);
+
+/* max over a uint32 volume (device result in out_dev[0]); helper for the host wrappers. */
+SYN_API int syn_max_u32(const uint32_t *labels, int64_t n, uint32_t *out_dev, void *stream);
+
+/*
+ * syn_face_pair_edges -- proc/seg/merge/merge_ccs.py:117-128 (match_continuations):
+ * for two facing 2-D faces (already in GLOBAL ids, 0 = nothing) emits the pair
+ * (a[i], b[i]) wherever both are nonzero.  Duplicates are allowed (the union is
+ * idempotent).  edges_out: uint32 [max_edges][2]; *n_edges_dev is incremented
+ * atomically (caller zeroes it); entries beyond max_edges are dropped.
+ */
+SYN_API int syn_face_pair_edges(const uint32_t *face_a, const uint32_t *face_b, int64_t n,
+                        uint32_t *edges_out, int64_t max_edges, unsigned long long *n_edges_dev, void *stream);
+
+/*
+ * syn_union_min_map -- proc/utils.py:39-86 (find_connected_components +
+ * make_id_map): union-find over `n_edges` edges on ids < n_ids; map_out[i] = the
+ * smallest id of i's component (map_out[i] = i for untouched ids).  The edge
+ * count is read from n_edges_dev (device) and clamped to max_edges.
+ */
+SYN_API int syn_union_min_map(const uint32_t *edges, const unsigned long long *n_edges_dev, int64_t max_edges,
+                      int64_t n_ids, uint32_t *map_out, void *stream);
+
+
+/*
+ * syn_threshold_dilate -- `mask = pred > thresh` (proc/seg/conncomps.py:17,43) then
+ * seg_utils.dilate_by_k(mask, k) (seg_utils/misc.py:28-46 -> _seg_utils.cpp:25-82,
+ * 180-200) for a boolean mask: out01 (uint32, same shape) receives 0/1, dilated by
+ * k in 2-D Manhattan distance over axes 1 and 2.  dil_k = 0 gives the plain mask.
+ */
+SYN_API int syn_threshold_dilate(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int dil_k,
+                                 uint32_t *out01, void *stream);
+
+/*
+ * syn_unique_u64 -- the distinct values of a uint64 array (np.unique of the base
+ * segmentation, seg_utils/overlap.py:28, seg_utils/describe.py:8-11), unordered.
+ * *count_dev receives the number of distinct values; if it exceeds cap the output
+ * is truncated (retry with a larger cap).
+ */
+SYN_API int syn_unique_u64(const uint64_t *vals, int64_t n, uint64_t *out, int64_t cap,
+                           unsigned long long *count_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNAPTOR_B200_H */

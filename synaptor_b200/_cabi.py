@@ -1,0 +1,94 @@
+"""
+ctypes binding of libsynaptor_b200.so (include/synaptor_b200.h).
+
+This is the only way Python reaches the CUDA kernels.  There is NO CPU fallback:
+if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsynaptor_b200.so")
+
+SYN_OK = 0
+SYN_ERR_INVALID = -1
+SYN_ERR_CUDA = -2
+SYN_ERR_CAPACITY = -3
+SYN_ERR_WORKSPACE = -4
+
+# counts[] indices (enum in synaptor_b200.h)
+CNT_RUNS, CNT_COMPONENTS, CNT_KEPT, CNT_PAIRS, CNT_MAX_BASE, CNT_MAX_LABEL, CNT_ERRFLAGS, CNT_FG_VOXELS, \
+    CNT_TABLE_SLOTS = range(9)
+NCOUNTS = 16
+SEG_NCOLS = 11
+
+EF_RUNS, EF_SEGS, EF_TABLE, EF_PAIRS = 1, 2, 4, 8
+
+_i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); exactly the declarations of include/synaptor_b200.h
+SIGNATURES = {
+    "syn_version": (_i32, []),
+    "syn_last_error": (ctypes.c_char_p, []),
+    "syn_ccs_workspace_bytes": (_i64, [_i64] * 5),
+    "syn_chunk_ccs": (_i32, [_vp, _i64, _i64, _i64, _f32, _i32, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp,
+                             _i64, _vp, _i64, _i64, _vp, _vp]),
+    "syn_read_counts": (_i32, [_vp, _vp, _vp]),
+    "syn_overlap_workspace_bytes": (_i64, [_i64] * 4),
+    "syn_count_overlaps": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "syn_extract_faces": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "syn_relabel_lut": (_i32, [_vp, _i64, _vp, _i64, _vp]),
+    "syn_segment_stats": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "syn_max_u32": (_i32, [_vp, _i64, _vp, _vp]),
+    "syn_face_pair_edges": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "syn_union_min_map": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "syn_threshold_dilate": (_i32, [_vp, _i64, _i64, _i64, _f32, _i32, _vp, _vp]),
+    "syn_unique_u64": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
+}
+
+
+class SynaptorB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libsynaptor_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CapacityError(SynaptorB200Error):
+    """A caller-provided capacity was too small; `counts` holds the needed sizes."""
+
+    def __init__(self, code, msg, counts):
+        super().__init__(code, msg)
+        self.counts = counts
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C synaptor_b200/csrc).  synaptor_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for (name, (res, args)) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().syn_last_error().decode("utf-8", "replace")
+
+
+def check(rc, counts=None):
+    if rc == SYN_OK:
+        return
+    msg = last_error()
+    if rc == SYN_ERR_CAPACITY:
+        raise CapacityError(rc, msg, counts)
+    raise SynaptorB200Error(rc, msg)

@@ -1,0 +1,490 @@
+// cabi.cu -- extern "C" entry points of libsynaptor_b200.so (see include/synaptor_b200.h)
+// and the host-side orchestration of the kernel pipeline.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "aux.cuh"
+#include "ccl.cuh"
+#include "finalize.cuh"
+
+using namespace syn;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(SYN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define CK_LAUNCH() CK(cudaGetLastError())
+
+int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+int make_geom(i64 nx, i64 ny, i64 nz, Geom *g)
+{
+    if (nx <= 0 || ny <= 0 || nz <= 0) return fail(SYN_ERR_INVALID, "empty or negative shape (%lld,%lld,%lld)",
+                                                  (long long)nx, (long long)ny, (long long)nz);
+    i64 wz = (nz + 31) / 32;
+    i64 rows = nx * ny;
+    i64 nwords = rows * wz;
+    i64 cpr = (wz + 3) / 4;
+    if (rows >= (1ll << 31) || nwords >= (1ll << 32) - 8192 || rows * cpr >= (1ll << 32) - 8192 ||
+        nx >= (1ll << 31) || ny >= (1ll << 31) || nz >= (1ll << 31))
+        return fail(SYN_ERR_INVALID, "chunk too large for 32-bit word indexing (%lld,%lld,%lld)", (long long)nx,
+                    (long long)ny, (long long)nz);
+    g->nx = nx; g->ny = ny; g->nz = nz;
+    g->nvox = nx * ny * nz;
+    g->rows = (u32)rows;
+    g->wz = (u32)wz;
+    g->nwords = (u32)nwords;
+    g->cpr = (u32)cpr;
+    g->nchunks = (u32)(rows * cpr);
+    return SYN_OK;
+}
+
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+u32 pow2_at_least(i64 v)
+{
+    u32 p = 1024;
+    while ((i64)p < v && p < (1u << 31)) p <<= 1;
+    return p;
+}
+
+// workspace carving (must match syn_ccs_workspace_bytes)
+struct Workspace {
+    Counts *cnt;
+    u32 *lmask, *omask, *runbase, *tiles;  // tiles: scan tile sums
+    u32 *par, *rank, *runlabel;
+    CompStat *stat;
+    PairKey *pkeys;
+    u64 *pcount, *pfirst;
+    u32 *bitmap, *wordbase;
+    u32 paircap;
+    size_t total;
+};
+
+size_t scan_tiles(i64 n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 1; }
+
+void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, Workspace *w)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += al(bytes); return p; };
+    const size_t nw = (size_t)g.nwords + 8;
+    i64 biggest = (i64)nw > max_runs ? (i64)nw : max_runs;
+    w->cnt = (Counts *)take(sizeof(Counts));
+    w->lmask = (u32 *)take(nw * 4);
+    w->omask = dilate ? (u32 *)take(nw * 4) : w->lmask;
+    w->runbase = (u32 *)take(nw * 4);
+    w->tiles = (u32 *)take(scan_tiles(biggest) * 4);
+    w->par = (u32 *)take((size_t)max_runs * 4);
+    w->rank = (u32 *)take((size_t)max_runs * 4);
+    w->runlabel = (u32 *)take((size_t)max_runs * 4);
+    w->stat = (CompStat *)take((size_t)max_runs * sizeof(CompStat));
+    w->paircap = 0;
+    w->pkeys = nullptr; w->pcount = w->pfirst = nullptr; w->bitmap = w->wordbase = nullptr;
+    if (max_pairs > 0) {
+        w->paircap = pow2_at_least(2 * max_pairs);
+        w->pkeys = (PairKey *)take((size_t)w->paircap * sizeof(PairKey));
+        w->pcount = (u64 *)take((size_t)w->paircap * 8);
+        w->pfirst = (u64 *)take((size_t)w->paircap * 8);
+        w->bitmap = (u32 *)take(nw * 4);
+        w->wordbase = (u32 *)take(nw * 4);
+    }
+    w->total = off;
+}
+
+int grid_for(i64 items, int threads, int per_sm)
+{
+    i64 need = (items + threads - 1) / threads;
+    i64 cap = (i64)sm_count() * per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// launches the ordering of the pair table entries + emission into the output arrays
+int order_and_emit_pairs(const Geom &g, const Workspace &W, PairTable T, u32 *rows, u64 *cols, i64 *vals,
+                         i64 max_pairs, cudaStream_t st)
+{
+    CK(cudaMemsetAsync(W.bitmap, 0, (size_t)g.nwords * 4, st));
+    k_pair_mark<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bitmap);
+    CK_LAUNCH();
+    PopcSrc src{W.bitmap, g.nwords};
+    const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
+    k_scan_a<<<ntiles, SCAN_THREADS, 0, st>>>(src, W.tiles);
+    CK_LAUNCH();
+    k_scan_b<<<1, SCAN_THREADS, 0, st>>>(src, W.tiles, &W.cnt->v[SYN_CNT_PAIRS], (u32 *)nullptr);
+    CK_LAUNCH();
+    k_scan_c<<<ntiles, SCAN_THREADS, 0, st>>>(src, WordBaseDst{W.wordbase}, W.tiles);
+    CK_LAUNCH();
+    k_pair_emit<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bitmap, W.wordbase, rows, cols, vals, max_pairs);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
+int finish_counts(const Workspace &W, i64 *counts_host, cudaStream_t st)
+{
+    if (!counts_host) return SYN_OK;
+    CK(cudaMemcpyAsync(counts_host, W.cnt, sizeof(Counts), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    i64 ef = counts_host[SYN_CNT_ERRFLAGS];
+    if (ef)
+        return fail(SYN_ERR_CAPACITY,
+                    "capacity exceeded (flags=%lld): runs=%lld kept=%lld table_slots=%lld pairs=%lld", (long long)ef,
+                    (long long)counts_host[SYN_CNT_RUNS], (long long)counts_host[SYN_CNT_KEPT],
+                    (long long)counts_host[SYN_CNT_TABLE_SLOTS], (long long)counts_host[SYN_CNT_PAIRS]);
+    return SYN_OK;
+}
+
+template <int CONN>
+void launch_union(const Workspace &W, const Geom &g, cudaStream_t st)
+{
+    k_union_rows<CONN><<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(W.lmask, W.runbase, W.par, g, W.cnt);
+}
+
+}  // namespace
+
+extern "C" {
+
+int syn_version(void) { return 100; }
+
+const char *syn_last_error(void) { return g_err; }
+
+int64_t syn_ccs_workspace_bytes(int64_t nx, int64_t ny, int64_t nz, int64_t max_runs, int64_t max_pairs)
+{
+    Geom g;
+    if (make_geom(nx, ny, nz, &g) != SYN_OK) return SYN_ERR_INVALID;
+    if (max_runs < 1) max_runs = 1;
+    Workspace w;
+    carve(nullptr, g, max_runs, max_pairs, true, &w);
+    return (int64_t)w.total;
+}
+
+int syn_read_counts(const void *workspace, int64_t *counts_host, void *stream)
+{
+    if (!workspace || !counts_host) return fail(SYN_ERR_INVALID, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(counts_host, workspace, sizeof(Counts), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SYN_OK;
+}
+
+int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity, int dil_k,
+                  int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out, int64_t *seg_table,
+                  int64_t max_segs, const uint64_t *base_seg, uint32_t *pair_rows, uint64_t *pair_cols,
+                  int64_t *pair_counts, int64_t max_pairs, void *workspace, int64_t workspace_bytes,
+                  int64_t max_runs, int64_t *counts_host, void *stream)
+{
+    Geom g;
+    int rc = make_geom(nx, ny, nz, &g);
+    if (rc != SYN_OK) return rc;
+    if (!pred || !labels_out || !workspace) return fail(SYN_ERR_INVALID, "null pointer argument");
+    if (connectivity != 6 && connectivity != 18 && connectivity != 26)
+        return fail(SYN_ERR_INVALID, "connectivity must be 6, 18 or 26 (got %d)", connectivity);
+    if (dil_k < 0 || dil_k > 32) return fail(SYN_ERR_INVALID, "dil_k must be in [0, 32] (got %d)", dil_k);
+    if (max_runs < 1 || max_runs >= (1ll << 32) - 8192) return fail(SYN_ERR_INVALID, "bad max_runs");
+    if (max_segs < 0 || (max_segs > 0 && !seg_table)) return fail(SYN_ERR_INVALID, "bad seg table arguments");
+    const bool has_base = base_seg != nullptr;
+    if (has_base && (max_pairs < 1 || !pair_rows || !pair_cols || !pair_counts))
+        return fail(SYN_ERR_INVALID, "base_seg given without pair output arrays");
+    if (!has_base) max_pairs = 0;
+    const bool dilate = dil_k > 0;
+    Workspace W;
+    carve((char *)workspace, g, max_runs, max_pairs, dilate, &W);
+    if ((i64)W.total > workspace_bytes)
+        return fail(SYN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %lld", W.total,
+                    (long long)workspace_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = sm_count();
+    (void)sms;
+
+    CK(cudaMemsetAsync(W.cnt, 0, sizeof(Counts), st));
+
+    // --- K1: threshold -> bitmask -------------------------------------------------------------
+    const bool vec_in = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
+    {
+        const int grid = grid_for((i64)g.nchunks * 32 / 4 + 1, 256, 8);
+        if (vec_in)
+            k_threshold<true, 4><<<grid, 256, 0, st>>>(pred, W.omask, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
+        else
+            k_threshold<false, 4><<<grid, 256, 0, st>>>(pred, W.omask, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
+        CK_LAUNCH();
+    }
+    if (dilate) {
+        k_dilate<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(W.omask, W.lmask, g, dil_k);
+        CK_LAUNCH();
+    }
+
+    // --- scan #1: run ids --------------------------------------------------------------------
+    {
+        RunStartSrc src{W.lmask, g.nwords, g.wz};
+        const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
+        k_scan_a<<<ntiles, SCAN_THREADS, 0, st>>>(src, W.tiles);
+        CK_LAUNCH();
+        k_scan_b<<<1, SCAN_THREADS, 0, st>>>(src, W.tiles, &W.cnt->v[SYN_CNT_RUNS], (u32 *)nullptr);
+        CK_LAUNCH();
+        k_scan_c<<<ntiles, SCAN_THREADS, 0, st>>>(src, RunBaseDst{W.runbase}, W.tiles);
+        CK_LAUNCH();
+    }
+    k_init_parents<<<grid_for(max_runs, 256, 8), 256, 0, st>>>(W.par, W.cnt, (u32)max_runs);
+    CK_LAUNCH();
+
+    // --- unions ------------------------------------------------------------------------------
+    if (connectivity == 6) launch_union<6>(W, g, st);
+    else if (connectivity == 18) launch_union<18>(W, g, st);
+    else launch_union<26>(W, g, st);
+    CK_LAUNCH();
+
+    // --- scan #2: flatten + canonical rank -----------------------------------------------------
+    {
+        const int ntiles = (int)((max_runs + SCAN_TILE - 1) / SCAN_TILE);
+        RootFlagSrc srcA{W.par, W.cnt, true}, srcC{W.par, W.cnt, false};
+        k_scan_a<<<ntiles, SCAN_THREADS, 0, st>>>(srcA, W.tiles);
+        CK_LAUNCH();
+        k_scan_b<<<1, SCAN_THREADS, 0, st>>>(srcC, W.tiles, &W.cnt->v[SYN_CNT_COMPONENTS], (u32 *)nullptr);
+        CK_LAUNCH();
+        k_scan_c<<<ntiles, SCAN_THREADS, 0, st>>>(srcC, RankDst{W.rank, W.stat}, W.tiles);
+        CK_LAUNCH();
+    }
+
+    // --- statistics ----------------------------------------------------------------------------
+    k_stats<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.par, W.rank, W.stat, g, W.cnt);
+    CK_LAUNCH();
+
+    // --- scan #3: dust decision + table ----------------------------------------------------------
+    {
+        const int ntiles = (int)((max_runs + SCAN_TILE - 1) / SCAN_TILE);
+        KeepSrc srcA{W.stat, W.cnt, dust_thresh, (u32)(nx - 1), (u32)(ny - 1), (u32)(nz - 1), true};
+        KeepSrc srcC = srcA;
+        srcC.decide = false;
+        i64 ox = offset_xyz ? offset_xyz[0] : 0, oy = offset_xyz ? offset_xyz[1] : 0, oz = offset_xyz ? offset_xyz[2] : 0;
+        k_scan_a<<<ntiles, SCAN_THREADS, 0, st>>>(srcA, W.tiles);
+        CK_LAUNCH();
+        k_scan_b<<<1, SCAN_THREADS, 0, st>>>(srcC, W.tiles, &W.cnt->v[SYN_CNT_KEPT], (u32 *)nullptr);
+        CK_LAUNCH();
+        k_scan_c<<<ntiles, SCAN_THREADS, 0, st>>>(srcC, TableDst{W.stat, (i64 *)seg_table, max_segs, ox, oy, oz}, W.tiles);
+        CK_LAUNCH();
+    }
+    k_run_labels<<<grid_for(max_runs, 256, 8), 256, 0, st>>>(W.par, W.rank, W.stat, W.runlabel, W.cnt, max_segs);
+    CK_LAUNCH();
+
+    // --- dense output (+ overlaps) ---------------------------------------------------------------
+    PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap ? W.paircap - 1 : 0, W.cnt};
+    if (has_base) {
+        k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
+        CK_LAUNCH();
+    }
+    {
+        const bool vec_out = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels_out) & 15) == 0) &&
+                             (!has_base || (reinterpret_cast<uintptr_t>(base_seg) & 15) == 0);
+        const int grid = grid_for((i64)g.nchunks * 32 / 2 + 1, 256, 8);
+        if (vec_out && has_base)
+            k_write_labels<true, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
+                                                               (const u64 *)base_seg, g, T, W.cnt);
+        else if (vec_out)
+            k_write_labels<true, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
+                                                                (const u64 *)base_seg, g, T, W.cnt);
+        else if (has_base)
+            k_write_labels<false, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
+                                                                (const u64 *)base_seg, g, T, W.cnt);
+        else
+            k_write_labels<false, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel,
+                                                                 labels_out, (const u64 *)base_seg, g, T, W.cnt);
+        CK_LAUNCH();
+    }
+    if (has_base) {
+        rc = order_and_emit_pairs(g, W, T, pair_rows, (u64 *)pair_cols, (i64 *)pair_counts, max_pairs, st);
+        if (rc != SYN_OK) return rc;
+    }
+    return finish_counts(W, (i64 *)counts_host, st);
+}
+
+int64_t syn_overlap_workspace_bytes(int64_t nx, int64_t ny, int64_t nz, int64_t max_pairs)
+{
+    return syn_ccs_workspace_bytes(nx, ny, nz, 1, max_pairs < 1 ? 1 : max_pairs);
+}
+
+int syn_count_overlaps(const uint32_t *seg1, const uint64_t *seg2, int64_t nx, int64_t ny, int64_t nz,
+                       uint32_t *pair_rows, uint64_t *pair_cols, int64_t *pair_counts, int64_t max_pairs,
+                       void *workspace, int64_t workspace_bytes, int64_t *counts_host, void *stream)
+{
+    Geom g;
+    int rc = make_geom(nx, ny, nz, &g);
+    if (rc != SYN_OK) return rc;
+    if (!seg1 || !seg2 || !workspace || !pair_rows || !pair_cols || !pair_counts || max_pairs < 1)
+        return fail(SYN_ERR_INVALID, "null pointer / bad capacity");
+    Workspace W;
+    carve((char *)workspace, g, 1, max_pairs, true, &W);
+    if ((i64)W.total > workspace_bytes)
+        return fail(SYN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %lld", W.total,
+                    (long long)workspace_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(W.cnt, 0, sizeof(Counts), st));
+    PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap - 1, W.cnt};
+    k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
+    CK_LAUNCH();
+    k_overlap_scan<<<grid_for((i64)g.nwords * 32, 256, 8), 256, 0, st>>>(seg1, (const u64 *)seg2, g, T, W.cnt);
+    CK_LAUNCH();
+    rc = order_and_emit_pairs(g, W, T, pair_rows, (u64 *)pair_cols, (i64 *)pair_counts, max_pairs, st);
+    if (rc != SYN_OK) return rc;
+    return finish_counts(W, (i64 *)counts_host, st);
+}
+
+int syn_extract_faces(const uint32_t *labels, int64_t nx, int64_t ny, int64_t nz, uint32_t *faces_out, void *stream)
+{
+    if (!labels || !faces_out || nx <= 0 || ny <= 0 || nz <= 0) return fail(SYN_ERR_INVALID, "bad arguments");
+    const i64 total = 2 * (ny * nz + nx * nz + nx * ny);
+    k_extract_faces<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(labels, nx, ny, nz, faces_out);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
+int syn_relabel_lut(uint32_t *labels, int64_t n, const uint32_t *lut, int64_t lut_len, void *stream)
+{
+    if (!labels || n < 0 || (lut_len > 0 && !lut)) return fail(SYN_ERR_INVALID, "bad arguments");
+    if (n == 0 || lut_len <= 0) return SYN_OK;
+    k_relabel_lut<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(labels, n, lut, lut_len);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
+int syn_max_u32(const uint32_t *labels, int64_t n, uint32_t *out_dev, void *stream)
+{
+    if (!labels || !out_dev || n < 0) return fail(SYN_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(out_dev, 0, 4, st));
+    if (n == 0) return SYN_OK;
+    k_max_u32<<<grid_for(n, 256, 8), 256, 0, st>>>(labels, n, out_dev);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
+int syn_segment_stats(const uint32_t *labels, int64_t nx, int64_t ny, int64_t nz, int64_t max_id, int64_t *stats,
+                      void *stream)
+{
+    Geom g;
+    int rc = make_geom(nx, ny, nz, &g);
+    if (rc != SYN_OK) return rc;
+    if (!labels || !stats || max_id < 0) return fail(SYN_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CompStat *stat = nullptr;
+    CK(cudaMallocAsync(&stat, (size_t)(max_id + 1) * sizeof(CompStat), st));
+    k_init_stats<<<grid_for(max_id + 1, 256, 8), 256, 0, st>>>(stat, max_id + 1);
+    CK_LAUNCH();
+    k_label_stats<<<grid_for((i64)g.nwords * 32, 256, 8), 256, 0, st>>>(labels, g, max_id, stat);
+    CK_LAUNCH();
+    k_stats_to_table<<<grid_for(max_id + 1, 256, 8), 256, 0, st>>>(stat, max_id + 1, (i64 *)stats);
+    CK_LAUNCH();
+    CK(cudaFreeAsync(stat, st));
+    return SYN_OK;
+}
+
+int syn_face_pair_edges(const uint32_t *face_a, const uint32_t *face_b, int64_t n, uint32_t *edges_out,
+                        int64_t max_edges, unsigned long long *n_edges_dev, void *stream)
+{
+    if (!face_a || !face_b || !edges_out || !n_edges_dev || n < 0 || max_edges < 0)
+        return fail(SYN_ERR_INVALID, "bad arguments");
+    if (n == 0) return SYN_OK;
+    k_face_pair_edges<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(face_a, face_b, n, edges_out, max_edges,
+                                                                          n_edges_dev);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
+int syn_union_min_map(const uint32_t *edges, const unsigned long long *n_edges_dev, int64_t max_edges, int64_t n_ids,
+                      uint32_t *map_out, void *stream)
+{
+    if (!edges || !n_edges_dev || !map_out || n_ids < 0 || max_edges < 0) return fail(SYN_ERR_INVALID, "bad arguments");
+    if (n_ids == 0) return SYN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_iota_u32<<<grid_for(n_ids, 256, 8), 256, 0, st>>>(map_out, n_ids);
+    CK_LAUNCH();
+    if (max_edges > 0) {
+        k_union_edges<<<grid_for(max_edges, 256, 8), 256, 0, st>>>(edges, n_edges_dev, max_edges, n_ids, map_out);
+        CK_LAUNCH();
+    }
+    k_flatten<<<grid_for(n_ids, 256, 8), 256, 0, st>>>(map_out, n_ids);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
+
+int syn_threshold_dilate(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int dil_k,
+                         uint32_t *out01, void *stream)
+{
+    Geom g;
+    int rc = make_geom(nx, ny, nz, &g);
+    if (rc != SYN_OK) return rc;
+    if (!pred || !out01) return fail(SYN_ERR_INVALID, "null pointer argument");
+    if (dil_k < 0 || dil_k > 32) return fail(SYN_ERR_INVALID, "dil_k must be in [0, 32] (got %d)", dil_k);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nw = (size_t)g.nwords + 8;
+    u32 *buf = nullptr;
+    CK(cudaMallocAsync(&buf, 2 * nw * 4 + 64, st));
+    u32 *m0 = buf, *m1 = buf + nw;
+    u64 *fg = (u64 *)(buf + 2 * nw);
+    CK(cudaMemsetAsync(fg, 0, 8, st));
+    const bool vec_in = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
+    const int grid = grid_for((i64)g.nchunks * 32 / 4 + 1, 256, 8);
+    if (vec_in) k_threshold<true, 4><<<grid, 256, 0, st>>>(pred, m0, g, thresh, fg);
+    else k_threshold<false, 4><<<grid, 256, 0, st>>>(pred, m0, g, thresh, fg);
+    CK_LAUNCH();
+    const u32 *res = m0;
+    if (dil_k > 0) {
+        k_dilate<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(m0, m1, g, dil_k);
+        CK_LAUNCH();
+        res = m1;
+    }
+    k_expand_mask<<<grid_for((i64)g.nwords * 32, 256, 8), 256, 0, st>>>(res, g, out01);
+    CK_LAUNCH();
+    CK(cudaFreeAsync(buf, st));
+    return SYN_OK;
+}
+
+int syn_unique_u64(const uint64_t *vals, int64_t n, uint64_t *out, int64_t cap, unsigned long long *count_dev,
+                   void *stream)
+{
+    if (!vals || !out || !count_dev || n < 0 || cap < 1) return fail(SYN_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(count_dev, 0, 8, st));
+    if (n == 0) return SYN_OK;
+    const u32 tcap = pow2_at_least(2 * cap);
+    u64 *table = nullptr;
+    CK(cudaMallocAsync(&table, ((size_t)tcap + 1) * 8, st));
+    k_fill_u64<<<grid_for(tcap, 256, 8), 256, 0, st>>>(table, tcap, ~0ull);
+    CK_LAUNCH();
+    CK(cudaMemsetAsync(table + tcap, 0, 8, st));
+    k_unique_u64<<<grid_for(n, 256, 8), 256, 0, st>>>((const u64 *)vals, n, table, tcap - 1, (u64 *)out, cap,
+                                                     count_dev);
+    CK_LAUNCH();
+    CK(cudaFreeAsync(table, st));
+    return SYN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,497 @@
+// ccl.cuh -- the labeler: threshold -> bitmask -> z-runs -> union-find ->
+// canonical (raster-first) numbering -> per-component statistics -> dust filter.
+//
+// Replaces, on the device:
+//   mask = d > thresh                                  synaptor/proc/seg/conncomps.py:17
+//   cc3d.connected_components(mask, connectivity=6)    conncomps.py:22  (third-party labeler)
+//   seg_utils.dilate_by_k                              seg_utils/_seg_utils.cpp:25-82,180-200
+//   segment_sizes / centers_of_mass / bounding_boxes   seg_utils/describe.py:14-80, _describe.cpp:23-64
+//   filter_segs_by_size(to_ignore=continuation ids)    seg_utils/filtering.py:7-40, proc/tasks.py:45-51
+#pragma once
+#include "common.cuh"
+
+namespace syn {
+
+// ===========================================================================
+// K1: float32 predictions -> 1 bit per voxel.  One warp per 128-voxel chunk of a
+// row; VEC path: one 128-bit streaming load per lane (4 voxels), the 4-bit
+// results are OR-reduced over each group of 8 lanes into a 32-bit mask word.
+// HBM traffic: 4 B/voxel read, 1/8 B/voxel written.
+// ===========================================================================
+template <bool VEC, int UNROLL>
+__global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ pred, u32 *__restrict__ mask,
+                                                   Geom g, float thr, u64 *__restrict__ fg_count)
+{
+    const int lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    u32 nfg = 0;
+    for (u32 c0 = warp * UNROLL; c0 < g.nchunks; c0 += nwarps * UNROLL) {
+        if (VEC) {
+            float4 v[UNROLL];
+            bool ok[UNROLL];
+            u32 widx[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                u32 c = c0 + u;
+                ok[u] = false;
+                widx[u] = 0;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < g.nchunks) {
+                    u32 row = c / g.cpr;
+                    u32 k4 = (c - row * g.cpr) * 4;
+                    i64 z = (i64)k4 * 32 + 4 * lane;
+                    widx[u] = row * g.wz + k4 + (lane >> 3);
+                    if (z < g.nz) {
+                        ok[u] = true;
+                        v[u] = __ldcs(reinterpret_cast<const float4 *>(pred + (i64)row * g.nz + z));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                if (c0 + u >= g.nchunks) break;  // warp-uniform
+                u32 nib = 0;
+                if (ok[u]) nib = (u32)(v[u].x > thr) | ((u32)(v[u].y > thr) << 1) | ((u32)(v[u].z > thr) << 2) |
+                                 ((u32)(v[u].w > thr) << 3);
+                u32 w = __reduce_or_sync(0xFFu << (lane & 24), nib << (4 * (lane & 7)));
+                // ok[] of the first lane of a group says whether the word exists
+                if ((lane & 7) == 0 && ok[u]) {
+                    mask[widx[u]] = w;
+                    nfg += __popc(w);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int u = 0; u < UNROLL; ++u) {
+                u32 c = c0 + u;
+                if (c >= g.nchunks) break;
+                u32 row = c / g.cpr;
+                u32 k4 = (c - row * g.cpr) * 4;
+                const float *p = pred + (i64)row * g.nz;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    i64 z = (i64)(k4 + j) * 32 + lane;
+                    bool b = false;
+                    if (z < g.nz) b = __ldcs(p + z) > thr;
+                    u32 w = __ballot_sync(SYN_FULL, b);
+                    if (lane == j && k4 + j < g.wz) {
+                        mask[row * g.wz + k4 + j] = w;
+                        nfg += __popc(w);
+                    }
+                }
+            }
+        }
+    }
+    // voxel count above threshold (diagnostic + fg fraction)
+    for (int d = 16; d; d >>= 1) nfg += __shfl_down_sync(SYN_FULL, nfg, d);
+    if (lane == 0 && nfg) atomicAdd(fg_count, (u64)nfg);
+}
+
+// ===========================================================================
+// K1d: 2-D L1 dilation by k over axes (y, z) on the bitmask -- what the chamfer
+// distance transform + `dist > k -> 0` of _seg_utils.cpp:25-82,180-200 computes
+// for a 0/1 mask.  out(y, z) = OR_{|dy| <= k} zdil(in(y + dy), k - |dy|).
+// One thread per output word; the bitmask is L2 resident.  k <= 32.
+// ===========================================================================
+__device__ __forceinline__ u32 zdil_word(u32 prev, u32 cur, u32 next, int r)
+{
+    // bits of `cur` row-word after smearing every set bit by +-r along z
+    u32 out = cur;
+    u64 lo = ((u64)cur << 32) | prev;   // cur in the high half: (lo >> (32 - s)) == (cur << s) | (prev >> (32 - s))
+    u64 hi = ((u64)next << 32) | cur;   // (hi >> s) low half == (cur >> s) | (next << (32 - s))
+    for (int s = 1; s <= r; ++s) {
+        out |= (u32)(lo >> (32 - s));
+        out |= (u32)(hi >> s);
+    }
+    return out;
+}
+
+__global__ void __launch_bounds__(256) k_dilate(const u32 *__restrict__ in, u32 *__restrict__ out, Geom g, int k)
+{
+    const u32 tail = (g.nz & 31) ? ((1u << (g.nz & 31)) - 1u) : 0xFFFFFFFFu;
+    for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < g.nwords; w += gridDim.x * blockDim.x) {
+        u32 row = w / g.wz;
+        u32 kw = w - row * g.wz;
+        u32 y = row % (u32)g.ny;
+        u32 acc = 0;
+        for (int dy = -k; dy <= k; ++dy) {
+            int yy = (int)y + dy;
+            if (yy < 0 || yy >= (int)g.ny) continue;
+            const u32 *r = in + (i64)(row + dy) * g.wz;  // same x, row index shifts by dy
+            u32 cur = r[kw];
+            u32 prev = kw > 0 ? r[kw - 1] : 0u;
+            u32 next = kw + 1 < g.wz ? r[kw + 1] : 0u;
+            if ((cur | prev | next) == 0) continue;
+            int rr = k - (dy < 0 ? -dy : dy);
+            acc |= zdil_word(prev, cur, next, rr);
+        }
+        if (kw == g.wz - 1) acc &= tail;
+        out[w] = acc;
+    }
+}
+
+// ===========================================================================
+// Generic 3-phase exclusive scan of a per-item count:
+//   phase A: per-tile sums      phase B: scan of the tile sums (one block)
+//   phase C: per-item exclusive prefix handed to a writer
+// `Src` provides n() (item count, may live on the device) and get(i).
+// ===========================================================================
+template <class Src>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_a(Src src, u32 *__restrict__ tilesum)
+{
+    __shared__ u32 sm[33];
+    const u64 n = src.n();
+    const u64 base = (u64)blockIdx.x * SCAN_TILE;
+    if (base >= n) return;  // block-uniform
+    u32 v = 0;
+    const u64 i0 = base + (u64)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t)
+        if (i0 + t < n) v += src.get(i0 + t);
+    u32 total;
+    block_excl_scan(v, sm, &total);
+    if (threadIdx.x == 0) tilesum[blockIdx.x] = total;
+}
+
+// one block; scans ceil(n / SCAN_TILE) tile sums in place (exclusive) and writes
+// the grand total to *total_out (as i64) and optionally to *total_u32.
+template <class Src>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_b(Src src, u32 *__restrict__ tilesum, i64 *total_out,
+                                                         u32 *total_u32)
+{
+    __shared__ u32 sm[33];
+    const u64 n = src.n();
+    const u32 ntiles = (u32)((n + SCAN_TILE - 1) / SCAN_TILE);
+    u32 carry = 0;
+    for (u32 b0 = 0; b0 < ntiles; b0 += SCAN_THREADS) {
+        u32 i = b0 + threadIdx.x;
+        u32 v = i < ntiles ? tilesum[i] : 0;
+        u32 total;
+        u32 ex = block_excl_scan(v, sm, &total);
+        if (i < ntiles) tilesum[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        if (total_out) *total_out = (i64)carry;
+        if (total_u32) *total_u32 = carry;
+    }
+}
+
+template <class Src, class Dst>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_c(Src src, Dst dst, const u32 *__restrict__ tilebase)
+{
+    __shared__ u32 sm[33];
+    const u64 n = src.n();
+    const u64 base = (u64)blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
+    u32 item[SCAN_ITEMS];
+    u32 v = 0;
+    const u64 i0 = base + (u64)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) {
+        item[t] = (i0 + t < n) ? src.get(i0 + t) : 0;
+        v += item[t];
+    }
+    u32 total;
+    u32 ex = block_excl_scan(v, sm, &total) + tilebase[blockIdx.x];
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) {
+        if (i0 + t < n) dst.put(i0 + t, ex, item[t]);
+        ex += item[t];
+    }
+}
+
+// --- scan #1: run starts per mask word -> runbase[w] ------------------------
+struct RunStartSrc {
+    const u32 *mask;
+    u32 nwords, wz;
+    __device__ __forceinline__ u64 n() const { return nwords; }
+    __device__ __forceinline__ u32 get(u64 w) const
+    {
+        u32 m = mask[w];
+        if (m == 0) return 0;
+        u32 k = (u32)w % wz;
+        u32 carry = k ? (mask[w - 1] >> 31) : 0u;
+        return __popc(run_starts(m, carry));
+    }
+};
+struct RunBaseDst {
+    u32 *runbase;
+    __device__ __forceinline__ void put(u64 w, u32 ex, u32) const { runbase[w] = ex; }
+};
+
+// validates the run count against capacity and initialises parent[g] = g
+__global__ void k_init_parents(u32 *__restrict__ par, Counts *cnt, u32 max_runs)
+{
+    const u64 nruns = (u64)cnt->v[SYN_CNT_RUNS];
+    if (nruns > max_runs) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr((u64 *)&cnt->v[SYN_CNT_ERRFLAGS], (u64)SYN_EF_RUNS);
+        return;
+    }
+    for (u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x; g < nruns; g += (u64)gridDim.x * blockDim.x)
+        par[g] = (u32)g;
+}
+
+// ===========================================================================
+// K3: unions between z-runs of neighbouring rows.  One thread per mask word of
+// the "current" row; neighbour rows are the already-visited ones in raster order
+// ((x, y-1), (x-1, y) for 6-connectivity; plus (x-1, y-1), (x-1, y+1) and the
+// +-1 z-shifts for 18 / 26).  Two runs are joined when their z-intervals meet
+// (after the shift).  Run id of the run covering bit b of word w:
+//     runbase[w] + popc(starts(w) & mask_le(b)) - 1
+// ===========================================================================
+struct RowView {
+    const u32 *mask;     // words of this row
+    const u32 *runbase;  // run-start prefix of this row's words
+    u32 wz;
+    __device__ __forceinline__ u32 word(int k) const { return (k >= 0 && k < (int)wz) ? mask[k] : 0u; }
+    // id of the run covering bit b (0..31) of word k; that bit must be set
+    __device__ __forceinline__ u32 run_at(int k, int b) const
+    {
+        u32 m = mask[k];
+        u32 carry = k ? (mask[k - 1] >> 31) : 0u;
+        return runbase[k] + __popc(run_starts(m, carry) & mask_le((u32)b)) - 1u;
+    }
+};
+
+// joins runs of row A (word k, bits `mine`) with runs of row B whose bit (b + shift) is set
+template <int SHIFT>
+__device__ __forceinline__ void union_shifted(u32 *par, const RowView &A, const RowView &B, int k, u32 mA)
+{
+    u32 nb;  // bit b set <=> B has bit (b + SHIFT) set
+    if (SHIFT == 0) nb = B.word(k);
+    else if (SHIFT < 0) nb = (B.word(k) << 1) | (B.word(k - 1) >> 31);
+    else nb = (B.word(k) >> 1) | (B.word(k + 1) << 31);
+    u32 o = mA & nb;
+    if (!o) return;
+    u32 os = o & ~(o << 1);  // first bit of every overlap span (a span lies inside one run of A and one of B)
+    while (os) {
+        int b = __ffs(os) - 1;
+        os &= os - 1;
+        u32 ga = A.run_at(k, b);
+        int bb = b + SHIFT, kb = k;
+        if (bb < 0) { bb = 31; kb = k - 1; }
+        else if (bb > 31) { bb = 0; kb = k + 1; }
+        u32 gb = B.run_at(kb, bb);
+        uf_union(par, ga, gb);
+    }
+}
+
+template <int CONN>
+__global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask, const u32 *__restrict__ runbase,
+                                                    u32 *par, Geom g, const Counts *cnt)
+{
+    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < g.nwords; w += gridDim.x * blockDim.x) {
+        u32 m = mask[w];
+        if (m == 0) continue;
+        u32 row = w / g.wz;
+        int k = (int)(w - row * g.wz);
+        u32 x = row / (u32)g.ny;
+        u32 y = row - x * (u32)g.ny;
+        RowView A{mask + (u64)row * g.wz, runbase + (u64)row * g.wz, g.wz};
+        if (y > 0) {
+            u32 r2 = row - 1;
+            RowView B{mask + (u64)r2 * g.wz, runbase + (u64)r2 * g.wz, g.wz};
+            union_shifted<0>(par, A, B, k, m);
+            if (CONN >= 18) { union_shifted<-1>(par, A, B, k, m); union_shifted<1>(par, A, B, k, m); }
+        }
+        if (x > 0) {
+            u32 r2 = row - (u32)g.ny;
+            RowView B{mask + (u64)r2 * g.wz, runbase + (u64)r2 * g.wz, g.wz};
+            union_shifted<0>(par, A, B, k, m);
+            if (CONN >= 18) { union_shifted<-1>(par, A, B, k, m); union_shifted<1>(par, A, B, k, m); }
+            if (CONN >= 18 && y > 0) {
+                u32 r3 = r2 - 1;
+                RowView C{mask + (u64)r3 * g.wz, runbase + (u64)r3 * g.wz, g.wz};
+                union_shifted<0>(par, A, C, k, m);
+                if (CONN == 26) { union_shifted<-1>(par, A, C, k, m); union_shifted<1>(par, A, C, k, m); }
+            }
+            if (CONN >= 18 && y + 1 < (u32)g.ny) {
+                u32 r3 = r2 + 1;
+                RowView C{mask + (u64)r3 * g.wz, runbase + (u64)r3 * g.wz, g.wz};
+                union_shifted<0>(par, A, C, k, m);
+                if (CONN == 26) { union_shifted<-1>(par, A, C, k, m); union_shifted<1>(par, A, C, k, m); }
+            }
+        }
+    }
+}
+
+// ===========================================================================
+// K4: flatten every run to its root, flag roots, rank the roots (scan #2).  The
+// rank of a root among all roots in run-id order is the canonical component
+// number minus one: run ids are in raster order of the run's first voxel and
+// the root is the smallest run of its component.
+// ===========================================================================
+struct RootFlagSrc {  // phase A also flattens
+    u32 *par;
+    const Counts *cnt;
+    bool flatten;
+    __device__ __forceinline__ u64 n() const
+    {
+        return (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) ? 0 : (u64)cnt->v[SYN_CNT_RUNS];
+    }
+    __device__ __forceinline__ u32 get(u64 g) const
+    {
+        if (flatten) {
+            u32 r = uf_find_ro(par, (u32)g);
+            par[g] = r;
+            return r == (u32)g;
+        }
+        return par[g] == (u32)g;
+    }
+};
+// rank[g] = canonical index for roots; also initialises the root's CompStat record
+struct RankDst {
+    u32 *rank;
+    CompStat *stat;
+    __device__ __forceinline__ void put(u64 g, u32 ex, u32 isroot) const
+    {
+        rank[g] = ex;
+        if (isroot) {
+            CompStat s;
+            s.size = s.sx = s.sy = s.sz = 0;
+            s.minx = s.miny = s.minz = 0xFFFFFFFFu;
+            s.maxx = s.maxy = s.maxz = 0;
+            s.keep = 0;
+            s.row = 0;
+            stat[ex] = s;
+        }
+    }
+};
+
+// ===========================================================================
+// K5: per-component size / coordinate sums / bounding box.  One thread per mask
+// word; every maximal span of set bits inside the word ("piece") belongs to one
+// run, hence one component.  In the dilation variant the spans come from the
+// dilated mask but only voxels of the original mask are counted
+// (conncomps.py:49-50 `ccs[mask == 0] = 0`).
+// ===========================================================================
+__global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
+                                               const u32 *__restrict__ runbase, const u32 *__restrict__ par,
+                                               const u32 *__restrict__ rank, CompStat *stat, Geom g,
+                                               const Counts *cnt)
+{
+    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < g.nwords; w += gridDim.x * blockDim.x) {
+        u32 m = lmask[w];
+        if (m == 0) continue;
+        u32 om = omask[w];
+        if (om == 0) continue;
+        u32 row = w / g.wz;
+        u32 k = w - row * g.wz;
+        u32 x = row / (u32)g.ny;
+        u32 y = row - x * (u32)g.ny;
+        u32 carry = k ? (lmask[w - 1] >> 31) : 0u;
+        u32 starts = run_starts(m, carry);
+        u32 rb = runbase[w];
+        u32 ps = m & ~(m << 1);  // piece starts (no carry: a continuing run still starts a piece here)
+        while (ps) {
+            int b0 = __ffs(ps) - 1;
+            ps &= ps - 1;
+            u32 span = ~(m >> b0);                       // zero bits above the piece
+            int len = span ? (__ffs(span) - 1) : 32;     // span==0 only when b0==0 and m is all ones
+            if (len > 32 - b0) len = 32 - b0;
+            u32 pm = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << b0;
+            u32 bits = om & pm;
+            if (!bits) continue;
+            u32 gidx = rb + __popc(starts & mask_le((u32)b0)) - 1u;
+            u32 c = rank[par[gidx]];
+            CompStat *s = stat + c;
+            u32 n = __popc(bits);
+            u32 z0 = k * 32;
+            atomicAdd(&s->size, (u64)n);
+            atomicAdd(&s->sx, (u64)n * x);
+            atomicAdd(&s->sy, (u64)n * y);
+            atomicAdd(&s->sz, (u64)n * z0 + bitpos_sum(bits));
+            atomicMin(&s->minx, x);
+            atomicMin(&s->miny, y);
+            atomicMin(&s->minz, z0 + (u32)__ffs(bits) - 1u);
+            atomicMax(&s->maxx, x);
+            atomicMax(&s->maxy, y);
+            atomicMax(&s->maxz, z0 + 31u - (u32)__clz(bits));
+        }
+    }
+}
+
+// ===========================================================================
+// K6: dust decision + compaction of the segment table (scan #3 over components).
+// keep = size >= dust  OR  the component touches one of the six chunk faces
+// (continuations are never filtered: proc/tasks.py:45-51).
+// ===========================================================================
+struct KeepSrc {
+    CompStat *stat;
+    const Counts *cnt;
+    i64 dust;
+    u32 mx, my, mz;  // nx-1, ny-1, nz-1
+    bool decide;
+    __device__ __forceinline__ u64 n() const
+    {
+        return (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) ? 0 : (u64)cnt->v[SYN_CNT_COMPONENTS];
+    }
+    __device__ __forceinline__ u32 get(u64 c) const
+    {
+        if (!decide) return stat[c].keep;
+        const CompStat s = stat[c];
+        bool face = s.minx == 0 || s.miny == 0 || s.minz == 0 || s.maxx == mx || s.maxy == my || s.maxz == mz;
+        u32 keep = (s.size > 0) && (face || (i64)s.size >= dust);
+        stat[c].keep = keep;
+        return keep;
+    }
+};
+
+// centroid exactly as _describe.cpp:54-61: float32(sum) / float32(size), round half away
+__device__ __forceinline__ i64 centroid_f32(u64 sum, u64 size)
+{
+    float q = __fdiv_rn(__ll2float_rn((i64)sum), __ll2float_rn((i64)size));
+    return (i64)roundf(q);
+}
+
+struct TableDst {
+    CompStat *stat;
+    i64 *table;
+    i64 max_segs;
+    i64 ox, oy, oz;
+    __device__ __forceinline__ void put(u64 c, u32 rowi, u32 keep) const
+    {
+        if (!keep) return;
+        stat[c].row = rowi;
+        if ((i64)rowi >= max_segs) return;
+        const CompStat s = stat[c];
+        i64 *r = table + (i64)rowi * SYN_SEG_NCOLS;
+        r[SYN_SEG_ID] = (i64)c + 1;
+        r[SYN_SEG_SIZE] = (i64)s.size;
+        r[SYN_SEG_CX] = centroid_f32(s.sx, s.size) + ox;
+        r[SYN_SEG_CY] = centroid_f32(s.sy, s.size) + oy;
+        r[SYN_SEG_CZ] = centroid_f32(s.sz, s.size) + oz;
+        r[SYN_SEG_BX] = (i64)s.minx + ox;
+        r[SYN_SEG_BY] = (i64)s.miny + oy;
+        r[SYN_SEG_BZ] = (i64)s.minz + oz;
+        r[SYN_SEG_EX] = (i64)s.maxx + 1 + ox;
+        r[SYN_SEG_EY] = (i64)s.maxy + 1 + oy;
+        r[SYN_SEG_EZ] = (i64)s.maxz + 1 + oz;
+    }
+};
+
+// final per-run label: canonical id if kept else 0; also tracks the largest kept id
+__global__ void __launch_bounds__(256) k_run_labels(const u32 *__restrict__ par, const u32 *__restrict__ rank,
+                                                    const CompStat *__restrict__ stat, u32 *__restrict__ runlabel,
+                                                    Counts *cnt, i64 max_segs)
+{
+    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    const u64 nruns = (u64)cnt->v[SYN_CNT_RUNS];
+    u32 mx = 0;
+    for (u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x; g < nruns; g += (u64)gridDim.x * blockDim.x) {
+        u32 c = rank[par[g]];
+        u32 lab = stat[c].keep ? c + 1 : 0;
+        runlabel[g] = lab;
+        mx = max(mx, lab);
+    }
+    mx = __reduce_max_sync(SYN_FULL, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax((u64 *)&cnt->v[SYN_CNT_MAX_LABEL], (u64)mx);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && cnt->v[SYN_CNT_KEPT] > max_segs)
+        atomicOr((u64 *)&cnt->v[SYN_CNT_ERRFLAGS], (u64)SYN_EF_SEGS);
+}
+
+}  // namespace syn

@@ -1,0 +1,189 @@
+// common.cuh -- shared device helpers for libsynaptor_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/synaptor_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define SYN_HOST 1
+#endif
+
+#define SYN_FULL 0xFFFFFFFFu
+
+// error flag bits (counts[SYN_CNT_ERRFLAGS])
+#define SYN_EF_RUNS 1
+#define SYN_EF_SEGS 2
+#define SYN_EF_TABLE 4
+#define SYN_EF_PAIRS 8
+
+namespace syn {
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+
+// ---------------------------------------------------------------------------
+// Volume geometry.  The 1-bit-per-voxel masks are stored row by row: a "row" is
+// one (x, y) pair, `wz` 32-bit words per row, bit b of word k <-> z = 32k + b;
+// bits at z >= nz are always zero.  Word index = row * wz + k fits in 32 bits
+// (checked on the host).
+// ---------------------------------------------------------------------------
+struct Geom {
+    i64 nx, ny, nz;
+    i64 nvox;
+    u32 rows;    // nx * ny
+    u32 wz;      // ceil(nz / 32)
+    u32 nwords;  // rows * wz
+    u32 cpr;     // 128-voxel chunks per row = ceil(wz / 4)
+    u32 nchunks; // rows * cpr
+};
+
+// per-component accumulator, one 64-byte record (two 32 B sectors)
+struct __align__(16) CompStat {
+    u64 size, sx, sy, sz;
+    u32 minx, miny, minz, maxx, maxy, maxz;
+    u32 keep;   // dust decision
+    u32 row;    // row in the compacted segment table
+};
+static_assert(sizeof(CompStat) == 64, "CompStat must be 64 bytes");
+
+// slot of the (label, base id) pair table: 16-byte key claimed with one 128-bit CAS
+struct __align__(16) PairKey {
+    u64 base;
+    u64 label;  // 0xFFFF...F = empty
+};
+
+// device-side counters at the head of the workspace
+struct Counts {
+    i64 v[SYN_NCOUNTS];
+};
+
+__host__ __device__ __forceinline__ u32 div_up_u32(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
+
+// bits 0..b inclusive
+__device__ __forceinline__ u32 mask_le(u32 b) { return (2u << b) - 1u; }
+// bits 0..b-1
+__device__ __forceinline__ u32 mask_lt(u32 b) { return (1u << b) - 1u; }
+
+// run-start bits of a mask word given the top bit of the previous word in the row
+__device__ __forceinline__ u32 run_starts(u32 m, u32 carry) { return m & ~((m << 1) | carry); }
+
+// sum of the positions of the set bits of w
+__device__ __forceinline__ u32 bitpos_sum(u32 w)
+{
+    return __popc(w & 0xAAAAAAAAu) + (__popc(w & 0xCCCCCCCCu) << 1) + (__popc(w & 0xF0F0F0F0u) << 2) +
+           (__popc(w & 0xFF00FF00u) << 3) + (__popc(w & 0xFFFF0000u) << 4);
+}
+
+__device__ __forceinline__ u32 ldcg_u32(const u32 *p) { return __ldcg(p); }
+
+// ---------------------------------------------------------------------------
+// Lock-free union-find on a u32 parent array in global memory.  Links always go
+// from the larger to the smaller index (atomicMin), so the root of a set is its
+// smallest member: with run ids in raster order that is the raster-first run,
+// which is what makes the final numbering canonical.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u32 uf_find(u32 *par, u32 x)
+{
+    u32 p = ldcg_u32(par + x);
+    while (p != x) {
+        u32 gp = ldcg_u32(par + p);
+        if (gp != p) par[x] = gp;  // path halving; always an ancestor, always smaller
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
+__device__ __forceinline__ u32 uf_find_ro(const u32 *par, u32 x)
+{
+    u32 p = ldcg_u32(par + x);
+    while (p != x) {
+        x = p;
+        p = ldcg_u32(par + x);
+    }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(u32 *par, u32 a, u32 b)
+{
+    while (true) {
+        a = uf_find(par, a);
+        b = uf_find(par, b);
+        if (a == b) return;
+        if (a > b) { u32 t = a; a = b; b = t; }
+        u32 old = atomicMin(par + b, a);
+        if (old == b) return;
+        b = old;  // b was no longer a root: keep merging a with its (former) parent
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 128-bit compare-and-swap (atom.global.cas.b128, sm_90+)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ PairKey cas128(PairKey *addr, PairKey cmp, PairKey val)
+{
+    PairKey old;
+    asm volatile(
+        "{\n\t.reg .b128 c, v, o;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 v, {%4, %5};\n\t"
+        "atom.global.cas.b128 o, [%6], c, v;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old.base), "=l"(old.label)
+        : "l"(cmp.base), "l"(cmp.label), "l"(val.base), "l"(val.label), "l"(addr)
+        : "memory");
+    return old;
+}
+
+__device__ __forceinline__ u64 mix64(u64 a, u64 b)
+{
+    u64 h = b * 0x9E3779B97F4A7C15ull;
+    h ^= a * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 32;
+    return h;
+}
+
+// ---------------------------------------------------------------------------
+// block-wide exclusive scan (blockDim.x == SCAN_THREADS)
+// ---------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ u32 warp_incl_scan(u32 v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(SYN_FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// returns the exclusive prefix of v over the block; *total = block sum.
+// smem: 33 u32 of shared scratch.  Ends with a __syncthreads().
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *smem, u32 *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    u32 inc = warp_incl_scan(v, lane);
+    if (lane == 31) smem[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        u32 w = lane < nw ? smem[lane] : 0;
+        u32 wi = warp_incl_scan(w, lane);
+        smem[lane] = wi - w;
+        if (lane == 31) smem[32] = wi;
+    }
+    __syncthreads();
+    u32 res = smem[wid] + inc - v;
+    *total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+}  // namespace syn

@@ -1,0 +1,370 @@
+"""
+Parity of the CUDA path (through the C-ABI) against the oracle and the committed
+golden fixtures of the executed reference.  Bit-exact: labels, sizes, bboxes,
+integer centroids, overlap triples and their order.  Needs a B200.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from util import flatten_conts, gold, sorted_triples, table_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def syn():
+    import synaptor_b200
+    return synaptor_b200
+
+
+def first_diff(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape:
+        return f"shape {a.shape} vs {b.shape}"
+    d = np.argwhere(a != b)
+    if len(d) == 0:
+        return "equal"
+    i = tuple(d[0])
+    return f"{len(d)} diffs; first at {i}: got {a[i]} want {b[i]}; max got {a.max()} want {b.max()}"
+
+
+def check_cc_task(syn, pred, thresh, dust, offset=(0, 0, 0), conn=6, dil=0):
+    want = orc.cc_task_c(pred, thresh, dust, offset=offset, connectivity=conn, dil_param=dil)
+    got = syn.proc.tasks.cc_task(pred, thresh, dust, offset=offset, connectivity=conn, dil_param=dil, verbose=False)
+    assert got[0].dtype == np.uint32 and got[0].flags.c_contiguous
+    assert np.array_equal(got[0], want[0]), first_diff(got[0], want[0])
+    gm, gc = flatten_conts(got[1])
+    wm, wc = flatten_conts(want[1])
+    assert np.array_equal(gm, wm), first_diff(gm, wm)
+    assert np.array_equal(gc, wc)
+    gi, gt = table_of(got[2])
+    wi, wt = table_of(want[2])
+    assert list(got[2].columns) == list(want[2].columns) and got[2].index.name == "cleft_segid"
+    assert np.array_equal(gi, wi), first_diff(gi, wi)
+    assert np.array_equal(gt, wt), first_diff(gt, wt)
+    return got
+
+
+# ----------------------------------------------------------------------------- goldens
+def test_g1_cc_task_golden(syn):
+    g = gold("g1_cc_task.npz")
+    ccs, conts, info = syn.proc.tasks.cc_task(g["pred"], float(g["thresh"]), int(g["dust"]),
+                                              offset=tuple(g["offset"].tolist()), verbose=False)
+    assert np.array_equal(ccs, g["ccs"]), first_diff(ccs, g["ccs"])
+    meta, coords = flatten_conts(conts)
+    assert np.array_equal(meta, g["cont_meta"]) and np.array_equal(coords, g["cont_coords"])
+    idx, tab = table_of(info)
+    assert list(info.columns) == g["info_columns"].tolist()
+    assert np.array_equal(idx, g["info_index"].astype(np.int64))
+    assert np.array_equal(tab, g["info_table"].astype(np.int64)), first_diff(tab, g["info_table"].astype(np.int64))
+
+
+def test_g2_overlap_golden(syn):
+    g = gold("g2_overlap_task.npz")
+    ov = syn.proc.tasks.overlap_task(g["ccs"], g["base"])
+    assert ov.shape == tuple(g["shape"].tolist())
+    assert np.array_equal(ov.row, g["row"]), first_diff(ov.row, g["row"])
+    assert np.array_equal(ov.col, g["col"]) and np.array_equal(ov.data, g["data"])
+    assert ov.data.dtype == np.int64
+    m = gold("g2_max_overlaps.npz")
+    mo = syn.proc.overlap.find_max_overlaps(ov)
+    assert np.array_equal(mo.row, m["row"]) and np.array_equal(mo.col, m["col"]) and np.array_equal(mo.data, m["data"])
+    mat, ids1, ids2 = syn.seg_utils.count_overlaps(g["ccs"], g["base"], orig_ids=False)
+    assert np.array_equal(ids1, np.unique(g["ccs"])[1:]) and np.array_equal(ids2, np.unique(g["base"])[1:])
+    assert np.array_equal(ids1[mat.row], g["row"]) and np.array_equal(ids2[mat.col].astype(np.int64), g["col"])
+
+
+def test_g3_dilated_golden(syn):
+    g = gold("g3_dilated.npz")
+    for k in (1, 2, 5):
+        ccs = syn.dilated_components(g["pred"], k, float(g["thresh"]))
+        assert np.array_equal(ccs, g[f"ccs_k{k}"]), (k, first_diff(ccs, g[f"ccs_k{k}"]))
+        dil = syn.seg_utils.dilate_by_k(g["pred"] > float(g["thresh"]), k)
+        assert dil.dtype == np.uint32 and np.array_equal(dil, g[f"dil_k{k}"]), (k, first_diff(dil, g[f"dil_k{k}"]))
+
+
+def test_g4_merge_golden(syn):
+    g = gold("g4_merge_ccs.npz")
+    vol = g["vol"]
+    cs = tuple(g["chunk_shape"].tolist())
+    boxes = syn.chunk_bboxes(vol.shape, cs)
+    grid = (2, 2, 2)
+    cont_arr = np.empty(grid, dtype=object)
+    info_arr = np.empty(grid, dtype=object)
+    segs = np.empty(grid, dtype=object)
+    for (i, (gi, bb)) in enumerate(zip(np.ndindex(grid), boxes)):
+        ccs, conts, info = syn.proc.tasks.cc_task(np.ascontiguousarray(vol[bb.index()]), float(g["thresh"]),
+                                                  int(g["dust"]), offset=tuple(bb.min()), verbose=False)
+        t = g[f"chunk_table_{i}"]
+        idx, tab = table_of(info)
+        assert np.array_equal(idx, t[:, 0]) and np.array_equal(tab, t[:, 1:])
+        assert np.array_equal(ccs, g[f"chunk_seg_{i}"])
+        cont_arr[gi], info_arr[gi], segs[gi] = conts, info, ccs
+    merged, id_maps = syn.proc.tasks.merge_ccs_task(cont_arr, info_arr, int(g["size_thr"]),
+                                                    tuple(g["max_face_shape"].tolist()))
+    gold_rows = {int(i): r.astype(np.int64) for (i, r) in zip(g["merged_index"], g["merged_table"])}
+    midx, mtab = table_of(merged)
+    assert sorted(midx.tolist()) == sorted(gold_rows)
+    for (k, row) in zip(midx.tolist(), mtab):
+        gr = gold_rows[k]
+        assert row[0] == gr[0] and np.array_equal(row[4:], gr[4:])
+        assert np.all(np.abs(row[1:4] - gr[1:4]) <= 1)   # float64 weighted mean, truncated (1e-6 rel. tolerance)
+    final = np.zeros(vol.shape, dtype=np.uint32)
+    for (i, (gi, bb)) in enumerate(zip(np.ndindex(grid), boxes)):
+        assert sorted((int(a), int(b)) for (a, b) in id_maps[gi].items()) == [tuple(x) for x in g[f"id_map_{i}"].tolist()]
+        final[bb.index()] = syn.proc.tasks.remap_ids_task(segs[gi].copy(), id_maps[gi], copy=False)
+    assert np.array_equal(final, g["final"]), first_diff(final, g["final"])
+
+
+def test_g5_centroids_golden(syn):
+    g = gold("g5_centroids.npz")
+    c = syn.centers_of_mass(g["seg"])
+    assert sorted(c) == g["ids"].tolist()
+    assert np.array_equal(np.array([c[i] for i in sorted(c)]), g["cents"])
+    big = np.ones(tuple(g["big_shape"].tolist()), dtype=np.uint32)
+    assert syn.centers_of_mass(big)[1] == tuple(g["big_cent"].tolist())
+    assert syn.centers_of_mass(g["seg"], offset=(1, 2, 3))[4] == tuple(int(a + b) for (a, b) in zip(c[4], (1, 2, 3)))
+
+
+def test_g6_threshold_golden(syn):
+    g = gold("g6_threshold.npz")
+    ccs = syn.connected_components(g["d"], float(g["thresh"]))
+    assert np.array_equal(ccs, g["ccs"]), (ccs, g["ccs"])
+
+
+# ----------------------------------------------------------------------------- random volumes vs the oracle
+SHAPES = [(1, 1, 1), (1, 1, 40), (3, 5, 7), (2, 3, 33), (9, 11, 64), (16, 8, 129), (7, 13, 131),
+          (20, 24, 128), (33, 31, 100), (12, 10, 260), (40, 40, 36)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("conn", [6, 18, 26])
+def test_random_noise_vs_oracle(syn, shape, conn):
+    rng = np.random.default_rng(hash((shape, conn)) % (2 ** 32))
+    for p in (0.05, 0.3, 0.5, 0.8, 1.0):
+        pred = rng.random(shape, dtype=np.float32)
+        check_cc_task(syn, pred, 1.0 - p, dust=3, conn=conn, offset=(7, -2, 100))
+
+
+@pytest.mark.parametrize("conn", [6, 26])
+@pytest.mark.parametrize("sigma,fg", [(1.0, 0.1), (2.0, 0.03), (3.0, 0.2)])
+def test_smooth_vs_oracle(syn, conn, sigma, fg):
+    pred = orc.synth_pred((64, 72, 96), seed=int(sigma * 10), sigma=sigma, fg=fg)
+    check_cc_task(syn, pred, 0.5, dust=50, conn=conn, offset=(1000, 2000, 3000))
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 9])
+@pytest.mark.parametrize("shape", [(6, 40, 44), (4, 33, 70), (3, 10, 200)])
+def test_dilated_vs_oracle(syn, k, shape):
+    pred = orc.synth_pred(shape, seed=k, sigma=1.2, fg=0.06)
+    check_cc_task(syn, pred, 0.5, dust=5, dil=k)
+    rng = np.random.default_rng(k)
+    check_cc_task(syn, rng.random(shape, dtype=np.float32), 0.9, dust=0, dil=k)
+
+
+def test_f_order_and_dtypes(syn):
+    pred = orc.synth_pred((24, 20, 28), seed=4, sigma=1.5, fg=0.1)
+    a = syn.connected_components(pred, 0.5)
+    b = syn.connected_components(np.asfortranarray(pred), 0.5)
+    assert np.array_equal(a, b) and b.flags.c_contiguous
+    u8 = (pred * 255).astype(np.uint8)
+    assert np.array_equal(syn.connected_components(u8, 127.5), orc.connected_components(u8, 127.5))
+    assert syn.connected_components(pred, 0.5, dtype=np.uint64).dtype == np.uint64
+    with pytest.raises(TypeError):
+        syn.connected_components(pred.astype(np.float64), 0.5)
+    with pytest.raises(ValueError):
+        syn.connected_components(pred[0], 0.5)
+
+
+def test_empty_and_full(syn):
+    z = np.zeros((8, 9, 10), dtype=np.float32)
+    ccs, conts, info = syn.proc.tasks.cc_task(z, 0.5, 10, verbose=False)
+    assert ccs.max() == 0 and len(info) == 0 and list(info.columns) == orc.SEG_INFO_COLUMNS
+    assert all(len(v) == 0 for v in conts.values()) and len(conts) == 6
+    check_cc_task(syn, z + 1, 0.5, 10)
+    e = syn.proc.tasks.cc_task(np.zeros((0, 4, 4), np.float32), 0.5, 1, verbose=False)
+    assert e[0].shape == (0, 4, 4) and len(e[2]) == 0
+    nan = np.full((4, 4, 8), np.nan, dtype=np.float32)
+    assert syn.connected_components(nan, 0.0).max() == 0
+
+
+def test_known_answers(syn):
+    def cc(m, conn=6):
+        return syn.connected_components(m.astype(np.float32), 0.5, connectivity=conn)
+    m = np.zeros((3, 3, 3), bool)
+    m[0, 0, 0] = m[1, 1, 1] = True                       # corner contact
+    assert cc(m, 6).max() == 2 and cc(m, 18).max() == 2 and cc(m, 26).max() == 1
+    m[:] = False
+    m[0, 0, 0] = m[0, 1, 1] = True                       # edge contact
+    assert cc(m, 6).max() == 2 and cc(m, 18).max() == 1 and cc(m, 26).max() == 1
+    m[:] = False
+    m[0, 0, 0] = m[0, 0, 1] = True                       # face contact
+    assert cc(m, 6).max() == 1
+    # U shape: the two arms get separate provisional labels and must merge late
+    u = np.zeros((1, 5, 40), bool)
+    u[0, :, 2] = u[0, :, 37] = True
+    u[0, 4, 2:38] = True
+    out = cc(u)
+    assert out.max() == 1 and out.sum() == u.sum()
+    # first voxel of component 1 is not its min-x voxel; numbering is by raster-first voxel
+    v = np.zeros((4, 4, 4), bool)
+    v[0, 3, 3] = True
+    v[1, 0, 0] = True
+    v[0:3, 2, 1] = True
+    o = cc(v)
+    assert o[0, 2, 1] == 1 and o[0, 3, 3] == 2 and o[1, 0, 0] == 3
+    # snake through the volume: deep union chains
+    s = np.zeros((6, 6, 70), bool)
+    for x in range(6):
+        for y in range(6):
+            if (x * 6 + y) % 2 == 0:
+                s[x, y, :] = True
+            else:
+                s[x, y, 0 if ((x * 6 + y) // 2) % 2 else 69] = True
+    want = orc.label_c(s, 6)[0]
+    assert np.array_equal(cc(s), want)
+
+
+def test_dust_and_face_exemption(syn):
+    m = np.zeros((10, 10, 40), np.float32)
+    m[5, 5, 10:14] = 1      # interior, size 4
+    m[0, 2, 3:5] = 1        # touches x-lo face, size 2
+    m[4, 4, 39] = 1         # touches z-hi face, size 1
+    m[7, 7, 20:30] = 1      # interior size 10
+    ccs, conts, info = syn.proc.tasks.cc_task(m, 0.5, 5, verbose=False)
+    assert sorted(info.index.tolist()) == [1, 2, 4]      # ids keep their raw numbers (gaps stay)
+    assert ccs[5, 5, 10] == 0 and ccs[0, 2, 3] == 1 and ccs[4, 4, 39] == 2 and ccs[7, 7, 25] == 4
+    assert info.loc[4, "size"] == 10 and tuple(info.loc[4, ["bbox_bz", "bbox_ez"]]) == (20, 30)
+    check_cc_task(syn, m, 0.5, 5)
+    check_cc_task(syn, m, 0.5, 0)
+    check_cc_task(syn, m, 0.5, 11)
+
+
+# ----------------------------------------------------------------------------- overlaps
+@pytest.mark.parametrize("shape", [(5, 6, 7), (16, 16, 33), (24, 20, 64), (10, 12, 130)])
+def test_overlaps_vs_oracle(syn, shape):
+    rng = np.random.default_rng(shape[2])
+    seg1 = rng.integers(0, 6, size=shape).astype(np.uint32) * rng.integers(0, 2, size=shape).astype(np.uint32)
+    seg2 = orc.synth_base(shape, seed=3, block=4, bg=0.2)
+    seg2[0, 0, 0] = np.uint64(2 ** 62 + 12345)
+    r, c, v, sh = orc.count_overlaps_c(seg1, seg2)
+    ov = syn.proc.tasks.overlap_task(seg1, seg2)
+    assert ov.shape == sh
+    assert np.array_equal(ov.row, r) and np.array_equal(ov.col, c) and np.array_equal(ov.data, v)
+
+
+def test_overlaps_empty(syn):
+    z = np.zeros((4, 5, 6), dtype=np.uint32)
+    b = np.ones((4, 5, 6), dtype=np.uint64)
+    assert syn.proc.tasks.overlap_task(z, b).shape == (0, 0)
+    assert syn.proc.tasks.overlap_task(z + 1, b * 0).shape == (0, 0)
+    one = syn.proc.tasks.overlap_task(z + 3, b * 7)
+    assert one.shape == (4, 8) and one.nnz == 1 and one.data[0] == 120
+
+
+@pytest.mark.parametrize("shape", [(40, 36, 64), (17, 19, 50)])
+def test_fused_cc_overlap(syn, shape):
+    pred = orc.synth_pred(shape, seed=9, sigma=1.5, fg=0.12)
+    base = orc.synth_base(shape, seed=2, block=8, bg=0.1)
+    ccs, conts, info, mat = syn.proc.tasks.cc_overlap_task(pred, base, 0.5, 20, offset=(5, 5, 5))
+    want = orc.cc_task_c(pred, 0.5, 20, offset=(5, 5, 5))
+    assert np.array_equal(ccs, want[0])
+    r, c, v, sh = orc.count_overlaps_c(want[0], base)
+    assert mat.shape == sh
+    assert np.array_equal(mat.row, r) and np.array_equal(mat.col, c) and np.array_equal(mat.data, v)
+
+
+# ----------------------------------------------------------------------------- seg_utils + capacity growth
+def test_seg_utils_describe(syn):
+    pred = orc.synth_pred((30, 28, 40), seed=6, sigma=1.5, fg=0.15)
+    seg = orc.connected_components(pred, 0.5)
+    seg[seg == 3] = 900       # non-dense ids
+    szs = syn.seg_utils.segment_sizes(seg)
+    assert szs == orc.segment_sizes_np(seg)
+    assert syn.seg_utils.centers_of_mass(seg, offset=(3, 4, 5)) == orc.centers_of_mass_np(seg, offset=(3, 4, 5))
+    bb = syn.seg_utils.bounding_boxes(seg, offset=(3, 4, 5))
+    assert {k: v.astuple() for (k, v) in bb.items()} == orc.bounding_boxes_np(seg, offset=(3, 4, 5))
+    assert np.array_equal(syn.seg_utils.nonzero_unique_ids(seg), np.unique(seg)[1:])
+    f, rem = syn.seg_utils.filter_segs_by_size(seg, 30, to_ignore=[1])
+    fo, remo = orc.filter_segs_by_size_np(seg, 30, to_ignore=[1])
+    assert np.array_equal(f, fo) and rem == remo
+    same, _ = syn.seg_utils.filter_segs_by_size(seg, 0)
+    assert same is seg
+    r = syn.seg_utils.relabel_data(seg, {1: 77, 900: 5, 123456: 9}, copy=True)
+    assert np.array_equal(r, orc.relabel_data_np(seg, {1: 77, 900: 5, 123456: 9}))
+    inplace = seg.copy()
+    out = syn.seg_utils.relabel_data(inplace, {1: 0}, copy=False)
+    assert out is inplace and (inplace == 1).sum() == 0
+
+
+def test_capacity_retry(syn):
+    # dense noise: far more runs / segments / pairs than the default capacities
+    rng = np.random.default_rng(0)
+    pred = rng.random((64, 64, 256), dtype=np.float32)
+    base = rng.integers(1, 2 ** 40, size=pred.shape, dtype=np.uint64)
+    want = orc.cc_task_c(pred, 0.5, 0, with_continuations=False)
+    ccs, _, info, mat = syn.proc.tasks.cc_overlap_task(pred, base, 0.5, 0)
+    assert np.array_equal(ccs, want[0])
+    assert np.array_equal(table_of(info)[1], table_of(want[2])[1])
+    assert mat.nnz == int((ccs != 0).sum())
+
+
+def test_determinism(syn):
+    pred = orc.synth_pred((96, 96, 128), seed=1, sigma=1.0, fg=0.1)
+    base = orc.synth_base(pred.shape, seed=1, block=16)
+    a = syn.proc.tasks.cc_overlap_task(pred, base, 0.5, 10)
+    b = syn.proc.tasks.cc_overlap_task(pred, base, 0.5, 10)
+    assert np.array_equal(a[0], b[0]) and a[2].equals(b[2])
+    assert np.array_equal(a[3].row, b[3].row) and np.array_equal(a[3].col, b[3].col)
+    assert np.array_equal(a[3].data, b[3].data)
+
+
+# ----------------------------------------------------------------------------- BASELINE configs (scaled to seconds)
+def test_config1_256cubed(syn):
+    pred = orc.synth_pred((256, 256, 256), seed=0, sigma=2.0, fg=0.03)
+    for conn in (6, 26):
+        check_cc_task(syn, pred, 0.5, 100, conn=conn)
+
+
+def test_config3_dense_small(syn):
+    pred = orc.synth_pred((256, 256, 128), seed=0, sigma=1.0, fg=0.10)
+    base = orc.synth_base(pred.shape, seed=1)
+    got = check_cc_task(syn, pred, 0.5, 100)
+    r, c, v, sh = orc.count_overlaps_c(got[0], base)
+    mat = syn.proc.tasks.cc_overlap_task(pred, base, 0.5, 100)[3]
+    assert mat.shape == sh and np.array_equal(mat.row, r) and np.array_equal(mat.col, c) and np.array_equal(mat.data, v)
+
+
+def test_full_size_properties(syn):
+    """512^3 (BASELINE config 2): size-independent properties + oracle on the labels."""
+    import torch
+    from synaptor_b200 import _device as D
+    shape = (512, 512, 512)
+    tile = orc.synth_pred((128, 128, 128), seed=0, sigma=2.0, fg=0.03)   # seamless (mode="wrap")
+    pred = np.tile(tile, (4, 4, 4))
+    base = orc.synth_base(shape, seed=1)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    p = torch.from_numpy(pred).to(dev)
+    b = torch.from_numpy(base.view(np.int64)).to(dev)
+    res = D.chunk_ccs_device(p, np.float32(0.5), 100, base=b)
+    labels = res.labels_numpy()
+    table = res.table_numpy()
+    mask = pred > 0.5
+    assert res.counts["fg_voxels"] == int(mask.sum())
+    # kept labels are exactly the table ids, ascending; sizes add up to the labelled voxels
+    assert np.all(np.diff(table[:, 0]) > 0)
+    assert int(table[:, 1].sum()) == int((labels != 0).sum())
+    assert not np.any(labels[~mask])
+    # idempotence: relabelling the label volume as a mask reproduces the partition
+    want, n = orc.label_c(mask, 6)
+    assert n == res.counts["components"]
+    kept = np.zeros(n + 1, dtype=np.uint32)
+    kept[table[:, 0]] = table[:, 0]
+    assert np.array_equal(labels, kept[want])
+    # overlaps: total count = voxels with both nonzero; checksum against the oracle
+    rows, cols, vals = res.pairs_numpy()
+    assert int(vals.sum()) == int(((labels != 0) & (base != 0)).sum())
+    r, c, v, sh = orc.count_overlaps_c(labels, base)
+    assert np.array_equal(rows, r) and np.array_equal(cols.astype(np.int64), c) and np.array_equal(vals, v)
+    assert (res.counts["max_label"] + 1, res.counts["max_base"] + 1) == sh
