@@ -187,6 +187,22 @@ SYN_API int syn_threshold_dilate(const float *pred, int64_t nx, int64_t ny, int6
 SYN_API int syn_unique_u64(const uint64_t *vals, int64_t n, uint64_t *out, int64_t cap,
                            unsigned long long *count_dev, void *stream);
 
+
+/*
+ * Measurement hooks (no reference counterpart).
+ * syn_launch_count   : kernels launched by this library in this process so far.
+ * syn_profile_enable : when on, syn_chunk_ccs records a CUDA event on its stream between
+ *                      pipeline stages (not thread-safe; for bench.py).
+ * syn_profile_read   : synchronises on the last recorded call and returns the elapsed ms
+ *                      of its SYN_PROF_STAGES stages: 0 threshold(+dilate), 1 run-id scan,
+ *                      2 unions, 3 flatten+rank, 4 statistics, 5 dust+table+run labels,
+ *                      6 dense label write (+pair histogram), 7 pair ordering.
+ */
+#define SYN_PROF_STAGES 8
+SYN_API long long syn_launch_count(void);
+SYN_API int syn_profile_enable(int on);
+SYN_API int syn_profile_read(float *stage_ms, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,7 +44,13 @@ SIGNATURES = {
     "syn_union_min_map": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "syn_threshold_dilate": (_i32, [_vp, _i64, _i64, _i64, _f32, _i32, _vp, _vp]),
     "syn_unique_u64": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "syn_launch_count": (ctypes.c_longlong, []),
+    "syn_profile_enable": (_i32, [_i32]),
+    "syn_profile_read": (_i32, [_vp, _i32]),
 }
+PROF_STAGES = 8
+PROF_STAGE_NAMES = ["threshold", "run_scan", "union", "flatten_rank", "stats", "dust_table", "write_labels",
+                    "pair_order"]
 
 
 class SynaptorB200Error(RuntimeError):

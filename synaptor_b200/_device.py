@@ -125,7 +125,11 @@ class ChunkResult:
         return self.seg_table[:n].cpu().numpy()
 
     def labels_numpy(self):
-        return self.labels.cpu().numpy().view(np.uint32)
+        """D2H through pinned memory (torch's caching host allocator recycles the block)."""
+        import torch
+        host = torch.empty(self.labels.shape, dtype=self.labels.dtype, device="cpu", pin_memory=True)
+        host.copy_(self.labels)
+        return host.numpy().view(np.uint32)
 
     def pairs_numpy(self):
         n = self.counts["pairs"]

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "aux.cuh"
@@ -31,7 +32,25 @@ int fail(int code, const char *fmt, ...)
             return fail(SYN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-#define CK_LAUNCH() CK(cudaGetLastError())
+std::atomic<long long> g_launches{0};
+
+#define CK_LAUNCH()            \
+    do {                       \
+        g_launches.fetch_add(1, std::memory_order_relaxed); \
+        CK(cudaGetLastError()); \
+    } while (0)
+
+// ---- optional per-stage profiling with CUDA events on the launching stream -------------------
+constexpr int PROF_STAGES = 8;
+bool g_prof_on = false;
+cudaEvent_t g_prof_ev[PROF_STAGES + 1];
+bool g_prof_created = false;
+bool g_prof_valid = false;
+
+#define PROF_MARK(i)                                                   \
+    do {                                                               \
+        if (g_prof_on) CK(cudaEventRecord(g_prof_ev[(i)], st));        \
+    } while (0)
 
 int sm_count()
 {
@@ -225,6 +244,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     (void)sms;
 
     CK(cudaMemsetAsync(W.cnt, 0, sizeof(Counts), st));
+    PROF_MARK(0);
 
     // --- K1: threshold -> bitmask -------------------------------------------------------------
     const bool vec_in = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
@@ -241,6 +261,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         CK_LAUNCH();
     }
 
+    PROF_MARK(1);
     // --- scan #1: run ids --------------------------------------------------------------------
     {
         RunStartSrc src{W.lmask, g.nwords, g.wz};
@@ -252,6 +273,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         k_scan_c<<<ntiles, SCAN_THREADS, 0, st>>>(src, RunBaseDst{W.runbase}, W.tiles);
         CK_LAUNCH();
     }
+    PROF_MARK(2);
     k_init_parents<<<grid_for(max_runs, 256, 8), 256, 0, st>>>(W.par, W.cnt, (u32)max_runs);
     CK_LAUNCH();
 
@@ -261,6 +283,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     else launch_union<26>(W, g, st);
     CK_LAUNCH();
 
+    PROF_MARK(3);
     // --- scan #2: flatten + canonical rank -----------------------------------------------------
     {
         const int ntiles = (int)((max_runs + SCAN_TILE - 1) / SCAN_TILE);
@@ -273,10 +296,12 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         CK_LAUNCH();
     }
 
+    PROF_MARK(4);
     // --- statistics ----------------------------------------------------------------------------
     k_stats<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.par, W.rank, W.stat, g, W.cnt);
     CK_LAUNCH();
 
+    PROF_MARK(5);
     // --- scan #3: dust decision + table ----------------------------------------------------------
     {
         const int ntiles = (int)((max_runs + SCAN_TILE - 1) / SCAN_TILE);
@@ -294,6 +319,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     k_run_labels<<<grid_for(max_runs, 256, 8), 256, 0, st>>>(W.par, W.rank, W.stat, W.runlabel, W.cnt, max_segs);
     CK_LAUNCH();
 
+    PROF_MARK(6);
     // --- dense output (+ overlaps) ---------------------------------------------------------------
     PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap ? W.paircap - 1 : 0, W.cnt};
     if (has_base) {
@@ -318,10 +344,13 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
                                                                  labels_out, (const u64 *)base_seg, g, T, W.cnt);
         CK_LAUNCH();
     }
+    PROF_MARK(7);
     if (has_base) {
         rc = order_and_emit_pairs(g, W, T, pair_rows, (u64 *)pair_cols, (i64 *)pair_counts, max_pairs, st);
         if (rc != SYN_OK) return rc;
     }
+    PROF_MARK(8);
+    if (g_prof_on) g_prof_valid = true;
     return finish_counts(W, (i64 *)counts_host, st);
 }
 
@@ -485,6 +514,29 @@ int syn_unique_u64(const uint64_t *vals, int64_t n, uint64_t *out, int64_t cap, 
     CK_LAUNCH();
     CK(cudaFreeAsync(table, st));
     return SYN_OK;
+}
+
+
+long long syn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int syn_profile_enable(int on)
+{
+    if (on && !g_prof_created) {
+        for (int i = 0; i <= PROF_STAGES; ++i) CK(cudaEventCreate(&g_prof_ev[i]));
+        g_prof_created = true;
+    }
+    g_prof_on = on != 0;
+    g_prof_valid = false;
+    return SYN_OK;
+}
+
+int syn_profile_read(float *stage_ms, int n)
+{
+    if (!stage_ms || n < PROF_STAGES) return fail(SYN_ERR_INVALID, "need room for %d stages", PROF_STAGES);
+    if (!g_prof_created || !g_prof_valid) return fail(SYN_ERR_INVALID, "no profiled syn_chunk_ccs call recorded");
+    CK(cudaEventSynchronize(g_prof_ev[PROF_STAGES]));
+    for (int i = 0; i < PROF_STAGES; ++i) CK(cudaEventElapsedTime(&stage_ms[i], g_prof_ev[i], g_prof_ev[i + 1]));
+    return PROF_STAGES;
 }
 
 }  // extern "C"

@@ -29,7 +29,7 @@ def assign_unique_ids_serial(cleft_info_arr):
         chunk_id_maps[idx], next_id = new_id_map(df, next_id)
         df.rename(chunk_id_maps[idx], inplace=True)
         parts.append(df)
-    return pd.concat(parts, copy=False), chunk_id_maps
+    return pd.concat(parts), chunk_id_maps
 
 
 def apply_id_map(continuations, id_map):

@@ -36,7 +36,7 @@ def flatten_conts(conts):
 
 def table_of(df):
     """(index int64, (n,10) int64 table) of a seg-info DataFrame."""
-    return np.asarray(df.index, dtype=np.int64), df.to_numpy(dtype=np.int64).reshape(len(df), -1)
+    return np.asarray(df.index, dtype=np.int64), df.to_numpy(dtype=np.int64).reshape(len(df), len(df.columns))
 
 
 def sorted_triples(r, c, v):
