@@ -37,7 +37,7 @@ CHUNK = (512, 512, 512)
 THRESH, DUST, CONN = 0.5, 100, 6
 METRIC = "Gvoxels/s chunk_ccs+overlaps"
 BYTES_PER_VOXEL_PIPELINE = 16   # 4 B pred read + 4 B label write + 8 B base read
-BYTES_PER_VOXEL_WRITE_KERNEL = 12  # k_write_labels: 4 B label write + 8 B base read
+BYTES_PER_VOXEL_WRITE_KERNEL = 12  # k_dense_fill: 4 B label write + 8 B base read
 CPU_SAMPLE = (256, 256, 256)
 
 
@@ -304,8 +304,7 @@ def main():
                        "l2": "inputs (1.6 GB/step) exceed the 126 MB L2; no flush needed",
                        "components": counts["components"], "kept": counts["kept"], "pairs": counts["pairs"],
                        "runs": counts["runs"], "fg_voxels": counts["fg_voxels"]},
-            "roofline": {"bound": "hbm", "kernel": "k_write_labels<vec,base> (dense label write + base read + pair "
-                                                   "histogram)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_dense_fill<base> (dense label write + base read for max(base))", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL_WRITE_KERNEL, "kernel_ms": wl_ms,
                          "pipeline": {"bytes_per_voxel": BYTES_PER_VOXEL_PIPELINE, "achieved": pipe_gbs,

@@ -52,6 +52,7 @@ enum {
                                 bit 3 pair output overflow */
     SYN_CNT_FG_VOXELS = 7,   /* voxels above threshold */
     SYN_CNT_TABLE_SLOTS = 8, /* occupied slots in the pair hash table */
+    SYN_CNT_ACTIVE_WORDS = 9, /* 32-voxel mask words holding at least one labelled voxel */
     SYN_NCOUNTS = 16
 };
 
@@ -196,9 +197,10 @@ SYN_API int syn_unique_u64(const uint64_t *vals, int64_t n, uint64_t *out, int64
  * syn_profile_read   : synchronises on the last recorded call and returns the elapsed ms
  *                      of its SYN_PROF_STAGES stages: 0 threshold(+dilate), 1 run-id scan,
  *                      2 unions, 3 flatten+rank, 4 statistics, 5 dust+table+run labels,
- *                      6 dense label write (+pair histogram), 7 pair ordering.
+ *                      6 dense zero fill (+ max(base)), 7 foreground sectors (+ pair histogram),
+ *                      8 pair ordering.
  */
-#define SYN_PROF_STAGES 8
+#define SYN_PROF_STAGES 9
 SYN_API long long syn_launch_count(void);
 SYN_API int syn_profile_enable(int on);
 SYN_API int syn_profile_read(float *stage_ms, int n);

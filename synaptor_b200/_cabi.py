@@ -18,7 +18,7 @@ SYN_ERR_WORKSPACE = -4
 
 # counts[] indices (enum in synaptor_b200.h)
 CNT_RUNS, CNT_COMPONENTS, CNT_KEPT, CNT_PAIRS, CNT_MAX_BASE, CNT_MAX_LABEL, CNT_ERRFLAGS, CNT_FG_VOXELS, \
-    CNT_TABLE_SLOTS = range(9)
+    CNT_TABLE_SLOTS, CNT_ACTIVE_WORDS = range(10)
 NCOUNTS = 16
 SEG_NCOLS = 11
 
@@ -48,9 +48,9 @@ SIGNATURES = {
     "syn_profile_enable": (_i32, [_i32]),
     "syn_profile_read": (_i32, [_vp, _i32]),
 }
-PROF_STAGES = 8
-PROF_STAGE_NAMES = ["threshold", "run_scan", "union", "flatten_rank", "stats", "dust_table", "write_labels",
-                    "pair_order"]
+PROF_STAGES = 9
+PROF_STAGE_NAMES = ["threshold", "run_scan", "union", "flatten_rank", "stats", "dust_table", "dense_fill",
+                    "sparse_labels", "pair_order"]
 
 
 class SynaptorB200Error(RuntimeError):

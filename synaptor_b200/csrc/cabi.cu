@@ -41,7 +41,7 @@ std::atomic<long long> g_launches{0};
     } while (0)
 
 // ---- optional per-stage profiling with CUDA events on the launching stream -------------------
-constexpr int PROF_STAGES = 8;
+constexpr int PROF_STAGES = 9;
 bool g_prof_on = false;
 cudaEvent_t g_prof_ev[PROF_STAGES + 1];
 bool g_prof_created = false;
@@ -97,9 +97,30 @@ u32 pow2_at_least(i64 v)
 }
 
 // workspace carving (must match syn_ccs_workspace_bytes)
+TileGeom make_tiles(const Geom &g)
+{
+    TileGeom t{0, 0, 0, 0, 0};
+    if (g.wz > TILE_WORDS / 2) return t;          // one row already fills a tile: no shared-memory pass
+    u32 rpt = TILE_WORDS / g.wz;                    // rows per tile, >= 2
+    u32 ty = 1;
+    while (ty * 2 <= 64 && (ty * 2) * (ty * 2) <= 2 * rpt) ty *= 2;
+    u32 tx = rpt / ty;
+    if (tx > TILE_MAXTX) tx = TILE_MAXTX;
+    if (tx < 1) tx = 1;
+    t.tx = tx;
+    t.ty = ty;
+    t.tiles_x = (u32)((g.nx + tx - 1) / tx);
+    t.tiles_y = (u32)((g.ny + ty - 1) / ty);
+    t.ntiles = t.tiles_x * t.tiles_y;
+    return t;
+}
+
 struct Workspace {
+    TileGeom tg;
+    u32 *tileflag;
     Counts *cnt;
     u32 *lmask, *omask, *runbase, *tiles;  // tiles: scan tile sums
+    u32 *actw;                             // compact list of non-empty mask words
     u32 *par, *rank, *runlabel;
     CompStat *stat;
     PairKey *pkeys;
@@ -121,7 +142,10 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     w->lmask = (u32 *)take(nw * 4);
     w->omask = dilate ? (u32 *)take(nw * 4) : w->lmask;
     w->runbase = (u32 *)take(nw * 4);
+    w->actw = (u32 *)take(nw * 4);
     w->tiles = (u32 *)take(scan_tiles(biggest) * 4);
+    w->tg = make_tiles(g);
+    w->tileflag = (u32 *)take(((size_t)w->tg.ntiles + 8) * 4);
     w->par = (u32 *)take((size_t)max_runs * 4);
     w->rank = (u32 *)take((size_t)max_runs * 4);
     w->runlabel = (u32 *)take((size_t)max_runs * 4);
@@ -137,6 +161,33 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
         w->wordbase = (u32 *)take(nw * 4);
     }
     w->total = off;
+}
+
+// grid = (resident CTAs per SM for this kernel) x (SM count): one full wave, no tail
+std::mutex g_occ_mu;
+struct OccEntry { const void *fn; int threads; int blocks; };
+OccEntry g_occ[128];
+int g_nocc = 0;
+
+template <class K>
+int occ_blocks(K kernel, int threads)
+{
+    const void *fn = (const void *)kernel;
+    std::lock_guard<std::mutex> lk(g_occ_mu);
+    for (int i = 0; i < g_nocc; ++i)
+        if (g_occ[i].fn == fn && g_occ[i].threads == threads) return g_occ[i].blocks;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) nb = 4;
+    if (g_nocc < 128) g_occ[g_nocc++] = OccEntry{fn, threads, nb};
+    return nb;
+}
+
+template <class K>
+int wave_grid(K kernel, int threads, i64 max_blocks)
+{
+    i64 g = (i64)occ_blocks(kernel, threads) * sm_count();
+    if (max_blocks < 1) max_blocks = 1;
+    return (int)(g < max_blocks ? g : max_blocks);
 }
 
 int grid_for(i64 items, int threads, int per_sm)
@@ -156,11 +207,12 @@ int order_and_emit_pairs(const Geom &g, const Workspace &W, PairTable T, u32 *ro
     CK_LAUNCH();
     PopcSrc src{W.bitmap, g.nwords};
     const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
-    k_scan_a<<<ntiles, SCAN_THREADS, 0, st>>>(src, W.tiles);
+    k_scan_a<<<wave_grid(k_scan_a<PopcSrc>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(src, W.tiles);
     CK_LAUNCH();
     k_scan_b<<<1, SCAN_THREADS, 0, st>>>(src, W.tiles, &W.cnt->v[SYN_CNT_PAIRS], (u32 *)nullptr);
     CK_LAUNCH();
-    k_scan_c<<<ntiles, SCAN_THREADS, 0, st>>>(src, WordBaseDst{W.wordbase}, W.tiles);
+    k_scan_c<<<wave_grid(k_scan_c<PopcSrc, WordBaseDst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
+        src, WordBaseDst{W.wordbase}, W.tiles);
     CK_LAUNCH();
     k_pair_emit<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bitmap, W.wordbase, rows, cols, vals, max_pairs);
     CK_LAUNCH();
@@ -184,7 +236,12 @@ int finish_counts(const Workspace &W, i64 *counts_host, cudaStream_t st)
 template <int CONN>
 void launch_union(const Workspace &W, const Geom &g, cudaStream_t st)
 {
-    k_union_rows<CONN><<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(W.lmask, W.runbase, W.par, g, W.cnt);
+    if (W.tg.tx) {
+        k_tile_ccl<CONN><<<W.tg.ntiles, 256, 0, st>>>(W.lmask, W.runbase, W.par, W.tileflag, g, W.tg, W.cnt);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    k_union_rows<CONN><<<wave_grid(k_union_rows<CONN>, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(
+        W.lmask, W.runbase, W.par, g, W.tg, W.tileflag, W.actw, W.cnt);
 }
 
 }  // namespace
@@ -249,11 +306,13 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     // --- K1: threshold -> bitmask -------------------------------------------------------------
     const bool vec_in = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
     {
-        const int grid = grid_for((i64)g.nchunks * 32 / 4 + 1, 256, 8);
+        const i64 need = div_up_u32((u64)g.nchunks, 8 * 4);
         if (vec_in)
-            k_threshold<true, 4><<<grid, 256, 0, st>>>(pred, W.omask, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
+            k_threshold<true, 4><<<wave_grid(k_threshold<true, 4>, 256, need), 256, 0, st>>>(
+                pred, W.omask, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
         else
-            k_threshold<false, 4><<<grid, 256, 0, st>>>(pred, W.omask, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
+            k_threshold<false, 4><<<wave_grid(k_threshold<false, 4>, 256, need), 256, 0, st>>>(
+                pred, W.omask, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
         CK_LAUNCH();
     }
     if (dilate) {
@@ -266,16 +325,25 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     {
         RunStartSrc src{W.lmask, g.nwords, g.wz};
         const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
-        k_scan_a<<<ntiles, SCAN_THREADS, 0, st>>>(src, W.tiles);
+        k_scan_a<<<wave_grid(k_scan_a<RunStartSrc>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(src, W.tiles);
         CK_LAUNCH();
         k_scan_b<<<1, SCAN_THREADS, 0, st>>>(src, W.tiles, &W.cnt->v[SYN_CNT_RUNS], (u32 *)nullptr);
         CK_LAUNCH();
-        k_scan_c<<<ntiles, SCAN_THREADS, 0, st>>>(src, RunBaseDst{W.runbase}, W.tiles);
+        k_scan_c<<<wave_grid(k_scan_c<RunStartSrc, RunBaseDst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
+            src, RunBaseDst{W.runbase}, W.tiles);
         CK_LAUNCH();
     }
     PROF_MARK(2);
-    k_init_parents<<<grid_for(max_runs, 256, 8), 256, 0, st>>>(W.par, W.cnt, (u32)max_runs);
+    {
+        const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
+        k_compact_active<<<wave_grid(k_compact_active, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(W.lmask, g.nwords,
+                                                                                                  W.actw, W.cnt);
+        CK_LAUNCH();
+    }
+    k_init_parents<<<wave_grid(k_init_parents, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.par, W.cnt,
+                                                                                          (u32)max_runs);
     CK_LAUNCH();
+    if (W.tg.tx) CK(cudaMemsetAsync(W.tileflag, 0, (size_t)W.tg.ntiles * 4, st));
 
     // --- unions ------------------------------------------------------------------------------
     if (connectivity == 6) launch_union<6>(W, g, st);
@@ -288,17 +356,19 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     {
         const int ntiles = (int)((max_runs + SCAN_TILE - 1) / SCAN_TILE);
         RootFlagSrc srcA{W.par, W.cnt, true}, srcC{W.par, W.cnt, false};
-        k_scan_a<<<ntiles, SCAN_THREADS, 0, st>>>(srcA, W.tiles);
+        k_scan_a<<<wave_grid(k_scan_a<RootFlagSrc>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(srcA, W.tiles);
         CK_LAUNCH();
         k_scan_b<<<1, SCAN_THREADS, 0, st>>>(srcC, W.tiles, &W.cnt->v[SYN_CNT_COMPONENTS], (u32 *)nullptr);
         CK_LAUNCH();
-        k_scan_c<<<ntiles, SCAN_THREADS, 0, st>>>(srcC, RankDst{W.rank, W.stat}, W.tiles);
+        k_scan_c<<<wave_grid(k_scan_c<RootFlagSrc, RankDst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
+            srcC, RankDst{W.rank, W.stat}, W.tiles);
         CK_LAUNCH();
     }
 
     PROF_MARK(4);
     // --- statistics ----------------------------------------------------------------------------
-    k_stats<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.par, W.rank, W.stat, g, W.cnt);
+    k_stats<<<wave_grid(k_stats, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.par,
+                                                                               W.rank, W.stat, g, W.actw, W.cnt);
     CK_LAUNCH();
 
     PROF_MARK(5);
@@ -309,14 +379,16 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         KeepSrc srcC = srcA;
         srcC.decide = false;
         i64 ox = offset_xyz ? offset_xyz[0] : 0, oy = offset_xyz ? offset_xyz[1] : 0, oz = offset_xyz ? offset_xyz[2] : 0;
-        k_scan_a<<<ntiles, SCAN_THREADS, 0, st>>>(srcA, W.tiles);
+        k_scan_a<<<wave_grid(k_scan_a<KeepSrc>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(srcA, W.tiles);
         CK_LAUNCH();
         k_scan_b<<<1, SCAN_THREADS, 0, st>>>(srcC, W.tiles, &W.cnt->v[SYN_CNT_KEPT], (u32 *)nullptr);
         CK_LAUNCH();
-        k_scan_c<<<ntiles, SCAN_THREADS, 0, st>>>(srcC, TableDst{W.stat, (i64 *)seg_table, max_segs, ox, oy, oz}, W.tiles);
+        k_scan_c<<<wave_grid(k_scan_c<KeepSrc, TableDst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
+            srcC, TableDst{W.stat, (i64 *)seg_table, max_segs, ox, oy, oz}, W.tiles);
         CK_LAUNCH();
     }
-    k_run_labels<<<grid_for(max_runs, 256, 8), 256, 0, st>>>(W.par, W.rank, W.stat, W.runlabel, W.cnt, max_segs);
+    k_run_labels<<<wave_grid(k_run_labels, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.par, W.rank, W.stat,
+                                                                                         W.runlabel, W.cnt, max_segs);
     CK_LAUNCH();
 
     PROF_MARK(6);
@@ -329,27 +401,44 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     {
         const bool vec_out = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels_out) & 15) == 0) &&
                              (!has_base || (reinterpret_cast<uintptr_t>(base_seg) & 15) == 0);
-        const int grid = grid_for((i64)g.nchunks * 32 / 2 + 1, 256, 8);
-        if (vec_out && has_base)
-            k_write_labels<true, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
-                                                               (const u64 *)base_seg, g, T, W.cnt);
-        else if (vec_out)
-            k_write_labels<true, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
-                                                                (const u64 *)base_seg, g, T, W.cnt);
-        else if (has_base)
-            k_write_labels<false, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
-                                                                (const u64 *)base_seg, g, T, W.cnt);
-        else
-            k_write_labels<false, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel,
-                                                                 labels_out, (const u64 *)base_seg, g, T, W.cnt);
-        CK_LAUNCH();
+        const u64 *bs = (const u64 *)base_seg;
+        if (vec_out) {
+            // dense zero fill (+ max(base)) at streaming speed, then the foreground sectors
+            const i64 need = div_up_u32((u64)g.nchunks, 8 * 4);
+            if (has_base)
+                k_dense_fill<true, 4><<<wave_grid(k_dense_fill<true, 4>, 256, need), 256, 0, st>>>(W.omask, labels_out,
+                                                                                                  bs, g, W.cnt);
+            else
+                k_dense_fill<false, 4><<<wave_grid(k_dense_fill<false, 4>, 256, need), 256, 0, st>>>(W.omask, labels_out,
+                                                                                                    bs, g, W.cnt);
+            CK_LAUNCH();
+            PROF_MARK(7);
+            const i64 needw = div_up_u32(g.nwords, 256);
+            if (has_base)
+                k_sparse_labels<true><<<wave_grid(k_sparse_labels<true>, 256, needw), 256, 0, st>>>(
+                    W.lmask, W.omask, W.runbase, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
+            else
+                k_sparse_labels<false><<<wave_grid(k_sparse_labels<false>, 256, needw), 256, 0, st>>>(
+                    W.lmask, W.omask, W.runbase, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
+            CK_LAUNCH();
+        } else {
+            const int grid = grid_for((i64)g.nchunks * 32 / 2 + 1, 256, 8);
+            if (has_base)
+                k_write_labels<false, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel,
+                                                                    labels_out, bs, g, T, W.cnt);
+            else
+                k_write_labels<false, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel,
+                                                                     labels_out, bs, g, T, W.cnt);
+            CK_LAUNCH();
+            PROF_MARK(7);
+        }
     }
-    PROF_MARK(7);
+    PROF_MARK(8);
     if (has_base) {
         rc = order_and_emit_pairs(g, W, T, pair_rows, (u64 *)pair_cols, (i64 *)pair_counts, max_pairs, st);
         if (rc != SYN_OK) return rc;
     }
-    PROF_MARK(8);
+    PROF_MARK(9);
     if (g_prof_on) g_prof_valid = true;
     return finish_counts(W, (i64 *)counts_host, st);
 }

@@ -142,16 +142,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_a(Src src, u32 *__restric
 {
     __shared__ u32 sm[33];
     const u64 n = src.n();
-    const u64 base = (u64)blockIdx.x * SCAN_TILE;
-    if (base >= n) return;  // block-uniform
-    u32 v = 0;
-    const u64 i0 = base + (u64)threadIdx.x * SCAN_ITEMS;
+    for (u64 tile = blockIdx.x; tile * SCAN_TILE < n; tile += gridDim.x) {  // block-uniform bounds
+        u32 v = 0;
+        const u64 i0 = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
 #pragma unroll
-    for (int t = 0; t < SCAN_ITEMS; ++t)
-        if (i0 + t < n) v += src.get(i0 + t);
-    u32 total;
-    block_excl_scan(v, sm, &total);
-    if (threadIdx.x == 0) tilesum[blockIdx.x] = total;
+        for (int t = 0; t < SCAN_ITEMS; ++t)
+            if (i0 + t < n) v += src.get(i0 + t);
+        u32 total;
+        block_excl_scan(v, sm, &total);
+        if (threadIdx.x == 0) tilesum[tile] = total;
+    }
 }
 
 // one block; scans ceil(n / SCAN_TILE) tile sums in place (exclusive) and writes
@@ -183,22 +183,22 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_c(Src src, Dst dst, const
 {
     __shared__ u32 sm[33];
     const u64 n = src.n();
-    const u64 base = (u64)blockIdx.x * SCAN_TILE;
-    if (base >= n) return;
-    u32 item[SCAN_ITEMS];
-    u32 v = 0;
-    const u64 i0 = base + (u64)threadIdx.x * SCAN_ITEMS;
+    for (u64 tile = blockIdx.x; tile * SCAN_TILE < n; tile += gridDim.x) {
+        u32 item[SCAN_ITEMS];
+        u32 v = 0;
+        const u64 i0 = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
 #pragma unroll
-    for (int t = 0; t < SCAN_ITEMS; ++t) {
-        item[t] = (i0 + t < n) ? src.get(i0 + t) : 0;
-        v += item[t];
-    }
-    u32 total;
-    u32 ex = block_excl_scan(v, sm, &total) + tilebase[blockIdx.x];
+        for (int t = 0; t < SCAN_ITEMS; ++t) {
+            item[t] = (i0 + t < n) ? src.get(i0 + t) : 0;
+            v += item[t];
+        }
+        u32 total;
+        u32 ex = block_excl_scan(v, sm, &total) + tilebase[tile];
 #pragma unroll
-    for (int t = 0; t < SCAN_ITEMS; ++t) {
-        if (i0 + t < n) dst.put(i0 + t, ex, item[t]);
-        ex += item[t];
+        for (int t = 0; t < SCAN_ITEMS; ++t) {
+            if (i0 + t < n) dst.put(i0 + t, ex, item[t]);
+            ex += item[t];
+        }
     }
 }
 
@@ -221,6 +221,40 @@ struct RunBaseDst {
     __device__ __forceinline__ void put(u64 w, u32 ex, u32) const { runbase[w] = ex; }
 };
 
+
+// ---------------------------------------------------------------------------
+// Compaction of the non-empty mask words.  The sparse kernels (unions, statistics,
+// foreground sectors) run one thread per ACTIVE word from this list, so every lane
+// of a warp has work (3 % foreground means ~10 % of the words are non-empty; a
+// thread-per-word grid over all words would run at ~2 active lanes per warp).
+// Order inside a block is raster order; blocks append with one atomicAdd each.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) k_compact_active(const u32 *__restrict__ mask, u32 nwords,
+                                                                 u32 *__restrict__ actw, Counts *cnt)
+{
+    __shared__ u32 sm[33];
+    __shared__ u32 s_base;
+    for (u64 tile = blockIdx.x; tile * SCAN_TILE < nwords; tile += gridDim.x) {
+        const u64 i0 = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+        u32 flag[SCAN_ITEMS];
+        u32 v = 0;
+#pragma unroll
+        for (int t = 0; t < SCAN_ITEMS; ++t) {
+            flag[t] = (i0 + t < nwords) && (mask[i0 + t] != 0);
+            v += flag[t];
+        }
+        u32 total;
+        u32 ex = block_excl_scan(v, sm, &total);
+        if (threadIdx.x == 0) s_base = total ? (u32)atomicAdd((u64 *)&cnt->v[SYN_CNT_ACTIVE_WORDS], (u64)total) : 0u;
+        __syncthreads();
+        ex += s_base;
+#pragma unroll
+        for (int t = 0; t < SCAN_ITEMS; ++t)
+            if (flag[t]) actw[ex++] = (u32)(i0 + t);
+        __syncthreads();
+    }
+}
+
 // validates the run count against capacity and initialises parent[g] = g
 __global__ void k_init_parents(u32 *__restrict__ par, Counts *cnt, u32 max_runs)
 {
@@ -241,6 +275,12 @@ __global__ void k_init_parents(u32 *__restrict__ par, Counts *cnt, u32 max_runs)
 // (after the shift).  Run id of the run covering bit b of word w:
 //     runbase[w] + popc(starts(w) & mask_le(b)) - 1
 // ===========================================================================
+struct TileGeom {
+    u32 tx, ty;          // rows per tile along x and y (0 = tiling disabled)
+    u32 tiles_x, tiles_y;
+    u32 ntiles;
+};
+
 struct RowView {
     const u32 *mask;     // words of this row
     const u32 *runbase;  // run-start prefix of this row's words
@@ -278,20 +318,35 @@ __device__ __forceinline__ void union_shifted(u32 *par, const RowView &A, const 
     }
 }
 
+// With tiling enabled (tg.tx != 0) a pair of rows inside one tile was already joined by K2 and is
+// skipped here unless that tile was flagged as too dense.
 template <int CONN>
 __global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask, const u32 *__restrict__ runbase,
-                                                    u32 *par, Geom g, const Counts *cnt)
+                                                    u32 *par, Geom g, TileGeom tg, const u32 *__restrict__ tileflag,
+                                                    const u32 *__restrict__ actw, const Counts *cnt)
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
-    for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < g.nwords; w += gridDim.x * blockDim.x) {
+    const u32 nact = (u32)cnt->v[SYN_CNT_ACTIVE_WORDS];
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nact; i += gridDim.x * blockDim.x) {
+        const u32 w = actw[i];
         u32 m = mask[w];
-        if (m == 0) continue;
         u32 row = w / g.wz;
         int k = (int)(w - row * g.wz);
         u32 x = row / (u32)g.ny;
         u32 y = row - x * (u32)g.ny;
         RowView A{mask + (u64)row * g.wz, runbase + (u64)row * g.wz, g.wz};
-        if (y > 0) {
+        bool do_y = true, do_x = true, do_dm = true, do_dp = true;   // (x,y-1) (x-1,y) (x-1,y-1) (x-1,y+1)
+        if (tg.tx) {
+            const u32 tX = x / tg.tx, tY = y / tg.ty;
+            const bool dense = tileflag[tX * tg.tiles_y + tY] != 0;
+            const bool xb = (x % tg.tx) == 0, yb = (y % tg.ty) == 0, ye = ((y + 1) % tg.ty) == 0;
+            do_y = dense || yb;
+            do_x = dense || xb;
+            do_dm = dense || xb || yb;
+            do_dp = dense || xb || ye;
+            if (!(do_y || do_x || do_dm || do_dp)) continue;
+        }
+        if (y > 0 && do_y) {
             u32 r2 = row - 1;
             RowView B{mask + (u64)r2 * g.wz, runbase + (u64)r2 * g.wz, g.wz};
             union_shifted<0>(par, A, B, k, m);
@@ -300,21 +355,194 @@ __global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask
         if (x > 0) {
             u32 r2 = row - (u32)g.ny;
             RowView B{mask + (u64)r2 * g.wz, runbase + (u64)r2 * g.wz, g.wz};
-            union_shifted<0>(par, A, B, k, m);
-            if (CONN >= 18) { union_shifted<-1>(par, A, B, k, m); union_shifted<1>(par, A, B, k, m); }
-            if (CONN >= 18 && y > 0) {
+            if (do_x) {
+                union_shifted<0>(par, A, B, k, m);
+                if (CONN >= 18) { union_shifted<-1>(par, A, B, k, m); union_shifted<1>(par, A, B, k, m); }
+            }
+            if (CONN >= 18 && y > 0 && do_dm) {
                 u32 r3 = r2 - 1;
                 RowView C{mask + (u64)r3 * g.wz, runbase + (u64)r3 * g.wz, g.wz};
                 union_shifted<0>(par, A, C, k, m);
                 if (CONN == 26) { union_shifted<-1>(par, A, C, k, m); union_shifted<1>(par, A, C, k, m); }
             }
-            if (CONN >= 18 && y + 1 < (u32)g.ny) {
+            if (CONN >= 18 && y + 1 < (u32)g.ny && do_dp) {
                 u32 r3 = r2 + 1;
                 RowView C{mask + (u64)r3 * g.wz, runbase + (u64)r3 * g.wz, g.wz};
                 union_shifted<0>(par, A, C, k, m);
                 if (CONN == 26) { union_shifted<-1>(par, A, C, k, m); union_shifted<1>(par, A, C, k, m); }
             }
         }
+    }
+}
+
+
+// ===========================================================================
+// K2: block-local union-find in shared memory.  A tile = TX x-slabs x TY rows x
+// the full z extent (<= TILE_WORDS mask words); one CTA per tile loads the tile's
+// mask words and run-id prefixes into shared memory, joins the z-runs of
+// neighbouring rows INSIDE the tile with atomicMin on a shared parent array
+// (local run ids keep raster order, so local roots are raster-first too), and
+// writes parent[run] = global id of the local root.  Only pairs of rows that
+// straddle a tile border are left for the global pass (K3).  A tile with more
+// than TILE_RUNS runs is flagged and handled entirely by K3.
+// ===========================================================================
+constexpr int TILE_WORDS = 2048;
+constexpr int TILE_RUNS = 4096;
+constexpr int TILE_MAXTX = 16;
+
+
+__device__ __forceinline__ u32 sm_find(volatile u32 *p, u32 x)
+{
+    u32 q;
+    while ((q = p[x]) != x) x = q;
+    return x;
+}
+
+__device__ __forceinline__ void sm_union(u32 *p, u32 a, u32 b)
+{
+    while (true) {
+        a = sm_find(p, a);
+        b = sm_find(p, b);
+        if (a == b) return;
+        if (a > b) { u32 t = a; a = b; b = t; }
+        u32 old = atomicMin(p + b, a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+template <int SHIFT>
+__device__ __forceinline__ void sm_union_shifted(u32 *par, const RowView &A, const RowView &B, int k, u32 mA)
+{
+    u32 nb;
+    if (SHIFT == 0) nb = B.word(k);
+    else if (SHIFT < 0) nb = (B.word(k) << 1) | (B.word(k - 1) >> 31);
+    else nb = (B.word(k) >> 1) | (B.word(k + 1) << 31);
+    u32 o = mA & nb;
+    if (!o) return;
+    u32 os = o & ~(o << 1);
+    while (os) {
+        int b = __ffs(os) - 1;
+        os &= os - 1;
+        u32 ga = A.run_at(k, b);
+        int bb = b + SHIFT, kb = k;
+        if (bb < 0) { bb = 31; kb = k - 1; }
+        else if (bb > 31) { bb = 0; kb = k + 1; }
+        u32 gb = B.run_at(kb, bb);
+        sm_union(par, ga, gb);
+    }
+}
+
+template <int CONN>
+__global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, const u32 *__restrict__ runbase,
+                                                  u32 *__restrict__ par, u32 *__restrict__ tileflag, Geom g,
+                                                  TileGeom tg, const Counts *cnt)
+{
+    __shared__ u32 s_mask[TILE_WORDS];
+    __shared__ u32 s_rb[TILE_WORDS];     // LOCAL run-id prefix per word
+    __shared__ u32 s_par[TILE_RUNS];
+    __shared__ unsigned short s_act[TILE_WORDS];   // tile-local indices of the non-empty words
+    __shared__ u32 s_nact;
+    __shared__ u32 s_segoff[TILE_MAXTX + 1];   // local id of the first run of x-slab segment xl
+    __shared__ u32 s_delta[TILE_MAXTX];        // global id = local id + delta[xl]
+    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    const u32 nruns = (u32)cnt->v[SYN_CNT_RUNS];
+    const u32 tile = blockIdx.x;
+    const u32 tX = tile / tg.tiles_y, tY = tile - tX * tg.tiles_y;
+    const u32 x0 = tX * tg.tx, y0 = tY * tg.ty;
+    const u32 vx = min(tg.tx, (u32)g.nx - x0), vy = min(tg.ty, (u32)g.ny - y0);   // valid rows in this tile
+    const u32 segw = vy * g.wz;                // words per x-slab segment (contiguous in memory)
+    const u32 tw = vx * segw;
+
+    if (threadIdx.x < vx) {
+        u32 first = ((x0 + threadIdx.x) * (u32)g.ny + y0) * g.wz;
+        u32 end = first + segw;
+        u32 b0 = runbase[first];
+        u32 b1 = end < g.nwords ? runbase[end] : nruns;
+        s_segoff[threadIdx.x + 1] = b1 - b0;   // run count, turned into a prefix below
+        s_delta[threadIdx.x] = b0;
+    }
+    if (threadIdx.x == 0) s_nact = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 acc = 0;
+        s_segoff[0] = 0;
+        for (u32 i = 0; i < vx; ++i) {
+            u32 c = s_segoff[i + 1];
+            s_delta[i] -= acc;                 // global = local - segoff + segbase
+            acc += c;
+            s_segoff[i + 1] = acc;
+        }
+    }
+    __syncthreads();
+    const u32 nloc = s_segoff[vx];
+    if (nloc == 0) return;                     // no foreground in this tile
+    if (nloc > TILE_RUNS) {                    // too dense for the shared-memory pass: K3 does the whole tile
+        if (threadIdx.x == 0) tileflag[tile] = 1;
+        return;
+    }
+    for (u32 i = threadIdx.x; i < tw; i += blockDim.x) {
+        u32 xl = i / segw;
+        u32 gw = ((x0 + xl) * (u32)g.ny + y0) * g.wz + (i - xl * segw);
+        const u32 m = mask[gw];
+        s_mask[i] = m;
+        s_rb[i] = runbase[gw] - s_delta[xl];
+        // warp-aggregated append of the non-empty words (tw is a multiple of... not necessarily 32: use activemask)
+        const u32 act = __activemask();
+        const u32 bal = __ballot_sync(act, m != 0);
+        if (bal) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(bal) - 1;
+            u32 basei = 0;
+            if (lane == leader) basei = atomicAdd(&s_nact, (u32)__popc(bal));
+            basei = __shfl_sync(act, basei, leader);
+            if (m) s_act[basei + __popc(bal & mask_lt((u32)lane))] = (unsigned short)i;
+        }
+    }
+    for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) s_par[i] = i;
+    __syncthreads();
+
+    // local unions: one thread per non-empty word i of the tile <-> (xl, yl, k)
+    const u32 nact = s_nact;
+    for (u32 a = threadIdx.x; a < nact; a += blockDim.x) {
+        const u32 i = s_act[a];
+        u32 m = s_mask[i];
+        u32 xl = i / segw;
+        u32 r = (i - xl * segw) / g.wz;        // yl
+        int k = (int)(i - xl * segw - r * g.wz);
+        const u32 rowoff = xl * segw + r * g.wz;
+        RowView A{s_mask + rowoff, s_rb + rowoff, g.wz};
+        if (r > 0) {
+            RowView B{s_mask + rowoff - g.wz, s_rb + rowoff - g.wz, g.wz};
+            sm_union_shifted<0>(s_par, A, B, k, m);
+            if (CONN >= 18) { sm_union_shifted<-1>(s_par, A, B, k, m); sm_union_shifted<1>(s_par, A, B, k, m); }
+        }
+        if (xl > 0) {
+            RowView B{s_mask + rowoff - segw, s_rb + rowoff - segw, g.wz};
+            sm_union_shifted<0>(s_par, A, B, k, m);
+            if (CONN >= 18) { sm_union_shifted<-1>(s_par, A, B, k, m); sm_union_shifted<1>(s_par, A, B, k, m); }
+            if (CONN >= 18 && r > 0) {
+                RowView C{s_mask + rowoff - segw - g.wz, s_rb + rowoff - segw - g.wz, g.wz};
+                sm_union_shifted<0>(s_par, A, C, k, m);
+                if (CONN == 26) { sm_union_shifted<-1>(s_par, A, C, k, m); sm_union_shifted<1>(s_par, A, C, k, m); }
+            }
+            if (CONN >= 18 && r + 1 < vy) {
+                RowView C{s_mask + rowoff - segw + g.wz, s_rb + rowoff - segw + g.wz, g.wz};
+                sm_union_shifted<0>(s_par, A, C, k, m);
+                if (CONN == 26) { sm_union_shifted<-1>(s_par, A, C, k, m); sm_union_shifted<1>(s_par, A, C, k, m); }
+            }
+        }
+    }
+    __syncthreads();
+    // write parent[global run] = global id of the local root
+    for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) {
+        u32 r = sm_find(s_par, i);
+        u32 xi = 0, xr = 0;
+        for (u32 j = 1; j < vx; ++j) {
+            xi += (i >= s_segoff[j]);
+            xr += (r >= s_segoff[j]);
+        }
+        par[i + s_delta[xi]] = r + s_delta[xr];
     }
 }
 
@@ -371,12 +599,13 @@ struct RankDst {
 __global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
                                                const u32 *__restrict__ runbase, const u32 *__restrict__ par,
                                                const u32 *__restrict__ rank, CompStat *stat, Geom g,
-                                               const Counts *cnt)
+                                               const u32 *__restrict__ actw, const Counts *cnt)
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
-    for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < g.nwords; w += gridDim.x * blockDim.x) {
+    const u32 nact = (u32)cnt->v[SYN_CNT_ACTIVE_WORDS];
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nact; i += gridDim.x * blockDim.x) {
+        const u32 w = actw[i];
         u32 m = lmask[w];
-        if (m == 0) continue;
         u32 om = omask[w];
         if (om == 0) continue;
         u32 row = w / g.wz;
@@ -405,12 +634,15 @@ __global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, co
             atomicAdd(&s->sx, (u64)n * x);
             atomicAdd(&s->sy, (u64)n * y);
             atomicAdd(&s->sz, (u64)n * z0 + bitpos_sum(bits));
-            atomicMin(&s->minx, x);
-            atomicMin(&s->miny, y);
-            atomicMin(&s->minz, z0 + (u32)__ffs(bits) - 1u);
-            atomicMax(&s->maxx, x);
-            atomicMax(&s->maxy, y);
-            atomicMax(&s->maxz, z0 + 31u - (u32)__clz(bits));
+            // the box only ever grows: a (possibly stale) read that already covers this piece makes the
+            // atomic unnecessary, which removes most of the min/max traffic
+            const u32 zlo = z0 + (u32)__ffs(bits) - 1u, zhi = z0 + 31u - (u32)__clz(bits);
+            if (x < ldcg_u32(&s->minx)) atomicMin(&s->minx, x);
+            if (y < ldcg_u32(&s->miny)) atomicMin(&s->miny, y);
+            if (zlo < ldcg_u32(&s->minz)) atomicMin(&s->minz, zlo);
+            if (x > ldcg_u32(&s->maxx)) atomicMax(&s->maxx, x);
+            if (y > ldcg_u32(&s->maxy)) atomicMax(&s->maxy, y);
+            if (zhi > ldcg_u32(&s->maxz)) atomicMax(&s->maxz, zhi);
         }
     }
 }
