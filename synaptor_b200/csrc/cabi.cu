@@ -406,14 +406,14 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
             // dense zero fill (+ max(base)) at streaming speed, then the foreground sectors
             const i64 need = div_up_u32((u64)g.nchunks, 8 * 4);
             if (has_base)
-                k_dense_fill<true, 4><<<wave_grid(k_dense_fill<true, 4>, 256, need), 256, 0, st>>>(W.omask, labels_out,
-                                                                                                  bs, g, W.cnt);
+                k_dense_fill<true, 4><<<wave_grid(k_dense_fill<true, 4>, 256, need), 256, 0, st>>>(labels_out, bs, g,
+                                                                                                  W.cnt);
             else
-                k_dense_fill<false, 4><<<wave_grid(k_dense_fill<false, 4>, 256, need), 256, 0, st>>>(W.omask, labels_out,
-                                                                                                    bs, g, W.cnt);
+                k_dense_fill<false, 4><<<wave_grid(k_dense_fill<false, 4>, 256, need), 256, 0, st>>>(labels_out, bs, g,
+                                                                                                    W.cnt);
             CK_LAUNCH();
             PROF_MARK(7);
-            const i64 needw = div_up_u32(g.nwords, 256);
+            const i64 needw = div_up_u32(g.nwords, 8);   // one warp per 32 active words, at most
             if (has_base)
                 k_sparse_labels<true><<<wave_grid(k_sparse_labels<true>, 256, needw), 256, 0, st>>>(
                     W.lmask, W.omask, W.runbase, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);

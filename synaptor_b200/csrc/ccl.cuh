@@ -31,22 +31,16 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ pre
             float4 v[UNROLL];
             bool ok[UNROLL];
             u32 widx[UNROLL];
+            u32 row = c0 / g.cpr;            // one division per iteration: the UNROLL chunks are consecutive
+            u32 kc = c0 - row * g.cpr;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
-                u32 c = c0 + u;
-                ok[u] = false;
-                widx[u] = 0;
+                const i64 z = (i64)kc * 128 + 4 * lane;
+                ok[u] = (c0 + u < g.nchunks) && z < g.nz;
+                widx[u] = row * g.wz + kc * 4 + (lane >> 3);
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < g.nchunks) {
-                    u32 row = c / g.cpr;
-                    u32 k4 = (c - row * g.cpr) * 4;
-                    i64 z = (i64)k4 * 32 + 4 * lane;
-                    widx[u] = row * g.wz + k4 + (lane >> 3);
-                    if (z < g.nz) {
-                        ok[u] = true;
-                        v[u] = __ldcs(reinterpret_cast<const float4 *>(pred + (i64)row * g.nz + z));
-                    }
-                }
+                if (ok[u]) v[u] = __ldcs(reinterpret_cast<const float4 *>(pred + (i64)row * g.nz + z));
+                if (++kc == g.cpr) { kc = 0; ++row; }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
@@ -393,8 +387,13 @@ constexpr int TILE_MAXTX = 16;
 
 __device__ __forceinline__ u32 sm_find(volatile u32 *p, u32 x)
 {
-    u32 q;
-    while ((q = p[x]) != x) x = q;
+    u32 q = p[x];
+    while (q != x) {
+        u32 gq = p[q];
+        if (gq != q) p[x] = gq;   // path halving (always an ancestor, always smaller)
+        x = q;
+        q = gq;
+    }
     return x;
 }
 
@@ -537,10 +536,12 @@ __global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, 
     // write parent[global run] = global id of the local root
     for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) {
         u32 r = sm_find(s_par, i);
+        // x-slab segment of a local run id: last xl with segoff[xl] <= id (vx <= 16: 4 steps)
         u32 xi = 0, xr = 0;
-        for (u32 j = 1; j < vx; ++j) {
-            xi += (i >= s_segoff[j]);
-            xr += (r >= s_segoff[j]);
+#pragma unroll
+        for (u32 s2 = 8; s2; s2 >>= 1) {
+            if (xi + s2 < vx && s_segoff[xi + s2] <= i) xi += s2;
+            if (xr + s2 < vx && s_segoff[xr + s2] <= r) xr += s2;
         }
         par[i + s_delta[xi]] = r + s_delta[xr];
     }

@@ -201,57 +201,49 @@ __global__ void __launch_bounds__(256) k_write_labels(const u32 *__restrict__ lm
 
 
 // ===========================================================================
-// Split output pass (VEC layout, nz % 4 == 0).  Voxels are handled in groups of 8
-// consecutive z (one 32 B sector of the label volume when nz % 8 == 0):
-//   k_dense_fill   : every group WITHOUT a foreground voxel gets zeros; pure streaming
-//                    (4 B/voxel written, + 8 B/voxel of base read for max(base)), no
-//                    dependent loads, so it runs at copy speed;
-//   k_sparse_labels: every group WITH a foreground voxel gets its 8 labels (run id ->
-//                    run label) and feeds the (label, base) pair histogram.  Driven by
-//                    the L2-resident bitmask, it touches only foreground sectors.
-// The two kernels write disjoint sectors, so no read-modify-write ever reaches HBM.
+// Split output pass (VEC layout, nz % 4 == 0):
+//   k_dense_fill   : zero-fills the label volume (4 B/voxel written) and streams the base
+//                    segmentation once for max(base) (8 B/voxel read).  No dependent loads,
+//                    so it runs at copy speed.
+//   k_sparse_labels: runs after it and overwrites the kept foreground voxels with their
+//                    labels (run id -> run label) and feeds the (label, base) pair
+//                    histogram.  Driven by the L2-resident bitmask, it touches only the
+//                    foreground sectors (~5 % extra HBM traffic).
 // ===========================================================================
 template <bool HAS_BASE, int UNROLL>
-__global__ void __launch_bounds__(256) k_dense_fill(const u32 *__restrict__ omask, u32 *__restrict__ labels,
-                                                    const u64 *__restrict__ base, Geom g, Counts *cnt)
+__global__ void __launch_bounds__(256) k_dense_fill(u32 *__restrict__ labels, const u64 *__restrict__ base, Geom g,
+                                                    Counts *cnt)
 {
     const int lane = threadIdx.x & 31;
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int gsh = 8 * ((lane & 7) >> 1);   // bit offset of this lane's 8-voxel group inside its mask word
     u64 bmax = 0;
     for (u32 c0 = warp * UNROLL; c0 < g.nchunks; c0 += nwarps * UNROLL) {
+        // chunk -> (row, first word) once per iteration; the UNROLL chunks of a warp are consecutive
+        u32 row = c0 / g.cpr;
+        u32 kc = c0 - row * g.cpr;
         ulonglong2 b01[UNROLL], b23[UNROLL];
-        u32 om[UNROLL];
         i64 vox[UNROLL];
         bool ok[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            u32 c = c0 + u;
-            ok[u] = false;
-            om[u] = 0;
-            vox[u] = 0;
-            if (HAS_BASE) { b01[u] = make_ulonglong2(0, 0); b23[u] = make_ulonglong2(0, 0); }
-            if (c < g.nchunks) {
-                u32 row = c / g.cpr;
-                u32 k4 = (c - row * g.cpr) * 4;
-                i64 z = (i64)k4 * 32 + 4 * lane;
-                if (z < g.nz) {
-                    ok[u] = true;
-                    vox[u] = (i64)row * g.nz + z;
-                    om[u] = omask[row * g.wz + k4 + (lane >> 3)];
-                    if (HAS_BASE) {
-                        const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(base + vox[u]);
-                        b01[u] = __ldcs(bp);
-                        b23[u] = __ldcs(bp + 1);
-                    }
+            const i64 z = (i64)kc * 128 + 4 * lane;
+            ok[u] = (c0 + u < g.nchunks) && z < g.nz;
+            vox[u] = (i64)row * g.nz + z;
+            if (HAS_BASE) {
+                b01[u] = make_ulonglong2(0, 0);
+                b23[u] = make_ulonglong2(0, 0);
+                if (ok[u]) {
+                    const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(base + vox[u]);
+                    b01[u] = __ldcs(bp);
+                    b23[u] = __ldcs(bp + 1);
                 }
             }
+            if (++kc == g.cpr) { kc = 0; ++row; }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            if (ok[u] && ((om[u] >> gsh) & 0xFFu) == 0)
-                __stcs(reinterpret_cast<uint4 *>(labels + vox[u]), make_uint4(0, 0, 0, 0));
+            if (ok[u]) __stcs(reinterpret_cast<uint4 *>(labels + vox[u]), make_uint4(0, 0, 0, 0));
             if (HAS_BASE) bmax = max(bmax, max(max(b01[u].x, b01[u].y), max(b23[u].x, b23[u].y)));
         }
     }
@@ -261,6 +253,12 @@ __global__ void __launch_bounds__(256) k_dense_fill(const u32 *__restrict__ omas
     }
 }
 
+// Foreground pass.  A warp takes 32 active mask words, prefix-sums their foreground
+// counts and then walks the batch's foreground voxels 32 at a time, ONE LANE PER
+// FOREGROUND VOXEL: owner word by a shuffle binary search over the prefix, bit position
+// by find-nth-set.  Control flow is uniform and every lane is busy (a thread-per-word
+// loop ran at ~6 active lanes).  Consecutive lanes holding the same (label, base) pair
+// are merged with a ballot, so the pair table sees about one insert per z-run.
 template <bool HAS_BASE>
 __global__ void __launch_bounds__(256) k_sparse_labels(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
                                                        const u32 *__restrict__ runbase,
@@ -270,57 +268,72 @@ __global__ void __launch_bounds__(256) k_sparse_labels(const u32 *__restrict__ l
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
     const u32 nact = (u32)cnt->v[SYN_CNT_ACTIVE_WORDS];
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nact; i += gridDim.x * blockDim.x) {
-        const u32 w = actw[i];
-        const u32 om = omask[w];
-        if (om == 0) continue;
-        const u32 m = lmask[w];
-        const u32 row = w / g.wz;
-        const u32 kw = w - row * g.wz;
-        const u32 carry = kw ? (lmask[w - 1] >> 31) : 0u;
-        const u32 starts = run_starts(m, carry);
-        const u32 rb = runbase[w];
-        const i64 vox0 = (i64)row * g.nz + (i64)kw * 32;
-        u32 prev_run = 0xFFFFFFFFu, prev_lab = 0;
-        PairAcc acc;
-#pragma unroll 1
-        for (int gi = 0; gi < 4; ++gi) {
-            const u32 bits = (om >> (8 * gi)) & 0xFFu;
-            if (!bits) continue;
-            u32 lab[8];
+    const int lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 i0 = warp * 32; i0 < nact; i0 += nwarps * 32) {
+        const u32 i = i0 + lane;
+        u32 w = 0, om = 0, starts = 0, rb = 0;
+        i64 vox0 = 0;
+        if (i < nact) {
+            w = actw[i];
+            om = omask[w];
+            const u32 m = lmask[w];
+            const u32 row = w / g.wz;
+            const u32 kw = w - row * g.wz;
+            const u32 carry = kw ? (lmask[w - 1] >> 31) : 0u;
+            starts = run_starts(m, carry);
+            rb = runbase[w];
+            vox0 = (i64)row * g.nz + (i64)kw * 32;
+        }
+        const u32 n = __popc(om);
+        const u32 incl = warp_incl_scan(n, lane);
+        const u32 excl = incl - n;
+        const u32 total = __shfl_sync(SYN_FULL, incl, 31);
+        for (u32 r0 = 0; r0 < total; r0 += 32) {
+            const u32 j = r0 + lane;
+            const bool valid = j < total;
+            // owner = last lane whose exclusive prefix is <= j
+            int o = 0;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                lab[t] = 0;
-                if ((bits >> t) & 1u) {
-                    u32 run = rb + __popc(starts & mask_le((u32)(8 * gi + t))) - 1u;
-                    if (run != prev_run) { prev_run = run; prev_lab = runlabel[run]; }
-                    lab[t] = prev_lab;
+            for (int s = 16; s; s >>= 1) {
+                const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
+                if (e <= j) o += s;
+            }
+            const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
+            const u32 om_o = __shfl_sync(SYN_FULL, om, o);
+            const u32 st_o = __shfl_sync(SYN_FULL, starts, o);
+            const u32 rb_o = __shfl_sync(SYN_FULL, rb, o);
+            const u32 w_o = __shfl_sync(SYN_FULL, w, o);
+            const i64 v_o = __shfl_sync(SYN_FULL, vox0, o);
+            u32 lab = 0;
+            u64 bval = 0;
+            u32 b = 0;
+            if (valid) {
+                b = __fns(om_o, 0, (int)(j - e_o) + 1);
+                const u32 run = rb_o + __popc(st_o & mask_le(b)) - 1u;
+                lab = runlabel[run];
+                if (lab) {
+                    labels[v_o + b] = lab;
+                    if (HAS_BASE) bval = base[v_o + b];
                 }
             }
-            const i64 v = vox0 + 8 * gi;
-            const bool second = (i64)kw * 32 + 8 * gi + 4 < g.nz;   // nz % 8 == 4: the last group of a row is half
-            __stcs(reinterpret_cast<uint4 *>(labels + v), make_uint4(lab[0], lab[1], lab[2], lab[3]));
-            if (second) __stcs(reinterpret_cast<uint4 *>(labels + v + 4), make_uint4(lab[4], lab[5], lab[6], lab[7]));
             if (HAS_BASE) {
-                if ((lab[0] | lab[1] | lab[2] | lab[3] | lab[4] | lab[5] | lab[6] | lab[7]) == 0) continue;
-                const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(base + v);
-                u64 bv[8];
-                ulonglong2 q = bp[0]; bv[0] = q.x; bv[1] = q.y;
-                q = bp[1]; bv[2] = q.x; bv[3] = q.y;
-                if (second) {
-                    q = bp[2]; bv[4] = q.x; bv[5] = q.y;
-                    q = bp[3]; bv[6] = q.x; bv[7] = q.y;
-                } else {
-                    bv[4] = bv[5] = bv[6] = bv[7] = 0;
+                const bool act = lab && bval;
+                const u32 actm = __ballot_sync(SYN_FULL, act);
+                if (actm) {
+                    const u32 pl = __shfl_up_sync(SYN_FULL, lab, 1);
+                    const u64 pb = __shfl_up_sync(SYN_FULL, bval, 1);
+                    const bool head = act && (lane == 0 || pl != lab || pb != bval);
+                    const u32 headm = __ballot_sync(SYN_FULL, head);
+                    if (head) {
+                        const u32 stop = (headm | ~actm) & ~mask_le((u32)lane);
+                        const int endl = stop ? (__ffs(stop) - 1) : 32;
+                        pair_insert(T, lab, bval, (u32)(endl - lane), (u64)w_o * 32 + b);
+                    }
                 }
-                const u64 pos0 = (u64)w * 32 + 8 * gi;
-#pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (lab[t] && bv[t]) acc.add(T, lab[t], bv[t], pos0 + t);
-                    else acc.flush(T);
             }
         }
-        if (HAS_BASE) acc.flush(T);
     }
 }
 
