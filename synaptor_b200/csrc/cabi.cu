@@ -84,6 +84,12 @@ int make_geom(i64 nx, i64 ny, i64 nz, Geom *g)
     g->nwords = (u32)nwords;
     g->cpr = (u32)cpr;
     g->nchunks = (u32)(rows * cpr);
+    g->wzs = 32;
+    g->nys = 32;
+    for (u32 b = 0; b < 31; ++b) {
+        if ((i64)1 << b == wz) g->wzs = b;
+        if ((i64)1 << b == ny) g->nys = b;
+    }
     return SYN_OK;
 }
 
@@ -99,16 +105,19 @@ u32 pow2_at_least(i64 v)
 // workspace carving (must match syn_ccs_workspace_bytes)
 TileGeom make_tiles(const Geom &g)
 {
-    TileGeom t{0, 0, 0, 0, 0};
+    TileGeom t{0, 0, 0, 0, 0, 0, 0};
     if (g.wz > TILE_WORDS / 2) return t;          // one row already fills a tile: no shared-memory pass
     u32 rpt = TILE_WORDS / g.wz;                    // rows per tile, >= 2
     u32 ty = 1;
     while (ty * 2 <= 64 && (ty * 2) * (ty * 2) <= 2 * rpt) ty *= 2;
-    u32 tx = rpt / ty;
-    if (tx > TILE_MAXTX) tx = TILE_MAXTX;
-    if (tx < 1) tx = 1;
+    u32 tx = 1;                                      // power of two as well: tile coordinates by shifts
+    while (tx * 2 <= TILE_MAXTX && tx * 2 * ty <= rpt) tx *= 2;
     t.tx = tx;
     t.ty = ty;
+    for (u32 b = 0; b < 8; ++b) {
+        if (1u << b == tx) t.txs = b;
+        if (1u << b == ty) t.tys = b;
+    }
     t.tiles_x = (u32)((g.nx + tx - 1) / tx);
     t.tiles_y = (u32)((g.ny + ty - 1) / ty);
     t.ntiles = t.tiles_x * t.tiles_y;

@@ -48,7 +48,11 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ pre
                 u32 nib = 0;
                 if (ok[u]) nib = (u32)(v[u].x > thr) | ((u32)(v[u].y > thr) << 1) | ((u32)(v[u].z > thr) << 2) |
                                  ((u32)(v[u].w > thr) << 3);
-                u32 w = __reduce_or_sync(0xFFu << (lane & 24), nib << (4 * (lane & 7)));
+                // OR over each group of 8 lanes (a sub-mask redux.sync compiles to a software loop: 3 shuffles instead)
+                u32 w = nib << (4 * (lane & 7));
+                w |= __shfl_xor_sync(SYN_FULL, w, 1);
+                w |= __shfl_xor_sync(SYN_FULL, w, 2);
+                w |= __shfl_xor_sync(SYN_FULL, w, 4);
                 // ok[] of the first lane of a group says whether the word exists
                 if ((lane & 7) == 0 && ok[u]) {
                     mask[widx[u]] = w;
@@ -270,9 +274,10 @@ __global__ void k_init_parents(u32 *__restrict__ par, Counts *cnt, u32 max_runs)
 //     runbase[w] + popc(starts(w) & mask_le(b)) - 1
 // ===========================================================================
 struct TileGeom {
-    u32 tx, ty;          // rows per tile along x and y (0 = tiling disabled)
+    u32 tx, ty;          // rows per tile along x and y, powers of two (tx == 0: tiling disabled)
     u32 tiles_x, tiles_y;
     u32 ntiles;
+    u32 txs, tys;        // log2(tx), log2(ty)
 };
 
 struct RowView {
@@ -324,16 +329,16 @@ __global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nact; i += gridDim.x * blockDim.x) {
         const u32 w = actw[i];
         u32 m = mask[w];
-        u32 row = w / g.wz;
-        int k = (int)(w - row * g.wz);
-        u32 x = row / (u32)g.ny;
-        u32 y = row - x * (u32)g.ny;
+        u32 row, kk, x, y;
+        split_word(g, w, row, kk);
+        split_row(g, row, x, y);
+        const int k = (int)kk;
         RowView A{mask + (u64)row * g.wz, runbase + (u64)row * g.wz, g.wz};
         bool do_y = true, do_x = true, do_dm = true, do_dp = true;   // (x,y-1) (x-1,y) (x-1,y-1) (x-1,y+1)
         if (tg.tx) {
-            const u32 tX = x / tg.tx, tY = y / tg.ty;
+            const u32 tX = x >> tg.txs, tY = y >> tg.tys;
             const bool dense = tileflag[tX * tg.tiles_y + tY] != 0;
-            const bool xb = (x % tg.tx) == 0, yb = (y % tg.ty) == 0, ye = ((y + 1) % tg.ty) == 0;
+            const bool xb = (x & (tg.tx - 1)) == 0, yb = (y & (tg.ty - 1)) == 0, ye = ((y + 1) & (tg.ty - 1)) == 0;
             do_y = dense || yb;
             do_x = dense || xb;
             do_dm = dense || xb || yb;
@@ -410,25 +415,61 @@ __device__ __forceinline__ void sm_union(u32 *p, u32 a, u32 b)
     }
 }
 
+// One pass over the tile's non-empty words for one (neighbour row, z shift) combination, ONE LANE PER
+// OVERLAP SPAN: every thread first finds the overlap spans of its word with the neighbour word, a warp
+// prefix sum turns the 32 counts into a work list, and the lanes then take the spans one each (owner by
+// shuffle binary search, span start by select_bit) and perform the unions with uniform control flow.
+// s_act entry: word index (11 bits) | k << 11 (10 bits) | yl << 21 (6 bits) | xl << 27.
 template <int SHIFT>
-__device__ __forceinline__ void sm_union_shifted(u32 *par, const RowView &A, const RowView &B, int k, u32 mA)
+__device__ __forceinline__ void tile_pass(const u32 *s_mask, const unsigned short *s_rb, const u32 *s_st, u32 *s_par,
+                                          const u32 *s_act, u32 nact, u32 wz, u32 vy, u32 dxl, int dyl, int off)
 {
-    u32 nb;
-    if (SHIFT == 0) nb = B.word(k);
-    else if (SHIFT < 0) nb = (B.word(k) << 1) | (B.word(k - 1) >> 31);
-    else nb = (B.word(k) >> 1) | (B.word(k + 1) << 31);
-    u32 o = mA & nb;
-    if (!o) return;
-    u32 os = o & ~(o << 1);
-    while (os) {
-        int b = __ffs(os) - 1;
-        os &= os - 1;
-        u32 ga = A.run_at(k, b);
-        int bb = b + SHIFT, kb = k;
-        if (bb < 0) { bb = 31; kb = k - 1; }
-        else if (bb > 31) { bb = 0; kb = k + 1; }
-        u32 gb = B.run_at(kb, bb);
-        sm_union(par, ga, gb);
+    const int lane = threadIdx.x & 31;
+    const u32 wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    for (u32 a0 = wib * 32; a0 < nact; a0 += nwb * 32) {
+        const u32 a = a0 + lane;
+        u32 os = 0, i = 0;
+        if (a < nact) {
+            const u32 e = s_act[a];
+            i = e & 2047u;
+            const u32 k = (e >> 11) & 1023u;
+            const int yl = (int)((e >> 21) & 63u);
+            const u32 xl = e >> 27;
+            if (xl >= dxl && yl + dyl >= 0 && yl + dyl < (int)vy) {
+                const int iB = (int)i + off;
+                u32 nb;
+                if (SHIFT == 0) nb = s_mask[iB];
+                else if (SHIFT < 0) nb = (s_mask[iB] << 1) | (k > 0 ? (s_mask[iB - 1] >> 31) : 0u);
+                else nb = (s_mask[iB] >> 1) | (k + 1 < wz ? (s_mask[iB + 1] << 31) : 0u);
+                const u32 o = s_mask[i] & nb;
+                os = o & ~(o << 1);
+            }
+        }
+        const u32 n = __popc(os);
+        const u32 incl = warp_incl_scan(n, lane);
+        const u32 excl = incl - n;
+        const u32 total = __shfl_sync(SYN_FULL, incl, 31);
+        for (u32 r0 = 0; r0 < total; r0 += 32) {
+            const u32 j = r0 + lane;
+            int o = 0;
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
+                if (e <= j) o += s;
+            }
+            const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
+            const u32 os_o = __shfl_sync(SYN_FULL, os, o);
+            const u32 i_o = __shfl_sync(SYN_FULL, i, o);
+            if (j < total) {
+                const u32 b = select_bit(os_o, j - e_o);
+                const u32 ga = (u32)s_rb[i_o] + __popc(s_st[i_o] & mask_le(b)) - 1u;
+                int iB = (int)i_o + off, bb = (int)b + SHIFT;
+                if (bb < 0) { bb = 31; --iB; }
+                else if (bb > 31) { bb = 0; ++iB; }
+                const u32 gb = (u32)s_rb[iB] + __popc(s_st[iB] & mask_le((u32)bb)) - 1u;
+                sm_union(s_par, ga, gb);
+            }
+        }
     }
 }
 
@@ -438,12 +479,13 @@ __global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, 
                                                   TileGeom tg, const Counts *cnt)
 {
     __shared__ u32 s_mask[TILE_WORDS];
-    __shared__ u32 s_rb[TILE_WORDS];     // LOCAL run-id prefix per word
+    __shared__ u32 s_st[TILE_WORDS];               // run-start bits of the non-empty words
+    __shared__ unsigned short s_rb[TILE_WORDS];    // LOCAL run-id prefix per word (< TILE_RUNS)
     __shared__ u32 s_par[TILE_RUNS];
-    __shared__ unsigned short s_act[TILE_WORDS];   // tile-local indices of the non-empty words
+    __shared__ u32 s_act[TILE_WORDS];              // packed coordinates of the non-empty words
     __shared__ u32 s_nact;
-    __shared__ u32 s_segoff[TILE_MAXTX + 1];   // local id of the first run of x-slab segment xl
-    __shared__ u32 s_delta[TILE_MAXTX];        // global id = local id + delta[xl]
+    __shared__ u32 s_segoff[TILE_MAXTX + 1];       // local id of the first run of x-slab segment xl
+    __shared__ u32 s_delta[TILE_MAXTX];            // global id = local id + delta[xl]
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
     const u32 nruns = (u32)cnt->v[SYN_CNT_RUNS];
     const u32 tile = blockIdx.x;
@@ -451,7 +493,6 @@ __global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, 
     const u32 x0 = tX * tg.tx, y0 = tY * tg.ty;
     const u32 vx = min(tg.tx, (u32)g.nx - x0), vy = min(tg.ty, (u32)g.ny - y0);   // valid rows in this tile
     const u32 segw = vy * g.wz;                // words per x-slab segment (contiguous in memory)
-    const u32 tw = vx * segw;
 
     if (threadIdx.x < vx) {
         u32 first = ((x0 + threadIdx.x) * (u32)g.ny + y0) * g.wz;
@@ -480,57 +521,55 @@ __global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, 
         if (threadIdx.x == 0) tileflag[tile] = 1;
         return;
     }
-    for (u32 i = threadIdx.x; i < tw; i += blockDim.x) {
-        u32 xl = i / segw;
-        u32 gw = ((x0 + xl) * (u32)g.ny + y0) * g.wz + (i - xl * segw);
-        const u32 m = mask[gw];
-        s_mask[i] = m;
-        s_rb[i] = runbase[gw] - s_delta[xl];
-        // warp-aggregated append of the non-empty words (tw is a multiple of... not necessarily 32: use activemask)
-        const u32 act = __activemask();
-        const u32 bal = __ballot_sync(act, m != 0);
-        if (bal) {
-            const int lane = threadIdx.x & 31;
-            const int leader = __ffs(bal) - 1;
-            u32 basei = 0;
-            if (lane == leader) basei = atomicAdd(&s_nact, (u32)__popc(bal));
-            basei = __shfl_sync(act, basei, leader);
-            if (m) s_act[basei + __popc(bal & mask_lt((u32)lane))] = (unsigned short)i;
+    // load the tile, x-slab segment by segment (each is contiguous in memory)
+    for (u32 xl = 0; xl < vx; ++xl) {
+        const u32 gw0 = ((x0 + xl) * (u32)g.ny + y0) * g.wz;
+        const u32 d = s_delta[xl];
+        for (u32 jj = threadIdx.x; jj < segw; jj += blockDim.x) {   // segw need not be a multiple of 32
+            const u32 i = xl * segw + jj;
+            const u32 m = mask[gw0 + jj];
+            s_mask[i] = m;
+            s_rb[i] = (unsigned short)(runbase[gw0 + jj] - d);
+            u32 yl, k;
+            if (g.wzs < 32) { yl = jj >> g.wzs; k = jj & (g.wz - 1u); }
+            else { yl = jj / g.wz; k = jj - yl * g.wz; }
+            const u32 act = __activemask();
+            const u32 bal = __ballot_sync(act, m != 0);
+            if (m) {
+                const u32 carry = k ? (mask[gw0 + jj - 1] >> 31) : 0u;
+                s_st[i] = run_starts(m, carry);
+            }
+            if (bal) {
+                const int lane = threadIdx.x & 31;
+                const int leader = __ffs(bal) - 1;
+                u32 basei = 0;
+                if (lane == leader) basei = atomicAdd(&s_nact, (u32)__popc(bal));
+                basei = __shfl_sync(act, basei, leader);
+                if (m) s_act[basei + __popc(bal & mask_lt((u32)lane))] = i | (k << 11) | (yl << 21) | (xl << 27);
+            }
         }
     }
     for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) s_par[i] = i;
     __syncthreads();
 
-    // local unions: one thread per non-empty word i of the tile <-> (xl, yl, k)
     const u32 nact = s_nact;
-    for (u32 a = threadIdx.x; a < nact; a += blockDim.x) {
-        const u32 i = s_act[a];
-        u32 m = s_mask[i];
-        u32 xl = i / segw;
-        u32 r = (i - xl * segw) / g.wz;        // yl
-        int k = (int)(i - xl * segw - r * g.wz);
-        const u32 rowoff = xl * segw + r * g.wz;
-        RowView A{s_mask + rowoff, s_rb + rowoff, g.wz};
-        if (r > 0) {
-            RowView B{s_mask + rowoff - g.wz, s_rb + rowoff - g.wz, g.wz};
-            sm_union_shifted<0>(s_par, A, B, k, m);
-            if (CONN >= 18) { sm_union_shifted<-1>(s_par, A, B, k, m); sm_union_shifted<1>(s_par, A, B, k, m); }
-        }
-        if (xl > 0) {
-            RowView B{s_mask + rowoff - segw, s_rb + rowoff - segw, g.wz};
-            sm_union_shifted<0>(s_par, A, B, k, m);
-            if (CONN >= 18) { sm_union_shifted<-1>(s_par, A, B, k, m); sm_union_shifted<1>(s_par, A, B, k, m); }
-            if (CONN >= 18 && r > 0) {
-                RowView C{s_mask + rowoff - segw - g.wz, s_rb + rowoff - segw - g.wz, g.wz};
-                sm_union_shifted<0>(s_par, A, C, k, m);
-                if (CONN == 26) { sm_union_shifted<-1>(s_par, A, C, k, m); sm_union_shifted<1>(s_par, A, C, k, m); }
-            }
-            if (CONN >= 18 && r + 1 < vy) {
-                RowView C{s_mask + rowoff - segw + g.wz, s_rb + rowoff - segw + g.wz, g.wz};
-                sm_union_shifted<0>(s_par, A, C, k, m);
-                if (CONN == 26) { sm_union_shifted<-1>(s_par, A, C, k, m); sm_union_shifted<1>(s_par, A, C, k, m); }
-            }
-        }
+    const int wz = (int)g.wz, sg = (int)segw;
+    // (x, y-1) and (x-1, y): face neighbours; the remaining rows / shifts only for 18 / 26
+    tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
+    tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
+    if (CONN >= 18) {
+        tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
+        tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
+        tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
+        tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
+        tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
+        tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
+    }
+    if (CONN == 26) {
+        tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
+        tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
+        tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
+        tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
     }
     __syncthreads();
     // write parent[global run] = global id of the local root
@@ -609,10 +648,9 @@ __global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, co
         u32 m = lmask[w];
         u32 om = omask[w];
         if (om == 0) continue;
-        u32 row = w / g.wz;
-        u32 k = w - row * g.wz;
-        u32 x = row / (u32)g.ny;
-        u32 y = row - x * (u32)g.ny;
+        u32 row, k, x, y;
+        split_word(g, w, row, k);
+        split_row(g, row, x, y);
         u32 carry = k ? (lmask[w - 1] >> 31) : 0u;
         u32 starts = run_starts(m, carry);
         u32 rb = runbase[w];

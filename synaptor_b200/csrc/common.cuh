@@ -37,7 +37,21 @@ struct Geom {
     u32 nwords;  // rows * wz
     u32 cpr;     // 128-voxel chunks per row = ceil(wz / 4)
     u32 nchunks; // rows * cpr
+    u32 wzs;     // log2(wz) when wz is a power of two, else 32
+    u32 nys;     // log2(ny) when ny is a power of two, else 32
 };
+
+// word index -> (row, word in row); row -> (x, y).  Shifts when the extents are powers of two.
+__device__ __forceinline__ void split_word(const Geom &g, u32 w, u32 &row, u32 &k)
+{
+    if (g.wzs < 32) { row = w >> g.wzs; k = w & (g.wz - 1u); }
+    else { row = w / g.wz; k = w - row * g.wz; }
+}
+__device__ __forceinline__ void split_row(const Geom &g, u32 row, u32 &x, u32 &y)
+{
+    if (g.nys < 32) { x = row >> g.nys; y = row & ((u32)g.ny - 1u); }
+    else { x = row / (u32)g.ny; y = row - x * (u32)g.ny; }
+}
 
 // per-component accumulator, one 64-byte record (two 32 B sectors)
 struct __align__(16) CompStat {
@@ -68,6 +82,18 @@ __device__ __forceinline__ u32 mask_lt(u32 b) { return (1u << b) - 1u; }
 
 // run-start bits of a mask word given the top bit of the previous word in the row
 __device__ __forceinline__ u32 run_starts(u32 m, u32 carry) { return m & ~((m << 1) | carry); }
+
+// position of the (n+1)-th set bit of w (n < popc(w)): 5-step binary search on popcounts
+__device__ __forceinline__ u32 select_bit(u32 w, u32 n)
+{
+    u32 pos = 0;
+#pragma unroll
+    for (u32 s = 16; s; s >>= 1) {
+        const u32 c = __popc(w & ((1u << (pos + s)) - 1u));   // set bits below pos+s
+        if (c <= n) pos += s;
+    }
+    return pos;
+}
 
 // sum of the positions of the set bits of w
 __device__ __forceinline__ u32 bitpos_sum(u32 w)

@@ -290,46 +290,57 @@ __global__ void __launch_bounds__(256) k_sparse_labels(const u32 *__restrict__ l
         const u32 incl = warp_incl_scan(n, lane);
         const u32 excl = incl - n;
         const u32 total = __shfl_sync(SYN_FULL, incl, 31);
-        for (u32 r0 = 0; r0 < total; r0 += 32) {
-            const u32 j = r0 + lane;
-            const bool valid = j < total;
-            // owner = last lane whose exclusive prefix is <= j
-            int o = 0;
+        // two rounds (64 foreground voxels) per iteration: both rounds' loads are in flight together, and the
+        // base value is fetched speculatively, in parallel with the run label it would otherwise depend on
+        for (u32 r0 = 0; r0 < total; r0 += 64) {
+            u32 lab[2], b[2], w_o[2];
+            u64 bval[2];
+            i64 vox[2];
+            bool valid[2];
 #pragma unroll
-            for (int s = 16; s; s >>= 1) {
-                const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
-                if (e <= j) o += s;
-            }
-            const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
-            const u32 om_o = __shfl_sync(SYN_FULL, om, o);
-            const u32 st_o = __shfl_sync(SYN_FULL, starts, o);
-            const u32 rb_o = __shfl_sync(SYN_FULL, rb, o);
-            const u32 w_o = __shfl_sync(SYN_FULL, w, o);
-            const i64 v_o = __shfl_sync(SYN_FULL, vox0, o);
-            u32 lab = 0;
-            u64 bval = 0;
-            u32 b = 0;
-            if (valid) {
-                b = __fns(om_o, 0, (int)(j - e_o) + 1);
-                const u32 run = rb_o + __popc(st_o & mask_le(b)) - 1u;
-                lab = runlabel[run];
-                if (lab) {
-                    labels[v_o + b] = lab;
-                    if (HAS_BASE) bval = base[v_o + b];
+            for (int q = 0; q < 2; ++q) {
+                const u32 j = r0 + 32 * q + lane;
+                valid[q] = j < total;
+                int o = 0;   // owner = last lane whose exclusive prefix is <= j
+#pragma unroll
+                for (int s = 16; s; s >>= 1) {
+                    const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
+                    if (e <= j) o += s;
+                }
+                const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
+                const u32 om_o = __shfl_sync(SYN_FULL, om, o);
+                const u32 st_o = __shfl_sync(SYN_FULL, starts, o);
+                const u32 rb_o = __shfl_sync(SYN_FULL, rb, o);
+                w_o[q] = __shfl_sync(SYN_FULL, w, o);
+                const i64 v_o = __shfl_sync(SYN_FULL, vox0, o);
+                lab[q] = 0;
+                bval[q] = 0;
+                b[q] = 0;
+                vox[q] = 0;
+                if (valid[q]) {
+                    b[q] = select_bit(om_o, j - e_o);
+                    vox[q] = v_o + b[q];
+                    const u32 run = rb_o + __popc(st_o & mask_le(b[q])) - 1u;
+                    lab[q] = runlabel[run];
+                    if (HAS_BASE) bval[q] = __ldcs(base + vox[q]);
                 }
             }
-            if (HAS_BASE) {
-                const bool act = lab && bval;
-                const u32 actm = __ballot_sync(SYN_FULL, act);
-                if (actm) {
-                    const u32 pl = __shfl_up_sync(SYN_FULL, lab, 1);
-                    const u64 pb = __shfl_up_sync(SYN_FULL, bval, 1);
-                    const bool head = act && (lane == 0 || pl != lab || pb != bval);
-                    const u32 headm = __ballot_sync(SYN_FULL, head);
-                    if (head) {
-                        const u32 stop = (headm | ~actm) & ~mask_le((u32)lane);
-                        const int endl = stop ? (__ffs(stop) - 1) : 32;
-                        pair_insert(T, lab, bval, (u32)(endl - lane), (u64)w_o * 32 + b);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (lab[q]) labels[vox[q]] = lab[q];
+                if (HAS_BASE) {
+                    const bool act = lab[q] && bval[q];
+                    const u32 actm = __ballot_sync(SYN_FULL, act);
+                    if (actm) {
+                        const u32 pl = __shfl_up_sync(SYN_FULL, lab[q], 1);
+                        const u64 pb = __shfl_up_sync(SYN_FULL, bval[q], 1);
+                        const bool head = act && (lane == 0 || pl != lab[q] || pb != bval[q]);
+                        const u32 headm = __ballot_sync(SYN_FULL, head);
+                        if (head) {
+                            const u32 stop = (headm | ~actm) & ~mask_le((u32)lane);
+                            const int endl = stop ? (__ffs(stop) - 1) : 32;
+                            pair_insert(T, lab[q], bval[q], (u32)(endl - lane), (u64)w_o[q] * 32 + b[q]);
+                        }
                     }
                 }
             }
