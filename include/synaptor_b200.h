@@ -195,10 +195,11 @@ SYN_API int syn_unique_u64(const uint64_t *vals, int64_t n, uint64_t *out, int64
  * syn_profile_enable : when on, syn_chunk_ccs records a CUDA event on its stream between
  *                      pipeline stages (not thread-safe; for bench.py).
  * syn_profile_read   : synchronises on the last recorded call and returns the elapsed ms
- *                      of its SYN_PROF_STAGES stages: 0 threshold(+dilate), 1 run-id scan,
- *                      2 unions, 3 flatten+rank, 4 statistics, 5 dust+table+run labels,
- *                      6 dense zero fill (+ max(base)), 7 foreground sectors (+ pair histogram),
- *                      8 pair ordering.
+ *                      of its SYN_PROF_STAGES stages: 0 threshold(+dilate), 1 dense zero fill
+ *                      + max(base) (run serially while profiling; concurrent with 2-6 otherwise),
+ *                      2 run-id scan, 3 unions (tile-local + boundary), 4 flatten+rank,
+ *                      5 statistics, 6 dust+table+run labels, 7 foreground voxels (+ pair
+ *                      histogram), 8 pair ordering.
  */
 #define SYN_PROF_STAGES 9
 SYN_API long long syn_launch_count(void);

@@ -49,7 +49,7 @@ SIGNATURES = {
     "syn_profile_read": (_i32, [_vp, _i32]),
 }
 PROF_STAGES = 9
-PROF_STAGE_NAMES = ["threshold", "run_scan", "union", "flatten_rank", "stats", "dust_table", "dense_fill",
+PROF_STAGE_NAMES = ["threshold", "dense_fill", "run_scan", "union", "flatten_rank", "stats", "dust_table",
                     "sparse_labels", "pair_order"]
 
 

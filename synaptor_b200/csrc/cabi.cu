@@ -2,6 +2,7 @@
 // and the host-side orchestration of the kernel pipeline.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -43,6 +44,7 @@ std::atomic<long long> g_launches{0};
 // ---- optional per-stage profiling with CUDA events on the launching stream -------------------
 constexpr int PROF_STAGES = 9;
 bool g_prof_on = false;
+bool g_prof_overlap = false;   // syn_profile_enable(2): keep the side-stream overlap while recording stage events
 cudaEvent_t g_prof_ev[PROF_STAGES + 1];
 bool g_prof_created = false;
 bool g_prof_valid = false;
@@ -63,6 +65,31 @@ int sm_count()
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// ---- per-device side stream: the dense zero-fill / max(base) pass is independent of the whole labelling
+// chain, so it runs concurrently with it (HBM-bound streaming next to latency-bound sparse kernels) ----------
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+};
+SideStream g_side[64];
+std::mutex g_side_mu;
+
+SideStream *side_stream()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(g_side_mu);
+    SideStream &S = g_side[dev];
+    if (!S.ok) {
+        if (cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        S.ok = true;
+    }
+    return &S;
 }
 
 int make_geom(i64 nx, i64 ny, i64 nz, Geom *g)
@@ -130,6 +157,8 @@ struct Workspace {
     Counts *cnt;
     u32 *lmask, *omask, *runbase, *tiles;  // tiles: scan tile sums
     u32 *actw;                             // compact list of non-empty mask words
+    u64 *scanstate;                        // 4 look-back state arrays + tickets, zeroed per call
+    size_t scan_cap, scanstate_bytes;
     u32 *par, *rank, *runlabel;
     CompStat *stat;
     PairKey *pkeys;
@@ -153,6 +182,9 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     w->runbase = (u32 *)take(nw * 4);
     w->actw = (u32 *)take(nw * 4);
     w->tiles = (u32 *)take(scan_tiles(biggest) * 4);
+    w->scan_cap = scan_tiles(biggest);
+    w->scanstate_bytes = (4 * w->scan_cap + 8) * 8;
+    w->scanstate = (u64 *)take(w->scanstate_bytes);
     w->tg = make_tiles(g);
     w->tileflag = (u32 *)take(((size_t)w->tg.ntiles + 8) * 4);
     w->par = (u32 *)take((size_t)max_runs * 4);
@@ -207,6 +239,19 @@ int grid_for(i64 items, int threads, int per_sm)
     return (int)(need < cap ? need : cap);
 }
 
+// single-pass scan #slot (0..3) with its own look-back state inside the workspace
+template <class Src, class Dst>
+int launch_scan(const Workspace &W, int slot, Src src, Dst dst, i64 max_items, i64 *total_out, cudaStream_t st)
+{
+    const i64 ntiles = (max_items + SCAN_TILE - 1) / SCAN_TILE;
+    u64 *state = W.scanstate + (size_t)slot * W.scan_cap;
+    u32 *ticket = (u32 *)(W.scanstate + 4 * W.scan_cap) + 2 * slot;
+    k_scan_1p<<<wave_grid(k_scan_1p<Src, Dst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(src, dst, state, ticket,
+                                                                                           total_out);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
 // launches the ordering of the pair table entries + emission into the output arrays
 int order_and_emit_pairs(const Geom &g, const Workspace &W, PairTable T, u32 *rows, u64 *cols, i64 *vals,
                          i64 max_pairs, cudaStream_t st)
@@ -215,14 +260,8 @@ int order_and_emit_pairs(const Geom &g, const Workspace &W, PairTable T, u32 *ro
     k_pair_mark<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bitmap);
     CK_LAUNCH();
     PopcSrc src{W.bitmap, g.nwords};
-    const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
-    k_scan_a<<<wave_grid(k_scan_a<PopcSrc>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(src, W.tiles);
-    CK_LAUNCH();
-    k_scan_b<<<1, SCAN_THREADS, 0, st>>>(src, W.tiles, &W.cnt->v[SYN_CNT_PAIRS], (u32 *)nullptr);
-    CK_LAUNCH();
-    k_scan_c<<<wave_grid(k_scan_c<PopcSrc, WordBaseDst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
-        src, WordBaseDst{W.wordbase}, W.tiles);
-    CK_LAUNCH();
+    int rc = launch_scan(W, 3, src, WordBaseDst{W.wordbase}, g.nwords, &W.cnt->v[SYN_CNT_PAIRS], st);
+    if (rc != SYN_OK) return rc;
     k_pair_emit<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bitmap, W.wordbase, rows, cols, vals, max_pairs);
     CK_LAUNCH();
     return SYN_OK;
@@ -310,6 +349,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     (void)sms;
 
     CK(cudaMemsetAsync(W.cnt, 0, sizeof(Counts), st));
+    CK(cudaMemsetAsync(W.scanstate, 0, W.scanstate_bytes, st));
     PROF_MARK(0);
 
     // --- K1: threshold -> bitmask -------------------------------------------------------------
@@ -329,20 +369,46 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         CK_LAUNCH();
     }
 
+    // --- dense zero fill + max(base): independent of the labelling chain -> side stream -------------------
+    const bool vec_out = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels_out) & 15) == 0) &&
+                         (!has_base || (reinterpret_cast<uintptr_t>(base_seg) & 15) == 0);
+    const u64 *bs = (const u64 *)base_seg;
+    PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap ? W.paircap - 1 : 0, W.cnt};
+    SideStream *side = (vec_out && (!g_prof_on || g_prof_overlap)) ? side_stream() : nullptr;   // profiling pass: serial, clean stage times
     PROF_MARK(1);
-    // --- scan #1: run ids --------------------------------------------------------------------
-    {
-        RunStartSrc src{W.lmask, g.nwords, g.wz};
-        const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
-        k_scan_a<<<wave_grid(k_scan_a<RunStartSrc>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(src, W.tiles);
+    if (vec_out) {
+        cudaStream_t ds = st;
+        if (side) {
+            CK(cudaEventRecord(side->fork, st));      // after the counters memset (max(base) lives there)
+            CK(cudaStreamWaitEvent(side->s, side->fork, 0));
+            ds = side->s;
+        }
+        // few resident threads with 8 chunks (8 x 48 B) in flight each keep HBM busy and leave most of every
+        // SM (registers, thread slots) to the sparse kernels of the main stream
+        const i64 need = div_up_u32((u64)g.nchunks, 8 * 8);
+        static const int dense_ctas = getenv("SYN_DENSE_CTAS") ? atoi(getenv("SYN_DENSE_CTAS")) : 1;
+        i64 gridd = (i64)sm_count() * (side ? dense_ctas : 2);
+        if (gridd > need) gridd = need;
+        if (has_base) k_dense_fill<true, 8><<<(int)gridd, 256, 0, ds>>>(labels_out, bs, g, W.cnt);
+        else k_dense_fill<false, 8><<<(int)gridd, 256, 0, ds>>>(labels_out, bs, g, W.cnt);
         CK_LAUNCH();
-        k_scan_b<<<1, SCAN_THREADS, 0, st>>>(src, W.tiles, &W.cnt->v[SYN_CNT_RUNS], (u32 *)nullptr);
-        CK_LAUNCH();
-        k_scan_c<<<wave_grid(k_scan_c<RunStartSrc, RunBaseDst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
-            src, RunBaseDst{W.runbase}, W.tiles);
+        if (has_base) {
+            k_pair_table_init<<<grid_for(W.paircap, 256, 2), 256, 0, ds>>>(T);
+            CK_LAUNCH();
+        }
+        if (side) CK(cudaEventRecord(side->join, side->s));
+    } else if (has_base) {
+        k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
         CK_LAUNCH();
     }
     PROF_MARK(2);
+    // --- scan #1: run ids --------------------------------------------------------------------
+    {
+        RunStartSrc src{W.lmask, g.nwords, g.wz};
+        rc = launch_scan(W, 0, src, RunBaseDst{W.runbase}, g.nwords, &W.cnt->v[SYN_CNT_RUNS], st);
+        if (rc != SYN_OK) return rc;
+    }
+    PROF_MARK(3);
     {
         const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
         k_compact_active<<<wave_grid(k_compact_active, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(W.lmask, g.nwords,
@@ -360,87 +426,56 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     else launch_union<26>(W, g, st);
     CK_LAUNCH();
 
-    PROF_MARK(3);
+    PROF_MARK(4);
     // --- scan #2: flatten + canonical rank -----------------------------------------------------
     {
-        const int ntiles = (int)((max_runs + SCAN_TILE - 1) / SCAN_TILE);
-        RootFlagSrc srcA{W.par, W.cnt, true}, srcC{W.par, W.cnt, false};
-        k_scan_a<<<wave_grid(k_scan_a<RootFlagSrc>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(srcA, W.tiles);
-        CK_LAUNCH();
-        k_scan_b<<<1, SCAN_THREADS, 0, st>>>(srcC, W.tiles, &W.cnt->v[SYN_CNT_COMPONENTS], (u32 *)nullptr);
-        CK_LAUNCH();
-        k_scan_c<<<wave_grid(k_scan_c<RootFlagSrc, RankDst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
-            srcC, RankDst{W.rank, W.stat}, W.tiles);
-        CK_LAUNCH();
+        RootFlagSrc src{W.par, W.cnt};
+        rc = launch_scan(W, 1, src, RankDst{W.rank, W.stat}, max_runs, &W.cnt->v[SYN_CNT_COMPONENTS], st);
+        if (rc != SYN_OK) return rc;
     }
 
-    PROF_MARK(4);
+    PROF_MARK(5);
     // --- statistics ----------------------------------------------------------------------------
     k_stats<<<wave_grid(k_stats, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.par,
                                                                                W.rank, W.stat, g, W.actw, W.cnt);
     CK_LAUNCH();
 
-    PROF_MARK(5);
+    PROF_MARK(6);
     // --- scan #3: dust decision + table ----------------------------------------------------------
     {
-        const int ntiles = (int)((max_runs + SCAN_TILE - 1) / SCAN_TILE);
-        KeepSrc srcA{W.stat, W.cnt, dust_thresh, (u32)(nx - 1), (u32)(ny - 1), (u32)(nz - 1), true};
-        KeepSrc srcC = srcA;
-        srcC.decide = false;
+        KeepSrc src{W.stat, W.cnt, dust_thresh, (u32)(nx - 1), (u32)(ny - 1), (u32)(nz - 1)};
         i64 ox = offset_xyz ? offset_xyz[0] : 0, oy = offset_xyz ? offset_xyz[1] : 0, oz = offset_xyz ? offset_xyz[2] : 0;
-        k_scan_a<<<wave_grid(k_scan_a<KeepSrc>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(srcA, W.tiles);
-        CK_LAUNCH();
-        k_scan_b<<<1, SCAN_THREADS, 0, st>>>(srcC, W.tiles, &W.cnt->v[SYN_CNT_KEPT], (u32 *)nullptr);
-        CK_LAUNCH();
-        k_scan_c<<<wave_grid(k_scan_c<KeepSrc, TableDst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
-            srcC, TableDst{W.stat, (i64 *)seg_table, max_segs, ox, oy, oz}, W.tiles);
-        CK_LAUNCH();
+        rc = launch_scan(W, 2, src, TableDst{W.stat, (i64 *)seg_table, max_segs, ox, oy, oz}, max_runs,
+                         &W.cnt->v[SYN_CNT_KEPT], st);
+        if (rc != SYN_OK) return rc;
     }
     k_run_labels<<<wave_grid(k_run_labels, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.par, W.rank, W.stat,
                                                                                          W.runlabel, W.cnt, max_segs);
     CK_LAUNCH();
 
-    PROF_MARK(6);
-    // --- dense output (+ overlaps) ---------------------------------------------------------------
-    PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap ? W.paircap - 1 : 0, W.cnt};
-    if (has_base) {
-        k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
+    
+    // --- foreground voxels (+ overlaps) -------------------------------------------------------------
+    if (vec_out) {
+        if (side) CK(cudaStreamWaitEvent(st, side->join, 0));      // zero fill must be complete
+        PROF_MARK(7);
+        const i64 needw = div_up_u32(g.nwords, 8);   // one warp per 32 active words, at most
+        if (has_base)
+            k_sparse_labels<true><<<wave_grid(k_sparse_labels<true>, 256, needw), 256, 0, st>>>(
+                W.lmask, W.omask, W.runbase, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
+        else
+            k_sparse_labels<false><<<wave_grid(k_sparse_labels<false>, 256, needw), 256, 0, st>>>(
+                W.lmask, W.omask, W.runbase, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
         CK_LAUNCH();
-    }
-    {
-        const bool vec_out = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels_out) & 15) == 0) &&
-                             (!has_base || (reinterpret_cast<uintptr_t>(base_seg) & 15) == 0);
-        const u64 *bs = (const u64 *)base_seg;
-        if (vec_out) {
-            // dense zero fill (+ max(base)) at streaming speed, then the foreground sectors
-            const i64 need = div_up_u32((u64)g.nchunks, 8 * 4);
-            if (has_base)
-                k_dense_fill<true, 4><<<wave_grid(k_dense_fill<true, 4>, 256, need), 256, 0, st>>>(labels_out, bs, g,
-                                                                                                  W.cnt);
-            else
-                k_dense_fill<false, 4><<<wave_grid(k_dense_fill<false, 4>, 256, need), 256, 0, st>>>(labels_out, bs, g,
-                                                                                                    W.cnt);
-            CK_LAUNCH();
-            PROF_MARK(7);
-            const i64 needw = div_up_u32(g.nwords, 8);   // one warp per 32 active words, at most
-            if (has_base)
-                k_sparse_labels<true><<<wave_grid(k_sparse_labels<true>, 256, needw), 256, 0, st>>>(
-                    W.lmask, W.omask, W.runbase, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
-            else
-                k_sparse_labels<false><<<wave_grid(k_sparse_labels<false>, 256, needw), 256, 0, st>>>(
-                    W.lmask, W.omask, W.runbase, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
-            CK_LAUNCH();
-        } else {
-            const int grid = grid_for((i64)g.nchunks * 32 / 2 + 1, 256, 8);
-            if (has_base)
-                k_write_labels<false, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel,
-                                                                    labels_out, bs, g, T, W.cnt);
-            else
-                k_write_labels<false, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel,
-                                                                     labels_out, bs, g, T, W.cnt);
-            CK_LAUNCH();
-            PROF_MARK(7);
-        }
+    } else {
+        PROF_MARK(7);
+        const int grid = grid_for((i64)g.nchunks * 32 / 2 + 1, 256, 8);
+        if (has_base)
+            k_write_labels<false, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
+                                                                bs, g, T, W.cnt);
+        else
+            k_write_labels<false, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
+                                                                 bs, g, T, W.cnt);
+        CK_LAUNCH();
     }
     PROF_MARK(8);
     if (has_base) {
@@ -473,6 +508,7 @@ int syn_count_overlaps(const uint32_t *seg1, const uint64_t *seg2, int64_t nx, i
                     (long long)workspace_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(W.cnt, 0, sizeof(Counts), st));
+    CK(cudaMemsetAsync(W.scanstate, 0, W.scanstate_bytes, st));
     PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap - 1, W.cnt};
     k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
     CK_LAUNCH();
@@ -624,6 +660,7 @@ int syn_profile_enable(int on)
         g_prof_created = true;
     }
     g_prof_on = on != 0;
+    g_prof_overlap = on == 2;
     g_prof_valid = false;
     return SYN_OK;
 }

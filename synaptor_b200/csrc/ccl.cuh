@@ -130,73 +130,78 @@ __global__ void __launch_bounds__(256) k_dilate(const u32 *__restrict__ in, u32 
 }
 
 // ===========================================================================
-// Generic 3-phase exclusive scan of a per-item count:
-//   phase A: per-tile sums      phase B: scan of the tile sums (one block)
-//   phase C: per-item exclusive prefix handed to a writer
-// `Src` provides n() (item count, may live on the device) and get(i).
+// Generic single-pass exclusive scan of a per-item count (decoupled look-back).
+// Tiles of SCAN_TILE items are handed out in order through an atomic ticket, so a
+// block that waits on a predecessor's prefix can only wait on a block that is
+// already running.  state[tile] packs (flag << 32 | value): flag 1 = the tile's own
+// sum, flag 2 = inclusive prefix up to and including the tile.  `state` and `ticket`
+// must be zero before the launch.  `Src` provides n() (item count, may live on the
+// device) and get(i); `Dst` receives put(i, exclusive prefix, item value).
 // ===========================================================================
-template <class Src>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_a(Src src, u32 *__restrict__ tilesum)
+template <class Src, class Dst>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_1p(Src src, Dst dst, volatile u64 *state, u32 *ticket,
+                                                          i64 *total_out)
 {
     __shared__ u32 sm[33];
-    const u64 n = src.n();
-    for (u64 tile = blockIdx.x; tile * SCAN_TILE < n; tile += gridDim.x) {  // block-uniform bounds
-        u32 v = 0;
-        const u64 i0 = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
-#pragma unroll
-        for (int t = 0; t < SCAN_ITEMS; ++t)
-            if (i0 + t < n) v += src.get(i0 + t);
-        u32 total;
-        block_excl_scan(v, sm, &total);
-        if (threadIdx.x == 0) tilesum[tile] = total;
-    }
-}
-
-// one block; scans ceil(n / SCAN_TILE) tile sums in place (exclusive) and writes
-// the grand total to *total_out (as i64) and optionally to *total_u32.
-template <class Src>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_b(Src src, u32 *__restrict__ tilesum, i64 *total_out,
-                                                         u32 *total_u32)
-{
-    __shared__ u32 sm[33];
+    __shared__ u32 s_tile, s_prefix;
     const u64 n = src.n();
     const u32 ntiles = (u32)((n + SCAN_TILE - 1) / SCAN_TILE);
-    u32 carry = 0;
-    for (u32 b0 = 0; b0 < ntiles; b0 += SCAN_THREADS) {
-        u32 i = b0 + threadIdx.x;
-        u32 v = i < ntiles ? tilesum[i] : 0;
-        u32 total;
-        u32 ex = block_excl_scan(v, sm, &total);
-        if (i < ntiles) tilesum[i] = carry + ex;
-        carry += total;
+    if (ntiles == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && total_out) *total_out = 0;
+        return;
     }
-    if (threadIdx.x == 0) {
-        if (total_out) *total_out = (i64)carry;
-        if (total_u32) *total_u32 = carry;
-    }
-}
-
-template <class Src, class Dst>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_c(Src src, Dst dst, const u32 *__restrict__ tilebase)
-{
-    __shared__ u32 sm[33];
-    const u64 n = src.n();
-    for (u64 tile = blockIdx.x; tile * SCAN_TILE < n; tile += gridDim.x) {
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= ntiles) break;  // block-uniform
         u32 item[SCAN_ITEMS];
         u32 v = 0;
-        const u64 i0 = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+        const u64 i0 = (u64)tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
 #pragma unroll
         for (int t = 0; t < SCAN_ITEMS; ++t) {
             item[t] = (i0 + t < n) ? src.get(i0 + t) : 0;
             v += item[t];
         }
         u32 total;
-        u32 ex = block_excl_scan(v, sm, &total) + tilebase[tile];
+        u32 ex = block_excl_scan(v, sm, &total);
+        if (threadIdx.x < 32) {
+            // warp-wide look-back: lane l inspects tile (p - l); tiles before 0 count as a zero prefix
+            const int lane = threadIdx.x;
+            u32 prefix = 0;
+            if (tile != 0) {
+                if (lane == 0) state[tile] = (1ull << 32) | total;
+                i64 p = (i64)tile - 1;
+                while (true) {
+                    const i64 idx = p - lane;
+                    const u64 sv = idx >= 0 ? state[idx] : (2ull << 32);
+                    const u32 flag = (u32)(sv >> 32);
+                    const u32 m2 = __ballot_sync(SYN_FULL, flag == 2);
+                    const u32 m0 = __ballot_sync(SYN_FULL, flag == 0);
+                    const u32 upto = m2 ? mask_le((u32)(__ffs(m2) - 1)) : 0xFFFFFFFFu;   // lanes that count
+                    if (m0 & upto) continue;                                              // someone not published yet
+                    u32 val = ((upto >> lane) & 1u) ? (u32)sv : 0u;
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(SYN_FULL, val, d);
+                    prefix += val;
+                    if (m2) break;
+                    p -= 32;
+                }
+            }
+            if (lane == 0) {
+                state[tile] = (2ull << 32) | (u64)(prefix + total);
+                s_prefix = prefix;
+                if (tile == ntiles - 1 && total_out) *total_out = (i64)(prefix + total);
+            }
+        }
+        __syncthreads();
+        ex += s_prefix;
 #pragma unroll
         for (int t = 0; t < SCAN_ITEMS; ++t) {
             if (i0 + t < n) dst.put(i0 + t, ex, item[t]);
             ex += item[t];
         }
+        __syncthreads();   // s_tile / s_prefix are rewritten in the next round
     }
 }
 
@@ -592,22 +597,18 @@ __global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, 
 // number minus one: run ids are in raster order of the run's first voxel and
 // the root is the smallest run of its component.
 // ===========================================================================
-struct RootFlagSrc {  // phase A also flattens
+struct RootFlagSrc {  // flattens while flagging
     u32 *par;
     const Counts *cnt;
-    bool flatten;
     __device__ __forceinline__ u64 n() const
     {
         return (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) ? 0 : (u64)cnt->v[SYN_CNT_RUNS];
     }
     __device__ __forceinline__ u32 get(u64 g) const
     {
-        if (flatten) {
-            u32 r = uf_find_ro(par, (u32)g);
-            par[g] = r;
-            return r == (u32)g;
-        }
-        return par[g] == (u32)g;
+        u32 r = uf_find_ro(par, (u32)g);
+        par[g] = r;
+        return r == (u32)g;
     }
 };
 // rank[g] = canonical index for roots; also initialises the root's CompStat record
@@ -696,14 +697,12 @@ struct KeepSrc {
     const Counts *cnt;
     i64 dust;
     u32 mx, my, mz;  // nx-1, ny-1, nz-1
-    bool decide;
     __device__ __forceinline__ u64 n() const
     {
         return (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) ? 0 : (u64)cnt->v[SYN_CNT_COMPONENTS];
     }
     __device__ __forceinline__ u32 get(u64 c) const
     {
-        if (!decide) return stat[c].keep;
         const CompStat s = stat[c];
         bool face = s.minx == 0 || s.miny == 0 || s.minz == 0 || s.maxx == mx || s.maxy == my || s.maxz == mz;
         u32 keep = (s.size > 0) && (face || (i64)s.size >= dust);
