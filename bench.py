@@ -213,11 +213,15 @@ def main():
     grid = (world, 1, 1)
     offset = (rank * shape[0], 0, 0)
 
+    merge_out = [None]
+    if world > 1:
+        from synaptor_b200 import multi
+
     def step(out=None):
         res = D.chunk_ccs_device(pred, t32, DUST, connectivity=CONN, base=base, offset=offset, sync=False, out=out)
         if world > 1:
-            from synaptor_b200 import multi
-            multi.merge_ccs_device(res, grid, rank, size_thr=DUST)
+            res.counts = {}
+            merge_out[0] = multi.merge_ccs_device(res, grid, rank=rank, world=world, size_thr=DUST)
         return res
 
     def barrier():
@@ -247,6 +251,7 @@ def main():
     clocks = sampler.stop()
     after = D.read_counts(res)
     assert after["errflags"] == 0 and after["kept"] == counts["kept"] and after["pairs"] == counts["pairs"], after
+    n_merged = merge_out[0].n_merged if merge_out[0] is not None else None
 
     # ---- event-instrumented pass for the per-kernel roofline ---------------------------------------
     C.check(L.syn_profile_enable(1))
@@ -313,7 +318,7 @@ def main():
                        "chunks_per_gpu": 1, "grid": list(grid), "merge_ccs_in_step": world > 1,
                        "l2": "inputs (1.6 GB/step) exceed the 126 MB L2; no flush needed",
                        "components": counts["components"], "kept": counts["kept"], "pairs": counts["pairs"],
-                       "runs": counts["runs"], "fg_voxels": counts["fg_voxels"]},
+                       "runs": counts["runs"], "fg_voxels": counts["fg_voxels"], "merged_segments": n_merged},
             "roofline": {"bound": "hbm", "kernel": "k_dense_fill<base> (dense label write + base read for max(base))", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL_WRITE_KERNEL, "kernel_ms": wl_ms,

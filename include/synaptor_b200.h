@@ -190,6 +190,26 @@ SYN_API int syn_unique_u64(const uint64_t *vals, int64_t n, uint64_t *out, int64
 
 
 /*
+ * syn_ids_to_lut -- proc/seg/merge/assign_ids.py:34-42 (new_id_map) on the device:
+ * lut[ids[i * stride]] = base + 1 + i for i < n, i.e. the chunk-local id of table row
+ * i becomes global id base + 1 + i.  The caller zeroes `lut` first.
+ */
+SYN_API int syn_ids_to_lut(const int64_t *ids, int64_t n, int64_t stride, uint32_t base, uint32_t *lut,
+                           int64_t lut_len, void *stream);
+
+/*
+ * syn_merge_seg_tables -- proc/seg/merge/merge_df.py:13-68 (merge_seginfo_df +
+ * enforce_size_threshold).  rows: int64 [n_rows][SYN_SEG_NCOLS], row i = the table row
+ * of GLOBAL id i+1; gmap: uint32 [n_rows+1] from syn_union_min_map.  merged_out receives
+ * one row per merged id with size >= size_thr, ascending id (size = sum, bbox = min/max,
+ * centroid = int(sum c_i * (s_i / S)) in float64, members in ascending id order, Kahan
+ * summation); *n_merged_dev the row count; fmap_out [n_rows+1] the final id map
+ * (merged ids under the threshold -> 0, merge_df.py:64-68).
+ */
+SYN_API int syn_merge_seg_tables(const int64_t *rows, int64_t n_rows, const uint32_t *gmap, int64_t size_thr,
+                                 int64_t *merged_out, uint32_t *fmap_out, int64_t *n_merged_dev, void *stream);
+
+/*
  * Measurement hooks (no reference counterpart).
  * syn_launch_count   : kernels launched by this library in this process so far.
  * syn_profile_enable : when on, syn_chunk_ccs records a CUDA event on its stream between

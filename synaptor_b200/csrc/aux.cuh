@@ -279,4 +279,132 @@ __global__ void __launch_bounds__(256) k_fill_u64(u64 *p, i64 n, u64 v)
     for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = v;
 }
 
+
+// ---------------------------------------------------------------------------
+// Cross-chunk merge of the seg-info tables (proc/seg/merge/merge_df.py:13-68,
+// assign_ids.py:8-42).  rows[i] is the table row of GLOBAL id i+1 (chunks
+// concatenated in np.ndindex order); gmap[gid] = smallest id of gid's merged
+// component.  Per destination id: size = sum, bbox = min / max (integer atomics,
+// order free); centroid = int(sum_i c_i * (s_i / S)) in float64 with the members
+// taken in ascending id order and Kahan-compensated like pandas' groupby().sum().
+// ---------------------------------------------------------------------------
+struct MergeAcc {
+    u64 size;
+    i64 lo[3], hi[3];
+    u32 count;   // fragments
+    u32 off;     // start of the member list
+    u32 cursor;  // fill position
+    u32 outrow;  // row in the compacted output (kept destinations only)
+};
+
+__global__ void __launch_bounds__(256) k_merge_init(MergeAcc *acc, i64 n)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= n; i += (i64)gridDim.x * blockDim.x) {
+        MergeAcc a;
+        a.size = 0;
+        a.lo[0] = a.lo[1] = a.lo[2] = 0x7FFFFFFFFFFFFFFFll;
+        a.hi[0] = a.hi[1] = a.hi[2] = -0x7FFFFFFFFFFFFFFFll - 1;
+        a.count = a.off = a.cursor = a.outrow = 0;
+        acc[i] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_merge_accumulate(const i64 *__restrict__ rows, i64 n,
+                                                          const u32 *__restrict__ gmap, MergeAcc *acc)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const i64 *r = rows + i * SYN_SEG_NCOLS;
+        MergeAcc *a = acc + gmap[i + 1];
+        atomicAdd(&a->size, (u64)r[SYN_SEG_SIZE]);
+        atomicAdd(&a->count, 1u);
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&a->lo[k], r[SYN_SEG_BX + k]);
+            atomicMax(&a->hi[k], r[SYN_SEG_EX + k]);
+        }
+    }
+}
+
+// one block: exclusive scans of the fragment counts (member list offsets) and of the kept flags (output rows)
+__global__ void __launch_bounds__(SCAN_THREADS) k_merge_scan(MergeAcc *acc, i64 n, i64 size_thr, i64 *n_merged)
+{
+    __shared__ u32 sm[33];
+    u32 carry_c = 0, carry_k = 0;
+    for (i64 b0 = 0; b0 <= n; b0 += SCAN_THREADS) {
+        const i64 i = b0 + threadIdx.x;
+        u32 c = 0, k = 0;
+        if (i <= n && i > 0) {
+            c = acc[i].count;
+            k = (c > 0) && ((i64)acc[i].size >= size_thr);
+        }
+        u32 tc, tk;
+        u32 ec = block_excl_scan(c, sm, &tc);
+        u32 ek = block_excl_scan(k, sm, &tk);
+        if (i <= n && i > 0) {
+            acc[i].off = carry_c + ec;
+            acc[i].outrow = k ? (carry_k + ek) : 0xFFFFFFFFu;
+        }
+        carry_c += tc;
+        carry_k += tk;
+    }
+    if (threadIdx.x == 0) *n_merged = (i64)carry_k;
+}
+
+__global__ void __launch_bounds__(256) k_merge_fill(i64 n, const u32 *__restrict__ gmap, MergeAcc *acc,
+                                                    u32 *__restrict__ members, u32 *__restrict__ fmap)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= n; i += (i64)gridDim.x * blockDim.x) {
+        if (i == 0) { fmap[0] = 0; continue; }
+        MergeAcc *a = acc + gmap[i];
+        members[a->off + atomicAdd(&a->cursor, 1u)] = (u32)i;
+        fmap[i] = a->outrow != 0xFFFFFFFFu ? gmap[i] : 0u;   // merged segments under the size threshold map to 0
+    }
+}
+
+__global__ void __launch_bounds__(256) k_merge_emit(const i64 *__restrict__ rows, i64 n, const MergeAcc *__restrict__ acc,
+                                                    u32 *members, i64 *__restrict__ out)
+{
+    for (i64 d = blockIdx.x * (i64)blockDim.x + threadIdx.x + 1; d <= n; d += (i64)gridDim.x * blockDim.x) {
+        const MergeAcc a = acc[d];
+        if (a.count == 0 || a.outrow == 0xFFFFFFFFu) continue;
+        u32 *m = members + a.off;
+        for (u32 i = 1; i < a.count; ++i) {   // ascending id order: the fill order is arbitrary
+            u32 v = m[i];
+            int j = (int)i - 1;
+            while (j >= 0 && m[j] > v) { m[j + 1] = m[j]; --j; }
+            m[j + 1] = v;
+        }
+        double sum[3] = {0.0, 0.0, 0.0}, comp[3] = {0.0, 0.0, 0.0};
+        const double S = (double)a.size;
+        for (u32 i = 0; i < a.count; ++i) {
+            const i64 *r = rows + (i64)(m[i] - 1) * SYN_SEG_NCOLS;
+            const double w = __ddiv_rn((double)r[SYN_SEG_SIZE], S);
+            for (int k = 0; k < 3; ++k) {
+                const double val = __dmul_rn((double)r[SYN_SEG_CX + k], w);
+                const double y = val - comp[k];           // Kahan, as pandas' group_sum
+                const double t = sum[k] + y;
+                comp[k] = (t - sum[k]) - y;
+                sum[k] = t;
+            }
+        }
+        i64 *o = out + (i64)a.outrow * SYN_SEG_NCOLS;
+        o[SYN_SEG_ID] = d;
+        o[SYN_SEG_SIZE] = (i64)a.size;
+        for (int k = 0; k < 3; ++k) {
+            o[SYN_SEG_CX + k] = (i64)sum[k];              // astype(int): truncation
+            o[SYN_SEG_BX + k] = a.lo[k];
+            o[SYN_SEG_EX + k] = a.hi[k];
+        }
+    }
+}
+
+// lut[ids[i * stride]] = base + 1 + i  (chunk-local id -> global id of its table row; assign_ids.py:34-42)
+__global__ void __launch_bounds__(256) k_ids_to_lut(const i64 *__restrict__ ids, i64 n, i64 stride, u32 base,
+                                                    u32 *__restrict__ lut, i64 lut_len)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const i64 id = ids[i * stride];
+        if (id >= 0 && id < lut_len) lut[id] = base + 1u + (u32)i;
+    }
+}
+
 }  // namespace syn

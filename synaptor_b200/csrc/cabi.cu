@@ -674,4 +674,45 @@ int syn_profile_read(float *stage_ms, int n)
     return PROF_STAGES;
 }
 
+
+int syn_ids_to_lut(const int64_t *ids, int64_t n, int64_t stride, uint32_t base, uint32_t *lut, int64_t lut_len,
+                   void *stream)
+{
+    if (!lut || n < 0 || lut_len < 0 || (n > 0 && !ids) || stride < 1) return fail(SYN_ERR_INVALID, "bad arguments");
+    if (n == 0) return SYN_OK;
+    k_ids_to_lut<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>((const i64 *)ids, n, stride, base, lut, lut_len);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
+int syn_merge_seg_tables(const int64_t *rows, int64_t n_rows, const uint32_t *gmap, int64_t size_thr,
+                         int64_t *merged_out, uint32_t *fmap_out, int64_t *n_merged_dev, void *stream)
+{
+    if (n_rows < 0 || !fmap_out || !n_merged_dev || (n_rows > 0 && (!rows || !gmap || !merged_out)))
+        return fail(SYN_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows == 0) {
+        CK(cudaMemsetAsync(n_merged_dev, 0, 8, st));
+        CK(cudaMemsetAsync(fmap_out, 0, 4, st));
+        return SYN_OK;
+    }
+    MergeAcc *acc = nullptr;
+    u32 *members = nullptr;
+    CK(cudaMallocAsync(&acc, (size_t)(n_rows + 1) * sizeof(MergeAcc), st));
+    CK(cudaMallocAsync(&members, (size_t)n_rows * 4, st));
+    k_merge_init<<<grid_for(n_rows + 1, 256, 8), 256, 0, st>>>(acc, n_rows);
+    CK_LAUNCH();
+    k_merge_accumulate<<<grid_for(n_rows, 256, 8), 256, 0, st>>>((const i64 *)rows, n_rows, gmap, acc);
+    CK_LAUNCH();
+    k_merge_scan<<<1, SCAN_THREADS, 0, st>>>(acc, n_rows, size_thr, (i64 *)n_merged_dev);
+    CK_LAUNCH();
+    k_merge_fill<<<grid_for(n_rows + 1, 256, 8), 256, 0, st>>>(n_rows, gmap, acc, members, fmap_out);
+    CK_LAUNCH();
+    k_merge_emit<<<grid_for(n_rows, 256, 8), 256, 0, st>>>((const i64 *)rows, n_rows, acc, members, (i64 *)merged_out);
+    CK_LAUNCH();
+    CK(cudaFreeAsync(acc, st));
+    CK(cudaFreeAsync(members, st));
+    return SYN_OK;
+}
+
 }  // extern "C"

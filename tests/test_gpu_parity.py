@@ -368,3 +368,46 @@ def test_full_size_properties(syn):
     r, c, v, sh = orc.count_overlaps_c(labels, base)
     assert np.array_equal(rows, r) and np.array_equal(cols.astype(np.int64), c) and np.array_equal(vals, v)
     assert (res.counts["max_label"] + 1, res.counts["max_base"] + 1) == sh
+
+
+# ----------------------------------------------------------------------------- device-resident cross-chunk merge
+@pytest.mark.parametrize("vshape,cshape", [((40, 36, 32), (20, 18, 16)), ((48, 24, 64), (16, 24, 32))])
+def test_merge_ccs_device_vs_oracle(syn, vshape, cshape):
+    import torch
+    from synaptor_b200 import _device as D
+    from synaptor_b200 import multi
+    vol = orc.synth_pred(vshape, seed=11, sigma=2.0, fg=0.10)
+    grid = tuple(v // c for (v, c) in zip(vshape, cshape))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    results, chunks = [], []
+    cont_arr = np.empty(grid, dtype=object)
+    info_arr = np.empty(grid, dtype=object)
+    for gi in np.ndindex(grid):
+        beg = tuple(a * b for (a, b) in zip(gi, cshape))
+        sl = tuple(slice(b, b + c) for (b, c) in zip(beg, cshape))
+        sub = np.ascontiguousarray(vol[sl])
+        res = D.chunk_ccs_device(torch.from_numpy(sub).to(dev), np.float32(0.5), 10, offset=beg)
+        ccs, conts, info = orc.cc_task_c(sub, 0.5, 10, offset=beg)
+        assert np.array_equal(res.labels_numpy(), ccs)
+        results.append(res)
+        chunks.append((gi, sl, ccs))
+        cont_arr[gi], info_arr[gi] = conts, info
+    face_shape = tuple(sorted(cshape)[1:])
+    # the oracle pads faces to (two largest dims); axis order inside a face is (smaller axis index, larger)
+    merged, id_maps = orc.merge_ccs_task(cont_arr, info_arr, 15, (max(cshape), max(cshape)))
+    out = multi.merge_ccs_device(results, grid, rank=0, world=1, size_thr=15)
+    got = {int(r[0]): r[1:].tolist() for r in out.merged_table.cpu().numpy()}
+    assert set(got) == set(merged) and out.n_merged == len(merged)
+    for (k, row) in merged.items():
+        assert got[k][0] == row[0] and got[k][4:] == row[4:], (k, got[k], row)
+        assert all(abs(a - b) <= 1 for (a, b) in zip(got[k][1:4], row[1:4]))   # float64 mean, truncated
+    final = np.zeros(vshape, dtype=np.uint32)
+    want = np.zeros(vshape, dtype=np.uint32)
+    for ((gi, sl, ccs), res) in zip(chunks, results):
+        final[sl] = res.labels_numpy()
+        want[sl] = orc.remap_ids(ccs.copy(), id_maps[gi])
+    assert np.array_equal(final, want), first_diff(final, want)
+    # the merged volume is a 1:1 relabelling of whole-volume CCL restricted to the surviving segments
+    whole = orc.label_c(vol > 0.5, 6)[0]
+    pairs = np.unique(np.stack([final[final != 0], whole[final != 0]], 1), axis=0)
+    assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1]))
