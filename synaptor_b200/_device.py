@@ -42,6 +42,23 @@ def release_workspaces():
     _ws_cache.clear()
 
 
+_side_streams = {}
+
+
+def side_stream(torch, device, name):
+    """Per-device auxiliary torch streams ("in": H2D copies, "out": D2H copies) for the host-array entry points."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), name)
+    s = _side_streams.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _side_streams[key] = s
+    return s
+
+
+def pinned_like(torch, t):
+    return torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+
+
 def float32_threshold(dtype, thresh):
     """
     The float32 value t such that `float32(d) > t` equals numpy's `d > thresh` for
@@ -130,6 +147,20 @@ class ChunkResult:
         host = torch.empty(self.labels.shape, dtype=self.labels.dtype, device="cpu", pin_memory=True)
         host.copy_(self.labels)
         return host.numpy().view(np.uint32)
+
+    def labels_numpy_async(self, stream):
+        """Starts the D2H of the label volume on `stream` (after the work queued on the current stream);
+        returns (pinned host tensor, event).  Synchronise the event before touching the array."""
+        import torch
+        cur = torch.cuda.current_stream()
+        host = torch.empty(self.labels.shape, dtype=self.labels.dtype, device="cpu", pin_memory=True)
+        stream.wait_stream(cur)
+        with torch.cuda.stream(stream):
+            host.copy_(self.labels, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self.labels.record_stream(stream)
+        return host, ev
 
     def pairs_numpy(self):
         n = self.counts["pairs"]

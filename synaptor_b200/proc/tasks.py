@@ -31,13 +31,24 @@ def cc_task_device(pred, cc_thresh, sz_thresh, offset=(0, 0, 0), base=None, conn
                               dil_k=int(dil_param), offset=offset, base=base, **kw)
 
 
-def _materialise_cc(res, shape):
-    """ChunkResult -> (ccs ndarray, {Face: [Continuation]}, seg-info DataFrame)."""
-    ccs = res.labels_numpy().reshape(shape)
+def _materialise_cc(res, shape, between=None):
+    """
+    ChunkResult -> (ccs ndarray, {Face: [Continuation]}, seg-info DataFrame).  The 4 B/voxel D2H of the
+    label volume runs on a copy stream while the host groups the face voxels into continuations and
+    builds the table; `between()` (optional) is called after the copy was queued (more device work that
+    can overlap it) and its result is appended.
+    """
+    torch = D._torch()
+    host, ev = res.labels_numpy_async(D.side_stream(torch, res.labels.device, "out"))
     faces = cont_mod.faces_from_device(res.labels)
-    continuations, _ = cont_mod.continuations_from_faces(faces)
+    continuations, _ = cont_mod.continuations_from_faces(faces)     # ~10 ms of host work, hidden under the copies
     table = res.table_numpy()
     info = seg.misc.seg_info_from_table(table[:, 0], table[:, 1:])
+    extra = between() if between is not None else None
+    ev.synchronize()
+    ccs = host.numpy().view(np.uint32).reshape(shape)
+    if between is not None:
+        return ccs, continuations, info, extra
     return ccs, continuations, info
 
 
@@ -86,28 +97,60 @@ def overlap_task(segs, base_segs, orig_ids=True):
 
 def cc_overlap_task(desc_vol, base_segs, cc_thresh, sz_thresh, offset=(0, 0, 0), connectivity=6, dil_param=0):
     """
-    chunk_ccs and chunk_overlaps fused into ONE device pass (the labels never leave
-    HBM between the two tasks).  Returns (ccs, continuations, seg_info, overlap_mat)
+    chunk_ccs followed by chunk_overlaps on the same chunk without the label volume making a round
+    trip through the host.  Returns (ccs, continuations, seg_info, overlap_mat)
     == cc_task(...) + (overlap_task(ccs, base_segs),).
+    CUDA-tensor base: one fused device pass.  Host arrays: copy / compute / copy pipelined over
+    three streams (see below).
     """
     torch = D._torch()
-    d = np.asarray(desc_vol)
-    shape = d.shape
+    d = desc_vol if isinstance(desc_vol, torch.Tensor) else np.asarray(desc_vol)
+    shape = tuple(int(x) for x in d.shape)
     if 0 in shape:
         return cc_task(d, cc_thresh, sz_thresh, offset, verbose=False) + (seg_utils.overlap.make_coo([], [], [], 0, 0),)
     device = torch.device("cuda", torch.cuda.current_device())
-    pred = D.to_device_f32(torch, d, device)
-    base = D.to_device_u64(torch, base_segs, device)
-    res = D.chunk_ccs_device(pred, D.float32_threshold(d.dtype, cc_thresh), int(sz_thresh),
-                             connectivity=connectivity, dil_k=int(dil_param),
-                             offset=tuple(int(o) for o in offset), base=base)
-    ccs, continuations, info = _materialise_cc(res, shape)
+    t32 = np.float32(cc_thresh) if isinstance(d, torch.Tensor) else D.float32_threshold(d.dtype, cc_thresh)
+    off = tuple(int(o) for o in offset)
+    if isinstance(base_segs, torch.Tensor) and base_segs.is_cuda:
+        # device-resident base: one fused pass (labels never leave HBM between the two tasks)
+        pred = D.to_device_f32(torch, d, device)
+        res = D.chunk_ccs_device(pred, t32, int(sz_thresh), connectivity=connectivity, dil_k=int(dil_param),
+                                 offset=off, base=D.to_device_u64(torch, base_segs, device))
+        ccs, continuations, info = _materialise_cc(res, shape)
+        return ccs, continuations, info, _coo_from_result(res)
+
+    # host arrays: the PCIe transfers dominate (1.6 GB in, 0.5 GB out for 512^3), so the work is pipelined:
+    #   copy-in stream : pred H2D, then base H2D
+    #   main stream    : chunk_ccs as soon as pred has arrived  ->  overlap counting once base has arrived
+    #   copy-out stream: label volume D2H, concurrent with the base H2D (PCIe is full duplex)
+    s_main = torch.cuda.current_stream()
+    s_in = D.side_stream(torch, device, "in")
+    s_in.wait_stream(s_main)
+    with torch.cuda.stream(s_in):
+        pred = D.to_device_f32(torch, d, device)
+        ev_pred = torch.cuda.Event()
+        ev_pred.record(s_in)
+        base = D.to_device_u64(torch, base_segs, device)
+        ev_base = torch.cuda.Event()
+        ev_base.record(s_in)
+    pred.record_stream(s_main)
+    base.record_stream(s_main)
+    s_main.wait_event(ev_pred)
+    res = D.chunk_ccs_device(pred, t32, int(sz_thresh), connectivity=connectivity, dil_k=int(dil_param), offset=off)
+
+    def overlaps():
+        s_main.wait_event(ev_base)
+        return D.count_overlaps_device(res.labels, base)
+
+    ccs, continuations, info, ov = _materialise_cc(res, shape, between=overlaps)
+    return ccs, continuations, info, _coo_from_result(ov)
+
+
+def _coo_from_result(res):
     rows, cols, vals = res.pairs_numpy()
     if res.counts["max_label"] == 0 or res.counts["max_base"] == 0:
-        mat = seg_utils.overlap.make_coo([], [], [], 0, 0)
-    else:
-        mat = seg_utils.overlap.make_coo(rows, cols, vals, res.counts["max_label"] + 1, res.counts["max_base"] + 1)
-    return ccs, continuations, info, mat
+        return seg_utils.overlap.make_coo([], [], [], 0, 0)
+    return seg_utils.overlap.make_coo(rows, cols, vals, res.counts["max_label"] + 1, res.counts["max_base"] + 1)
 
 
 def merge_ccs_task(cont_info_arr, cleft_info_arr, size_thr, max_face_shape, enforce_overlaps=False):
