@@ -53,6 +53,8 @@ enum {
     SYN_CNT_FG_VOXELS = 7,   /* voxels above threshold */
     SYN_CNT_TABLE_SLOTS = 8, /* occupied slots in the pair hash table */
     SYN_CNT_ACTIVE_WORDS = 9, /* 32-voxel mask words holding at least one labelled voxel */
+    SYN_CNT_TILE_RECORDS = 10, /* per-tile partial statistics records written by the tile pass */
+    SYN_CNT_FLAGGED_TILES = 11, /* tiles left to the global kernels (too dense for shared memory) */
     SYN_NCOUNTS = 16
 };
 

@@ -18,7 +18,7 @@ SYN_ERR_WORKSPACE = -4
 
 # counts[] indices (enum in synaptor_b200.h)
 CNT_RUNS, CNT_COMPONENTS, CNT_KEPT, CNT_PAIRS, CNT_MAX_BASE, CNT_MAX_LABEL, CNT_ERRFLAGS, CNT_FG_VOXELS, \
-    CNT_TABLE_SLOTS, CNT_ACTIVE_WORDS = range(10)
+    CNT_TABLE_SLOTS, CNT_ACTIVE_WORDS, CNT_TILE_RECORDS, CNT_FLAGGED_TILES = range(12)
 NCOUNTS = 16
 SEG_NCOLS = 11
 

@@ -161,6 +161,7 @@ struct Workspace {
     size_t scan_cap, scanstate_bytes;
     u32 *par, *rank, *runlabel;
     CompStat *stat;
+    TileRec *recs;
     PairKey *pkeys;
     u64 *pcount, *pfirst;
     u32 *bitmap, *wordbase;
@@ -191,6 +192,7 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     w->rank = (u32 *)take((size_t)max_runs * 4);
     w->runlabel = (u32 *)take((size_t)max_runs * 4);
     w->stat = (CompStat *)take((size_t)max_runs * sizeof(CompStat));
+    w->recs = (TileRec *)take((size_t)max_runs * sizeof(TileRec));
     w->paircap = 0;
     w->pkeys = nullptr; w->pcount = w->pfirst = nullptr; w->bitmap = w->wordbase = nullptr;
     if (max_pairs > 0) {
@@ -285,7 +287,13 @@ template <int CONN>
 void launch_union(const Workspace &W, const Geom &g, cudaStream_t st)
 {
     if (W.tg.tx) {
-        k_tile_ccl<CONN><<<W.tg.ntiles, 256, 0, st>>>(W.lmask, W.runbase, W.par, W.tileflag, g, W.tg, W.cnt);
+        static bool attr_set = false;   // one flag per template instantiation
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_tile_ccl<CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM);
+            attr_set = true;
+        }
+        k_tile_ccl<CONN><<<W.tg.ntiles, TILE_THREADS, TILE_SMEM, st>>>(W.lmask, W.omask, W.runbase, W.par, W.tileflag, W.recs, g,
+                                                            W.tg, W.cnt);
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     k_union_rows<CONN><<<wave_grid(k_union_rows<CONN>, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(
@@ -436,8 +444,14 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
 
     PROF_MARK(5);
     // --- statistics ----------------------------------------------------------------------------
+    if (W.tg.tx) {
+        k_stats_merge<<<wave_grid(k_stats_merge, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.recs, W.par, W.rank,
+                                                                                               W.stat, W.cnt);
+        CK_LAUNCH();
+    }
     k_stats<<<wave_grid(k_stats, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.par,
-                                                                               W.rank, W.stat, g, W.actw, W.cnt);
+                                                                               W.rank, W.stat, g, W.tg, W.tileflag,
+                                                                               W.actw, W.cnt);
     CK_LAUNCH();
 
     PROF_MARK(6);

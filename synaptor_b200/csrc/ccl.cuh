@@ -393,6 +393,10 @@ __global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask
 constexpr int TILE_WORDS = 2048;
 constexpr int TILE_RUNS = 4096;
 constexpr int TILE_MAXTX = 16;
+constexpr int TILE_ROOTS = 512;    // tile-local components with statistics accumulated in shared memory
+constexpr int TILE_SLOT = 10;      // u32 per root: size, sum dx, sum dy, sum z, min/max dx, dy, z
+constexpr size_t TILE_SMEM = (size_t)TILE_WORDS * 4 * 3 + (size_t)TILE_WORDS * 2 + (size_t)TILE_RUNS * 4 +
+                             (size_t)TILE_RUNS * 2 + (size_t)TILE_ROOTS * 2 + (size_t)TILE_ROOTS * TILE_SLOT * 4;
 
 
 __device__ __forceinline__ u32 sm_find(volatile u32 *p, u32 x)
@@ -404,6 +408,13 @@ __device__ __forceinline__ u32 sm_find(volatile u32 *p, u32 x)
         x = q;
         q = gq;
     }
+    return x;
+}
+
+__device__ __forceinline__ u32 sm_find_ro(const volatile u32 *p, u32 x)
+{
+    u32 q;
+    while ((q = p[x]) != x) x = q;
     return x;
 }
 
@@ -478,17 +489,24 @@ __device__ __forceinline__ void tile_pass(const u32 *s_mask, const unsigned shor
     }
 }
 
+constexpr int TILE_THREADS = 512;   // 3 CTAs/SM by shared memory -> 48 warps/SM
+
 template <int CONN>
-__global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, const u32 *__restrict__ runbase,
-                                                  u32 *__restrict__ par, u32 *__restrict__ tileflag, Geom g,
-                                                  TileGeom tg, const Counts *cnt)
+__global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict__ mask, const u32 *__restrict__ omask,
+                                                  const u32 *__restrict__ runbase, u32 *__restrict__ par,
+                                                  u32 *__restrict__ tileflag, TileRec *__restrict__ recs, Geom g,
+                                                  TileGeom tg, Counts *cnt)
 {
-    __shared__ u32 s_mask[TILE_WORDS];
-    __shared__ u32 s_st[TILE_WORDS];               // run-start bits of the non-empty words
-    __shared__ unsigned short s_rb[TILE_WORDS];    // LOCAL run-id prefix per word (< TILE_RUNS)
-    __shared__ u32 s_par[TILE_RUNS];
-    __shared__ u32 s_act[TILE_WORDS];              // packed coordinates of the non-empty words
-    __shared__ u32 s_nact;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    u32 *s_mask = reinterpret_cast<u32 *>(s_raw);                 // [TILE_WORDS]
+    u32 *s_st = s_mask + TILE_WORDS;                              // run-start bits of the non-empty words
+    u32 *s_act = s_st + TILE_WORDS;                               // packed coordinates of the non-empty words
+    u32 *s_par = s_act + TILE_WORDS;                              // [TILE_RUNS]
+    u32 *s_slot = s_par + TILE_RUNS;                              // [TILE_ROOTS][TILE_SLOT] statistics
+    unsigned short *s_rb = reinterpret_cast<unsigned short *>(s_slot + TILE_ROOTS * TILE_SLOT);   // LOCAL run-id prefix
+    unsigned short *s_rootidx = s_rb + TILE_WORDS;                // [TILE_RUNS] compact index of a local root
+    unsigned short *s_rootrun = s_rootidx + TILE_RUNS;            // [TILE_ROOTS] local run id of root #idx
+    __shared__ u32 s_nact, s_nroots, s_recbase;
     __shared__ u32 s_segoff[TILE_MAXTX + 1];       // local id of the first run of x-slab segment xl
     __shared__ u32 s_delta[TILE_MAXTX];            // global id = local id + delta[xl]
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
@@ -507,7 +525,7 @@ __global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, 
         s_segoff[threadIdx.x + 1] = b1 - b0;   // run count, turned into a prefix below
         s_delta[threadIdx.x] = b0;
     }
-    if (threadIdx.x == 0) s_nact = 0;
+    if (threadIdx.x == 0) { s_nact = 0; s_nroots = 0; }
     __syncthreads();
     if (threadIdx.x == 0) {
         u32 acc = 0;
@@ -522,8 +540,11 @@ __global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, 
     __syncthreads();
     const u32 nloc = s_segoff[vx];
     if (nloc == 0) return;                     // no foreground in this tile
-    if (nloc > TILE_RUNS) {                    // too dense for the shared-memory pass: K3 does the whole tile
-        if (threadIdx.x == 0) tileflag[tile] = 1;
+    if (nloc > TILE_RUNS) {                    // too dense for the shared-memory pass: K3 / k_stats do the whole tile
+        if (threadIdx.x == 0) {
+            tileflag[tile] = 1;
+            atomicAdd((u64 *)&cnt->v[SYN_CNT_FLAGGED_TILES], 1ull);
+        }
         return;
     }
     // load the tile, x-slab segment by segment (each is contiguous in memory)
@@ -577,9 +598,10 @@ __global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, 
         tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
     }
     __syncthreads();
-    // write parent[global run] = global id of the local root
+    // flatten; write parent[global run] = global id of the local root; give every local root a compact index
     for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) {
-        u32 r = sm_find(s_par, i);
+        u32 r = sm_find_ro(s_par, i);          // read-only walk: a halving store could undo a neighbour's flatten
+        s_par[i] = r;
         // x-slab segment of a local run id: last xl with segoff[xl] <= id (vx <= 16: 4 steps)
         u32 xi = 0, xr = 0;
 #pragma unroll
@@ -588,6 +610,102 @@ __global__ void __launch_bounds__(256) k_tile_ccl(const u32 *__restrict__ mask, 
             if (xr + s2 < vx && s_segoff[xr + s2] <= r) xr += s2;
         }
         par[i + s_delta[xi]] = r + s_delta[xr];
+        if (r == i) {
+            const u32 idx = atomicAdd(&s_nroots, 1u);
+            s_rootidx[i] = (unsigned short)idx;
+            if (idx < TILE_ROOTS) s_rootrun[idx] = (unsigned short)i;
+        }
+    }
+    __syncthreads();
+    // ---- statistics of the tile-local components in shared memory (one record per local root afterwards) ----
+    const u32 nroots = s_nroots;
+    if (nroots > TILE_ROOTS) {                 // statistics of this tile are left to k_stats
+        if (threadIdx.x == 0) {
+            tileflag[tile] = 2;
+            atomicAdd((u64 *)&cnt->v[SYN_CNT_FLAGGED_TILES], 1ull);
+        }
+        return;
+    }
+    for (u32 j = threadIdx.x; j < nroots * TILE_SLOT; j += blockDim.x) {
+        const u32 f = j % TILE_SLOT;
+        s_slot[j] = (f >= 4 && f <= 6) ? 0xFFFFFFFFu : 0u;
+    }
+    if (threadIdx.x == 0) s_recbase = (u32)atomicAdd((u64 *)&cnt->v[SYN_CNT_TILE_RECORDS], (u64)nroots);
+    __syncthreads();
+    const bool same_mask = (omask == mask);
+    for (u32 a = threadIdx.x; a < nact; a += blockDim.x) {
+        const u32 e = s_act[a];
+        const u32 i = e & 2047u, k = (e >> 11) & 1023u, yl = (e >> 21) & 63u, xl = e >> 27;
+        const u32 m = s_mask[i];
+        const u32 om = same_mask ? m : omask[((x0 + xl) * (u32)g.ny + y0 + yl) * g.wz + k];
+        if (!om) continue;
+        const u32 starts = s_st[i], rb = s_rb[i], z0 = k * 32;
+        u32 ps = m & ~(m << 1);                // piece starts
+        while (ps) {
+            const int b0 = __ffs(ps) - 1;
+            ps &= ps - 1;
+            const u32 span = ~(m >> b0);
+            int len = span ? (__ffs(span) - 1) : 32;
+            if (len > 32 - b0) len = 32 - b0;
+            const u32 pm = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << b0;
+            const u32 bits = om & pm;
+            if (!bits) continue;
+            const u32 li = rb + __popc(starts & mask_le((u32)b0)) - 1u;
+            u32 *sl = s_slot + (u32)s_rootidx[s_par[li]] * TILE_SLOT;
+            const u32 n = __popc(bits);
+            atomicAdd(sl + 0, n);
+            atomicAdd(sl + 1, n * xl);
+            atomicAdd(sl + 2, n * yl);
+            atomicAdd(sl + 3, n * z0 + bitpos_sum(bits));
+            atomicMin(sl + 4, xl);
+            atomicMin(sl + 5, yl);
+            atomicMin(sl + 6, z0 + (u32)__ffs(bits) - 1u);
+            atomicMax(sl + 7, xl);
+            atomicMax(sl + 8, yl);
+            atomicMax(sl + 9, z0 + 31u - (u32)__clz(bits));
+        }
+    }
+    __syncthreads();
+    for (u32 idx = threadIdx.x; idx < nroots; idx += blockDim.x) {
+        const u32 *sl = s_slot + idx * TILE_SLOT;
+        const u32 r = s_rootrun[idx];
+        u32 xr = 0;
+#pragma unroll
+        for (u32 s2 = 8; s2; s2 >>= 1)
+            if (xr + s2 < vx && s_segoff[xr + s2] <= r) xr += s2;
+        TileRec rec;
+        rec.root = r + s_delta[xr];
+        rec.size = sl[0];
+        rec.sx = (u64)sl[1] + (u64)sl[0] * x0;
+        rec.sy = (u64)sl[2] + (u64)sl[0] * y0;
+        rec.sz = sl[3];
+        rec.minx = sl[4] + x0; rec.miny = sl[5] + y0; rec.minz = sl[6];
+        rec.maxx = sl[7] + x0; rec.maxy = sl[8] + y0; rec.maxz = sl[9];
+        rec.pad[0] = rec.pad[1] = 0;
+        recs[s_recbase + idx] = rec;           // a local root with no ORIGINAL voxel (dilation) has size 0: harmless
+    }
+}
+
+// merges the tile records into the per-component statistics (after the canonical ranks are known)
+__global__ void __launch_bounds__(256) k_stats_merge(const TileRec *__restrict__ recs, const u32 *__restrict__ par,
+                                                     const u32 *__restrict__ rank, CompStat *stat, const Counts *cnt)
+{
+    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    const u64 n = (u64)cnt->v[SYN_CNT_TILE_RECORDS];
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const TileRec r = recs[i];
+        if (r.size == 0) continue;
+        CompStat *s = stat + rank[par[r.root]];
+        atomicAdd(&s->size, (u64)r.size);
+        atomicAdd(&s->sx, r.sx);
+        atomicAdd(&s->sy, r.sy);
+        atomicAdd(&s->sz, r.sz);
+        if (r.minx < ldcg_u32(&s->minx)) atomicMin(&s->minx, r.minx);
+        if (r.miny < ldcg_u32(&s->miny)) atomicMin(&s->miny, r.miny);
+        if (r.minz < ldcg_u32(&s->minz)) atomicMin(&s->minz, r.minz);
+        if (r.maxx > ldcg_u32(&s->maxx)) atomicMax(&s->maxx, r.maxx);
+        if (r.maxy > ldcg_u32(&s->maxy)) atomicMax(&s->maxy, r.maxy);
+        if (r.maxz > ldcg_u32(&s->maxz)) atomicMax(&s->maxz, r.maxz);
     }
 }
 
@@ -639,10 +757,13 @@ struct RankDst {
 // ===========================================================================
 __global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
                                                const u32 *__restrict__ runbase, const u32 *__restrict__ par,
-                                               const u32 *__restrict__ rank, CompStat *stat, Geom g,
+                                               const u32 *__restrict__ rank, CompStat *stat, Geom g, TileGeom tg,
+                                               const u32 *__restrict__ tileflag,
                                                const u32 *__restrict__ actw, const Counts *cnt)
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    // with tiling, the tile pass already produced the statistics of every tile it did not flag
+    if (tg.tx && cnt->v[SYN_CNT_FLAGGED_TILES] == 0) return;
     const u32 nact = (u32)cnt->v[SYN_CNT_ACTIVE_WORDS];
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nact; i += gridDim.x * blockDim.x) {
         const u32 w = actw[i];
@@ -652,6 +773,7 @@ __global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, co
         u32 row, k, x, y;
         split_word(g, w, row, k);
         split_row(g, row, x, y);
+        if (tg.tx && tileflag[(x >> tg.txs) * tg.tiles_y + (y >> tg.tys)] == 0) continue;
         u32 carry = k ? (lmask[w - 1] >> 31) : 0u;
         u32 starts = run_starts(m, carry);
         u32 rb = runbase[w];

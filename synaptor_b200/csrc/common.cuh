@@ -62,6 +62,16 @@ struct __align__(16) CompStat {
 };
 static_assert(sizeof(CompStat) == 64, "CompStat must be 64 bytes");
 
+// partial statistics of one tile-local component (written by the tile pass, merged per canonical component)
+struct __align__(16) TileRec {
+    u32 root;   // global run id of the tile-local root
+    u32 size;
+    u64 sx, sy, sz;
+    u32 minx, miny, minz, maxx, maxy, maxz;
+    u32 pad[2];
+};
+static_assert(sizeof(TileRec) == 64, "TileRec must be 64 bytes");
+
 // slot of the (label, base id) pair table: 16-byte key claimed with one 128-bit CAS
 struct __align__(16) PairKey {
     u64 base;
