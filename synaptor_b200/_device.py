@@ -175,6 +175,8 @@ def _counts_dict(arr):
         "pairs": int(arr[C.CNT_PAIRS]), "max_base": int(np.uint64(arr[C.CNT_MAX_BASE].view(np.uint64))),
         "max_label": int(arr[C.CNT_MAX_LABEL]), "errflags": int(arr[C.CNT_ERRFLAGS]),
         "fg_voxels": int(arr[C.CNT_FG_VOXELS]), "table_slots": int(arr[C.CNT_TABLE_SLOTS]),
+        "active_words": int(arr[C.CNT_ACTIVE_WORDS]), "tile_records": int(arr[C.CNT_TILE_RECORDS]),
+        "flagged_tiles": int(arr[C.CNT_FLAGGED_TILES]),
     }
 
 
