@@ -344,7 +344,10 @@ def main():
                        "components": counts["components"], "kept": counts["kept"], "pairs": counts["pairs"],
                        "runs": counts["runs"], "fg_voxels": counts["fg_voxels"], "merged_segments": n_merged},
             "roofline": {"bound": "hbm", "kernel": "k_dense_fill<base> (dense label write + base read for max(base))", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_dense_fill launch on this
+                         # workload (ncu --set full, profiles/r01e_top_summary.txt): 1.0738 GB + 0.5016 GB
+                         "traffic": 1575342784 if shape == (512, 512, 512) else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL_WRITE_KERNEL, "kernel_ms": wl_ms,
                          "pipeline": {"bytes_per_voxel": BYTES_PER_VOXEL_PIPELINE, "achieved": pipe_gbs,
                                       "frac": pipe_gbs / peak, "frac_of_8TBs_nominal": pipe_gbs / 8000.0},
