@@ -37,8 +37,11 @@ CHUNK = (512, 512, 512)
 THRESH, DUST, CONN = 0.5, 100, 6
 METRIC = "Gvoxels/s chunk_ccs+overlaps"
 BYTES_PER_VOXEL_PIPELINE = 16   # 4 B pred read + 4 B label write + 8 B base read
-BYTES_PER_VOXEL_WRITE_KERNEL = 12  # k_dense_fill: 4 B label write + 8 B base read
+BYTES_PER_VOXEL_STREAM_KERNEL = 16  # k_stream: 4 B pred read + 8 B base read + 4 B label (zero-fill) write
 CPU_SAMPLE = (256, 256, 256)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_stream launch on the 512^3 workload (ncu --set full,
+# profiles/): filled in from the committed capture
+STREAM_TRAFFIC_512 = None
 
 
 def peaks():
@@ -274,27 +277,17 @@ def main():
         n_merged = merge_out[0].n_merged
         merge_ms = float(np.median(times))
 
-    # ---- event-instrumented pass for the per-kernel roofline ---------------------------------------
-    C.check(L.syn_profile_enable(1))
-    stage = np.zeros((args.steps, C.PROF_STAGES), dtype=np.float32)
-    for i in range(args.steps):
-        r2 = D.chunk_ccs_device(pred, t32, DUST, connectivity=CONN, base=base, offset=offset, sync=False, out=res)
-        buf = np.zeros(C.PROF_STAGES, dtype=np.float32)
-        n = L.syn_profile_read(buf.ctypes.data, C.PROF_STAGES)
-        assert n == C.PROF_STAGES, C.last_error()
-        stage[i] = buf
-    C.check(L.syn_profile_enable(0))
-    stage_ms = stage.mean(axis=0)
-    # same, but with the side-stream overlap left on: how long the labelling chain takes next to the dense fill
-    C.check(L.syn_profile_enable(2))
-    stage2 = np.zeros((args.steps, C.PROF_STAGES), dtype=np.float32)
-    for i in range(args.steps):
-        r2 = D.chunk_ccs_device(pred, t32, DUST, connectivity=CONN, base=base, offset=offset, sync=False, out=res)
-        buf = np.zeros(C.PROF_STAGES, dtype=np.float32)
-        assert L.syn_profile_read(buf.ctypes.data, C.PROF_STAGES) == C.PROF_STAGES, C.last_error()
-        stage2[i] = buf
-    C.check(L.syn_profile_enable(0))
-    stage_ms_overlap = stage2.mean(axis=0)
+    # ---- event-instrumented passes: one CUDA event after every kernel of syn_chunk_ccs ----------------
+    def profiled(mode):
+        C.check(L.syn_profile_enable(mode))
+        acc = {}
+        for _ in range(args.steps):
+            D.chunk_ccs_device(pred, t32, DUST, connectivity=CONN, base=base, offset=offset, sync=False, out=res)
+            for (k, v) in C.profile_read().items():
+                acc[k] = acc.get(k, 0.0) + v / args.steps
+        C.check(L.syn_profile_enable(0))
+        return acc
+    stage_ms = profiled(1)
 
     # ---- e2e through the public API with pinned host buffers ---------------------------------------
     e2e = None
@@ -329,8 +322,8 @@ def main():
         peak, peak_src = peaks()
         ms_step = ms_max / args.steps
         value = world * nvox / (ms_step * 1e-3) / 1e9
-        wl_ms = float(stage_ms[C.PROF_STAGE_NAMES.index('dense_fill')])
-        achieved = BYTES_PER_VOXEL_WRITE_KERNEL * nvox / (wl_ms * 1e-3) / 1e9
+        wl_ms = float(stage_ms['stream'])
+        achieved = BYTES_PER_VOXEL_STREAM_KERNEL * nvox / (wl_ms * 1e-3) / 1e9
         pipe_gbs = BYTES_PER_VOXEL_PIPELINE * nvox / (ms_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps,
@@ -343,16 +336,13 @@ def main():
                        "l2": "inputs (1.6 GB/step) exceed the 126 MB L2; no flush needed",
                        "components": counts["components"], "kept": counts["kept"], "pairs": counts["pairs"],
                        "runs": counts["runs"], "fg_voxels": counts["fg_voxels"], "merged_segments": n_merged},
-            "roofline": {"bound": "hbm", "kernel": "k_dense_fill<base> (dense label write + base read for max(base))", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_stream<base,scan> (pred + base read, threshold, label zero-fill, run prefix)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one k_dense_fill launch on this
-                         # workload (ncu --set full, profiles/r01e_top_summary.txt): 1.0738 GB + 0.5016 GB
-                         "traffic": 1575342784 if shape == (512, 512, 512) else None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL_WRITE_KERNEL, "kernel_ms": wl_ms,
+                         "traffic": STREAM_TRAFFIC_512 if shape == (512, 512, 512) else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL_STREAM_KERNEL, "kernel_ms": wl_ms,
                          "pipeline": {"bytes_per_voxel": BYTES_PER_VOXEL_PIPELINE, "achieved": pipe_gbs,
                                       "frac": pipe_gbs / peak, "frac_of_8TBs_nominal": pipe_gbs / 8000.0},
-                         "stage_ms": {n: float(v) for (n, v) in zip(C.PROF_STAGE_NAMES, stage_ms)},
-                         "stage_ms_overlapped": {n: float(v) for (n, v) in zip(C.PROF_STAGE_NAMES, stage_ms_overlap)}},
+                         "stage_ms": {n: round(float(v), 5) for (n, v) in stage_ms.items()}},
             "clocks": clocks,
             "gpu_launches": int(launches),
         }

@@ -55,6 +55,7 @@ enum {
     SYN_CNT_ACTIVE_WORDS = 9, /* 32-voxel mask words holding at least one labelled voxel */
     SYN_CNT_TILE_RECORDS = 10, /* per-tile partial statistics records written by the tile pass */
     SYN_CNT_FLAGGED_TILES = 11, /* tiles left to the global kernels (too dense for shared memory) */
+    SYN_CNT_BND_WORDS = 12,  /* non-empty mask words on a tile border (input of the global union pass) */
     SYN_NCOUNTS = 16
 };
 
@@ -214,19 +215,21 @@ SYN_API int syn_merge_seg_tables(const int64_t *rows, int64_t n_rows, const uint
 /*
  * Measurement hooks (no reference counterpart).
  * syn_launch_count   : kernels launched by this library in this process so far.
- * syn_profile_enable : when on, syn_chunk_ccs records a CUDA event on its stream between
- *                      pipeline stages (not thread-safe; for bench.py).
- * syn_profile_read   : synchronises on the last recorded call and returns the elapsed ms
- *                      of its SYN_PROF_STAGES stages: 0 threshold(+dilate), 1 dense zero fill
- *                      + max(base) (run serially while profiling; concurrent with 2-6 otherwise),
- *                      2 run-id scan, 3 unions (tile-local + boundary), 4 flatten+rank,
- *                      5 statistics, 6 dust+table+run labels, 7 foreground voxels (+ pair
- *                      histogram), 8 pair ordering.
+ * syn_profile_enable : 1 = syn_chunk_ccs records a CUDA event on its stream after every kernel and
+ *                      runs the dense fill serially (clean per-kernel times); 2 = the same marks
+ *                      with the side-stream overlap left on; 0 = off.  Not thread-safe; for bench.py.
+ * syn_profile_read   : synchronises on the last recorded call and returns the number K of
+ *                      intervals (<= SYN_PROF_MAX), stage_ms[i] = elapsed ms of interval i.
+ * syn_profile_name   : name of interval i of the last recorded call = the kernel that ended it
+ *                      ("threshold_runs", "dense_fill", "tile_ccl", "union_bnd", "flatten_rank",
+ *                      "stats_merge", "dust_table", "run_labels", "sector_labels", "pair_mark",
+ *                      "pair_scan", "pair_emit", "join_dense", ...).
  */
-#define SYN_PROF_STAGES 9
+#define SYN_PROF_MAX 40
 SYN_API long long syn_launch_count(void);
 SYN_API int syn_profile_enable(int on);
 SYN_API int syn_profile_read(float *stage_ms, int n);
+SYN_API const char *syn_profile_name(int i);
 
 #ifdef __cplusplus
 }

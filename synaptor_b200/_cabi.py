@@ -18,7 +18,7 @@ SYN_ERR_WORKSPACE = -4
 
 # counts[] indices (enum in synaptor_b200.h)
 CNT_RUNS, CNT_COMPONENTS, CNT_KEPT, CNT_PAIRS, CNT_MAX_BASE, CNT_MAX_LABEL, CNT_ERRFLAGS, CNT_FG_VOXELS, \
-    CNT_TABLE_SLOTS, CNT_ACTIVE_WORDS, CNT_TILE_RECORDS, CNT_FLAGGED_TILES = range(12)
+    CNT_TABLE_SLOTS, CNT_ACTIVE_WORDS, CNT_TILE_RECORDS, CNT_FLAGGED_TILES, CNT_BND_WORDS = range(13)
 NCOUNTS = 16
 SEG_NCOLS = 11
 
@@ -49,10 +49,9 @@ SIGNATURES = {
     "syn_launch_count": (ctypes.c_longlong, []),
     "syn_profile_enable": (_i32, [_i32]),
     "syn_profile_read": (_i32, [_vp, _i32]),
+    "syn_profile_name": (ctypes.c_char_p, [_i32]),
 }
-PROF_STAGES = 9
-PROF_STAGE_NAMES = ["threshold", "dense_fill", "run_scan", "union", "flatten_rank", "stats", "dust_table",
-                    "sparse_labels", "pair_order"]
+PROF_MAX = 40
 
 
 class SynaptorB200Error(RuntimeError):
@@ -87,6 +86,20 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def profile_read():
+    """{kernel name: elapsed ms} of the last syn_chunk_ccs call recorded with syn_profile_enable on (ordered)."""
+    import numpy as np
+    buf = np.zeros(PROF_MAX, dtype=np.float32)
+    k = lib().syn_profile_read(buf.ctypes.data, PROF_MAX)
+    if k < 0:
+        check(k)
+    out = {}
+    for i in range(k):
+        name = lib().syn_profile_name(i).decode()
+        out[name] = out.get(name, 0.0) + float(buf[i])
+    return out
 
 
 def last_error():

@@ -185,7 +185,7 @@ def default_capacities(shape):
     worst_runs = int(shape[0]) * int(shape[1]) * ((int(shape[2]) + 1) // 2)
     max_runs = min(max(1 << 16, nvox // 8), max(worst_runs, 1))
     max_segs = min(max(1 << 14, nvox // 256), max(worst_runs, 1))
-    max_pairs = max(1 << 14, nvox // 256)
+    max_pairs = max(1 << 14, nvox // 1024)   # grown on overflow (SYN_ERR_CAPACITY retry)
     return max_runs, max_segs, max_pairs
 
 

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <atomic>
 #include <mutex>
+#include <cstdint>
 
 #include "aux.cuh"
 #include "ccl.cuh"
@@ -41,17 +42,30 @@ std::atomic<long long> g_launches{0};
         CK(cudaGetLastError()); \
     } while (0)
 
-// ---- optional per-stage profiling with CUDA events on the launching stream -------------------
-constexpr int PROF_STAGES = 9;
+// ---- optional per-kernel profiling with CUDA events on the launching stream -------------------
+// While enabled, syn_chunk_ccs records an event after every kernel; interval i is named after the kernel that
+// ended at mark i + 1.
+constexpr int PROF_MAX = 40;
 bool g_prof_on = false;
-bool g_prof_overlap = false;   // syn_profile_enable(2): keep the side-stream overlap while recording stage events
-cudaEvent_t g_prof_ev[PROF_STAGES + 1];
+bool g_prof_overlap = false;   // syn_profile_enable(2): keep the side-stream overlap while recording events
+cudaEvent_t g_prof_ev[PROF_MAX];
+const char *g_prof_name[PROF_MAX];
+int g_prof_n = 0;
 bool g_prof_created = false;
 bool g_prof_valid = false;
 
-#define PROF_MARK(i)                                                   \
-    do {                                                               \
-        if (g_prof_on) CK(cudaEventRecord(g_prof_ev[(i)], st));        \
+int prof_mark(const char *name, cudaStream_t st)
+{
+    if (!g_prof_on || g_prof_n >= PROF_MAX) return SYN_OK;
+    g_prof_name[g_prof_n] = name;
+    CK(cudaEventRecord(g_prof_ev[g_prof_n], st));
+    ++g_prof_n;
+    return SYN_OK;
+}
+#define PROF(name)                                   \
+    do {                                             \
+        int prc__ = prof_mark((name), st);           \
+        if (prc__ != SYN_OK) return prc__;           \
     } while (0)
 
 int sm_count()
@@ -65,31 +79,6 @@ int sm_count()
         cached[dev] = n;
     }
     return cached[dev];
-}
-
-// ---- per-device side stream: the dense zero-fill / max(base) pass is independent of the whole labelling
-// chain, so it runs concurrently with it (HBM-bound streaming next to latency-bound sparse kernels) ----------
-struct SideStream {
-    cudaStream_t s = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-    bool ok = false;
-};
-SideStream g_side[64];
-std::mutex g_side_mu;
-
-SideStream *side_stream()
-{
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lk(g_side_mu);
-    SideStream &S = g_side[dev];
-    if (!S.ok) {
-        if (cudaStreamCreateWithFlags(&S.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&S.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&S.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        S.ok = true;
-    }
-    return &S;
 }
 
 int make_geom(i64 nx, i64 ny, i64 nz, Geom *g)
@@ -157,9 +146,11 @@ struct Workspace {
     Counts *cnt;
     u32 *lmask, *omask, *runbase, *tiles;  // tiles: scan tile sums
     u32 *actw;                             // compact list of non-empty mask words
+    u32 *bndw;                             // non-empty words on a tile border
     u64 *scanstate;                        // 4 look-back state arrays + tickets, zeroed per call
-    size_t scan_cap, scanstate_bytes;
-    u32 *par, *rank, *runlabel;
+    u32 *tileagg, *tilebase;               // run counts / run-id bases of the stream tiles (k_stream, k_tile_prefix)
+    size_t scan_cap, ts_cap, scanstate_bytes;
+    u32 *par, *rank, *runlabel, *complab;
     CompStat *stat;
     TileRec *recs;
     PairKey *pkeys;
@@ -169,7 +160,8 @@ struct Workspace {
     size_t total;
 };
 
-size_t scan_tiles(i64 n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 1; }
+constexpr int SCAN_MIN_TILE = SCAN_THREADS * 2;   // smallest tile any scan instance uses (look-back state capacity)
+size_t scan_tiles(i64 n) { return (size_t)((n + SCAN_MIN_TILE - 1) / SCAN_MIN_TILE) + 1; }
 
 void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, Workspace *w)
 {
@@ -182,15 +174,20 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     w->omask = dilate ? (u32 *)take(nw * 4) : w->lmask;
     w->runbase = (u32 *)take(nw * 4);
     w->actw = (u32 *)take(nw * 4);
+    w->bndw = (u32 *)take(nw * 4);
     w->tiles = (u32 *)take(scan_tiles(biggest) * 4);
     w->scan_cap = scan_tiles(biggest);
+    w->ts_cap = (size_t)g.nchunks / TS_CHUNKS + 2;
     w->scanstate_bytes = (4 * w->scan_cap + 8) * 8;
     w->scanstate = (u64 *)take(w->scanstate_bytes);
+    w->tileagg = (u32 *)take(w->ts_cap * 4);
+    w->tilebase = (u32 *)take(w->ts_cap * 4);
     w->tg = make_tiles(g);
     w->tileflag = (u32 *)take(((size_t)w->tg.ntiles + 8) * 4);
     w->par = (u32 *)take((size_t)max_runs * 4);
     w->rank = (u32 *)take((size_t)max_runs * 4);
     w->runlabel = (u32 *)take((size_t)max_runs * 4);
+    w->complab = (u32 *)take((size_t)max_runs * 4);
     w->stat = (CompStat *)take((size_t)max_runs * sizeof(CompStat));
     w->recs = (TileRec *)take((size_t)max_runs * sizeof(TileRec));
     w->paircap = 0;
@@ -242,30 +239,33 @@ int grid_for(i64 items, int threads, int per_sm)
 }
 
 // single-pass scan #slot (0..3) with its own look-back state inside the workspace
-template <class Src, class Dst>
+template <int ITEMS, class Src, class Dst>
 int launch_scan(const Workspace &W, int slot, Src src, Dst dst, i64 max_items, i64 *total_out, cudaStream_t st)
 {
-    const i64 ntiles = (max_items + SCAN_TILE - 1) / SCAN_TILE;
+    static_assert(SCAN_THREADS * ITEMS >= SCAN_MIN_TILE, "look-back state capacity");
+    const i64 ntiles = (max_items + SCAN_THREADS * ITEMS - 1) / (SCAN_THREADS * ITEMS);
     u64 *state = W.scanstate + (size_t)slot * W.scan_cap;
     u32 *ticket = (u32 *)(W.scanstate + 4 * W.scan_cap) + 2 * slot;
-    k_scan_1p<<<wave_grid(k_scan_1p<Src, Dst>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(src, dst, state, ticket,
-                                                                                           total_out);
+    k_scan_1p<Src, Dst, ITEMS><<<wave_grid(k_scan_1p<Src, Dst, ITEMS>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
+        src, dst, state, ticket, total_out);
     CK_LAUNCH();
     return SYN_OK;
 }
 
-// launches the ordering of the pair table entries + emission into the output arrays
+// launches the ordering of the pair table entries + emission into the output arrays (the bitmap is already zero)
 int order_and_emit_pairs(const Geom &g, const Workspace &W, PairTable T, u32 *rows, u64 *cols, i64 *vals,
                          i64 max_pairs, cudaStream_t st)
 {
-    CK(cudaMemsetAsync(W.bitmap, 0, (size_t)g.nwords * 4, st));
     k_pair_mark<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bitmap);
     CK_LAUNCH();
+    PROF("pair_mark");
     PopcSrc src{W.bitmap, g.nwords};
-    int rc = launch_scan(W, 3, src, WordBaseDst{W.wordbase}, g.nwords, &W.cnt->v[SYN_CNT_PAIRS], st);
+    int rc = launch_scan<16>(W, 3, src, WordBaseDst{W.wordbase}, g.nwords, &W.cnt->v[SYN_CNT_PAIRS], st);
     if (rc != SYN_OK) return rc;
+    PROF("pair_scan");
     k_pair_emit<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bitmap, W.wordbase, rows, cols, vals, max_pairs);
     CK_LAUNCH();
+    PROF("pair_emit");
     return SYN_OK;
 }
 
@@ -284,7 +284,7 @@ int finish_counts(const Workspace &W, i64 *counts_host, cudaStream_t st)
 }
 
 template <int CONN>
-void launch_union(const Workspace &W, const Geom &g, cudaStream_t st)
+int launch_union(const Workspace &W, const Geom &g, RunIdx R, bool bnd_list, i64 max_runs, cudaStream_t st)
 {
     if (W.tg.tx) {
         static bool attr_set = false;   // one flag per template instantiation
@@ -292,12 +292,28 @@ void launch_union(const Workspace &W, const Geom &g, cudaStream_t st)
             cudaFuncSetAttribute(k_tile_ccl<CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM);
             attr_set = true;
         }
-        k_tile_ccl<CONN><<<W.tg.ntiles, TILE_THREADS, TILE_SMEM, st>>>(W.lmask, W.omask, W.runbase, W.par, W.tileflag, W.recs, g,
-                                                            W.tg, W.cnt);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        k_tile_ccl<CONN><<<W.tg.ntiles, TILE_THREADS, TILE_SMEM, st>>>(W.lmask, W.omask, R, W.par, W.tileflag, W.recs, g,
+                                                            W.tg, W.cnt, (u32)max_runs);
+        CK_LAUNCH();
+        PROF("tile_ccl");
     }
-    k_union_rows<CONN><<<wave_grid(k_union_rows<CONN>, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(
-        W.lmask, W.runbase, W.par, g, W.tg, W.tileflag, W.actw, W.cnt);
+    if (CONN == 6 && bnd_list) {
+        // tile borders from the compact border-word list; flagged tiles (normally none) by the row kernel
+        k_union_bnd<<<wave_grid(k_union_bnd, 256, div_up_u32(g.nwords, 256 * 4)), 256, 0, st>>>(W.lmask, R, W.par, g,
+                                                                                        W.tg, W.bndw, W.cnt);
+        CK_LAUNCH();
+        PROF("union_bnd");
+        k_union_rows<CONN, true><<<wave_grid(k_union_rows<CONN, true>, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(
+            W.lmask, R, W.par, g, W.tg, W.tileflag, W.actw, W.cnt);
+        CK_LAUNCH();
+        PROF("union_flagged");
+    } else {
+        k_union_rows<CONN, false><<<wave_grid(k_union_rows<CONN, false>, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(
+            W.lmask, R, W.par, g, W.tg, W.tileflag, W.actw, W.cnt);
+        CK_LAUNCH();
+        PROF("union_rows");
+    }
+    return SYN_OK;
 }
 
 }  // namespace
@@ -358,11 +374,35 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
 
     CK(cudaMemsetAsync(W.cnt, 0, sizeof(Counts), st));
     CK(cudaMemsetAsync(W.scanstate, 0, W.scanstate_bytes, st));
-    PROF_MARK(0);
+    g_prof_n = 0;
+    PROF("start");
 
-    // --- K1: threshold -> bitmask -------------------------------------------------------------
+    // --- K1.  Sector mode (nz % 8 == 0, aligned buffers): ONE streaming kernel reads the predictions and the
+    // base volume and zero-fills the label sectors without foreground (16 B/voxel, HBM bound); without dilation
+    // it also produces the tiled run-id prefix and the active / border word lists.  Otherwise: plain threshold
+    // kernel, and the generic output pass at the end. ---------------------------------------------------------
     const bool vec_in = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
-    {
+    const bool sector_out = (nz % 8 == 0) && vec_in && ((reinterpret_cast<uintptr_t>(labels_out) & 31) == 0) &&
+                            (!has_base || (reinterpret_cast<uintptr_t>(base_seg) & 15) == 0);
+    static const bool no_fuse = getenv("SYN_NO_FUSED_SCAN") != nullptr;
+    const bool fused_scan = sector_out && !dilate && !no_fuse;
+    const u64 *bs = (const u64 *)base_seg;
+    if (sector_out) {
+        const i64 ntiles = ((i64)g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
+#define SYN_STREAM(HB, FS)                                                                                         \
+    k_stream<HB, FS><<<wave_grid(k_stream<HB, FS>, TS_THREADS, ntiles), TS_THREADS, 0, st>>>(                      \
+        pred, bs, labels_out, W.omask, W.runbase, W.tileagg, W.actw, W.bndw, g, W.tg, thresh, W.cnt)
+        if (has_base) { if (fused_scan) SYN_STREAM(true, true); else SYN_STREAM(true, false); }
+        else { if (fused_scan) SYN_STREAM(false, true); else SYN_STREAM(false, false); }
+#undef SYN_STREAM
+        CK_LAUNCH();
+        PROF("stream");
+        if (fused_scan) {
+            k_tile_prefix<<<1, 1024, 0, st>>>(W.tileagg, W.tilebase, (u32)ntiles, W.cnt, (u32)max_runs);
+            CK_LAUNCH();
+            PROF("tile_prefix");
+        }
+    } else {
         const i64 need = div_up_u32((u64)g.nchunks, 8 * 4);
         if (vec_in)
             k_threshold<true, 4><<<wave_grid(k_threshold<true, 4>, 256, need), 256, 0, st>>>(
@@ -371,117 +411,96 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
             k_threshold<false, 4><<<wave_grid(k_threshold<false, 4>, 256, need), 256, 0, st>>>(
                 pred, W.omask, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
         CK_LAUNCH();
+        PROF("threshold");
     }
     if (dilate) {
         k_dilate<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(W.omask, W.lmask, g, dil_k);
         CK_LAUNCH();
+        PROF("dilate");
     }
-
-    // --- dense zero fill + max(base): independent of the labelling chain -> side stream -------------------
-    const bool vec_out = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(labels_out) & 15) == 0) &&
-                         (!has_base || (reinterpret_cast<uintptr_t>(base_seg) & 15) == 0);
-    const u64 *bs = (const u64 *)base_seg;
+    const RunIdx R{W.runbase, fused_scan ? W.tilebase : nullptr, g.cpr};
     PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap ? W.paircap - 1 : 0, W.cnt};
-    SideStream *side = (vec_out && (!g_prof_on || g_prof_overlap)) ? side_stream() : nullptr;   // profiling pass: serial, clean stage times
-    PROF_MARK(1);
-    if (vec_out) {
-        cudaStream_t ds = st;
-        if (side) {
-            CK(cudaEventRecord(side->fork, st));      // after the counters memset (max(base) lives there)
-            CK(cudaStreamWaitEvent(side->s, side->fork, 0));
-            ds = side->s;
-        }
-        // few resident threads with 8 chunks (8 x 48 B) in flight each keep HBM busy and leave most of every
-        // SM (registers, thread slots) to the sparse kernels of the main stream
-        const i64 need = div_up_u32((u64)g.nchunks, 8 * 8);
-        static const int dense_ctas = getenv("SYN_DENSE_CTAS") ? atoi(getenv("SYN_DENSE_CTAS")) : 1;
-        i64 gridd = (i64)sm_count() * (side ? dense_ctas : 2);
-        if (gridd > need) gridd = need;
-        if (has_base) k_dense_fill<true, 8><<<(int)gridd, 256, 0, ds>>>(labels_out, bs, g, W.cnt);
-        else k_dense_fill<false, 8><<<(int)gridd, 256, 0, ds>>>(labels_out, bs, g, W.cnt);
-        CK_LAUNCH();
-        if (has_base) {
-            k_pair_table_init<<<grid_for(W.paircap, 256, 2), 256, 0, ds>>>(T);
-            CK_LAUNCH();
-        }
-        if (side) CK(cudaEventRecord(side->join, side->s));
-    } else if (has_base) {
+    if (has_base) {
         k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
         CK_LAUNCH();
+        CK(cudaMemsetAsync(W.bitmap, 0, (size_t)g.nwords * 4, st));
+        PROF("pair_init");
     }
-    PROF_MARK(2);
-    // --- scan #1: run ids --------------------------------------------------------------------
-    {
+
+    // --- scan #1: run ids (already done by the streaming kernel on the plain path) ----------------------
+    if (!fused_scan) {
         RunStartSrc src{W.lmask, g.nwords, g.wz};
-        rc = launch_scan(W, 0, src, RunBaseDst{W.runbase}, g.nwords, &W.cnt->v[SYN_CNT_RUNS], st);
+        rc = launch_scan<16>(W, 0, src, RunBaseDst{W.runbase}, g.nwords, &W.cnt->v[SYN_CNT_RUNS], st);
         if (rc != SYN_OK) return rc;
-    }
-    PROF_MARK(3);
-    {
+        PROF("run_scan");
         const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
         k_compact_active<<<wave_grid(k_compact_active, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(W.lmask, g.nwords,
                                                                                                   W.actw, W.cnt);
         CK_LAUNCH();
+        PROF("compact_active");
     }
-    k_init_parents<<<wave_grid(k_init_parents, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.par, W.cnt,
-                                                                                          (u32)max_runs);
-    CK_LAUNCH();
-    if (W.tg.tx) CK(cudaMemsetAsync(W.tileflag, 0, (size_t)W.tg.ntiles * 4, st));
+    if (!W.tg.tx) {   // with tiling the tile pass writes every parent (and checks the run capacity)
+        k_init_parents<<<wave_grid(k_init_parents, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.par, W.cnt,
+                                                                                              (u32)max_runs);
+        CK_LAUNCH();
+    } else {
+        CK(cudaMemsetAsync(W.tileflag, 0, (size_t)W.tg.ntiles * 4, st));
+    }
 
     // --- unions ------------------------------------------------------------------------------
-    if (connectivity == 6) launch_union<6>(W, g, st);
-    else if (connectivity == 18) launch_union<18>(W, g, st);
-    else launch_union<26>(W, g, st);
-    CK_LAUNCH();
+    const bool bnd_list = fused_scan && W.tg.tx;
+    if (connectivity == 6) rc = launch_union<6>(W, g, R, bnd_list, max_runs, st);
+    else if (connectivity == 18) rc = launch_union<18>(W, g, R, false, max_runs, st);
+    else rc = launch_union<26>(W, g, R, false, max_runs, st);
+    if (rc != SYN_OK) return rc;
 
-    PROF_MARK(4);
     // --- scan #2: flatten + canonical rank -----------------------------------------------------
     {
         RootFlagSrc src{W.par, W.cnt};
-        rc = launch_scan(W, 1, src, RankDst{W.rank, W.stat}, max_runs, &W.cnt->v[SYN_CNT_COMPONENTS], st);
+        rc = launch_scan<4>(W, 1, src, RankDst{W.rank, W.stat}, max_runs, &W.cnt->v[SYN_CNT_COMPONENTS], st);
         if (rc != SYN_OK) return rc;
+        PROF("flatten_rank");
     }
 
-    PROF_MARK(5);
     // --- statistics ----------------------------------------------------------------------------
     if (W.tg.tx) {
         k_stats_merge<<<wave_grid(k_stats_merge, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.recs, W.par, W.rank,
                                                                                                W.stat, W.cnt);
         CK_LAUNCH();
+        PROF("stats_merge");
     }
-    k_stats<<<wave_grid(k_stats, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.par,
+    k_stats<<<wave_grid(k_stats, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(W.lmask, W.omask, R, W.par,
                                                                                W.rank, W.stat, g, W.tg, W.tileflag,
                                                                                W.actw, W.cnt);
     CK_LAUNCH();
+    PROF("stats_flagged");
 
-    PROF_MARK(6);
     // --- scan #3: dust decision + table ----------------------------------------------------------
     {
         KeepSrc src{W.stat, W.cnt, dust_thresh, (u32)(nx - 1), (u32)(ny - 1), (u32)(nz - 1)};
         i64 ox = offset_xyz ? offset_xyz[0] : 0, oy = offset_xyz ? offset_xyz[1] : 0, oz = offset_xyz ? offset_xyz[2] : 0;
-        rc = launch_scan(W, 2, src, TableDst{W.stat, (i64 *)seg_table, max_segs, ox, oy, oz}, max_runs,
-                         &W.cnt->v[SYN_CNT_KEPT], st);
+        rc = launch_scan<2>(W, 2, src, TableDst{W.stat, W.complab, (i64 *)seg_table, max_segs, ox, oy, oz}, max_runs,
+                            &W.cnt->v[SYN_CNT_KEPT], st);
         if (rc != SYN_OK) return rc;
+        PROF("dust_table");
     }
-    k_run_labels<<<wave_grid(k_run_labels, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.par, W.rank, W.stat,
-                                                                                         W.runlabel, W.cnt, max_segs);
+    k_run_labels<<<wave_grid(k_run_labels, 256, div_up_u32(max_runs, 256 * 4)), 256, 0, st>>>(W.par, W.rank, W.complab,
+                                                                                             W.runlabel, W.cnt, max_segs);
     CK_LAUNCH();
+    PROF("run_labels");
 
-    
-    // --- foreground voxels (+ overlaps) -------------------------------------------------------------
-    if (vec_out) {
-        if (side) CK(cudaStreamWaitEvent(st, side->join, 0));      // zero fill must be complete
-        PROF_MARK(7);
+    // --- foreground sectors (+ overlaps) -------------------------------------------------------------
+    if (sector_out) {
         const i64 needw = div_up_u32(g.nwords, 8);   // one warp per 32 active words, at most
         if (has_base)
-            k_sparse_labels<true><<<wave_grid(k_sparse_labels<true>, 256, needw), 256, 0, st>>>(
-                W.lmask, W.omask, W.runbase, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
+            k_sector_labels<true><<<wave_grid(k_sector_labels<true>, 256, needw), 256, 0, st>>>(
+                W.lmask, W.omask, R, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
         else
-            k_sparse_labels<false><<<wave_grid(k_sparse_labels<false>, 256, needw), 256, 0, st>>>(
-                W.lmask, W.omask, W.runbase, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
+            k_sector_labels<false><<<wave_grid(k_sector_labels<false>, 256, needw), 256, 0, st>>>(
+                W.lmask, W.omask, R, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
         CK_LAUNCH();
+        PROF("sector_labels");
     } else {
-        PROF_MARK(7);
         const int grid = grid_for((i64)g.nchunks * 32 / 2 + 1, 256, 8);
         if (has_base)
             k_write_labels<false, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
@@ -490,13 +509,12 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
             k_write_labels<false, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
                                                                  bs, g, T, W.cnt);
         CK_LAUNCH();
+        PROF("write_labels");
     }
-    PROF_MARK(8);
     if (has_base) {
         rc = order_and_emit_pairs(g, W, T, pair_rows, (u64 *)pair_cols, (i64 *)pair_counts, max_pairs, st);
         if (rc != SYN_OK) return rc;
     }
-    PROF_MARK(9);
     if (g_prof_on) g_prof_valid = true;
     return finish_counts(W, (i64 *)counts_host, st);
 }
@@ -528,6 +546,7 @@ int syn_count_overlaps(const uint32_t *seg1, const uint64_t *seg2, int64_t nx, i
     CK_LAUNCH();
     k_overlap_scan<<<grid_for((i64)g.nwords * 32, 256, 8), 256, 0, st>>>(seg1, (const u64 *)seg2, g, T, W.cnt);
     CK_LAUNCH();
+    CK(cudaMemsetAsync(W.bitmap, 0, (size_t)g.nwords * 4, st));
     rc = order_and_emit_pairs(g, W, T, pair_rows, (u64 *)pair_cols, (i64 *)pair_counts, max_pairs, st);
     if (rc != SYN_OK) return rc;
     return finish_counts(W, (i64 *)counts_host, st);
@@ -670,22 +689,32 @@ long long syn_launch_count(void) { return g_launches.load(std::memory_order_rela
 int syn_profile_enable(int on)
 {
     if (on && !g_prof_created) {
-        for (int i = 0; i <= PROF_STAGES; ++i) CK(cudaEventCreate(&g_prof_ev[i]));
+        for (int i = 0; i < PROF_MAX; ++i) CK(cudaEventCreate(&g_prof_ev[i]));
         g_prof_created = true;
     }
     g_prof_on = on != 0;
     g_prof_overlap = on == 2;
     g_prof_valid = false;
+    g_prof_n = 0;
     return SYN_OK;
 }
 
 int syn_profile_read(float *stage_ms, int n)
 {
-    if (!stage_ms || n < PROF_STAGES) return fail(SYN_ERR_INVALID, "need room for %d stages", PROF_STAGES);
-    if (!g_prof_created || !g_prof_valid) return fail(SYN_ERR_INVALID, "no profiled syn_chunk_ccs call recorded");
-    CK(cudaEventSynchronize(g_prof_ev[PROF_STAGES]));
-    for (int i = 0; i < PROF_STAGES; ++i) CK(cudaEventElapsedTime(&stage_ms[i], g_prof_ev[i], g_prof_ev[i + 1]));
-    return PROF_STAGES;
+    if (!stage_ms || n < 0) return fail(SYN_ERR_INVALID, "bad arguments");
+    if (!g_prof_created || !g_prof_valid || g_prof_n < 2)
+        return fail(SYN_ERR_INVALID, "no profiled syn_chunk_ccs call recorded");
+    const int k = g_prof_n - 1;
+    if (n < k) return fail(SYN_ERR_INVALID, "need room for %d intervals", k);
+    CK(cudaEventSynchronize(g_prof_ev[k]));
+    for (int i = 0; i < k; ++i) CK(cudaEventElapsedTime(&stage_ms[i], g_prof_ev[i], g_prof_ev[i + 1]));
+    return k;
+}
+
+const char *syn_profile_name(int i)
+{
+    if (i < 0 || i + 1 >= g_prof_n) return "";
+    return g_prof_name[i + 1];
 }
 
 

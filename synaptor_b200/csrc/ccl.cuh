@@ -87,6 +87,212 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ pre
 }
 
 // ===========================================================================
+// Run-id prefix.  runbase[w] = number of z-runs that start before mask word w.
+// Two representations:
+//   global : rb[w] holds the value itself (generic scan, k_scan_1p<RunStartSrc>), tb == nullptr
+//   tiled  : rb[w] holds the prefix INSIDE the word's stream tile (TS_CHUNKS chunks) and tb[tile] the
+//            number of runs before the tile (k_stream + k_tile_prefix: no look-back chain in the
+//            streaming kernel, no fix-up pass over the words)
+// ===========================================================================
+constexpr int TS_THREADS = 256;
+constexpr int TS_CHUNKS = 128;              // 128 chunks = 16384 voxels = 64 KB of float32 per tile
+constexpr int TS_SLOTS = TS_CHUNKS * 4;     // word slots per tile (a slot past the end of a row holds no word)
+
+struct RunIdx {
+    const u32 *rb;
+    const u32 *tb;
+    u32 cpr;
+    __device__ __forceinline__ u32 at(u32 w, u32 row, u32 k) const
+    {
+        u32 v = rb[w];
+        if (tb) v += tb[(row * cpr + (k >> 2)) / TS_CHUNKS];
+        return v;
+    }
+};
+
+// ===========================================================================
+// K1 (sector mode, nz % 8 == 0): ONE streaming pass over the dense inputs, at HBM speed:
+//   pred (4 B/voxel read)   -> mask[w]    the foreground bits
+//   base (8 B/voxel read)   -> max(base)  (shape of the overlap matrix)
+//   labels (4 B/voxel write)   zero-fill of every 32-byte label sector WITHOUT foreground; the sectors
+//                              that hold foreground are written whole by k_sector_labels later
+// and, FUSE_SCAN (no dilation), per tile of TS_CHUNKS chunks, from shared memory:
+//   rb[w]       run starts before word w INSIDE the tile;  tileagg[tile] = runs of the tile
+//   actw[]      compact list of the non-empty words (tile order by one atomic per tile)
+//   bndw[]      non-empty words on a tile border of k_tile_ccl (the input of k_union_bnd)
+// No dependence between CTAs: 16 B/voxel of pure streaming.
+// ===========================================================================
+template <bool HAS_BASE, bool FUSE_SCAN>
+__global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__ pred, const u64 *__restrict__ base,
+                                                       u32 *__restrict__ labels, u32 *__restrict__ mask,
+                                                       u32 *__restrict__ rb, u32 *__restrict__ tileagg,
+                                                       u32 *__restrict__ actw, u32 *__restrict__ bndw, Geom g,
+                                                       TileGeom tg, float thr, Counts *cnt)
+{
+    __shared__ u32 s_m[TS_SLOTS + 1];   // s_m[0]: the word before the tile's first slot; slot s at s_m[s + 1]
+    __shared__ u32 sm[33];
+    __shared__ u32 s_bcount, s_abase, s_bbase;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u32 ntiles = (g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
+    u32 nfg = 0;
+    u64 bmax = 0;
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u32 cbase = tile * TS_CHUNKS;
+        if (FUSE_SCAN && threadIdx.x == 0) s_bcount = 0;
+        // ---- phase 1: the tile's 128 chunks, 16 per warp, 4 chunks (4 x 48 B per lane) in flight ----
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            const u32 cl0 = (u32)wid * 16 + it * 4;      // chunk index inside the tile
+            const u32 c0 = cbase + cl0;
+            float4 v[4];
+            ulonglong2 b01[4], b23[4];
+            bool ok[4];
+            u32 widx[4];
+            i64 vox[4];
+            u32 row = c0 / g.cpr;
+            u32 kc = c0 - row * g.cpr;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const i64 z = (i64)kc * 128 + 4 * lane;
+                ok[u] = (c0 + u < g.nchunks) && z < g.nz;
+                widx[u] = row * g.wz + kc * 4 + (lane >> 3);
+                vox[u] = (i64)row * g.nz + z;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (HAS_BASE) { b01[u] = make_ulonglong2(0, 0); b23[u] = make_ulonglong2(0, 0); }
+                if (ok[u]) {
+                    v[u] = __ldcs(reinterpret_cast<const float4 *>(pred + vox[u]));
+                    if (HAS_BASE) {
+                        const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(base + vox[u]);
+                        b01[u] = __ldcs(bp);
+                        b23[u] = __ldcs(bp + 1);
+                    }
+                }
+                if (++kc == g.cpr) { kc = 0; ++row; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                u32 nib = 0;
+                if (ok[u]) nib = (u32)(v[u].x > thr) | ((u32)(v[u].y > thr) << 1) | ((u32)(v[u].z > thr) << 2) |
+                                 ((u32)(v[u].w > thr) << 3);
+                u32 w = nib << (4 * (lane & 7));
+                w |= __shfl_xor_sync(SYN_FULL, w, 1);
+                // after the first step w holds exactly this lane pair's sector (8 voxels = 32 B of labels)
+                if (ok[u] && w == 0) __stcs(reinterpret_cast<uint4 *>(labels + vox[u]), make_uint4(0, 0, 0, 0));
+                w |= __shfl_xor_sync(SYN_FULL, w, 2);
+                w |= __shfl_xor_sync(SYN_FULL, w, 4);
+                if ((lane & 7) == 0) {
+                    if (FUSE_SCAN) s_m[1 + (cl0 + u) * 4 + (lane >> 3)] = w;      // 0 for a slot that holds no word
+                    if (ok[u]) {
+                        mask[widx[u]] = w;
+                        nfg += __popc(w);
+                    }
+                }
+                if (HAS_BASE) bmax = max(bmax, max(max(b01[u].x, b01[u].y), max(b23[u].x, b23[u].y)));
+            }
+        }
+        if (!FUSE_SCAN) continue;
+        if (threadIdx.x == 0) {
+            // top bit of the word before the tile's first slot (same row), recomputed from the prediction
+            const u32 row0 = cbase / g.cpr;
+            const u32 kc0 = cbase - row0 * g.cpr;
+            u32 prev = 0;
+            if (kc0) prev = (__ldg(pred + (i64)row0 * g.nz + (i64)kc0 * 128 - 1) > thr) ? 0x80000000u : 0u;
+            s_m[0] = prev;
+        }
+        __syncthreads();
+        // ---- phase 2: thread t owns slots 2t, 2t+1: run starts, active flag, tile-border list position ----
+        u32 wi[2], st[2], bpos[2];
+        bool act[2], exists[2];
+        u32 v2 = 0;
+        {
+            const u32 c = cbase + (threadIdx.x >> 1);
+            const bool cok = c < g.nchunks;
+            const u32 row = cok ? c / g.cpr : 0;
+            const u32 kc = cok ? c - row * g.cpr : 0;
+            u32 x, y;
+            split_row(g, row, x, y);
+            const bool border = tg.tx && ((x && (x & (tg.tx - 1)) == 0) || (y && (y & (tg.ty - 1)) == 0));
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const u32 s = 2 * threadIdx.x + q;
+                const u32 k = kc * 4 + (s & 3);
+                const u32 m = s_m[s + 1];                       // 0 for a slot that holds no word
+                const u32 carry = k ? (s_m[s] >> 31) : 0u;
+                exists[q] = cok && k < g.wz;
+                st[q] = __popc(run_starts(m, carry));
+                act[q] = m != 0;
+                wi[q] = row * g.wz + k;
+                v2 += st[q] + ((u32)act[q] << 16);
+                bpos[q] = 0xFFFFFFFFu;
+                if (act[q] && border) bpos[q] = atomicAdd(&s_bcount, 1u);
+            }
+        }
+        u32 total;
+        const u32 ex = block_excl_scan(v2, sm, &total);
+        if (threadIdx.x == 0) {
+            tileagg[tile] = total & 0xFFFFu;
+            const u32 na = total >> 16, nb = s_bcount;
+            s_abase = na ? (u32)atomicAdd((u64 *)&cnt->v[SYN_CNT_ACTIVE_WORDS], (u64)na) : 0u;
+            s_bbase = nb ? (u32)atomicAdd((u64 *)&cnt->v[SYN_CNT_BND_WORDS], (u64)nb) : 0u;
+        }
+        __syncthreads();
+        // ---- phase 3: outputs ----
+        {
+            u32 r = ex & 0xFFFFu;
+            u32 ab = s_abase + (ex >> 16);
+            const u32 bb = s_bbase;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (exists[q]) rb[wi[q]] = r;
+                r += st[q];
+                if (act[q]) actw[ab++] = wi[q];
+                if (bpos[q] != 0xFFFFFFFFu) bndw[bb + bpos[q]] = wi[q];
+            }
+        }
+        __syncthreads();   // s_m, s_bcount, s_abase are rewritten in the next round
+    }
+    for (int d = 16; d; d >>= 1) nfg += __shfl_down_sync(SYN_FULL, nfg, d);
+    if (lane == 0 && nfg) atomicAdd((u64 *)&cnt->v[SYN_CNT_FG_VOXELS], (u64)nfg);
+    if (HAS_BASE) {
+        for (int d = 16; d; d >>= 1) bmax = max(bmax, __shfl_down_sync(SYN_FULL, bmax, d));
+        if (lane == 0 && bmax) atomicMax((u64 *)&cnt->v[SYN_CNT_MAX_BASE], bmax);
+    }
+}
+
+// exclusive scan of the stream tiles' run counts (one CTA: <= a few thousand values per 512^3 chunk);
+// publishes the total run count and checks it against the capacity of the per-run arrays
+__global__ void __launch_bounds__(1024) k_tile_prefix(const u32 *__restrict__ tileagg, u32 *__restrict__ tilebase,
+                                                      u32 ntiles, Counts *cnt, u32 max_runs)
+{
+    __shared__ u32 sm[33];
+    u64 carry = 0;
+    for (u32 t0 = 0; t0 < ntiles; t0 += 4096) {
+        const u32 i0 = t0 + threadIdx.x * 4;
+        u32 a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = (i0 + q < ntiles) ? tileagg[i0 + q] : 0u;
+        u32 total;
+        u32 ex = block_excl_scan(a[0] + a[1] + a[2] + a[3], sm, &total);
+        if (carry + total > 0xFFFFFFFFull) {                 // more runs than 32 bits: reported through the count
+            carry += total;
+            break;
+        }
+        ex += (u32)carry;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i0 + q < ntiles) tilebase[i0 + q] = ex;
+            ex += a[q];
+        }
+        carry += total;
+    }
+    // (the loop exits uniformly: `carry` and `total` are block-wide values)
+    if (threadIdx.x == 0) {
+        cnt->v[SYN_CNT_RUNS] = (i64)carry;
+        if (carry > (u64)max_runs) atomicOr((u64 *)&cnt->v[SYN_CNT_ERRFLAGS], (u64)SYN_EF_RUNS);
+    }
+}
+
+// ===========================================================================
 // K1d: 2-D L1 dilation by k over axes (y, z) on the bitmask -- what the chamfer
 // distance transform + `dist > k -> 0` of _seg_utils.cpp:25-82,180-200 computes
 // for a 0/1 mask.  out(y, z) = OR_{|dy| <= k} zdil(in(y + dy), k - |dy|).
@@ -135,17 +341,46 @@ __global__ void __launch_bounds__(256) k_dilate(const u32 *__restrict__ in, u32 
 // block that waits on a predecessor's prefix can only wait on a block that is
 // already running.  state[tile] packs (flag << 32 | value): flag 1 = the tile's own
 // sum, flag 2 = inclusive prefix up to and including the tile.  `state` and `ticket`
-// must be zero before the launch.  `Src` provides n() (item count, may live on the
-// device) and get(i); `Dst` receives put(i, exclusive prefix, item value).
+// must be zero before the launch.  A thread owns SCAN_ITEMS CONSECUTIVE items:
+// `Src` provides n() (item count, may live on the device) and load(i0, n, item[]);
+// `Dst` receives store(i0, n, exclusive prefix of item 0, item[]).
 // ===========================================================================
-template <class Src, class Dst>
+__device__ __forceinline__ u32 lookback_u32(volatile u64 *state, u32 tile, u32 total, int lane)
+{
+    // warp-wide look-back: lane l inspects tile (p - l); tiles before 0 count as a zero prefix
+    u32 prefix = 0;
+    if (tile != 0) {
+        if (lane == 0) state[tile] = (1ull << 32) | total;
+        i64 p = (i64)tile - 1;
+        while (true) {
+            const i64 idx = p - lane;
+            const u64 sv = idx >= 0 ? state[idx] : (2ull << 32);
+            const u32 flag = (u32)(sv >> 32);
+            const u32 m2 = __ballot_sync(SYN_FULL, flag == 2);
+            const u32 m0 = __ballot_sync(SYN_FULL, flag == 0);
+            const u32 upto = m2 ? mask_le((u32)(__ffs(m2) - 1)) : 0xFFFFFFFFu;   // lanes that count
+            if (m0 & upto) continue;                                              // someone not published yet
+            u32 val = ((upto >> lane) & 1u) ? (u32)sv : 0u;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(SYN_FULL, val, d);
+            prefix += val;
+            if (m2) break;
+            p -= 32;
+        }
+    }
+    if (lane == 0) state[tile] = (2ull << 32) | (u64)(prefix + total);
+    return prefix;
+}
+
+template <class Src, class Dst, int ITEMS>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_1p(Src src, Dst dst, volatile u64 *state, u32 *ticket,
                                                           i64 *total_out)
 {
+    constexpr int TILE = SCAN_THREADS * ITEMS;
     __shared__ u32 sm[33];
     __shared__ u32 s_tile, s_prefix;
     const u64 n = src.n();
-    const u32 ntiles = (u32)((n + SCAN_TILE - 1) / SCAN_TILE);
+    const u32 ntiles = (u32)((n + TILE - 1) / TILE);
     if (ntiles == 0) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && total_out) *total_out = 0;
         return;
@@ -155,73 +390,97 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_1p(Src src, Dst dst, vola
         __syncthreads();
         const u32 tile = s_tile;
         if (tile >= ntiles) break;  // block-uniform
-        u32 item[SCAN_ITEMS];
+        u32 item[ITEMS];
+        const u64 i0 = (u64)tile * TILE + (u64)threadIdx.x * ITEMS;
+        src.load(i0, n, item);
         u32 v = 0;
-        const u64 i0 = (u64)tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
 #pragma unroll
-        for (int t = 0; t < SCAN_ITEMS; ++t) {
-            item[t] = (i0 + t < n) ? src.get(i0 + t) : 0;
-            v += item[t];
-        }
+        for (int t = 0; t < ITEMS; ++t) v += item[t];
         u32 total;
         u32 ex = block_excl_scan(v, sm, &total);
         if (threadIdx.x < 32) {
-            // warp-wide look-back: lane l inspects tile (p - l); tiles before 0 count as a zero prefix
-            const int lane = threadIdx.x;
-            u32 prefix = 0;
-            if (tile != 0) {
-                if (lane == 0) state[tile] = (1ull << 32) | total;
-                i64 p = (i64)tile - 1;
-                while (true) {
-                    const i64 idx = p - lane;
-                    const u64 sv = idx >= 0 ? state[idx] : (2ull << 32);
-                    const u32 flag = (u32)(sv >> 32);
-                    const u32 m2 = __ballot_sync(SYN_FULL, flag == 2);
-                    const u32 m0 = __ballot_sync(SYN_FULL, flag == 0);
-                    const u32 upto = m2 ? mask_le((u32)(__ffs(m2) - 1)) : 0xFFFFFFFFu;   // lanes that count
-                    if (m0 & upto) continue;                                              // someone not published yet
-                    u32 val = ((upto >> lane) & 1u) ? (u32)sv : 0u;
-#pragma unroll
-                    for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(SYN_FULL, val, d);
-                    prefix += val;
-                    if (m2) break;
-                    p -= 32;
-                }
-            }
-            if (lane == 0) {
-                state[tile] = (2ull << 32) | (u64)(prefix + total);
+            const u32 prefix = lookback_u32(state, tile, total, threadIdx.x);
+            if (threadIdx.x == 0) {
                 s_prefix = prefix;
                 if (tile == ntiles - 1 && total_out) *total_out = (i64)(prefix + total);
             }
         }
         __syncthreads();
         ex += s_prefix;
-#pragma unroll
-        for (int t = 0; t < SCAN_ITEMS; ++t) {
-            if (i0 + t < n) dst.put(i0 + t, ex, item[t]);
-            ex += item[t];
-        }
+        dst.store(i0, n, ex, item);
+        if (gridDim.x >= ntiles) break;   // one tile per CTA: no second ticket round trip
         __syncthreads();   // s_tile / s_prefix are rewritten in the next round
     }
 }
 
-// --- scan #1: run starts per mask word -> runbase[w] ------------------------
+// N consecutive u32 of a 256-byte aligned array (i0 is a multiple of N); zero past n
+template <int N>
+__device__ __forceinline__ void load_items_u32(const u32 *a, u64 i0, u64 n, u32 (&m)[N])
+{
+    if (N % 4 == 0 && i0 + N <= n) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(a + i0);
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            const uint4 v = __ldcg(p + q);
+            m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < N; ++t) m[t] = (i0 + t < n) ? __ldcg(a + i0 + t) : 0u;
+    }
+}
+template <int N>
+__device__ __forceinline__ void store_prefix_u32(u32 *a, u64 i0, u64 n, u32 ex, const u32 (&item)[N])
+{
+    u32 pre[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) { pre[t] = ex; ex += item[t]; }
+    if (N % 4 == 0 && i0 + N <= n) {
+        uint4 *p = reinterpret_cast<uint4 *>(a + i0);
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q)
+            p[q] = make_uint4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int t = 0; t < N; ++t)
+            if (i0 + t < n) a[i0 + t] = pre[t];
+    }
+}
+
+// --- scan #1: run starts per mask word -> runbase[w]  (dilation variant only; the plain path fuses this
+// scan into the threshold kernel, k_threshold_runs) ------------------------
 struct RunStartSrc {
     const u32 *mask;
     u32 nwords, wz;
     __device__ __forceinline__ u64 n() const { return nwords; }
-    __device__ __forceinline__ u32 get(u64 w) const
+    template <int N>
+    __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
     {
-        u32 m = mask[w];
-        if (m == 0) return 0;
-        u32 k = (u32)w % wz;
-        u32 carry = k ? (mask[w - 1] >> 31) : 0u;
-        return __popc(run_starts(m, carry));
+        if (i0 >= n) {
+#pragma unroll
+            for (int t = 0; t < N; ++t) item[t] = 0;
+            return;
+        }
+        u32 m[N];
+        load_items_u32(mask, i0, n, m);
+        u32 prev = i0 ? __ldcg(mask + i0 - 1) : 0u;
+        u32 k = (u32)(i0 % wz);
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            const u32 carry = k ? (prev >> 31) : 0u;
+            item[t] = __popc(run_starts(m[t], carry));
+            prev = m[t];
+            if (++k == wz) k = 0;
+        }
     }
 };
 struct RunBaseDst {
     u32 *runbase;
-    __device__ __forceinline__ void put(u64 w, u32 ex, u32) const { runbase[w] = ex; }
+    template <int N>
+    __device__ __forceinline__ void store(u64 i0, u64 n, u32 ex, const u32 (&item)[N]) const
+    {
+        store_prefix_u32(runbase, i0, n, ex, item);
+    }
 };
 
 
@@ -278,24 +537,18 @@ __global__ void k_init_parents(u32 *__restrict__ par, Counts *cnt, u32 max_runs)
 // (after the shift).  Run id of the run covering bit b of word w:
 //     runbase[w] + popc(starts(w) & mask_le(b)) - 1
 // ===========================================================================
-struct TileGeom {
-    u32 tx, ty;          // rows per tile along x and y, powers of two (tx == 0: tiling disabled)
-    u32 tiles_x, tiles_y;
-    u32 ntiles;
-    u32 txs, tys;        // log2(tx), log2(ty)
-};
 
 struct RowView {
     const u32 *mask;     // words of this row
-    const u32 *runbase;  // run-start prefix of this row's words
-    u32 wz;
+    RunIdx R;            // run-start prefix
+    u32 row, wz;
     __device__ __forceinline__ u32 word(int k) const { return (k >= 0 && k < (int)wz) ? mask[k] : 0u; }
     // id of the run covering bit b (0..31) of word k; that bit must be set
     __device__ __forceinline__ u32 run_at(int k, int b) const
     {
         u32 m = mask[k];
         u32 carry = k ? (mask[k - 1] >> 31) : 0u;
-        return runbase[k] + __popc(run_starts(m, carry) & mask_le((u32)b)) - 1u;
+        return R.at(row * wz + (u32)k, row, (u32)k) + __popc(run_starts(m, carry) & mask_le((u32)b)) - 1u;
     }
 };
 
@@ -324,12 +577,14 @@ __device__ __forceinline__ void union_shifted(u32 *par, const RowView &A, const 
 
 // With tiling enabled (tg.tx != 0) a pair of rows inside one tile was already joined by K2 and is
 // skipped here unless that tile was flagged as too dense.
-template <int CONN>
-__global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask, const u32 *__restrict__ runbase,
+// BND_DONE: the tile borders were already joined by k_union_bnd; only flagged tiles are left (usually none).
+template <int CONN, bool BND_DONE>
+__global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask, RunIdx R,
                                                     u32 *par, Geom g, TileGeom tg, const u32 *__restrict__ tileflag,
                                                     const u32 *__restrict__ actw, const Counts *cnt)
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    if (BND_DONE && cnt->v[SYN_CNT_FLAGGED_TILES] == 0) return;
     const u32 nact = (u32)cnt->v[SYN_CNT_ACTIVE_WORDS];
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nact; i += gridDim.x * blockDim.x) {
         const u32 w = actw[i];
@@ -338,40 +593,40 @@ __global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask
         split_word(g, w, row, kk);
         split_row(g, row, x, y);
         const int k = (int)kk;
-        RowView A{mask + (u64)row * g.wz, runbase + (u64)row * g.wz, g.wz};
+        RowView A{mask + (u64)row * g.wz, R, row, g.wz};
         bool do_y = true, do_x = true, do_dm = true, do_dp = true;   // (x,y-1) (x-1,y) (x-1,y-1) (x-1,y+1)
         if (tg.tx) {
             const u32 tX = x >> tg.txs, tY = y >> tg.tys;
             const bool dense = tileflag[tX * tg.tiles_y + tY] != 0;
             const bool xb = (x & (tg.tx - 1)) == 0, yb = (y & (tg.ty - 1)) == 0, ye = ((y + 1) & (tg.ty - 1)) == 0;
-            do_y = dense || yb;
-            do_x = dense || xb;
+            do_y = dense || (!BND_DONE && yb);
+            do_x = dense || (!BND_DONE && xb);
             do_dm = dense || xb || yb;
             do_dp = dense || xb || ye;
             if (!(do_y || do_x || do_dm || do_dp)) continue;
         }
         if (y > 0 && do_y) {
             u32 r2 = row - 1;
-            RowView B{mask + (u64)r2 * g.wz, runbase + (u64)r2 * g.wz, g.wz};
+            RowView B{mask + (u64)r2 * g.wz, R, r2, g.wz};
             union_shifted<0>(par, A, B, k, m);
             if (CONN >= 18) { union_shifted<-1>(par, A, B, k, m); union_shifted<1>(par, A, B, k, m); }
         }
         if (x > 0) {
             u32 r2 = row - (u32)g.ny;
-            RowView B{mask + (u64)r2 * g.wz, runbase + (u64)r2 * g.wz, g.wz};
+            RowView B{mask + (u64)r2 * g.wz, R, r2, g.wz};
             if (do_x) {
                 union_shifted<0>(par, A, B, k, m);
                 if (CONN >= 18) { union_shifted<-1>(par, A, B, k, m); union_shifted<1>(par, A, B, k, m); }
             }
             if (CONN >= 18 && y > 0 && do_dm) {
                 u32 r3 = r2 - 1;
-                RowView C{mask + (u64)r3 * g.wz, runbase + (u64)r3 * g.wz, g.wz};
+                RowView C{mask + (u64)r3 * g.wz, R, r3, g.wz};
                 union_shifted<0>(par, A, C, k, m);
                 if (CONN == 26) { union_shifted<-1>(par, A, C, k, m); union_shifted<1>(par, A, C, k, m); }
             }
             if (CONN >= 18 && y + 1 < (u32)g.ny && do_dp) {
                 u32 r3 = r2 + 1;
-                RowView C{mask + (u64)r3 * g.wz, runbase + (u64)r3 * g.wz, g.wz};
+                RowView C{mask + (u64)r3 * g.wz, R, r3, g.wz};
                 union_shifted<0>(par, A, C, k, m);
                 if (CONN == 26) { union_shifted<-1>(par, A, C, k, m); union_shifted<1>(par, A, C, k, m); }
             }
@@ -489,13 +744,65 @@ __device__ __forceinline__ void tile_pass(const u32 *s_mask, const unsigned shor
     }
 }
 
-constexpr int TILE_THREADS = 512;   // 3 CTAs/SM by shared memory -> 48 warps/SM
+// 6-connectivity: both neighbour rows ((x, y-1) and (x-1, y)) in ONE pass -- the overlap spans of a word with
+// its two neighbour words form one work list, so the tile needs half as many warp rounds.
+__device__ __forceinline__ void tile_pass6(const u32 *s_mask, const unsigned short *s_rb, const u32 *s_st, u32 *s_par,
+                                           const u32 *s_act, u32 nact, u32 wz, u32 segw)
+{
+    const int lane = threadIdx.x & 31;
+    const u32 wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    for (u32 a0 = wib * 32; a0 < nact; a0 += nwb * 32) {
+        const u32 a = a0 + lane;
+        u32 osy = 0, osx = 0, i = 0;
+        if (a < nact) {
+            const u32 e = s_act[a];
+            i = e & 2047u;
+            const u32 m = s_mask[i];
+            if ((e >> 21) & 63u) { const u32 o = m & s_mask[i - wz]; osy = o & ~(o << 1); }
+            if (e >> 27) { const u32 o = m & s_mask[i - segw]; osx = o & ~(o << 1); }
+        }
+        const u32 ny_ = __popc(osy);
+        const u32 n = ny_ + __popc(osx);
+        const u32 incl = warp_incl_scan(n, lane);
+        const u32 excl = incl - n;
+        const u32 total = __shfl_sync(SYN_FULL, incl, 31);
+        for (u32 r0 = 0; r0 < total; r0 += 32) {
+            const u32 j = r0 + lane;
+            int o = 0;
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
+                if (e <= j) o += s;
+            }
+            const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
+            const u32 osy_o = __shfl_sync(SYN_FULL, osy, o);
+            const u32 osx_o = __shfl_sync(SYN_FULL, osx, o);
+            const u32 i_o = __shfl_sync(SYN_FULL, i, o);
+            if (j < total) {
+                u32 idx = j - e_o;
+                const u32 nyo = __popc(osy_o);
+                const bool isy = idx < nyo;
+                if (!isy) idx -= nyo;
+                const u32 b = select_bit(isy ? osy_o : osx_o, idx);
+                const u32 iB = i_o - (isy ? wz : segw);
+                const u32 ga = (u32)s_rb[i_o] + __popc(s_st[i_o] & mask_le(b)) - 1u;
+                const u32 gb = (u32)s_rb[iB] + __popc(s_st[iB] & mask_le(b)) - 1u;
+                sm_union(s_par, ga, gb);
+            }
+        }
+    }
+}
 
+constexpr int TILE_THREADS = 512;   // 3 CTAs/SM by shared memory -> 48 warps/SM
+constexpr int TILE_WPT = TILE_WORDS / TILE_THREADS;   // mask words per thread (consecutive)
+
+// Local run ids come from a block-wide scan of the tile's own run starts (no per-word read of the global
+// prefix); only the global id of the first run of each x-slab segment is fetched (<= 16 values per tile).
 template <int CONN>
 __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict__ mask, const u32 *__restrict__ omask,
-                                                  const u32 *__restrict__ runbase, u32 *__restrict__ par,
+                                                  RunIdx R, u32 *__restrict__ par,
                                                   u32 *__restrict__ tileflag, TileRec *__restrict__ recs, Geom g,
-                                                  TileGeom tg, Counts *cnt)
+                                                  TileGeom tg, Counts *cnt, u32 max_runs)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     u32 *s_mask = reinterpret_cast<u32 *>(s_raw);                 // [TILE_WORDS]
@@ -506,96 +813,137 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     unsigned short *s_rb = reinterpret_cast<unsigned short *>(s_slot + TILE_ROOTS * TILE_SLOT);   // LOCAL run-id prefix
     unsigned short *s_rootidx = s_rb + TILE_WORDS;                // [TILE_RUNS] compact index of a local root
     unsigned short *s_rootrun = s_rootidx + TILE_RUNS;            // [TILE_ROOTS] local run id of root #idx
-    __shared__ u32 s_nact, s_nroots, s_recbase;
+    __shared__ u32 sm[33];
+    __shared__ u32 s_nroots, s_recbase;
     __shared__ u32 s_segoff[TILE_MAXTX + 1];       // local id of the first run of x-slab segment xl
     __shared__ u32 s_delta[TILE_MAXTX];            // global id = local id + delta[xl]
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
-    const u32 nruns = (u32)cnt->v[SYN_CNT_RUNS];
+    if ((u64)cnt->v[SYN_CNT_RUNS] > (u64)max_runs) {      // parent array too small: nothing may be written
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr((u64 *)&cnt->v[SYN_CNT_ERRFLAGS], (u64)SYN_EF_RUNS);
+        return;
+    }
     const u32 tile = blockIdx.x;
     const u32 tX = tile / tg.tiles_y, tY = tile - tX * tg.tiles_y;
     const u32 x0 = tX * tg.tx, y0 = tY * tg.ty;
     const u32 vx = min(tg.tx, (u32)g.nx - x0), vy = min(tg.ty, (u32)g.ny - y0);   // valid rows in this tile
     const u32 segw = vy * g.wz;                // words per x-slab segment (contiguous in memory)
+    const u32 ntw = vx * segw;                 // words of this tile (<= TILE_WORDS)
 
+    // global id of the first run of every segment: latency overlaps the mask loads below
+    u32 segbase = 0;
     if (threadIdx.x < vx) {
-        u32 first = ((x0 + threadIdx.x) * (u32)g.ny + y0) * g.wz;
-        u32 end = first + segw;
-        u32 b0 = runbase[first];
-        u32 b1 = end < g.nwords ? runbase[end] : nruns;
-        s_segoff[threadIdx.x + 1] = b1 - b0;   // run count, turned into a prefix below
-        s_delta[threadIdx.x] = b0;
+        const u32 row = (x0 + threadIdx.x) * (u32)g.ny + y0;
+        segbase = R.at(row * g.wz, row, 0);
     }
-    if (threadIdx.x == 0) { s_nact = 0; s_nroots = 0; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 acc = 0;
-        s_segoff[0] = 0;
-        for (u32 i = 0; i < vx; ++i) {
-            u32 c = s_segoff[i + 1];
-            s_delta[i] -= acc;                 // global = local - segoff + segbase
-            acc += c;
-            s_segoff[i + 1] = acc;
+    if (threadIdx.x == 0) s_nroots = 0;
+    // ---- load: thread t owns words 4t .. 4t+3 of the tile (segment-major order) ----
+    const u32 i0 = threadIdx.x * TILE_WPT;
+    u32 m[TILE_WPT];
+    u32 xl0 = 0, jj0 = 0;                      // segment / offset in segment of word i0
+    if (i0 < ntw) { xl0 = i0 / segw; jj0 = i0 - xl0 * segw; }
+    if ((segw & 3u) == 0 && (g.wz & 3u) == 0) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i0 < ntw) v = *reinterpret_cast<const uint4 *>(mask + ((x0 + xl0) * (u32)g.ny + y0) * g.wz + jj0);
+        m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+    } else {
+        u32 xl = xl0, jj = jj0;
+#pragma unroll
+        for (int q = 0; q < TILE_WPT; ++q) {
+            m[q] = 0;
+            if (i0 + q < ntw) {
+                m[q] = mask[((x0 + xl) * (u32)g.ny + y0) * g.wz + jj];
+                if (++jj == segw) { jj = 0; ++xl; }
+            }
         }
     }
+    *reinterpret_cast<uint4 *>(s_mask + i0) = make_uint4(m[0], m[1], m[2], m[3]);
     __syncthreads();
-    const u32 nloc = s_segoff[vx];
-    if (nloc == 0) return;                     // no foreground in this tile
-    if (nloc > TILE_RUNS) {                    // too dense for the shared-memory pass: K3 / k_stats do the whole tile
+    // ---- run starts (carry from shared memory), local run ids by a block scan ----
+    u32 st[TILE_WPT], pk[TILE_WPT];            // pk: packed (i | k << 11 | yl << 21 | xl << 27)
+    u32 v = 0;
+    {
+        u32 xl = xl0, jj = jj0;
+#pragma unroll
+        for (int q = 0; q < TILE_WPT; ++q) {
+            st[q] = 0;
+            pk[q] = 0;
+            if (i0 + q < ntw) {
+                u32 yl, k;
+                if (g.wzs < 32) { yl = jj >> g.wzs; k = jj & (g.wz - 1u); }
+                else { yl = jj / g.wz; k = jj - yl * g.wz; }
+                if (m[q]) {
+                    const u32 carry = k ? (s_mask[i0 + q - 1] >> 31) : 0u;
+                    st[q] = run_starts(m[q], carry);
+                    v += __popc(st[q]) + (1u << 16);
+                }
+                pk[q] = (i0 + q) | (k << 11) | (yl << 21) | (xl << 27);
+                if (++jj == segw) { jj = 0; ++xl; }
+            }
+        }
+    }
+    u32 total;
+    const u32 ex = block_excl_scan(v, sm, &total);
+    const u32 nloc = total & 0xFFFFu, nact = total >> 16;
+    if (nloc == 0) return;                     // no foreground in this tile (block-uniform)
+    const bool dense = nloc > TILE_RUNS;       // too dense for the shared-memory pass: K3 / k_stats do the whole tile
+    {
+        u32 rb = ex & 0xFFFFu, ab = ex >> 16;
+#pragma unroll
+        for (int q = 0; q < TILE_WPT; ++q) {
+            if (i0 + q < ntw) {
+                if (((pk[q] >> 11) & 0xFFFFu) == 0) s_segoff[pk[q] >> 27] = rb;   // k == 0 && yl == 0: segment start
+                if (!dense) {
+                    s_rb[i0 + q] = (unsigned short)rb;
+                    if (m[q]) {
+                        s_st[i0 + q] = st[q];
+                        s_act[ab++] = pk[q];
+                    }
+                }
+                rb += __popc(st[q]);
+            }
+        }
+    }
+    if (threadIdx.x == 0) s_segoff[vx] = nloc;
+    if (!dense)
+        for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) s_par[i] = i;
+    __syncthreads();
+    if (threadIdx.x < vx) s_delta[threadIdx.x] = segbase - s_segoff[threadIdx.x];
+    if (dense) {
+        __syncthreads();
+        // identity parents for the tile's runs (the global pass joins them), then leave
+        u32 rb = ex & 0xFFFFu;
+#pragma unroll
+        for (int q = 0; q < TILE_WPT; ++q) {
+            const u32 d = s_delta[pk[q] >> 27];
+            for (u32 r = 0; r < (u32)__popc(st[q]); ++r) par[rb + r + d] = rb + r + d;
+            rb += __popc(st[q]);
+        }
         if (threadIdx.x == 0) {
             tileflag[tile] = 1;
             atomicAdd((u64 *)&cnt->v[SYN_CNT_FLAGGED_TILES], 1ull);
         }
         return;
     }
-    // load the tile, x-slab segment by segment (each is contiguous in memory)
-    for (u32 xl = 0; xl < vx; ++xl) {
-        const u32 gw0 = ((x0 + xl) * (u32)g.ny + y0) * g.wz;
-        const u32 d = s_delta[xl];
-        for (u32 jj = threadIdx.x; jj < segw; jj += blockDim.x) {   // segw need not be a multiple of 32
-            const u32 i = xl * segw + jj;
-            const u32 m = mask[gw0 + jj];
-            s_mask[i] = m;
-            s_rb[i] = (unsigned short)(runbase[gw0 + jj] - d);
-            u32 yl, k;
-            if (g.wzs < 32) { yl = jj >> g.wzs; k = jj & (g.wz - 1u); }
-            else { yl = jj / g.wz; k = jj - yl * g.wz; }
-            const u32 act = __activemask();
-            const u32 bal = __ballot_sync(act, m != 0);
-            if (m) {
-                const u32 carry = k ? (mask[gw0 + jj - 1] >> 31) : 0u;
-                s_st[i] = run_starts(m, carry);
-            }
-            if (bal) {
-                const int lane = threadIdx.x & 31;
-                const int leader = __ffs(bal) - 1;
-                u32 basei = 0;
-                if (lane == leader) basei = atomicAdd(&s_nact, (u32)__popc(bal));
-                basei = __shfl_sync(act, basei, leader);
-                if (m) s_act[basei + __popc(bal & mask_lt((u32)lane))] = i | (k << 11) | (yl << 21) | (xl << 27);
-            }
-        }
-    }
-    for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) s_par[i] = i;
-    __syncthreads();
 
-    const u32 nact = s_nact;
     const int wz = (int)g.wz, sg = (int)segw;
-    // (x, y-1) and (x-1, y): face neighbours; the remaining rows / shifts only for 18 / 26
-    tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
-    tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
-    if (CONN >= 18) {
+    if (CONN == 6) {
+        tile_pass6(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, segw);
+    } else {
+        // (x, y-1) and (x-1, y): face neighbours; the remaining rows / shifts only for 18 / 26
+        tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
+        tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
         tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
         tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
         tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
         tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
         tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
         tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
-    }
-    if (CONN == 26) {
-        tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
-        tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
-        tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
-        tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
+        if (CONN == 26) {
+            tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
+            tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
+            tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
+            tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
+        }
     }
     __syncthreads();
     // flatten; write parent[global run] = global id of the local root; give every local root a compact index
@@ -636,15 +984,15 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     for (u32 a = threadIdx.x; a < nact; a += blockDim.x) {
         const u32 e = s_act[a];
         const u32 i = e & 2047u, k = (e >> 11) & 1023u, yl = (e >> 21) & 63u, xl = e >> 27;
-        const u32 m = s_mask[i];
-        const u32 om = same_mask ? m : omask[((x0 + xl) * (u32)g.ny + y0 + yl) * g.wz + k];
+        const u32 mm = s_mask[i];
+        const u32 om = same_mask ? mm : omask[((x0 + xl) * (u32)g.ny + y0 + yl) * g.wz + k];
         if (!om) continue;
         const u32 starts = s_st[i], rb = s_rb[i], z0 = k * 32;
-        u32 ps = m & ~(m << 1);                // piece starts
+        u32 ps = mm & ~(mm << 1);                // piece starts
         while (ps) {
             const int b0 = __ffs(ps) - 1;
             ps &= ps - 1;
-            const u32 span = ~(m >> b0);
+            const u32 span = ~(mm >> b0);
             int len = span ? (__ffs(span) - 1) : 32;
             if (len > 32 - b0) len = 32 - b0;
             const u32 pm = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << b0;
@@ -686,6 +1034,77 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     }
 }
 
+// ===========================================================================
+// K3 (6-connectivity): unions across tile borders.  Input: the compact list of non-empty words lying on a
+// tile border (bndw, written by k_threshold_runs).  ONE LANE PER OVERLAP SPAN, as in the tile pass; the run
+// ids come from the global prefix (runbase) and the unions go to the global parent array.
+// ===========================================================================
+__global__ void __launch_bounds__(256) k_union_bnd(const u32 *__restrict__ mask, RunIdx R,
+                                                   u32 *par, Geom g, TileGeom tg, const u32 *__restrict__ bndw,
+                                                   const Counts *cnt)
+{
+    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    const u32 nb = (u32)cnt->v[SYN_CNT_BND_WORDS];
+    const int lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    const u32 xstride = (u32)g.ny * g.wz;
+    for (u32 a0 = warp * 32; a0 < nb; a0 += nwarps * 32) {
+        const u32 a = a0 + lane;
+        u32 w = 0, osy = 0, osx = 0, starts = 0, rb = 0, k = 0, row = 0;
+        if (a < nb) {
+            w = bndw[a];
+            const u32 m = mask[w];
+            u32 x, y;
+            split_word(g, w, row, k);
+            split_row(g, row, x, y);
+            if (y && (y & (tg.ty - 1)) == 0) { const u32 o = m & mask[w - g.wz]; osy = o & ~(o << 1); }
+            if (x && (x & (tg.tx - 1)) == 0) { const u32 o = m & mask[w - xstride]; osx = o & ~(o << 1); }
+            if (osy | osx) {
+                const u32 carry = k ? (mask[w - 1] >> 31) : 0u;
+                starts = run_starts(m, carry);
+                rb = R.at(w, row, k);
+            }
+        }
+        const u32 ny_ = __popc(osy);
+        const u32 n = ny_ + __popc(osx);
+        const u32 incl = warp_incl_scan(n, lane);
+        const u32 excl = incl - n;
+        const u32 total = __shfl_sync(SYN_FULL, incl, 31);
+        for (u32 r0 = 0; r0 < total; r0 += 32) {
+            const u32 j = r0 + lane;
+            int o = 0;
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
+                if (e <= j) o += s;
+            }
+            const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
+            const u32 osy_o = __shfl_sync(SYN_FULL, osy, o);
+            const u32 osx_o = __shfl_sync(SYN_FULL, osx, o);
+            const u32 w_o = __shfl_sync(SYN_FULL, w, o);
+            const u32 st_o = __shfl_sync(SYN_FULL, starts, o);
+            const u32 rb_o = __shfl_sync(SYN_FULL, rb, o);
+            const u32 k_o = __shfl_sync(SYN_FULL, k, o);
+            const u32 row_o = __shfl_sync(SYN_FULL, row, o);
+            if (j < total) {
+                u32 idx = j - e_o;
+                const u32 nyo = __popc(osy_o);
+                const bool isy = idx < nyo;
+                if (!isy) idx -= nyo;
+                const u32 b = select_bit(isy ? osy_o : osx_o, idx);
+                const u32 wB = w_o - (isy ? g.wz : xstride);
+                const u32 rowB = row_o - (isy ? 1u : (u32)g.ny);
+                const u32 mB = mask[wB];
+                const u32 carryB = k_o ? (mask[wB - 1] >> 31) : 0u;
+                const u32 ga = rb_o + __popc(st_o & mask_le(b)) - 1u;
+                const u32 gb = R.at(wB, rowB, k_o) + __popc(run_starts(mB, carryB) & mask_le(b)) - 1u;
+                uf_union(par, ga, gb);
+            }
+        }
+    }
+}
+
 // merges the tile records into the per-component statistics (after the canonical ranks are known)
 __global__ void __launch_bounds__(256) k_stats_merge(const TileRec *__restrict__ recs, const u32 *__restrict__ par,
                                                      const u32 *__restrict__ rank, CompStat *stat, const Counts *cnt)
@@ -722,28 +1141,50 @@ struct RootFlagSrc {  // flattens while flagging
     {
         return (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) ? 0 : (u64)cnt->v[SYN_CNT_RUNS];
     }
-    __device__ __forceinline__ u32 get(u64 g) const
+    template <int N>
+    __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
     {
-        u32 r = uf_find_ro(par, (u32)g);
-        par[g] = r;
-        return r == (u32)g;
+        u32 p[N], q[N];
+        load_items_u32(par, i0, n, p);
+        // second hop for all items at once (independent loads); most runs are roots or children of a root
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            const u32 g = (u32)(i0 + t);
+            q[t] = (i0 + t < n && p[t] != g) ? ldcg_u32(par + p[t]) : p[t];
+        }
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            item[t] = 0;
+            if (i0 + t < n) {
+                const u32 g = (u32)(i0 + t);
+                u32 x = p[t], r = q[t];
+                while (r != x) { x = r; r = ldcg_u32(par + x); }
+                if (x != p[t]) par[g] = x;    // flatten (a concurrent reader sees the old ancestor or the root)
+                item[t] = (x == g);
+            }
+        }
     }
 };
 // rank[g] = canonical index for roots; also initialises the root's CompStat record
 struct RankDst {
     u32 *rank;
     CompStat *stat;
-    __device__ __forceinline__ void put(u64 g, u32 ex, u32 isroot) const
+    template <int N>
+    __device__ __forceinline__ void store(u64 i0, u64 n, u32 ex, const u32 (&item)[N]) const
     {
-        rank[g] = ex;
-        if (isroot) {
-            CompStat s;
-            s.size = s.sx = s.sy = s.sz = 0;
-            s.minx = s.miny = s.minz = 0xFFFFFFFFu;
-            s.maxx = s.maxy = s.maxz = 0;
-            s.keep = 0;
-            s.row = 0;
-            stat[ex] = s;
+        store_prefix_u32(rank, i0, n, ex, item);
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            if (item[t]) {
+                CompStat s;
+                s.size = s.sx = s.sy = s.sz = 0;
+                s.minx = s.miny = s.minz = 0xFFFFFFFFu;
+                s.maxx = s.maxy = s.maxz = 0;
+                s.keep = 0;
+                s.row = 0;
+                stat[ex] = s;
+            }
+            ex += item[t];
         }
     }
 };
@@ -756,7 +1197,7 @@ struct RankDst {
 // (conncomps.py:49-50 `ccs[mask == 0] = 0`).
 // ===========================================================================
 __global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
-                                               const u32 *__restrict__ runbase, const u32 *__restrict__ par,
+                                               RunIdx R, const u32 *__restrict__ par,
                                                const u32 *__restrict__ rank, CompStat *stat, Geom g, TileGeom tg,
                                                const u32 *__restrict__ tileflag,
                                                const u32 *__restrict__ actw, const Counts *cnt)
@@ -776,7 +1217,7 @@ __global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, co
         if (tg.tx && tileflag[(x >> tg.txs) * tg.tiles_y + (y >> tg.tys)] == 0) continue;
         u32 carry = k ? (lmask[w - 1] >> 31) : 0u;
         u32 starts = run_starts(m, carry);
-        u32 rb = runbase[w];
+        u32 rb = R.at(w, row, k);
         u32 ps = m & ~(m << 1);  // piece starts (no carry: a continuing run still starts a piece here)
         while (ps) {
             int b0 = __ffs(ps) - 1;
@@ -815,7 +1256,7 @@ __global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, co
 // (continuations are never filtered: proc/tasks.py:45-51).
 // ===========================================================================
 struct KeepSrc {
-    CompStat *stat;
+    const CompStat *stat;
     const Counts *cnt;
     i64 dust;
     u32 mx, my, mz;  // nx-1, ny-1, nz-1
@@ -823,13 +1264,21 @@ struct KeepSrc {
     {
         return (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) ? 0 : (u64)cnt->v[SYN_CNT_COMPONENTS];
     }
-    __device__ __forceinline__ u32 get(u64 c) const
+    template <int N>
+    __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
     {
-        const CompStat s = stat[c];
-        bool face = s.minx == 0 || s.miny == 0 || s.minz == 0 || s.maxx == mx || s.maxy == my || s.maxz == mz;
-        u32 keep = (s.size > 0) && (face || (i64)s.size >= dust);
-        stat[c].keep = keep;
-        return keep;
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            item[t] = 0;
+            if (i0 + t < n) {
+                const CompStat *s = stat + i0 + t;
+                const u64 size = __ldcg(&s->size);
+                const uint4 lo = __ldcg(reinterpret_cast<const uint4 *>(&s->minx));   // minx miny minz maxx
+                const uint2 hi = __ldcg(reinterpret_cast<const uint2 *>(&s->maxy));   // maxy maxz
+                const bool face = lo.x == 0 || lo.y == 0 || lo.z == 0 || lo.w == mx || hi.x == my || hi.y == mz;
+                item[t] = (size > 0) && (face || (i64)size >= dust);
+            }
+        }
     }
 };
 
@@ -840,45 +1289,74 @@ __device__ __forceinline__ i64 centroid_f32(u64 sum, u64 size)
     return (i64)roundf(q);
 }
 
+// complab[c] = final label of component c (c + 1 if kept, else 0); kept components get a table row
 struct TableDst {
-    CompStat *stat;
+    const CompStat *stat;
+    u32 *complab;
     i64 *table;
     i64 max_segs;
     i64 ox, oy, oz;
-    __device__ __forceinline__ void put(u64 c, u32 rowi, u32 keep) const
+    template <int N>
+    __device__ __forceinline__ void store(u64 i0, u64 n, u32 ex, const u32 (&item)[N]) const
     {
-        if (!keep) return;
-        stat[c].row = rowi;
-        if ((i64)rowi >= max_segs) return;
-        const CompStat s = stat[c];
-        i64 *r = table + (i64)rowi * SYN_SEG_NCOLS;
-        r[SYN_SEG_ID] = (i64)c + 1;
-        r[SYN_SEG_SIZE] = (i64)s.size;
-        r[SYN_SEG_CX] = centroid_f32(s.sx, s.size) + ox;
-        r[SYN_SEG_CY] = centroid_f32(s.sy, s.size) + oy;
-        r[SYN_SEG_CZ] = centroid_f32(s.sz, s.size) + oz;
-        r[SYN_SEG_BX] = (i64)s.minx + ox;
-        r[SYN_SEG_BY] = (i64)s.miny + oy;
-        r[SYN_SEG_BZ] = (i64)s.minz + oz;
-        r[SYN_SEG_EX] = (i64)s.maxx + 1 + ox;
-        r[SYN_SEG_EY] = (i64)s.maxy + 1 + oy;
-        r[SYN_SEG_EZ] = (i64)s.maxz + 1 + oz;
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            const u64 c = i0 + t;
+            if (c < n) complab[c] = item[t] ? (u32)c + 1u : 0u;
+            if (item[t]) {
+                const u32 rowi = ex;
+                if ((i64)rowi < max_segs) {
+                    const CompStat s = stat[c];
+                    i64 *r = table + (i64)rowi * SYN_SEG_NCOLS;
+                    r[SYN_SEG_ID] = (i64)c + 1;
+                    r[SYN_SEG_SIZE] = (i64)s.size;
+                    r[SYN_SEG_CX] = centroid_f32(s.sx, s.size) + ox;
+                    r[SYN_SEG_CY] = centroid_f32(s.sy, s.size) + oy;
+                    r[SYN_SEG_CZ] = centroid_f32(s.sz, s.size) + oz;
+                    r[SYN_SEG_BX] = (i64)s.minx + ox;
+                    r[SYN_SEG_BY] = (i64)s.miny + oy;
+                    r[SYN_SEG_BZ] = (i64)s.minz + oz;
+                    r[SYN_SEG_EX] = (i64)s.maxx + 1 + ox;
+                    r[SYN_SEG_EY] = (i64)s.maxy + 1 + oy;
+                    r[SYN_SEG_EZ] = (i64)s.maxz + 1 + oz;
+                }
+            }
+            ex += item[t];
+        }
     }
 };
 
 // final per-run label: canonical id if kept else 0; also tracks the largest kept id
 __global__ void __launch_bounds__(256) k_run_labels(const u32 *__restrict__ par, const u32 *__restrict__ rank,
-                                                    const CompStat *__restrict__ stat, u32 *__restrict__ runlabel,
+                                                    const u32 *__restrict__ complab, u32 *__restrict__ runlabel,
                                                     Counts *cnt, i64 max_segs)
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
     const u64 nruns = (u64)cnt->v[SYN_CNT_RUNS];
     u32 mx = 0;
-    for (u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x; g < nruns; g += (u64)gridDim.x * blockDim.x) {
-        u32 c = rank[par[g]];
-        u32 lab = stat[c].keep ? c + 1 : 0;
-        runlabel[g] = lab;
-        mx = max(mx, lab);
+    // 4 consecutive runs per thread: 16-byte loads of the (flattened) parents, 16-byte stores of the labels
+    for (u64 g0 = (blockIdx.x * (u64)blockDim.x + threadIdx.x) * 4; g0 < nruns; g0 += (u64)gridDim.x * blockDim.x * 4) {
+        u32 p[4], lab[4];
+        if (g0 + 4 <= nruns) {
+            const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(par + g0));
+            p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) p[t] = (g0 + t < nruns) ? __ldcg(par + g0 + t) : 0u;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) lab[t] = (g0 + t < nruns) ? __ldcg(rank + p[t]) : 0u;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            lab[t] = (g0 + t < nruns) ? __ldcg(complab + lab[t]) : 0u;
+            mx = max(mx, lab[t]);
+        }
+        if (g0 + 4 <= nruns) *reinterpret_cast<uint4 *>(runlabel + g0) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+        else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (g0 + t < nruns) runlabel[g0 + t] = lab[t];
+        }
     }
     mx = __reduce_max_sync(SYN_FULL, mx);
     if ((threadIdx.x & 31) == 0 && mx) atomicMax((u64 *)&cnt->v[SYN_CNT_MAX_LABEL], (u64)mx);

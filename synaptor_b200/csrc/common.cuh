@@ -53,6 +53,14 @@ __device__ __forceinline__ void split_row(const Geom &g, u32 row, u32 &x, u32 &y
     else { x = row / (u32)g.ny; y = row - x * (u32)g.ny; }
 }
 
+// tiling of the (x, y) row grid for the shared-memory labelling pass (k_tile_ccl)
+struct TileGeom {
+    u32 tx, ty;          // rows per tile along x and y, powers of two (tx == 0: tiling disabled)
+    u32 tiles_x, tiles_y;
+    u32 ntiles;
+    u32 txs, tys;        // log2(tx), log2(ty)
+};
+
 // per-component accumulator, one 64-byte record (two 32 B sectors)
 struct __align__(16) CompStat {
     u64 size, sx, sy, sz;
@@ -113,6 +121,11 @@ __device__ __forceinline__ u32 bitpos_sum(u32 w)
 }
 
 __device__ __forceinline__ u32 ldcg_u32(const u32 *p) { return __ldcg(p); }
+
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int d)
+{
+    return ((u64)__shfl_xor_sync(SYN_FULL, (u32)(v >> 32), d) << 32) | __shfl_xor_sync(SYN_FULL, (u32)v, d);
+}
 
 // ---------------------------------------------------------------------------
 // Lock-free union-find on a u32 parent array in global memory.  Links always go
@@ -186,8 +199,10 @@ __device__ __forceinline__ u64 mix64(u64 a, u64 b)
 // ---------------------------------------------------------------------------
 // block-wide exclusive scan (blockDim.x == SCAN_THREADS)
 // ---------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 1024;
-constexpr int SCAN_ITEMS = 4;
+// 256 threads x 16 consecutive items: 8 CTAs per SM are resident, so a whole 512^3 mask (4.2 M words = 1024
+// tiles) is scanned in ONE round of CTAs and a block waiting in the look-back only stalls its own 8 warps
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 __device__ __forceinline__ u32 warp_incl_scan(u32 v, int lane)

@@ -9,7 +9,7 @@
 //   ordering       : Counter insertion order (overlap.py:47) == ascending first-occurrence
 //                    voxel index; recovered with a bitmap + popcount scan.
 #pragma once
-#include "common.cuh"
+#include "ccl.cuh"
 
 namespace syn {
 
@@ -44,7 +44,8 @@ __device__ __forceinline__ void pair_insert(const PairTable &T, u32 label, u64 b
         }
         if (hit) {
             atomicAdd(T.count + h, (u64)n);
-            atomicMin(T.first + h, pos);
+            // `first` only ever decreases: a (possibly stale) read that is already below pos makes the atomic useless
+            if (pos < __ldcg(T.first + h)) atomicMin(T.first + h, pos);
             return;
         }
         h = (h + 1) & T.capmask;
@@ -201,67 +202,19 @@ __global__ void __launch_bounds__(256) k_write_labels(const u32 *__restrict__ lm
 
 
 // ===========================================================================
-// Split output pass (VEC layout, nz % 4 == 0):
-//   k_dense_fill   : zero-fills the label volume (4 B/voxel written) and streams the base
-//                    segmentation once for max(base) (8 B/voxel read).  No dependent loads,
-//                    so it runs at copy speed.
-//   k_sparse_labels: runs after it and overwrites the kept foreground voxels with their
-//                    labels (run id -> run label) and feeds the (label, base) pair
-//                    histogram.  Driven by the L2-resident bitmask, it touches only the
-//                    foreground sectors (~5 % extra HBM traffic).
+// Output pass, sector mode (nz % 8 == 0: a 32-byte sector of the label volume = 8 voxels
+// = one byte of a mask word, never straddling two rows).  k_stream has already zero-filled
+// every sector WITHOUT foreground; k_sector_labels writes the sectors that DO hold
+// foreground, whole (kept labels or 0), one lane per sector, and feeds the (label, base)
+// pair histogram.  The two kernels write disjoint sectors.
 // ===========================================================================
-template <bool HAS_BASE, int UNROLL>
-__global__ void __launch_bounds__(256) k_dense_fill(u32 *__restrict__ labels, const u64 *__restrict__ base, Geom g,
-                                                    Counts *cnt)
-{
-    const int lane = threadIdx.x & 31;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-    u64 bmax = 0;
-    for (u32 c0 = warp * UNROLL; c0 < g.nchunks; c0 += nwarps * UNROLL) {
-        // chunk -> (row, first word) once per iteration; the UNROLL chunks of a warp are consecutive
-        u32 row = c0 / g.cpr;
-        u32 kc = c0 - row * g.cpr;
-        ulonglong2 b01[UNROLL], b23[UNROLL];
-        i64 vox[UNROLL];
-        bool ok[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const i64 z = (i64)kc * 128 + 4 * lane;
-            ok[u] = (c0 + u < g.nchunks) && z < g.nz;
-            vox[u] = (i64)row * g.nz + z;
-            if (HAS_BASE) {
-                b01[u] = make_ulonglong2(0, 0);
-                b23[u] = make_ulonglong2(0, 0);
-                if (ok[u]) {
-                    const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(base + vox[u]);
-                    b01[u] = __ldcs(bp);
-                    b23[u] = __ldcs(bp + 1);
-                }
-            }
-            if (++kc == g.cpr) { kc = 0; ++row; }
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            if (ok[u]) __stcs(reinterpret_cast<uint4 *>(labels + vox[u]), make_uint4(0, 0, 0, 0));
-            if (HAS_BASE) bmax = max(bmax, max(max(b01[u].x, b01[u].y), max(b23[u].x, b23[u].y)));
-        }
-    }
-    if (HAS_BASE) {
-        for (int d = 16; d; d >>= 1) bmax = max(bmax, __shfl_down_sync(SYN_FULL, bmax, d));
-        if (lane == 0 && bmax) atomicMax((u64 *)&cnt->v[SYN_CNT_MAX_BASE], bmax);
-    }
-}
-
-// Foreground pass.  A warp takes 32 active mask words, prefix-sums their foreground
-// counts and then walks the batch's foreground voxels 32 at a time, ONE LANE PER
-// FOREGROUND VOXEL: owner word by a shuffle binary search over the prefix, bit position
-// by find-nth-set.  Control flow is uniform and every lane is busy (a thread-per-word
-// loop ran at ~6 active lanes).  Consecutive lanes holding the same (label, base) pair
-// are merged with a ballot, so the pair table sees about one insert per z-run.
+// Foreground sectors.  A warp takes 32 active mask words, prefix-sums their non-empty bytes and then walks the
+// batch's sectors 32 at a time, ONE LANE PER SECTOR: owner word by a shuffle binary search over the prefix,
+// byte by find-nth-set.  A sector holds at most 4 pieces of runs: their labels are fetched together, the (at
+// most 8) base ids of the foreground voxels too, then the whole 32-byte sector is stored.
 template <bool HAS_BASE>
-__global__ void __launch_bounds__(256) k_sparse_labels(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
-                                                       const u32 *__restrict__ runbase,
+__global__ void __launch_bounds__(256) k_sector_labels(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
+                                                       RunIdx R,
                                                        const u32 *__restrict__ runlabel, u32 *__restrict__ labels,
                                                        const u64 *__restrict__ base, Geom g, PairTable T,
                                                        const u32 *__restrict__ actw, const Counts *cnt)
@@ -273,76 +226,88 @@ __global__ void __launch_bounds__(256) k_sparse_labels(const u32 *__restrict__ l
     const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
     for (u32 i0 = warp * 32; i0 < nact; i0 += nwarps * 32) {
         const u32 i = i0 + lane;
-        u32 w = 0, om = 0, starts = 0, rb = 0;
+        u32 w = 0, om = 0, m = 0, starts = 0, rb = 0;
         i64 vox0 = 0;
         if (i < nact) {
             w = actw[i];
             om = omask[w];
-            const u32 m = lmask[w];
-            const u32 row = w / g.wz;
-            const u32 kw = w - row * g.wz;
+            m = lmask[w];
+            u32 row, kw;
+            split_word(g, w, row, kw);
             const u32 carry = kw ? (lmask[w - 1] >> 31) : 0u;
             starts = run_starts(m, carry);
-            rb = runbase[w];
+            rb = R.at(w, row, kw);
             vox0 = (i64)row * g.nz + (i64)kw * 32;
         }
-        const u32 n = __popc(om);
+        const u32 f = (u32)((om & 0xFFu) != 0) | ((u32)((om & 0xFF00u) != 0) << 1) |
+                      ((u32)((om & 0xFF0000u) != 0) << 2) | ((u32)((om & 0xFF000000u) != 0) << 3);
+        const u32 n = __popc(f);
         const u32 incl = warp_incl_scan(n, lane);
         const u32 excl = incl - n;
         const u32 total = __shfl_sync(SYN_FULL, incl, 31);
-        // two rounds (64 foreground voxels) per iteration: both rounds' loads are in flight together, and the
-        // base value is fetched speculatively, in parallel with the run label it would otherwise depend on
-        for (u32 r0 = 0; r0 < total; r0 += 64) {
-            u32 lab[2], b[2], w_o[2];
-            u64 bval[2];
-            i64 vox[2];
-            bool valid[2];
+        for (u32 r0 = 0; r0 < total; r0 += 32) {
+            const u32 j = r0 + lane;
+            int o = 0;   // owner = last lane whose exclusive prefix is <= j
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const u32 j = r0 + 32 * q + lane;
-                valid[q] = j < total;
-                int o = 0;   // owner = last lane whose exclusive prefix is <= j
+            for (int s = 16; s; s >>= 1) {
+                const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
+                if (e <= j) o += s;
+            }
+            const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
+            const u32 f_o = __shfl_sync(SYN_FULL, f, o);
+            const u32 om_o = __shfl_sync(SYN_FULL, om, o);
+            const u32 m_o = __shfl_sync(SYN_FULL, m, o);
+            const u32 st_o = __shfl_sync(SYN_FULL, starts, o);
+            const u32 rb_o = __shfl_sync(SYN_FULL, rb, o);
+            const u32 w_o = __shfl_sync(SYN_FULL, w, o);
+            const i64 v_o = __shfl_sync(SYN_FULL, vox0, o);
+            if (j >= total) continue;
+            const u32 q8 = 8u * select_bit(f_o, j - e_o);      // first bit of the sector inside the word
+            const u32 ob = (om_o >> q8) & 0xFFu;               // voxels that receive a label
+            const u32 mb = (m_o >> q8) & 0xFFu;                // labelled mask (differs from ob only with dilation)
+            const i64 vox = v_o + q8;
+            // base ids of the foreground voxels: up to four 16-byte loads, issued before the label lookups
+            ulonglong2 bq[4];
+            if (HAS_BASE) {
 #pragma unroll
-                for (int s = 16; s; s >>= 1) {
-                    const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
-                    if (e <= j) o += s;
-                }
-                const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
-                const u32 om_o = __shfl_sync(SYN_FULL, om, o);
-                const u32 st_o = __shfl_sync(SYN_FULL, starts, o);
-                const u32 rb_o = __shfl_sync(SYN_FULL, rb, o);
-                w_o[q] = __shfl_sync(SYN_FULL, w, o);
-                const i64 v_o = __shfl_sync(SYN_FULL, vox0, o);
-                lab[q] = 0;
-                bval[q] = 0;
-                b[q] = 0;
-                vox[q] = 0;
-                if (valid[q]) {
-                    b[q] = select_bit(om_o, j - e_o);
-                    vox[q] = v_o + b[q];
-                    const u32 run = rb_o + __popc(st_o & mask_le(b[q])) - 1u;
-                    lab[q] = runlabel[run];
-                    if (HAS_BASE) bval[q] = __ldcs(base + vox[q]);
+                for (int u = 0; u < 4; ++u) {
+                    bq[u] = make_ulonglong2(0, 0);
+                    if ((ob >> (2 * u)) & 3u) bq[u] = __ldcs(reinterpret_cast<const ulonglong2 *>(base + vox) + u);
                 }
             }
+            // pieces of runs inside the byte (<= 4) and their labels
+            const u32 ps = mb & ~(mb << 1) & 0xFFu;
+            u32 plab[4];
+            {
+                u32 rest = ps;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (lab[q]) labels[vox[q]] = lab[q];
-                if (HAS_BASE) {
-                    const bool act = lab[q] && bval[q];
-                    const u32 actm = __ballot_sync(SYN_FULL, act);
-                    if (actm) {
-                        const u32 pl = __shfl_up_sync(SYN_FULL, lab[q], 1);
-                        const u64 pb = __shfl_up_sync(SYN_FULL, bval[q], 1);
-                        const bool head = act && (lane == 0 || pl != lab[q] || pb != bval[q]);
-                        const u32 headm = __ballot_sync(SYN_FULL, head);
-                        if (head) {
-                            const u32 stop = (headm | ~actm) & ~mask_le((u32)lane);
-                            const int endl = stop ? (__ffs(stop) - 1) : 32;
-                            pair_insert(T, lab[q], bval[q], (u32)(endl - lane), (u64)w_o[q] * 32 + b[q]);
-                        }
+                for (int p = 0; p < 4; ++p) {
+                    plab[p] = 0;
+                    if (rest) {
+                        const u32 t = (u32)__ffs(rest) - 1u;
+                        rest &= rest - 1;
+                        plab[p] = runlabel[rb_o + __popc(st_o & mask_le(q8 + t)) - 1u];
                     }
                 }
+            }
+            u32 lab[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const u32 pi = __popc(ps & mask_le((u32)t));   // 1-based piece index of voxel t
+                const u32 l = pi <= 1 ? plab[0] : pi == 2 ? plab[1] : pi == 3 ? plab[2] : plab[3];
+                lab[t] = ((ob >> t) & 1u) ? l : 0u;
+            }
+            uint4 *lp = reinterpret_cast<uint4 *>(labels + vox);
+            lp[0] = make_uint4(lab[0], lab[1], lab[2], lab[3]);
+            lp[1] = make_uint4(lab[4], lab[5], lab[6], lab[7]);
+            if (HAS_BASE) {
+                const u64 bv[8] = {bq[0].x, bq[0].y, bq[1].x, bq[1].y, bq[2].x, bq[2].y, bq[3].x, bq[3].y};
+                PairAcc acc;
+                const u64 pos0 = (u64)w_o * 32 + q8;
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (lab[t] && bv[t]) acc.add(T, lab[t], bv[t], pos0 + t);
+                acc.flush(T);
             }
         }
     }
@@ -413,11 +378,22 @@ struct PopcSrc {
     const u32 *bitmap;
     u32 nwords;
     __device__ __forceinline__ u64 n() const { return nwords; }
-    __device__ __forceinline__ u32 get(u64 w) const { return __popc(bitmap[w]); }
+    template <int N>
+    __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
+    {
+        u32 m[N];
+        load_items_u32(bitmap, i0, n, m);
+#pragma unroll
+        for (int t = 0; t < N; ++t) item[t] = __popc(m[t]);
+    }
 };
 struct WordBaseDst {
     u32 *wordbase;
-    __device__ __forceinline__ void put(u64 w, u32 ex, u32) const { wordbase[w] = ex; }
+    template <int N>
+    __device__ __forceinline__ void store(u64 i0, u64 n, u32 ex, const u32 (&item)[N]) const
+    {
+        store_prefix_u32(wordbase, i0, n, ex, item);
+    }
 };
 
 __global__ void __launch_bounds__(256) k_pair_emit(PairTable T, const u32 *__restrict__ bitmap,
