@@ -56,7 +56,9 @@ enum {
     SYN_CNT_TILE_RECORDS = 10, /* per-tile partial statistics records written by the tile pass */
     SYN_CNT_FLAGGED_TILES = 11, /* tiles left to the global kernels (too dense for shared memory) */
     SYN_CNT_BND_WORDS = 12,  /* non-empty mask words on a tile border (input of the global union pass) */
-    SYN_NCOUNTS = 16
+    SYN_CNT_TICKET = 13,     /* internal: CTAs of the streaming kernel that have finished */
+    SYN_CNT_DBG0 = 16,       /* 16..31: phase timers of instrumented builds (-DSYN_PHASE_TIMING), else 0 */
+    SYN_NCOUNTS = 32
 };
 
 /* columns of one segment-table row (int64 each), in the order of the reference's

@@ -18,8 +18,9 @@ SYN_ERR_WORKSPACE = -4
 
 # counts[] indices (enum in synaptor_b200.h)
 CNT_RUNS, CNT_COMPONENTS, CNT_KEPT, CNT_PAIRS, CNT_MAX_BASE, CNT_MAX_LABEL, CNT_ERRFLAGS, CNT_FG_VOXELS, \
-    CNT_TABLE_SLOTS, CNT_ACTIVE_WORDS, CNT_TILE_RECORDS, CNT_FLAGGED_TILES, CNT_BND_WORDS = range(13)
-NCOUNTS = 16
+    CNT_TABLE_SLOTS, CNT_ACTIVE_WORDS, CNT_TILE_RECORDS, CNT_FLAGGED_TILES, CNT_BND_WORDS, CNT_TICKET = range(14)
+NCOUNTS = 32
+CNT_DBG0 = 16
 SEG_NCOLS = 11
 
 EF_RUNS, EF_SEGS, EF_TABLE, EF_PAIRS = 1, 2, 4, 8

@@ -176,7 +176,8 @@ def _counts_dict(arr):
         "max_label": int(arr[C.CNT_MAX_LABEL]), "errflags": int(arr[C.CNT_ERRFLAGS]),
         "fg_voxels": int(arr[C.CNT_FG_VOXELS]), "table_slots": int(arr[C.CNT_TABLE_SLOTS]),
         "active_words": int(arr[C.CNT_ACTIVE_WORDS]), "tile_records": int(arr[C.CNT_TILE_RECORDS]),
-        "flagged_tiles": int(arr[C.CNT_FLAGGED_TILES]),
+        "flagged_tiles": int(arr[C.CNT_FLAGGED_TILES]), "bnd_words": int(arr[C.CNT_BND_WORDS]),
+        "dbg": [int(v) for v in arr[C.CNT_DBG0:]],
     }
 
 

@@ -155,7 +155,8 @@ struct Workspace {
     TileRec *recs;
     PairKey *pkeys;
     u64 *pcount, *pfirst;
-    u32 *bitmap, *wordbase;
+    u32 *bcount, *bfill, *sorted_slot;     // pair ordering: bucket counts (nb + 1), fill cursors (nb), bucket order
+    u32 nbuckets;
     u32 paircap;
     size_t total;
 };
@@ -191,41 +192,46 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     w->stat = (CompStat *)take((size_t)max_runs * sizeof(CompStat));
     w->recs = (TileRec *)take((size_t)max_runs * sizeof(TileRec));
     w->paircap = 0;
-    w->pkeys = nullptr; w->pcount = w->pfirst = nullptr; w->bitmap = w->wordbase = nullptr;
+    w->pkeys = nullptr; w->pcount = w->pfirst = nullptr; w->bcount = w->bfill = w->sorted_slot = nullptr;
+    w->nbuckets = 0;
     if (max_pairs > 0) {
         w->paircap = pow2_at_least(2 * max_pairs);
         w->pkeys = (PairKey *)take((size_t)w->paircap * sizeof(PairKey));
         w->pcount = (u64 *)take((size_t)w->paircap * 8);
         w->pfirst = (u64 *)take((size_t)w->paircap * 8);
-        w->bitmap = (u32 *)take(nw * 4);
-        w->wordbase = (u32 *)take(nw * 4);
+        w->nbuckets = (u32)((((u64)g.nwords * 32) >> PB_SHIFT) + 1);
+        w->bcount = (u32 *)take(((size_t)w->nbuckets + 1) * 4 + (size_t)w->nbuckets * 4);   // counts + cursors: one memset
+        w->bfill = w->bcount ? w->bcount + w->nbuckets + 1 : nullptr;
+        w->sorted_slot = (u32 *)take((size_t)max_pairs * 4);
     }
     w->total = off;
 }
 
 // grid = (resident CTAs per SM for this kernel) x (SM count): one full wave, no tail
 std::mutex g_occ_mu;
-struct OccEntry { const void *fn; int threads; int blocks; };
+struct OccEntry { const void *fn; int threads; size_t smem; int blocks; };
 OccEntry g_occ[128];
 int g_nocc = 0;
 
 template <class K>
-int occ_blocks(K kernel, int threads)
+int occ_blocks(K kernel, int threads, size_t dyn_smem)
 {
     const void *fn = (const void *)kernel;
     std::lock_guard<std::mutex> lk(g_occ_mu);
     for (int i = 0; i < g_nocc; ++i)
-        if (g_occ[i].fn == fn && g_occ[i].threads == threads) return g_occ[i].blocks;
+        if (g_occ[i].fn == fn && g_occ[i].threads == threads && g_occ[i].smem == dyn_smem) return g_occ[i].blocks;
+    if (dyn_smem > 48 * 1024)
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) nb = 4;
-    if (g_nocc < 128) g_occ[g_nocc++] = OccEntry{fn, threads, nb};
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, dyn_smem) != cudaSuccess || nb < 1) nb = 1;
+    if (g_nocc < 128) g_occ[g_nocc++] = OccEntry{fn, threads, dyn_smem, nb};
     return nb;
 }
 
 template <class K>
-int wave_grid(K kernel, int threads, i64 max_blocks)
+int wave_grid(K kernel, int threads, i64 max_blocks, size_t dyn_smem = 0)
 {
-    i64 g = (i64)occ_blocks(kernel, threads) * sm_count();
+    i64 g = (i64)occ_blocks(kernel, threads, dyn_smem) * sm_count();
     if (max_blocks < 1) max_blocks = 1;
     return (int)(g < max_blocks ? g : max_blocks);
 }
@@ -252,18 +258,30 @@ int launch_scan(const Workspace &W, int slot, Src src, Dst dst, i64 max_items, i
     return SYN_OK;
 }
 
-// launches the ordering of the pair table entries + emission into the output arrays (the bitmap is already zero)
+// zeroes the bucket counters of the pair ordering (any time before order_and_emit_pairs)
+int pair_order_init(const Workspace &W, cudaStream_t st)
+{
+    CK(cudaMemsetAsync(W.bcount, 0, ((size_t)2 * W.nbuckets + 1) * 4, st));
+    return SYN_OK;
+}
+
+// orders the pair table entries by first occurrence and emits them into the output arrays
 int order_and_emit_pairs(const Geom &g, const Workspace &W, PairTable T, u32 *rows, u64 *cols, i64 *vals,
                          i64 max_pairs, cudaStream_t st)
 {
-    k_pair_mark<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bitmap);
+    (void)g;
+    k_pair_count<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bcount);
     CK_LAUNCH();
-    PROF("pair_mark");
-    PopcSrc src{W.bitmap, g.nwords};
-    int rc = launch_scan<16>(W, 3, src, WordBaseDst{W.wordbase}, g.nwords, &W.cnt->v[SYN_CNT_PAIRS], st);
+    PROF("pair_count");
+    int rc = launch_scan<8>(W, 3, U32Src{W.bcount, W.nbuckets}, U32PrefixDst{W.bcount}, W.nbuckets,
+                            &W.cnt->v[SYN_CNT_PAIRS], st);
     if (rc != SYN_OK) return rc;
-    PROF("pair_scan");
-    k_pair_emit<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bitmap, W.wordbase, rows, cols, vals, max_pairs);
+    PROF("pair_bucket_scan");
+    k_pair_scatter<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T, W.bcount, W.bfill, W.sorted_slot, max_pairs);
+    CK_LAUNCH();
+    PROF("pair_scatter");
+    k_pair_emit<<<grid_for(max_pairs, 256, 8), 256, 0, st>>>(T, W.bcount, W.nbuckets, W.sorted_slot, rows, cols, vals,
+                                                            max_pairs);
     CK_LAUNCH();
     PROF("pair_emit");
     return SYN_OK;
@@ -298,17 +316,13 @@ int launch_union(const Workspace &W, const Geom &g, RunIdx R, bool bnd_list, i64
         PROF("tile_ccl");
     }
     if (CONN == 6 && bnd_list) {
-        // tile borders from the compact border-word list; flagged tiles (normally none) by the row kernel
-        k_union_bnd<<<wave_grid(k_union_bnd, 256, div_up_u32(g.nwords, 256 * 4)), 256, 0, st>>>(W.lmask, R, W.par, g,
-                                                                                        W.tg, W.bndw, W.cnt);
+        // tile borders from the compact border-word list (+ the tiles the shared-memory pass had to leave)
+        k_union_bnd<<<wave_grid(k_union_bnd, 256, div_up_u32(g.nwords, 256 * 4)), 256, 0, st>>>(
+            W.lmask, R, W.par, g, W.tg, W.bndw, W.tileflag, W.actw, W.cnt);
         CK_LAUNCH();
         PROF("union_bnd");
-        k_union_rows<CONN, true><<<wave_grid(k_union_rows<CONN, true>, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(
-            W.lmask, R, W.par, g, W.tg, W.tileflag, W.actw, W.cnt);
-        CK_LAUNCH();
-        PROF("union_flagged");
     } else {
-        k_union_rows<CONN, false><<<wave_grid(k_union_rows<CONN, false>, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(
+        k_union_rows<CONN><<<wave_grid(k_union_rows<CONN>, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(
             W.lmask, R, W.par, g, W.tg, W.tileflag, W.actw, W.cnt);
         CK_LAUNCH();
         PROF("union_rows");
@@ -391,17 +405,13 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         const i64 ntiles = ((i64)g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
 #define SYN_STREAM(HB, FS)                                                                                         \
     k_stream<HB, FS><<<wave_grid(k_stream<HB, FS>, TS_THREADS, ntiles), TS_THREADS, 0, st>>>(                      \
-        pred, bs, labels_out, W.omask, W.runbase, W.tileagg, W.actw, W.bndw, g, W.tg, thresh, W.cnt)
+        pred, bs, labels_out, W.omask, W.runbase, W.tileagg, W.tilebase, W.actw, W.bndw, g, W.tg, thresh, W.cnt,   \
+        (u32)max_runs)
         if (has_base) { if (fused_scan) SYN_STREAM(true, true); else SYN_STREAM(true, false); }
         else { if (fused_scan) SYN_STREAM(false, true); else SYN_STREAM(false, false); }
 #undef SYN_STREAM
         CK_LAUNCH();
         PROF("stream");
-        if (fused_scan) {
-            k_tile_prefix<<<1, 1024, 0, st>>>(W.tileagg, W.tilebase, (u32)ntiles, W.cnt, (u32)max_runs);
-            CK_LAUNCH();
-            PROF("tile_prefix");
-        }
     } else {
         const i64 need = div_up_u32((u64)g.nchunks, 8 * 4);
         if (vec_in)
@@ -423,7 +433,8 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     if (has_base) {
         k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
         CK_LAUNCH();
-        CK(cudaMemsetAsync(W.bitmap, 0, (size_t)g.nwords * 4, st));
+        rc = pair_order_init(W, st);
+        if (rc != SYN_OK) return rc;
         PROF("pair_init");
     }
 
@@ -457,23 +468,16 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     // --- scan #2: flatten + canonical rank -----------------------------------------------------
     {
         RootFlagSrc src{W.par, W.cnt};
-        rc = launch_scan<4>(W, 1, src, RankDst{W.rank, W.stat}, max_runs, &W.cnt->v[SYN_CNT_COMPONENTS], st);
+        rc = launch_scan<8>(W, 1, src, RankDst{W.rank, W.stat}, max_runs, &W.cnt->v[SYN_CNT_COMPONENTS], st);
         if (rc != SYN_OK) return rc;
         PROF("flatten_rank");
     }
 
-    // --- statistics ----------------------------------------------------------------------------
-    if (W.tg.tx) {
-        k_stats_merge<<<wave_grid(k_stats_merge, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.recs, W.par, W.rank,
-                                                                                               W.stat, W.cnt);
-        CK_LAUNCH();
-        PROF("stats_merge");
-    }
-    k_stats<<<wave_grid(k_stats, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(W.lmask, W.omask, R, W.par,
-                                                                               W.rank, W.stat, g, W.tg, W.tileflag,
-                                                                               W.actw, W.cnt);
+    // --- statistics: tile records -> components (flagged tiles, normally none, per piece) -----------------
+    k_stats_merge<<<wave_grid(k_stats_merge, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(
+        W.recs, W.par, W.rank, W.stat, W.lmask, W.omask, R, g, W.tg, W.tileflag, W.actw, W.cnt);
     CK_LAUNCH();
-    PROF("stats_flagged");
+    PROF("stats_merge");
 
     // --- scan #3: dust decision + table ----------------------------------------------------------
     {
@@ -491,7 +495,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
 
     // --- foreground sectors (+ overlaps) -------------------------------------------------------------
     if (sector_out) {
-        const i64 needw = div_up_u32(g.nwords, 8);   // one warp per 32 active words, at most
+        const i64 needw = div_up_u32(g.nwords, SL_BATCH * SL_WARPS);   // one warp per batch of active words, at most
         if (has_base)
             k_sector_labels<true><<<wave_grid(k_sector_labels<true>, 256, needw), 256, 0, st>>>(
                 W.lmask, W.omask, R, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
@@ -546,7 +550,8 @@ int syn_count_overlaps(const uint32_t *seg1, const uint64_t *seg2, int64_t nx, i
     CK_LAUNCH();
     k_overlap_scan<<<grid_for((i64)g.nwords * 32, 256, 8), 256, 0, st>>>(seg1, (const u64 *)seg2, g, T, W.cnt);
     CK_LAUNCH();
-    CK(cudaMemsetAsync(W.bitmap, 0, (size_t)g.nwords * 4, st));
+    rc = pair_order_init(W, st);
+    if (rc != SYN_OK) return rc;
     rc = order_and_emit_pairs(g, W, T, pair_rows, (u64 *)pair_cols, (i64 *)pair_counts, max_pairs, st);
     if (rc != SYN_OK) return rc;
     return finish_counts(W, (i64 *)counts_host, st);

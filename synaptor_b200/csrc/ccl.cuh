@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ pre
 // Two representations:
 //   global : rb[w] holds the value itself (generic scan, k_scan_1p<RunStartSrc>), tb == nullptr
 //   tiled  : rb[w] holds the prefix INSIDE the word's stream tile (TS_CHUNKS chunks) and tb[tile] the
-//            number of runs before the tile (k_stream + k_tile_prefix: no look-back chain in the
-//            streaming kernel, no fix-up pass over the words)
+//            number of runs before the tile (k_stream; its last CTA scans the tile counts: no look-back
+//            chain in the streaming kernel, no fix-up pass over the words)
 // ===========================================================================
 constexpr int TS_THREADS = 256;
 constexpr int TS_CHUNKS = 128;              // 128 chunks = 16384 voxels = 64 KB of float32 per tile
@@ -126,8 +126,9 @@ template <bool HAS_BASE, bool FUSE_SCAN>
 __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__ pred, const u64 *__restrict__ base,
                                                        u32 *__restrict__ labels, u32 *__restrict__ mask,
                                                        u32 *__restrict__ rb, u32 *__restrict__ tileagg,
-                                                       u32 *__restrict__ actw, u32 *__restrict__ bndw, Geom g,
-                                                       TileGeom tg, float thr, Counts *cnt)
+                                                       u32 *__restrict__ tilebase, u32 *__restrict__ actw,
+                                                       u32 *__restrict__ bndw, Geom g, TileGeom tg, float thr,
+                                                       Counts *cnt, u32 max_runs)
 {
     __shared__ u32 s_m[TS_SLOTS + 1];   // s_m[0]: the word before the tile's first slot; slot s at s_m[s + 1]
     __shared__ u32 sm[33];
@@ -257,35 +258,36 @@ __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__
         for (int d = 16; d; d >>= 1) bmax = max(bmax, __shfl_down_sync(SYN_FULL, bmax, d));
         if (lane == 0 && bmax) atomicMax((u64 *)&cnt->v[SYN_CNT_MAX_BASE], bmax);
     }
-}
-
-// exclusive scan of the stream tiles' run counts (one CTA: <= a few thousand values per 512^3 chunk);
-// publishes the total run count and checks it against the capacity of the per-run arrays
-__global__ void __launch_bounds__(1024) k_tile_prefix(const u32 *__restrict__ tileagg, u32 *__restrict__ tilebase,
-                                                      u32 ntiles, Counts *cnt, u32 max_runs)
-{
-    __shared__ u32 sm[33];
+    if (!FUSE_SCAN) return;
+    // ---- the CTA that finishes last turns the tiles' run counts into run-id bases (exclusive scan of a few
+    // thousand values), publishes the total run count and checks it against the capacity of the per-run arrays ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_abase = (u32)atomicAdd((u64 *)&cnt->v[SYN_CNT_TICKET], 1ull);
+    __syncthreads();
+    if (s_abase != gridDim.x - 1) return;
+    __threadfence();
     u64 carry = 0;
-    for (u32 t0 = 0; t0 < ntiles; t0 += 4096) {
-        const u32 i0 = t0 + threadIdx.x * 4;
-        u32 a[4];
+    for (u32 t0 = 0; t0 < ntiles; t0 += TS_THREADS * 8) {
+        const u32 i0 = t0 + threadIdx.x * 8;
+        u32 a[8];
+        u32 v = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = (i0 + q < ntiles) ? tileagg[i0 + q] : 0u;
+        for (int q = 0; q < 8; ++q) { a[q] = (i0 + q < ntiles) ? __ldcg(tileagg + i0 + q) : 0u; v += a[q]; }
         u32 total;
-        u32 ex = block_excl_scan(a[0] + a[1] + a[2] + a[3], sm, &total);
+        u32 ex = block_excl_scan(v, sm, &total);
         if (carry + total > 0xFFFFFFFFull) {                 // more runs than 32 bits: reported through the count
             carry += total;
             break;
         }
         ex += (u32)carry;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
             if (i0 + q < ntiles) tilebase[i0 + q] = ex;
             ex += a[q];
         }
         carry += total;
     }
-    // (the loop exits uniformly: `carry` and `total` are block-wide values)
     if (threadIdx.x == 0) {
         cnt->v[SYN_CNT_RUNS] = (i64)carry;
         if (carry > (u64)max_runs) atomicOr((u64 *)&cnt->v[SYN_CNT_ERRFLAGS], (u64)SYN_EF_RUNS);
@@ -577,13 +579,12 @@ __device__ __forceinline__ void union_shifted(u32 *par, const RowView &A, const 
 
 // With tiling enabled (tg.tx != 0) a pair of rows inside one tile was already joined by K2 and is
 // skipped here unless that tile was flagged as too dense.
-// BND_DONE: the tile borders were already joined by k_union_bnd; only flagged tiles are left (usually none).
+// BND_DONE: the tile borders are joined by k_union_bnd; only flagged tiles are left (usually none).
 template <int CONN, bool BND_DONE>
-__global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask, RunIdx R,
-                                                    u32 *par, Geom g, TileGeom tg, const u32 *__restrict__ tileflag,
-                                                    const u32 *__restrict__ actw, const Counts *cnt)
+__device__ __forceinline__ void union_rows_body(const u32 *__restrict__ mask, const RunIdx &R, u32 *par, const Geom &g,
+                                                const TileGeom &tg, const u32 *__restrict__ tileflag,
+                                                const u32 *__restrict__ actw, const Counts *cnt)
 {
-    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
     if (BND_DONE && cnt->v[SYN_CNT_FLAGGED_TILES] == 0) return;
     const u32 nact = (u32)cnt->v[SYN_CNT_ACTIVE_WORDS];
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nact; i += gridDim.x * blockDim.x) {
@@ -634,6 +635,15 @@ __global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask
     }
 }
 
+template <int CONN>
+__global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask, RunIdx R, u32 *par, Geom g, TileGeom tg,
+                                                    const u32 *__restrict__ tileflag, const u32 *__restrict__ actw,
+                                                    const Counts *cnt)
+{
+    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    union_rows_body<CONN, false>(mask, R, par, g, tg, tileflag, actw, cnt);
+}
+
 
 // ===========================================================================
 // K2: block-local union-find in shared memory.  A tile = TX x-slabs x TY rows x
@@ -650,10 +660,17 @@ constexpr int TILE_RUNS = 4096;
 constexpr int TILE_MAXTX = 16;
 constexpr int TILE_ROOTS = 512;    // tile-local components with statistics accumulated in shared memory
 constexpr int TILE_SLOT = 10;      // u32 per root: size, sum dx, sum dy, sum z, min/max dx, dy, z
-constexpr size_t TILE_SMEM = (size_t)TILE_WORDS * 4 * 3 + (size_t)TILE_WORDS * 2 + (size_t)TILE_RUNS * 4 +
-                             (size_t)TILE_RUNS * 2 + (size_t)TILE_ROOTS * 2 + (size_t)TILE_ROOTS * TILE_SLOT * 4;
+constexpr int TILE_THREADS = 512;
+constexpr int TILE_WPT = TILE_WORDS / TILE_THREADS;   // mask words per thread (consecutive)
+// shared memory of one tile CTA (3 CTAs = 48 warps per SM; the kernel is instruction-issue bound, not
+// occupancy bound): mask words, run-start words, packed active list, parents, statistics slots, global ids of
+// the local roots, local run-id prefix
+constexpr size_t TILE_AUX = (size_t)TILE_ROOTS * TILE_SLOT * 4;
+constexpr size_t TILE_SMEM = (size_t)TILE_WORDS * 4 * 3 + (size_t)TILE_RUNS * 4 + TILE_AUX + (size_t)TILE_WORDS * 2 +
+                             (size_t)TILE_ROOTS * 4;
 
-
+// Shared parent array: low 16 bits = parent (local run id < TILE_RUNS), high 16 bits = compact index of a root
+// (written after the flatten).  During the unions the high half is zero, so values compare like plain ids.
 __device__ __forceinline__ u32 sm_find(volatile u32 *p, u32 x)
 {
     u32 q = p[x];
@@ -686,11 +703,19 @@ __device__ __forceinline__ void sm_union(u32 *p, u32 a, u32 b)
     }
 }
 
+// position of the (n+1)-th set bit of w when n is small (the usual case: one or two spans per word)
+__device__ __forceinline__ u32 select_bit_small(u32 w, u32 n)
+{
+    for (; n; --n) w &= w - 1;
+    return (u32)__ffs(w) - 1u;
+}
+
+// s_act entry: word index (11 bits) | k << 11 (10 bits) | yl << 21 (6 bits) | xl << 27
 // One pass over the tile's non-empty words for one (neighbour row, z shift) combination, ONE LANE PER
 // OVERLAP SPAN: every thread first finds the overlap spans of its word with the neighbour word, a warp
 // prefix sum turns the 32 counts into a work list, and the lanes then take the spans one each (owner by
 // shuffle binary search, span start by select_bit) and perform the unions with uniform control flow.
-// s_act entry: word index (11 bits) | k << 11 (10 bits) | yl << 21 (6 bits) | xl << 27.
+// Used for 18 / 26 connectivity (6-connectivity has the combined pass below).
 template <int SHIFT>
 __device__ __forceinline__ void tile_pass(const u32 *s_mask, const unsigned short *s_rb, const u32 *s_st, u32 *s_par,
                                           const u32 *s_act, u32 nact, u32 wz, u32 vy, u32 dxl, int dyl, int off)
@@ -745,14 +770,14 @@ __device__ __forceinline__ void tile_pass(const u32 *s_mask, const unsigned shor
 }
 
 // 6-connectivity: both neighbour rows ((x, y-1) and (x-1, y)) in ONE pass -- the overlap spans of a word with
-// its two neighbour words form one work list, so the tile needs half as many warp rounds.
+// its two neighbour words form one work list, so the per-batch set-up is paid once.
 __device__ __forceinline__ void tile_pass6(const u32 *s_mask, const unsigned short *s_rb, const u32 *s_st, u32 *s_par,
                                            const u32 *s_act, u32 nact, u32 wz, u32 segw)
 {
     const int lane = threadIdx.x & 31;
     const u32 wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
-    for (u32 a0 = wib * 32; a0 < nact; a0 += nwb * 32) {
-        const u32 a = a0 + lane;
+    for (u32 a0 = wib * 32; a0 < nact; a0 += nwb * 32) {   // whole batches: the kernel is issue bound, so fewer,
+        const u32 a = a0 + lane;                           // fuller batches beat an even split over the warps
         u32 osy = 0, osx = 0, i = 0;
         if (a < nact) {
             const u32 e = s_act[a];
@@ -761,8 +786,7 @@ __device__ __forceinline__ void tile_pass6(const u32 *s_mask, const unsigned sho
             if ((e >> 21) & 63u) { const u32 o = m & s_mask[i - wz]; osy = o & ~(o << 1); }
             if (e >> 27) { const u32 o = m & s_mask[i - segw]; osx = o & ~(o << 1); }
         }
-        const u32 ny_ = __popc(osy);
-        const u32 n = ny_ + __popc(osx);
+        const u32 n = __popc(osy) + __popc(osx);
         const u32 incl = warp_incl_scan(n, lane);
         const u32 excl = incl - n;
         const u32 total = __shfl_sync(SYN_FULL, incl, 31);
@@ -783,7 +807,7 @@ __device__ __forceinline__ void tile_pass6(const u32 *s_mask, const unsigned sho
                 const u32 nyo = __popc(osy_o);
                 const bool isy = idx < nyo;
                 if (!isy) idx -= nyo;
-                const u32 b = select_bit(isy ? osy_o : osx_o, idx);
+                const u32 b = select_bit_small(isy ? osy_o : osx_o, idx);
                 const u32 iB = i_o - (isy ? wz : segw);
                 const u32 ga = (u32)s_rb[i_o] + __popc(s_st[i_o] & mask_le(b)) - 1u;
                 const u32 gb = (u32)s_rb[iB] + __popc(s_st[iB] & mask_le(b)) - 1u;
@@ -792,9 +816,6 @@ __device__ __forceinline__ void tile_pass6(const u32 *s_mask, const unsigned sho
         }
     }
 }
-
-constexpr int TILE_THREADS = 512;   // 3 CTAs/SM by shared memory -> 48 warps/SM
-constexpr int TILE_WPT = TILE_WORDS / TILE_THREADS;   // mask words per thread (consecutive)
 
 // Local run ids come from a block-wide scan of the tile's own run starts (no per-word read of the global
 // prefix); only the global id of the first run of each x-slab segment is fetched (<= 16 values per tile).
@@ -808,20 +829,16 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     u32 *s_mask = reinterpret_cast<u32 *>(s_raw);                 // [TILE_WORDS]
     u32 *s_st = s_mask + TILE_WORDS;                              // run-start bits of the non-empty words
     u32 *s_act = s_st + TILE_WORDS;                               // packed coordinates of the non-empty words
-    u32 *s_par = s_act + TILE_WORDS;                              // [TILE_RUNS]
-    u32 *s_slot = s_par + TILE_RUNS;                              // [TILE_ROOTS][TILE_SLOT] statistics
-    unsigned short *s_rb = reinterpret_cast<unsigned short *>(s_slot + TILE_ROOTS * TILE_SLOT);   // LOCAL run-id prefix
-    unsigned short *s_rootidx = s_rb + TILE_WORDS;                // [TILE_RUNS] compact index of a local root
-    unsigned short *s_rootrun = s_rootidx + TILE_RUNS;            // [TILE_ROOTS] local run id of root #idx
+    u32 *s_par = s_act + TILE_WORDS;                              // [TILE_RUNS] parent | root index << 16
+    u32 *s_aux = s_par + TILE_RUNS;
+    u32 *s_slot = s_aux;                                          // [TILE_ROOTS][TILE_SLOT] statistics
+    u32 *s_rootgid = reinterpret_cast<u32 *>(reinterpret_cast<unsigned char *>(s_aux) + TILE_AUX);   // [TILE_ROOTS]
+    unsigned short *s_rb = reinterpret_cast<unsigned short *>(s_rootgid + TILE_ROOTS);            // LOCAL run-id prefix
     __shared__ u32 sm[33];
     __shared__ u32 s_nroots, s_recbase;
     __shared__ u32 s_segoff[TILE_MAXTX + 1];       // local id of the first run of x-slab segment xl
     __shared__ u32 s_delta[TILE_MAXTX];            // global id = local id + delta[xl]
-    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
-    if ((u64)cnt->v[SYN_CNT_RUNS] > (u64)max_runs) {      // parent array too small: nothing may be written
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr((u64 *)&cnt->v[SYN_CNT_ERRFLAGS], (u64)SYN_EF_RUNS);
-        return;
-    }
+    SYN_TIMER_INIT();
     const u32 tile = blockIdx.x;
     const u32 tX = tile / tg.tiles_y, tY = tile - tX * tg.tiles_y;
     const u32 x0 = tX * tg.tx, y0 = tY * tg.ty;
@@ -829,14 +846,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     const u32 segw = vy * g.wz;                // words per x-slab segment (contiguous in memory)
     const u32 ntw = vx * segw;                 // words of this tile (<= TILE_WORDS)
 
-    // global id of the first run of every segment: latency overlaps the mask loads below
-    u32 segbase = 0;
-    if (threadIdx.x < vx) {
-        const u32 row = (x0 + threadIdx.x) * (u32)g.ny + y0;
-        segbase = R.at(row * g.wz, row, 0);
-    }
-    if (threadIdx.x == 0) s_nroots = 0;
-    // ---- load: thread t owns words 4t .. 4t+3 of the tile (segment-major order) ----
+    // ---- load: thread t owns words 4t .. 4t+3 of the tile (segment-major order); all global loads of the
+    // prologue are issued before anything waits on them ----
     const u32 i0 = threadIdx.x * TILE_WPT;
     u32 m[TILE_WPT];
     u32 xl0 = 0, jj0 = 0;                      // segment / offset in segment of word i0
@@ -856,50 +867,66 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
             }
         }
     }
+    // global id of the first run of every segment
+    u32 segbase = 0;
+    if (threadIdx.x < vx) {
+        const u32 row = (x0 + threadIdx.x) * (u32)g.ny + y0;
+        segbase = R.at(row * g.wz, row, 0);
+    }
+    const u64 errflags = (u64)cnt->v[SYN_CNT_ERRFLAGS];
+    const u64 nruns_all = (u64)cnt->v[SYN_CNT_RUNS];
+    if (threadIdx.x == 0) s_nroots = 0;
     *reinterpret_cast<uint4 *>(s_mask + i0) = make_uint4(m[0], m[1], m[2], m[3]);
+    if (errflags & SYN_EF_RUNS) return;
+    if (nruns_all > (u64)max_runs) {             // parent array too small: nothing may be written
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr((u64 *)&cnt->v[SYN_CNT_ERRFLAGS], (u64)SYN_EF_RUNS);
+        return;
+    }
     __syncthreads();
+    SYN_TIMER_MARK(cnt, 0);   // load
     // ---- run starts (carry from shared memory), local run ids by a block scan ----
-    u32 st[TILE_WPT], pk[TILE_WPT];            // pk: packed (i | k << 11 | yl << 21 | xl << 27)
+    u32 st[TILE_WPT];                          // run-start bits per word
+    u32 yl0 = 0, k0 = 0;
+    if (i0 < ntw) {
+        if (g.wzs < 32) { yl0 = jj0 >> g.wzs; k0 = jj0 & (g.wz - 1u); }
+        else { yl0 = jj0 / g.wz; k0 = jj0 - yl0 * g.wz; }
+    }
     u32 v = 0;
     {
-        u32 xl = xl0, jj = jj0;
+        u32 k = k0;
 #pragma unroll
         for (int q = 0; q < TILE_WPT; ++q) {
             st[q] = 0;
-            pk[q] = 0;
-            if (i0 + q < ntw) {
-                u32 yl, k;
-                if (g.wzs < 32) { yl = jj >> g.wzs; k = jj & (g.wz - 1u); }
-                else { yl = jj / g.wz; k = jj - yl * g.wz; }
-                if (m[q]) {
-                    const u32 carry = k ? (s_mask[i0 + q - 1] >> 31) : 0u;
-                    st[q] = run_starts(m[q], carry);
-                    v += __popc(st[q]) + (1u << 16);
-                }
-                pk[q] = (i0 + q) | (k << 11) | (yl << 21) | (xl << 27);
-                if (++jj == segw) { jj = 0; ++xl; }
+            if (i0 + q < ntw && m[q]) {
+                st[q] = run_starts(m[q], k ? (s_mask[i0 + q - 1] >> 31) : 0u);
+                v += __popc(st[q]) + (1u << 16);
             }
+            if (++k == g.wz) k = 0;
         }
     }
     u32 total;
     const u32 ex = block_excl_scan(v, sm, &total);
     const u32 nloc = total & 0xFFFFu, nact = total >> 16;
+    SYN_TIMER_MARK(cnt, 1);   // run starts + scan
     if (nloc == 0) return;                     // no foreground in this tile (block-uniform)
     const bool dense = nloc > TILE_RUNS;       // too dense for the shared-memory pass: K3 / k_stats do the whole tile
     {
         u32 rb = ex & 0xFFFFu, ab = ex >> 16;
+        u32 jj = jj0, xl = xl0, yl = yl0, k = k0;
 #pragma unroll
         for (int q = 0; q < TILE_WPT; ++q) {
             if (i0 + q < ntw) {
-                if (((pk[q] >> 11) & 0xFFFFu) == 0) s_segoff[pk[q] >> 27] = rb;   // k == 0 && yl == 0: segment start
+                if (jj == 0) s_segoff[xl] = rb;            // segment start
                 if (!dense) {
                     s_rb[i0 + q] = (unsigned short)rb;
                     if (m[q]) {
                         s_st[i0 + q] = st[q];
-                        s_act[ab++] = pk[q];
+                        s_act[ab++] = (i0 + q) | (k << 11) | (yl << 21) | (xl << 27);
                     }
                 }
                 rb += __popc(st[q]);
+                if (++k == g.wz) { k = 0; ++yl; }
+                if (++jj == segw) { jj = 0; yl = 0; ++xl; }
             }
         }
     }
@@ -912,12 +939,20 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
         __syncthreads();
         // identity parents for the tile's runs (the global pass joins them), then leave
         u32 rb = ex & 0xFFFFu;
+        u32 jj = jj0, xl = xl0;
 #pragma unroll
         for (int q = 0; q < TILE_WPT; ++q) {
-            const u32 d = s_delta[pk[q] >> 27];
-            for (u32 r = 0; r < (u32)__popc(st[q]); ++r) par[rb + r + d] = rb + r + d;
-            rb += __popc(st[q]);
+            if (i0 + q < ntw) {
+                const u32 d = s_delta[xl];
+                const u32 n = __popc(st[q]);
+                for (u32 r = 0; r < n; ++r) par[rb + r + d] = rb + r + d;
+                rb += n;
+                if (++jj == segw) { jj = 0; ++xl; }
+            }
         }
+    }
+    SYN_TIMER_MARK(cnt, 2);   // local tables
+    if (dense) {
         if (threadIdx.x == 0) {
             tileflag[tile] = 1;
             atomicAdd((u64 *)&cnt->v[SYN_CNT_FLAGGED_TILES], 1ull);
@@ -946,10 +981,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
         }
     }
     __syncthreads();
-    // flatten; write parent[global run] = global id of the local root; give every local root a compact index
+    SYN_TIMER_MARK(cnt, 3);   // unions
+    // flatten; write parent[global run] = global id of the local root
     for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) {
-        u32 r = sm_find_ro(s_par, i);          // read-only walk: a halving store could undo a neighbour's flatten
-        s_par[i] = r;
+        const u32 r = sm_find_ro(s_par, i);    // read-only walk; a concurrent walk through i meets the old
+        s_par[i] = r;                          // ancestor or the root: both fine
         // x-slab segment of a local run id: last xl with segoff[xl] <= id (vx <= 16: 4 steps)
         u32 xi = 0, xr = 0;
 #pragma unroll
@@ -958,13 +994,34 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
             if (xr + s2 < vx && s_segoff[xr + s2] <= r) xr += s2;
         }
         par[i + s_delta[xi]] = r + s_delta[xr];
-        if (r == i) {
-            const u32 idx = atomicAdd(&s_nroots, 1u);
-            s_rootidx[i] = (unsigned short)idx;
-            if (idx < TILE_ROOTS) s_rootrun[idx] = (unsigned short)i;
+    }
+    __syncthreads();
+    // every parent is a root now: give every local root a compact index (one shared atomic per warp), remember
+    // its global id, and put the index into the high half of the root's own word (nobody walks any more)
+    for (u32 i0r = 0; i0r < nloc; i0r += blockDim.x) {
+        const u32 i = i0r + threadIdx.x;
+        const bool isroot = i < nloc && s_par[i] == i;
+        const u32 bal = __ballot_sync(SYN_FULL, isroot);
+        if (bal) {
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(bal) - 1;
+            u32 basei = 0;
+            if (lane == leader) basei = atomicAdd(&s_nroots, (u32)__popc(bal));
+            basei = __shfl_sync(SYN_FULL, basei, leader) + __popc(bal & mask_lt((u32)lane));
+            if (isroot) {
+                if (basei < TILE_ROOTS) {
+                    u32 xr = 0;
+#pragma unroll
+                    for (u32 s2 = 8; s2; s2 >>= 1)
+                        if (xr + s2 < vx && s_segoff[xr + s2] <= i) xr += s2;
+                    s_rootgid[basei] = i + s_delta[xr];
+                }
+                s_par[i] = i | (basei << 16);
+            }
         }
     }
     __syncthreads();
+    SYN_TIMER_MARK(cnt, 4);   // flatten
     // ---- statistics of the tile-local components in shared memory (one record per local root afterwards) ----
     const u32 nroots = s_nroots;
     if (nroots > TILE_ROOTS) {                 // statistics of this tile are left to k_stats
@@ -980,6 +1037,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     }
     if (threadIdx.x == 0) s_recbase = (u32)atomicAdd((u64 *)&cnt->v[SYN_CNT_TILE_RECORDS], (u64)nroots);
     __syncthreads();
+    SYN_TIMER_MARK(cnt, 5);   // slot init
     const bool same_mask = (omask == mask);
     for (u32 a = threadIdx.x; a < nact; a += blockDim.x) {
         const u32 e = s_act[a];
@@ -999,7 +1057,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
             const u32 bits = om & pm;
             if (!bits) continue;
             const u32 li = rb + __popc(starts & mask_le((u32)b0)) - 1u;
-            u32 *sl = s_slot + (u32)s_rootidx[s_par[li]] * TILE_SLOT;
+            const u32 root = s_par[li] & 0xFFFFu;
+            u32 *sl = s_slot + (s_par[root] >> 16) * TILE_SLOT;
             const u32 n = __popc(bits);
             atomicAdd(sl + 0, n);
             atomicAdd(sl + 1, n * xl);
@@ -1014,15 +1073,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
         }
     }
     __syncthreads();
+    SYN_TIMER_MARK(cnt, 6);   // statistics
     for (u32 idx = threadIdx.x; idx < nroots; idx += blockDim.x) {
         const u32 *sl = s_slot + idx * TILE_SLOT;
-        const u32 r = s_rootrun[idx];
-        u32 xr = 0;
-#pragma unroll
-        for (u32 s2 = 8; s2; s2 >>= 1)
-            if (xr + s2 < vx && s_segoff[xr + s2] <= r) xr += s2;
         TileRec rec;
-        rec.root = r + s_delta[xr];
+        rec.root = s_rootgid[idx];
         rec.size = sl[0];
         rec.sx = (u64)sl[1] + (u64)sl[0] * x0;
         rec.sy = (u64)sl[2] + (u64)sl[0] * y0;
@@ -1032,6 +1087,10 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
         rec.pad[0] = rec.pad[1] = 0;
         recs[s_recbase + idx] = rec;           // a local root with no ORIGINAL voxel (dilation) has size 0: harmless
     }
+    SYN_TIMER_MARK(cnt, 7);   // records
+#ifdef SYN_PHASE_TIMING
+    if (threadIdx.x == 0) atomicAdd((u64 *)&cnt->v[SYN_CNT_DBG0 + 8], 1ull);
+#endif
 }
 
 // ===========================================================================
@@ -1041,9 +1100,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
 // ===========================================================================
 __global__ void __launch_bounds__(256) k_union_bnd(const u32 *__restrict__ mask, RunIdx R,
                                                    u32 *par, Geom g, TileGeom tg, const u32 *__restrict__ bndw,
+                                                   const u32 *__restrict__ tileflag, const u32 *__restrict__ actw,
                                                    const Counts *cnt)
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    // tiles the shared-memory pass had to leave (too many runs; normally none): every row pair inside them
+    union_rows_body<6, true>(mask, R, par, g, tg, tileflag, actw, cnt);
     const u32 nb = (u32)cnt->v[SYN_CNT_BND_WORDS];
     const int lane = threadIdx.x & 31;
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1102,29 +1164,6 @@ __global__ void __launch_bounds__(256) k_union_bnd(const u32 *__restrict__ mask,
                 uf_union(par, ga, gb);
             }
         }
-    }
-}
-
-// merges the tile records into the per-component statistics (after the canonical ranks are known)
-__global__ void __launch_bounds__(256) k_stats_merge(const TileRec *__restrict__ recs, const u32 *__restrict__ par,
-                                                     const u32 *__restrict__ rank, CompStat *stat, const Counts *cnt)
-{
-    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
-    const u64 n = (u64)cnt->v[SYN_CNT_TILE_RECORDS];
-    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        const TileRec r = recs[i];
-        if (r.size == 0) continue;
-        CompStat *s = stat + rank[par[r.root]];
-        atomicAdd(&s->size, (u64)r.size);
-        atomicAdd(&s->sx, r.sx);
-        atomicAdd(&s->sy, r.sy);
-        atomicAdd(&s->sz, r.sz);
-        if (r.minx < ldcg_u32(&s->minx)) atomicMin(&s->minx, r.minx);
-        if (r.miny < ldcg_u32(&s->miny)) atomicMin(&s->miny, r.miny);
-        if (r.minz < ldcg_u32(&s->minz)) atomicMin(&s->minz, r.minz);
-        if (r.maxx > ldcg_u32(&s->maxx)) atomicMax(&s->maxx, r.maxx);
-        if (r.maxy > ldcg_u32(&s->maxy)) atomicMax(&s->maxy, r.maxy);
-        if (r.maxz > ldcg_u32(&s->maxz)) atomicMax(&s->maxz, r.maxz);
     }
 }
 
@@ -1196,13 +1235,12 @@ struct RankDst {
 // dilated mask but only voxels of the original mask are counted
 // (conncomps.py:49-50 `ccs[mask == 0] = 0`).
 // ===========================================================================
-__global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
-                                               RunIdx R, const u32 *__restrict__ par,
-                                               const u32 *__restrict__ rank, CompStat *stat, Geom g, TileGeom tg,
-                                               const u32 *__restrict__ tileflag,
-                                               const u32 *__restrict__ actw, const Counts *cnt)
+__device__ __forceinline__ void stats_body(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
+                                           const RunIdx &R, const u32 *__restrict__ par,
+                                           const u32 *__restrict__ rank, CompStat *stat, const Geom &g,
+                                           const TileGeom &tg, const u32 *__restrict__ tileflag,
+                                           const u32 *__restrict__ actw, const Counts *cnt)
 {
-    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
     // with tiling, the tile pass already produced the statistics of every tile it did not flag
     if (tg.tx && cnt->v[SYN_CNT_FLAGGED_TILES] == 0) return;
     const u32 nact = (u32)cnt->v[SYN_CNT_ACTIVE_WORDS];
@@ -1248,6 +1286,34 @@ __global__ void __launch_bounds__(256) k_stats(const u32 *__restrict__ lmask, co
             if (zhi > ldcg_u32(&s->maxz)) atomicMax(&s->maxz, zhi);
         }
     }
+}
+
+// Merges the tile records into the per-component statistics (after the canonical ranks are known); tiles whose
+// statistics the shared-memory pass could not hold (flagged, normally none) are accumulated per piece.
+__global__ void __launch_bounds__(256) k_stats_merge(const TileRec *__restrict__ recs, const u32 *__restrict__ par,
+                                                     const u32 *__restrict__ rank, CompStat *stat,
+                                                     const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
+                                                     RunIdx R, Geom g, TileGeom tg, const u32 *__restrict__ tileflag,
+                                                     const u32 *__restrict__ actw, const Counts *cnt)
+{
+    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    const u64 n = (u64)cnt->v[SYN_CNT_TILE_RECORDS];
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const TileRec r = recs[i];
+        if (r.size == 0) continue;
+        CompStat *s = stat + rank[par[r.root]];
+        atomicAdd(&s->size, (u64)r.size);
+        atomicAdd(&s->sx, r.sx);
+        atomicAdd(&s->sy, r.sy);
+        atomicAdd(&s->sz, r.sz);
+        if (r.minx < ldcg_u32(&s->minx)) atomicMin(&s->minx, r.minx);
+        if (r.miny < ldcg_u32(&s->miny)) atomicMin(&s->miny, r.miny);
+        if (r.minz < ldcg_u32(&s->minz)) atomicMin(&s->minz, r.minz);
+        if (r.maxx > ldcg_u32(&s->maxx)) atomicMax(&s->maxx, r.maxx);
+        if (r.maxy > ldcg_u32(&s->maxy)) atomicMax(&s->maxy, r.maxy);
+        if (r.maxz > ldcg_u32(&s->maxz)) atomicMax(&s->maxz, r.maxz);
+    }
+    stats_body(lmask, omask, R, par, rank, stat, g, tg, tileflag, actw, cnt);
 }
 
 // ===========================================================================

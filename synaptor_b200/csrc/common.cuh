@@ -91,6 +91,23 @@ struct Counts {
     i64 v[SYN_NCOUNTS];
 };
 
+// phase timers of instrumented builds (make TIMING=1): thread 0 of a CTA adds the cycles since the previous
+// mark to counts[SYN_CNT_DBG0 + slot]
+#ifdef SYN_PHASE_TIMING
+#define SYN_TIMER_INIT() long long syn_t0__ = clock64()
+#define SYN_TIMER_MARK(cnt, slot)                                                              \
+    do {                                                                                       \
+        if (threadIdx.x == 0) {                                                                \
+            const long long t__ = clock64();                                                   \
+            atomicAdd((u64 *)&(cnt)->v[SYN_CNT_DBG0 + (slot)], (u64)(t__ - syn_t0__));         \
+            syn_t0__ = t__;                                                                    \
+        }                                                                                      \
+    } while (0)
+#else
+#define SYN_TIMER_INIT() do { } while (0)
+#define SYN_TIMER_MARK(cnt, slot) do { } while (0)
+#endif
+
 __host__ __device__ __forceinline__ u32 div_up_u32(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
 
 // bits 0..b inclusive

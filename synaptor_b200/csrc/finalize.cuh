@@ -7,7 +7,7 @@
 //   k_overlap_scan : the same histogram for an arbitrary uint32 label volume
 //                    (seg_utils.count_overlaps as a standalone call).
 //   ordering       : Counter insertion order (overlap.py:47) == ascending first-occurrence
-//                    voxel index; recovered with a bitmap + popcount scan.
+//                    voxel index; recovered with a bucket sort on the first positions.
 #pragma once
 #include "ccl.cuh"
 
@@ -21,12 +21,22 @@ struct PairTable {
     Counts *cnt;
 };
 
+// 32-bit mixing of (label, base): cheap (three 32-bit multiplies) and good enough for open addressing
+__device__ __forceinline__ u32 pair_hash(u32 label, u64 base)
+{
+    u32 h = label * 0x9E3779B1u ^ (u32)base * 0x85EBCA77u ^ (u32)(base >> 32) * 0xC2B2AE3Du;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h;
+}
+
 // Adds `n` occurrences of (label, base) first seen at padded position `pos`.
 __device__ __forceinline__ void pair_insert(const PairTable &T, u32 label, u64 base, u32 n, u64 pos)
 {
     const PairKey want{base, (u64)label};
     const PairKey empty{~0ull, ~0ull};
-    u32 h = (u32)mix64(label, base) & T.capmask;
+    u32 h = pair_hash(label, base) & T.capmask;
     for (u32 probe = 0; probe <= T.capmask; ++probe) {
         // Keys are write-once (empty -> key).  A plain 16 B read can only be stale or torn
         // while the slot is being claimed, and then at least one half still reads all-ones:
@@ -44,8 +54,7 @@ __device__ __forceinline__ void pair_insert(const PairTable &T, u32 label, u64 b
         }
         if (hit) {
             atomicAdd(T.count + h, (u64)n);
-            // `first` only ever decreases: a (possibly stale) read that is already below pos makes the atomic useless
-            if (pos < __ldcg(T.first + h)) atomicMin(T.first + h, pos);
+            atomicMin(T.first + h, pos);
             return;
         }
         h = (h + 1) & T.capmask;
@@ -208,64 +217,102 @@ __global__ void __launch_bounds__(256) k_write_labels(const u32 *__restrict__ lm
 // foreground, whole (kept labels or 0), one lane per sector, and feeds the (label, base)
 // pair histogram.  The two kernels write disjoint sectors.
 // ===========================================================================
-// Foreground sectors.  A warp takes 32 active mask words, prefix-sums their non-empty bytes and then walks the
-// batch's sectors 32 at a time, ONE LANE PER SECTOR: owner word by a shuffle binary search over the prefix,
-// byte by find-nth-set.  A sector holds at most 4 pieces of runs: their labels are fetched together, the (at
-// most 8) base ids of the foreground voxels too, then the whole 32-byte sector is stored.
+// Foreground sectors.  A warp takes a batch of SL_BATCH = 128 active mask words (4 per lane, all loads of the batch in flight together),
+// stages the per-word data in its slice of shared memory and writes one entry per non-empty byte into a SECTOR
+// LIST; the lanes then walk the list 32 sectors at a time, ONE LANE PER SECTOR, with no search.  A sector holds
+// at most 4 pieces of runs: their labels are fetched together, the (at most 8) base ids of the foreground voxels
+// too, then the whole 32-byte sector is stored and the (label, base) groups go to the pair table.
+constexpr int SL_WPL = 4;                   // words per lane per batch
+constexpr int SL_BATCH = 32 * SL_WPL;
+constexpr int SL_WARPS = 8;
+
+struct SlWarp {                             // per-warp staging area
+    u32 w[SL_BATCH], om[SL_BATCH], m[SL_BATCH], st[SL_BATCH], rb[SL_BATCH];
+    unsigned short list[SL_BATCH * 4];      // slot | byte << 7
+};
+
+static_assert(sizeof(SlWarp) % 16 == 0, "staging area alignment");
+
 template <bool HAS_BASE>
-__global__ void __launch_bounds__(256) k_sector_labels(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
-                                                       RunIdx R,
-                                                       const u32 *__restrict__ runlabel, u32 *__restrict__ labels,
-                                                       const u64 *__restrict__ base, Geom g, PairTable T,
-                                                       const u32 *__restrict__ actw, const Counts *cnt)
+__global__ void __launch_bounds__(32 * SL_WARPS) k_sector_labels(const u32 *__restrict__ lmask,
+                                                                const u32 *__restrict__ omask, RunIdx R,
+                                                                const u32 *__restrict__ runlabel,
+                                                                u32 *__restrict__ labels, const u64 *__restrict__ base,
+                                                                Geom g, PairTable T, const u32 *__restrict__ actw,
+                                                                const Counts *cnt)
 {
+    __shared__ SlWarp s_warp[SL_WARPS];
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
     const u32 nact = (u32)cnt->v[SYN_CNT_ACTIVE_WORDS];
     const int lane = threadIdx.x & 31;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (u32 i0 = warp * 32; i0 < nact; i0 += nwarps * 32) {
-        const u32 i = i0 + lane;
-        u32 w = 0, om = 0, m = 0, starts = 0, rb = 0;
-        i64 vox0 = 0;
-        if (i < nact) {
-            w = actw[i];
-            om = omask[w];
-            m = lmask[w];
-            u32 row, kw;
-            split_word(g, w, row, kw);
-            const u32 carry = kw ? (lmask[w - 1] >> 31) : 0u;
-            starts = run_starts(m, carry);
-            rb = R.at(w, row, kw);
-            vox0 = (i64)row * g.nz + (i64)kw * 32;
+    const u32 wib = threadIdx.x >> 5;
+    SlWarp &S = s_warp[wib];
+    const u32 nbatch = (nact + SL_BATCH - 1) / SL_BATCH;
+    for (u32 bi = blockIdx.x * SL_WARPS + wib; bi < nbatch; bi += gridDim.x * SL_WARPS) {
+        // ---- stage the batch: slot = q * 32 + lane <-> active word bi * 128 + slot ----
+        u32 w[SL_WPL], om[SL_WPL], m[SL_WPL], pv[SL_WPL], rbv[SL_WPL];
+        bool ok[SL_WPL];
+#pragma unroll
+        for (int q = 0; q < SL_WPL; ++q) {
+            const u32 i = bi * SL_BATCH + q * 32 + lane;
+            ok[q] = i < nact;
+            w[q] = ok[q] ? actw[i] : 0u;
         }
-        const u32 f = (u32)((om & 0xFFu) != 0) | ((u32)((om & 0xFF00u) != 0) << 1) |
-                      ((u32)((om & 0xFF0000u) != 0) << 2) | ((u32)((om & 0xFF000000u) != 0) << 3);
-        const u32 n = __popc(f);
-        const u32 incl = warp_incl_scan(n, lane);
-        const u32 excl = incl - n;
-        const u32 total = __shfl_sync(SYN_FULL, incl, 31);
+#pragma unroll
+        for (int q = 0; q < SL_WPL; ++q) {
+            om[q] = m[q] = pv[q] = rbv[q] = 0;
+            if (ok[q]) {
+                u32 row, kw;
+                split_word(g, w[q], row, kw);
+                om[q] = omask[w[q]];
+                m[q] = lmask[w[q]];
+                pv[q] = kw ? lmask[w[q] - 1] : 0u;
+                rbv[q] = R.at(w[q], row, kw);
+            }
+        }
+        u32 packed = 0;     // non-empty bytes per slot, 8 bits each (a warp total is <= 128)
+        u32 f[SL_WPL];
+#pragma unroll
+        for (int q = 0; q < SL_WPL; ++q) {
+            f[q] = (u32)((om[q] & 0xFFu) != 0) | ((u32)((om[q] & 0xFF00u) != 0) << 1) |
+                   ((u32)((om[q] & 0xFF0000u) != 0) << 2) | ((u32)((om[q] & 0xFF000000u) != 0) << 3);
+            packed |= (u32)__popc(f[q]) << (8 * q);
+        }
+        const u32 incl = warp_incl_scan(packed, lane);
+        const u32 tot = __shfl_sync(SYN_FULL, incl, 31);
+        const u32 excl = incl - packed;
+        u32 total = 0;
+#pragma unroll
+        for (int q = 0; q < SL_WPL; ++q) {
+            const u32 slot = q * 32 + lane;
+            S.w[slot] = w[q];
+            S.om[slot] = om[q];
+            S.m[slot] = m[q];
+            S.st[slot] = run_starts(m[q], pv[q] >> 31);
+            S.rb[slot] = rbv[q];
+            u32 pos = total + ((excl >> (8 * q)) & 0xFFu);
+            u32 rest = f[q];
+            while (rest) {
+                const u32 t = (u32)__ffs(rest) - 1u;
+                rest &= rest - 1;
+                S.list[pos++] = (unsigned short)(slot | (t << 7));
+            }
+            total += (tot >> (8 * q)) & 0xFFu;
+        }
+        __syncwarp();
+        // ---- one lane per sector ----
         for (u32 r0 = 0; r0 < total; r0 += 32) {
             const u32 j = r0 + lane;
-            int o = 0;   // owner = last lane whose exclusive prefix is <= j
-#pragma unroll
-            for (int s = 16; s; s >>= 1) {
-                const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
-                if (e <= j) o += s;
-            }
-            const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
-            const u32 f_o = __shfl_sync(SYN_FULL, f, o);
-            const u32 om_o = __shfl_sync(SYN_FULL, om, o);
-            const u32 m_o = __shfl_sync(SYN_FULL, m, o);
-            const u32 st_o = __shfl_sync(SYN_FULL, starts, o);
-            const u32 rb_o = __shfl_sync(SYN_FULL, rb, o);
-            const u32 w_o = __shfl_sync(SYN_FULL, w, o);
-            const i64 v_o = __shfl_sync(SYN_FULL, vox0, o);
             if (j >= total) continue;
-            const u32 q8 = 8u * select_bit(f_o, j - e_o);      // first bit of the sector inside the word
+            const u32 e = S.list[j];
+            const u32 slot = e & 127u;
+            const u32 q8 = 8u * (e >> 7);                      // first bit of the sector inside the word
+            const u32 w_o = S.w[slot], om_o = S.om[slot], m_o = S.m[slot], st_o = S.st[slot], rb_o = S.rb[slot];
+            u32 row, kw;
+            split_word(g, w_o, row, kw);
+            const i64 vox = (i64)row * g.nz + (i64)kw * 32 + q8;
             const u32 ob = (om_o >> q8) & 0xFFu;               // voxels that receive a label
             const u32 mb = (m_o >> q8) & 0xFFu;                // labelled mask (differs from ob only with dilation)
-            const i64 vox = v_o + q8;
             // base ids of the foreground voxels: up to four 16-byte loads, issued before the label lookups
             ulonglong2 bq[4];
             if (HAS_BASE) {
@@ -302,14 +349,22 @@ __global__ void __launch_bounds__(256) k_sector_labels(const u32 *__restrict__ l
             lp[1] = make_uint4(lab[4], lab[5], lab[6], lab[7]);
             if (HAS_BASE) {
                 const u64 bv[8] = {bq[0].x, bq[0].y, bq[1].x, bq[1].y, bq[2].x, bq[2].y, bq[3].x, bq[3].y};
-                PairAcc acc;
                 const u64 pos0 = (u64)w_o * 32 + q8;
+                // groups of voxels with the same (label, base) -> pair cache
+                u32 gl = 0, gn = 0;
+                u64 gb = 0, gp = 0;
 #pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (lab[t] && bv[t]) acc.add(T, lab[t], bv[t], pos0 + t);
-                acc.flush(T);
+                for (int t = 0; t < 8; ++t) {
+                    if (lab[t] && bv[t]) {
+                        if (gn && lab[t] == gl && bv[t] == gb) { ++gn; continue; }
+                        if (gn) pair_insert(T, gl, gb, gn, gp);
+                        gl = lab[t]; gb = bv[t]; gn = 1; gp = pos0 + t;
+                    }
+                }
+                if (gn) pair_insert(T, gl, gb, gn, gp);
             }
         }
+        __syncwarp();   // the staging area is rewritten by the next batch
     }
 }
 
@@ -364,55 +419,69 @@ __global__ void __launch_bounds__(256) k_overlap_scan(const u32 *__restrict__ se
 }
 
 // ---------------------------------------------------------------------------
-// ordering of the table entries by first occurrence
+// Ordering of the table entries by first occurrence (Counter insertion order, overlap.py:47 == ascending
+// first position).  Bucket sort on the position: bucket = position >> PB_SHIFT (4096 voxel positions, so a
+// bucket holds a handful of pairs at most), counts -> exclusive scan -> scatter into bucket order -> the rank
+// inside a bucket by counting the smaller positions of the same bucket.  Four tiny kernels over the table
+// (a few 100 k slots) instead of a bitmap + popcount scan over every voxel position.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pair_mark(PairTable T, u32 *__restrict__ bitmap)
+constexpr int PB_SHIFT = 12;
+
+__global__ void __launch_bounds__(256) k_pair_count(PairTable T, u32 *__restrict__ bcount)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.capmask; i += gridDim.x * blockDim.x) {
-        u64 f = T.first[i];
-        if (f != ~0ull) atomicOr(bitmap + (f >> 5), 1u << (f & 31));
+        const u64 f = T.first[i];
+        if (f != ~0ull) atomicAdd(bcount + (f >> PB_SHIFT), 1u);
     }
 }
 
-struct PopcSrc {
-    const u32 *bitmap;
-    u32 nwords;
-    __device__ __forceinline__ u64 n() const { return nwords; }
+// bucket counts -> bucket bases: generic single-pass scan (k_scan_1p), in place
+struct U32Src {
+    const u32 *a;
+    u32 len;
+    __device__ __forceinline__ u64 n() const { return len; }
     template <int N>
-    __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
-    {
-        u32 m[N];
-        load_items_u32(bitmap, i0, n, m);
-#pragma unroll
-        for (int t = 0; t < N; ++t) item[t] = __popc(m[t]);
-    }
+    __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const { load_items_u32(a, i0, n, item); }
 };
-struct WordBaseDst {
-    u32 *wordbase;
+struct U32PrefixDst {
+    u32 *a;
     template <int N>
     __device__ __forceinline__ void store(u64 i0, u64 n, u32 ex, const u32 (&item)[N]) const
     {
-        store_prefix_u32(wordbase, i0, n, ex, item);
+        store_prefix_u32(a, i0, n, ex, item);
     }
 };
 
-__global__ void __launch_bounds__(256) k_pair_emit(PairTable T, const u32 *__restrict__ bitmap,
-                                                   const u32 *__restrict__ wordbase, u32 *__restrict__ rows,
-                                                   u64 *__restrict__ cols, i64 *__restrict__ vals, i64 max_pairs)
+__global__ void __launch_bounds__(256) k_pair_scatter(PairTable T, const u32 *__restrict__ bbase, u32 *__restrict__ bfill,
+                                                      u32 *__restrict__ sorted_slot, i64 max_pairs)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.capmask; i += gridDim.x * blockDim.x) {
-        u64 f = T.first[i];
+        const u64 f = T.first[i];
         if (f == ~0ull) continue;
-        u32 w = (u32)(f >> 5), b = (u32)(f & 31);
-        i64 r = (i64)wordbase[w] + __popc(bitmap[w] & mask_lt(b));
-        if (r >= max_pairs) {
-            atomicOr((u64 *)&T.cnt->v[SYN_CNT_ERRFLAGS], (u64)SYN_EF_PAIRS);
-            continue;
-        }
-        PairKey k = T.keys[i];
+        const u32 b = (u32)(f >> PB_SHIFT);
+        const u32 j = bbase[b] + atomicAdd(bfill + b, 1u);
+        if ((i64)j < max_pairs) sorted_slot[j] = i;
+        else atomicOr((u64 *)&T.cnt->v[SYN_CNT_ERRFLAGS], (u64)SYN_EF_PAIRS);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pair_emit(PairTable T, const u32 *__restrict__ bbase, u32 nb,
+                                                   const u32 *__restrict__ sorted_slot, u32 *__restrict__ rows,
+                                                   u64 *__restrict__ cols, i64 *__restrict__ vals, i64 max_pairs)
+{
+    const u32 np = (u32)T.cnt->v[SYN_CNT_PAIRS];
+    if ((i64)np > max_pairs) return;     // capacity error already flagged by the scatter
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < np; j += gridDim.x * blockDim.x) {
+        const u32 slot = sorted_slot[j];
+        const u64 f = T.first[slot];
+        const u32 b = (u32)(f >> PB_SHIFT);
+        const u32 lo = bbase[b], hi = (b + 1 < nb) ? bbase[b + 1] : np;
+        u32 r = lo;
+        for (u32 t = lo; t < hi; ++t) r += (T.first[sorted_slot[t]] < f);
+        const PairKey k = T.keys[slot];
         rows[r] = (u32)k.label;
         cols[r] = k.base;
-        vals[r] = (i64)T.count[i];
+        vals[r] = (i64)T.count[slot];
     }
 }
 

@@ -147,6 +147,48 @@ def test_random_noise_vs_oracle(syn, shape, conn):
         check_cc_task(syn, pred, 1.0 - p, dust=3, conn=conn, offset=(7, -2, 100))
 
 
+# shapes with nz % 8 == 0 take the streaming / sector path (k_stream, k_sector_labels); (16, 32, 512) holds
+# exactly one 2048-word tile of the shared-memory labelling pass, the larger ones several tiles and tile borders
+SECTOR_SHAPES = [(16, 32, 512), (20, 40, 256), (9, 70, 96), (33, 17, 64), (5, 6, 8), (40, 24, 1032)]
+
+
+@pytest.mark.parametrize("shape", SECTOR_SHAPES)
+@pytest.mark.parametrize("conn", [6, 26])
+def test_sector_path_noise_vs_oracle(syn, shape, conn):
+    """0.5 noise on a full tile gives > 4096 runs per tile (tile left to the global union pass), 0.06 noise gives
+    > 512 tile-local components (statistics left to the global pass): both fallbacks of k_tile_ccl are exercised
+    and reported through the counts."""
+    from synaptor_b200 import _device as D
+    import torch
+    rng = np.random.default_rng(hash((shape, conn, "sector")) % (2 ** 32))
+    flagged = 0
+    for p in (0.02, 0.06, 0.25, 0.5, 0.97):
+        pred = rng.random(shape, dtype=np.float32)
+        check_cc_task(syn, pred, 1.0 - p, dust=2, conn=conn, offset=(3, 5, -7))
+        res = D.chunk_ccs_device(torch.from_numpy(pred).cuda(), np.float32(1.0 - p), 2, connectivity=conn)
+        flagged += res.counts["flagged_tiles"]
+    if shape == (16, 32, 512):
+        assert flagged > 0, "the dense / many-roots fallbacks were never taken"
+
+
+@pytest.mark.parametrize("shape", [(16, 32, 512), (24, 40, 128)])
+def test_sector_path_fused_overlap_noise(syn, shape):
+    rng = np.random.default_rng(99)
+    for p in (0.06, 0.5):
+        pred = rng.random(shape, dtype=np.float32)
+        base = orc.synth_base(shape, seed=3, block=4)
+        want_ccs, _, want_info = orc.cc_task_c(pred, 1.0 - p, 2)
+        r, c, v, shp = orc.count_overlaps_c(want_ccs, base)
+        import torch
+        base_dev = torch.from_numpy(base.view(np.int64)).cuda()       # device-resident base: the fused device pass
+        for b in (base_dev, base):                                    # host base: pipelined two-call path
+            ccs, conts, info, mat = syn.proc.tasks.cc_overlap_task(pred, b, 1.0 - p, 2)
+            assert np.array_equal(ccs, want_ccs), first_diff(ccs, want_ccs)
+            assert np.array_equal(info.to_numpy(), want_info.to_numpy())
+            assert mat.shape == shp and np.array_equal(mat.row, r) and np.array_equal(mat.col, c) \
+                and np.array_equal(mat.data, v)
+
+
 @pytest.mark.parametrize("conn", [6, 26])
 @pytest.mark.parametrize("sigma,fg", [(1.0, 0.1), (2.0, 0.03), (3.0, 0.2)])
 def test_smooth_vs_oracle(syn, conn, sigma, fg):
