@@ -40,8 +40,9 @@ BYTES_PER_VOXEL_PIPELINE = 16   # 4 B pred read + 4 B label write + 8 B base rea
 BYTES_PER_VOXEL_STREAM_KERNEL = 16  # k_stream: 4 B pred read + 8 B base read + 4 B label (zero-fill) write
 CPU_SAMPLE = (256, 256, 256)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_stream launch on the 512^3 workload (ncu --set full,
-# profiles/): filled in from the committed capture
-STREAM_TRAFFIC_512 = None
+# profiles/r01h_top_summary.txt: 1.610975 GB read + 477.26 MB written; the algorithmic 16 B/voxel are 2.147 GB --
+# the foreground sectors are not zero-filled by this kernel)
+STREAM_TRAFFIC_512 = 2088233752
 
 
 def peaks():

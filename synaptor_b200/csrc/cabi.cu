@@ -144,12 +144,15 @@ struct Workspace {
     TileGeom tg;
     u32 *tileflag;
     Counts *cnt;
-    u32 *lmask, *omask, *runbase, *tiles;  // tiles: scan tile sums
+    u32 *lmask, *omask, *runbase;
     u32 *actw;                             // compact list of non-empty mask words
     u32 *bndw;                             // non-empty words on a tile border
     u64 *scanstate;                        // 4 look-back state arrays + tickets, zeroed per call
-    u32 *tileagg, *tilebase;               // run counts / run-id bases of the stream tiles (k_stream, k_tile_prefix)
-    size_t scan_cap, ts_cap, scanstate_bytes;
+    u32 *scan_tickets;
+    size_t scan_off[4];
+    size_t zero_bytes;                     // head of the workspace that every call zeroes
+    u32 *tileagg, *tilebase;               // run counts / run-id bases of the stream tiles (k_stream)
+    size_t ts_cap;
     u32 *par, *rank, *runlabel, *complab;
     CompStat *stat;
     TileRec *recs;
@@ -161,47 +164,53 @@ struct Workspace {
     size_t total;
 };
 
-constexpr int SCAN_MIN_TILE = SCAN_THREADS * 2;   // smallest tile any scan instance uses (look-back state capacity)
-size_t scan_tiles(i64 n) { return (size_t)((n + SCAN_MIN_TILE - 1) / SCAN_MIN_TILE) + 1; }
 
 void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, Workspace *w)
 {
     size_t off = 0;
     auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += al(bytes); return p; };
     const size_t nw = (size_t)g.nwords + 8;
-    i64 biggest = (i64)nw > max_runs ? (i64)nw : max_runs;
+    // ---- everything that must be zero at the start of a call sits at the head of the workspace: one memset ----
     w->cnt = (Counts *)take(sizeof(Counts));
+    // look-back state of the four scan instances (slot 0: mask words, 16 items; 1: runs, 8; 2: components, 2;
+    // 3: pair buckets, 8) + their tickets
+    const u32 nb = max_pairs > 0 ? (u32)((((u64)g.nwords * 32) >> PB_SHIFT) + 1) : 0;
+    const size_t cap[4] = {nw / (SCAN_THREADS * 16) + 2, (size_t)max_runs / (SCAN_THREADS * 8) + 2,
+                           (size_t)max_runs / (SCAN_THREADS * 2) + 2, (size_t)nb / (SCAN_THREADS * 8) + 2};
+    size_t so = 0;
+    for (int i = 0; i < 4; ++i) { w->scan_off[i] = so; so += cap[i]; }
+    w->scanstate = (u64 *)take((so + 8) * 8);
+    w->scan_tickets = w->scanstate ? (u32 *)(w->scanstate + so) : nullptr;
+    w->tg = make_tiles(g);
+    w->tileflag = (u32 *)take(((size_t)w->tg.ntiles + 8) * 4);
+    w->paircap = 0;
+    w->pkeys = nullptr; w->pcount = w->pfirst = nullptr; w->bcount = w->bfill = w->sorted_slot = nullptr;
+    w->nbuckets = nb;
+    if (max_pairs > 0) {
+        w->bcount = (u32 *)take(((size_t)nb + 1) * 4 + (size_t)nb * 4);   // bucket counts + fill cursors
+        w->bfill = w->bcount ? w->bcount + nb + 1 : nullptr;
+    }
+    w->zero_bytes = off;
+    // ---- the rest is fully written before it is read ----
     w->lmask = (u32 *)take(nw * 4);
     w->omask = dilate ? (u32 *)take(nw * 4) : w->lmask;
     w->runbase = (u32 *)take(nw * 4);
     w->actw = (u32 *)take(nw * 4);
     w->bndw = (u32 *)take(nw * 4);
-    w->tiles = (u32 *)take(scan_tiles(biggest) * 4);
-    w->scan_cap = scan_tiles(biggest);
     w->ts_cap = (size_t)g.nchunks / TS_CHUNKS + 2;
-    w->scanstate_bytes = (4 * w->scan_cap + 8) * 8;
-    w->scanstate = (u64 *)take(w->scanstate_bytes);
     w->tileagg = (u32 *)take(w->ts_cap * 4);
     w->tilebase = (u32 *)take(w->ts_cap * 4);
-    w->tg = make_tiles(g);
-    w->tileflag = (u32 *)take(((size_t)w->tg.ntiles + 8) * 4);
     w->par = (u32 *)take((size_t)max_runs * 4);
     w->rank = (u32 *)take((size_t)max_runs * 4);
     w->runlabel = (u32 *)take((size_t)max_runs * 4);
     w->complab = (u32 *)take((size_t)max_runs * 4);
     w->stat = (CompStat *)take((size_t)max_runs * sizeof(CompStat));
     w->recs = (TileRec *)take((size_t)max_runs * sizeof(TileRec));
-    w->paircap = 0;
-    w->pkeys = nullptr; w->pcount = w->pfirst = nullptr; w->bcount = w->bfill = w->sorted_slot = nullptr;
-    w->nbuckets = 0;
     if (max_pairs > 0) {
         w->paircap = pow2_at_least(2 * max_pairs);
         w->pkeys = (PairKey *)take((size_t)w->paircap * sizeof(PairKey));
         w->pcount = (u64 *)take((size_t)w->paircap * 8);
         w->pfirst = (u64 *)take((size_t)w->paircap * 8);
-        w->nbuckets = (u32)((((u64)g.nwords * 32) >> PB_SHIFT) + 1);
-        w->bcount = (u32 *)take(((size_t)w->nbuckets + 1) * 4 + (size_t)w->nbuckets * 4);   // counts + cursors: one memset
-        w->bfill = w->bcount ? w->bcount + w->nbuckets + 1 : nullptr;
         w->sorted_slot = (u32 *)take((size_t)max_pairs * 4);
     }
     w->total = off;
@@ -248,20 +257,13 @@ int grid_for(i64 items, int threads, int per_sm)
 template <int ITEMS, class Src, class Dst>
 int launch_scan(const Workspace &W, int slot, Src src, Dst dst, i64 max_items, i64 *total_out, cudaStream_t st)
 {
-    static_assert(SCAN_THREADS * ITEMS >= SCAN_MIN_TILE, "look-back state capacity");
+    // (the capacity of slot `slot` in carve() assumes exactly this ITEMS)
     const i64 ntiles = (max_items + SCAN_THREADS * ITEMS - 1) / (SCAN_THREADS * ITEMS);
-    u64 *state = W.scanstate + (size_t)slot * W.scan_cap;
-    u32 *ticket = (u32 *)(W.scanstate + 4 * W.scan_cap) + 2 * slot;
+    u64 *state = W.scanstate + W.scan_off[slot];
+    u32 *ticket = W.scan_tickets + 2 * slot;
     k_scan_1p<Src, Dst, ITEMS><<<wave_grid(k_scan_1p<Src, Dst, ITEMS>, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
         src, dst, state, ticket, total_out);
     CK_LAUNCH();
-    return SYN_OK;
-}
-
-// zeroes the bucket counters of the pair ordering (any time before order_and_emit_pairs)
-int pair_order_init(const Workspace &W, cudaStream_t st)
-{
-    CK(cudaMemsetAsync(W.bcount, 0, ((size_t)2 * W.nbuckets + 1) * 4, st));
     return SYN_OK;
 }
 
@@ -386,8 +388,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     const int sms = sm_count();
     (void)sms;
 
-    CK(cudaMemsetAsync(W.cnt, 0, sizeof(Counts), st));
-    CK(cudaMemsetAsync(W.scanstate, 0, W.scanstate_bytes, st));
+    CK(cudaMemsetAsync(workspace, 0, W.zero_bytes, st));     // counters, scan state, tile flags, pair buckets
     g_prof_n = 0;
     PROF("start");
 
@@ -433,8 +434,6 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     if (has_base) {
         k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
         CK_LAUNCH();
-        rc = pair_order_init(W, st);
-        if (rc != SYN_OK) return rc;
         PROF("pair_init");
     }
 
@@ -454,8 +453,6 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         k_init_parents<<<wave_grid(k_init_parents, 256, div_up_u32(max_runs, 256)), 256, 0, st>>>(W.par, W.cnt,
                                                                                               (u32)max_runs);
         CK_LAUNCH();
-    } else {
-        CK(cudaMemsetAsync(W.tileflag, 0, (size_t)W.tg.ntiles * 4, st));
     }
 
     // --- unions ------------------------------------------------------------------------------
@@ -543,15 +540,12 @@ int syn_count_overlaps(const uint32_t *seg1, const uint64_t *seg2, int64_t nx, i
         return fail(SYN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %lld", W.total,
                     (long long)workspace_bytes);
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemsetAsync(W.cnt, 0, sizeof(Counts), st));
-    CK(cudaMemsetAsync(W.scanstate, 0, W.scanstate_bytes, st));
+    CK(cudaMemsetAsync(workspace, 0, W.zero_bytes, st));
     PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap - 1, W.cnt};
     k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
     CK_LAUNCH();
     k_overlap_scan<<<grid_for((i64)g.nwords * 32, 256, 8), 256, 0, st>>>(seg1, (const u64 *)seg2, g, T, W.cnt);
     CK_LAUNCH();
-    rc = pair_order_init(W, st);
-    if (rc != SYN_OK) return rc;
     rc = order_and_emit_pairs(g, W, T, pair_rows, (u64 *)pair_cols, (i64 *)pair_counts, max_pairs, st);
     if (rc != SYN_OK) return rc;
     return finish_counts(W, (i64 *)counts_host, st);
