@@ -402,6 +402,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     static const bool no_fuse = getenv("SYN_NO_FUSED_SCAN") != nullptr;
     const bool fused_scan = sector_out && !dilate && !no_fuse;
     const u64 *bs = (const u64 *)base_seg;
+    PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap ? W.paircap - 1 : 0, W.cnt};
     if (sector_out) {
         const i64 ntiles = ((i64)g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
 #define SYN_STREAM(HB, FS)                                                                                         \
@@ -430,8 +431,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         PROF("dilate");
     }
     const RunIdx R{W.runbase, fused_scan ? W.tilebase : nullptr, g.cpr};
-    PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap ? W.paircap - 1 : 0, W.cnt};
-    if (has_base) {
+    if (has_base) {      // (folding this into the streaming kernel cost it 10 % of its bandwidth: measured, reverted)
         k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
         CK_LAUNCH();
         PROF("pair_init");

@@ -664,10 +664,10 @@ constexpr int TILE_THREADS = 512;
 constexpr int TILE_WPT = TILE_WORDS / TILE_THREADS;   // mask words per thread (consecutive)
 // shared memory of one tile CTA (3 CTAs = 48 warps per SM; the kernel is instruction-issue bound, not
 // occupancy bound): mask words, run-start words, packed active list, parents, statistics slots, global ids of
-// the local roots, local run-id prefix
+// the local roots, local run-id prefix, x-slab of every run
 constexpr size_t TILE_AUX = (size_t)TILE_ROOTS * TILE_SLOT * 4;
 constexpr size_t TILE_SMEM = (size_t)TILE_WORDS * 4 * 3 + (size_t)TILE_RUNS * 4 + TILE_AUX + (size_t)TILE_WORDS * 2 +
-                             (size_t)TILE_ROOTS * 4;
+                             (size_t)TILE_ROOTS * 4 + (size_t)TILE_RUNS;
 
 // Shared parent array: low 16 bits = parent (local run id < TILE_RUNS), high 16 bits = compact index of a root
 // (written after the flatten).  During the unions the high half is zero, so values compare like plain ids.
@@ -834,6 +834,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     u32 *s_slot = s_aux;                                          // [TILE_ROOTS][TILE_SLOT] statistics
     u32 *s_rootgid = reinterpret_cast<u32 *>(reinterpret_cast<unsigned char *>(s_aux) + TILE_AUX);   // [TILE_ROOTS]
     unsigned short *s_rb = reinterpret_cast<unsigned short *>(s_rootgid + TILE_ROOTS);            // LOCAL run-id prefix
+    unsigned char *s_segof = reinterpret_cast<unsigned char *>(s_rb + TILE_WORDS);                // [TILE_RUNS] x-slab of a run
     __shared__ u32 sm[33];
     __shared__ u32 s_nroots, s_recbase;
     __shared__ u32 s_segoff[TILE_MAXTX + 1];       // local id of the first run of x-slab segment xl
@@ -917,14 +918,16 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
         for (int q = 0; q < TILE_WPT; ++q) {
             if (i0 + q < ntw) {
                 if (jj == 0) s_segoff[xl] = rb;            // segment start
+                const u32 n = __popc(st[q]);
                 if (!dense) {
                     s_rb[i0 + q] = (unsigned short)rb;
                     if (m[q]) {
                         s_st[i0 + q] = st[q];
                         s_act[ab++] = (i0 + q) | (k << 11) | (yl << 21) | (xl << 27);
+                        for (u32 r = 0; r < n; ++r) s_segof[rb + r] = (unsigned char)xl;   // no search in the flatten
                     }
                 }
-                rb += __popc(st[q]);
+                rb += n;
                 if (++k == g.wz) { k = 0; ++yl; }
                 if (++jj == segw) { jj = 0; yl = 0; ++xl; }
             }
@@ -986,14 +989,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) {
         const u32 r = sm_find_ro(s_par, i);    // read-only walk; a concurrent walk through i meets the old
         s_par[i] = r;                          // ancestor or the root: both fine
-        // x-slab segment of a local run id: last xl with segoff[xl] <= id (vx <= 16: 4 steps)
-        u32 xi = 0, xr = 0;
-#pragma unroll
-        for (u32 s2 = 8; s2; s2 >>= 1) {
-            if (xi + s2 < vx && s_segoff[xi + s2] <= i) xi += s2;
-            if (xr + s2 < vx && s_segoff[xr + s2] <= r) xr += s2;
-        }
-        par[i + s_delta[xi]] = r + s_delta[xr];
+        par[i + s_delta[s_segof[i]]] = r + s_delta[s_segof[r]];
     }
     __syncthreads();
     // every parent is a root now: give every local root a compact index (one shared atomic per warp), remember
@@ -1009,13 +1005,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
             if (lane == leader) basei = atomicAdd(&s_nroots, (u32)__popc(bal));
             basei = __shfl_sync(SYN_FULL, basei, leader) + __popc(bal & mask_lt((u32)lane));
             if (isroot) {
-                if (basei < TILE_ROOTS) {
-                    u32 xr = 0;
-#pragma unroll
-                    for (u32 s2 = 8; s2; s2 >>= 1)
-                        if (xr + s2 < vx && s_segoff[xr + s2] <= i) xr += s2;
-                    s_rootgid[basei] = i + s_delta[xr];
-                }
+                if (basei < TILE_ROOTS) s_rootgid[basei] = i + s_delta[s_segof[i]];
                 s_par[i] = i | (basei << 16);
             }
         }

@@ -108,6 +108,15 @@ struct Counts {
 #define SYN_TIMER_MARK(cnt, slot) do { } while (0)
 #endif
 
+// open-addressing table of (label, base id) pairs in HBM (finalize.cuh)
+struct PairTable {
+    PairKey *keys;   // [cap] 16-byte keys, all-ones = empty
+    u64 *count;      // [cap]
+    u64 *first;      // [cap] smallest padded bit position (row * wz * 32 + z) of the pair
+    u32 capmask;     // cap - 1 (cap is a power of two)
+    Counts *cnt;
+};
+
 __host__ __device__ __forceinline__ u32 div_up_u32(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
 
 // bits 0..b inclusive

@@ -13,13 +13,6 @@
 
 namespace syn {
 
-struct PairTable {
-    PairKey *keys;   // [cap] 16-byte keys, all-ones = empty
-    u64 *count;      // [cap]
-    u64 *first;      // [cap] smallest padded bit position (row * wz * 32 + z) of the pair
-    u32 capmask;     // cap - 1 (cap is a power of two)
-    Counts *cnt;
-};
 
 // 32-bit mixing of (label, base): cheap (three 32-bit multiplies) and good enough for open addressing
 __device__ __forceinline__ u32 pair_hash(u32 label, u64 base)

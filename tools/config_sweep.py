@@ -36,8 +36,7 @@ def run_case(name, shape, sigma, fg, conn, dil, with_base, iters, torch, D, orc,
     L = C.lib()
     C.check(L.syn_profile_enable(1))
     D.chunk_ccs_device(pred, np.float32(0.5), 100, connectivity=conn, dil_k=dil, base=base, sync=False, out=res)
-    buf = np.zeros(C.PROF_STAGES, dtype=np.float32)
-    L.syn_profile_read(buf.ctypes.data, C.PROF_STAGES)
+    stages = C.profile_read()
     C.check(L.syn_profile_enable(0))
     after = D.read_counts(res)
     nvox = int(np.prod(shape))
@@ -46,7 +45,7 @@ def run_case(name, shape, sigma, fg, conn, dil, with_base, iters, torch, D, orc,
             "overlaps": with_base, "ms": ms, "gvox_s": nvox / ms / 1e6, "gb_s_algorithmic": bpv * nvox / ms / 1e6,
             "runs": counts["runs"], "components": counts["components"], "kept": counts["kept"],
             "pairs": counts["pairs"], "errflags": int(after.get("errflags", 0)), "flagged_tiles": after["flagged_tiles"], "tile_records": after["tile_records"],
-            "stage_ms": {n: float(v) for (n, v) in zip(C.PROF_STAGE_NAMES, buf)}}
+            "stage_us": {n: round(1e3 * float(v), 1) for (n, v) in stages.items()}}
     print(json.dumps(line), flush=True)
     del pred, base, res
     torch.cuda.empty_cache()
@@ -55,7 +54,7 @@ def run_case(name, shape, sigma, fg, conn, dil, with_base, iters, torch, D, orc,
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", default="c1,c1_26,c3,c5_128,c5_256,c5_256_k2,c5_256_k5,c5_512_k5")
+    ap.add_argument("--cases", default="c1,c1_26,c2,c2_ccs_only,c3,c5_128,c5_256,c5_256_k2,c5_256_k5,c5_512_k5,c5_1024")
     ap.add_argument("--iters", type=int, default=5)
     a = ap.parse_args()
     import torch
@@ -66,6 +65,7 @@ def main():
         "c1": ((256, 256, 256), 2.0, 0.03, 6, 0, False),
         "c1_26": ((256, 256, 256), 2.0, 0.03, 26, 0, False),
         "c2": ((512, 512, 512), 2.0, 0.03, 6, 0, True),
+        "c2_ccs_only": ((512, 512, 512), 2.0, 0.03, 6, 0, False),
         "c3": ((1024, 1024, 128), 1.0, 0.10, 6, 0, True),
         "c5_128": ((128, 128, 128), 2.0, 0.03, 6, 0, False),
         "c5_256": ((256, 256, 256), 2.0, 0.03, 6, 0, False),
