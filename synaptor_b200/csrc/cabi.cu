@@ -426,8 +426,14 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         PROF("threshold");
     }
     if (dilate) {
-        k_dilate<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(W.omask, W.lmask, g, dil_k);
-        CK_LAUNCH();
+        // k radius-1 passes, ping-pong between lmask and the (not yet used) run-prefix array; the last lands in lmask
+        const u32 *src = W.omask;
+        for (int i = 1; i <= dil_k; ++i) {
+            u32 *dst = ((dil_k - i) & 1) ? W.runbase : W.lmask;
+            k_dilate_step<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(src, dst, g);
+            CK_LAUNCH();
+            src = dst;
+        }
         PROF("dilate");
     }
     const RunIdx R{W.runbase, fused_scan ? W.tilebase : nullptr, g.cpr};
@@ -444,8 +450,8 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         if (rc != SYN_OK) return rc;
         PROF("run_scan");
         const int ntiles = (int)((g.nwords + SCAN_TILE - 1) / SCAN_TILE);
-        k_compact_active<<<wave_grid(k_compact_active, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(W.lmask, g.nwords,
-                                                                                                  W.actw, W.cnt);
+        k_compact_active<<<wave_grid(k_compact_active, SCAN_THREADS, ntiles), SCAN_THREADS, 0, st>>>(
+            W.lmask, g.nwords, W.actw, W.bndw, g, W.tg, W.cnt);
         CK_LAUNCH();
         PROF("compact_active");
     }
@@ -456,7 +462,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     }
 
     // --- unions ------------------------------------------------------------------------------
-    const bool bnd_list = fused_scan && W.tg.tx;
+    const bool bnd_list = W.tg.tx != 0;   // both producers of the active-word list also list the border words
     if (connectivity == 6) rc = launch_union<6>(W, g, R, bnd_list, max_runs, st);
     else if (connectivity == 18) rc = launch_union<18>(W, g, R, false, max_runs, st);
     else rc = launch_union<26>(W, g, R, false, max_runs, st);
@@ -651,10 +657,11 @@ int syn_threshold_dilate(const float *pred, int64_t nx, int64_t ny, int64_t nz, 
     else k_threshold<false, 4><<<grid, 256, 0, st>>>(pred, m0, g, thresh, fg);
     CK_LAUNCH();
     const u32 *res = m0;
-    if (dil_k > 0) {
-        k_dilate<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(m0, m1, g, dil_k);
+    for (int i = 1; i <= dil_k; ++i) {      // k radius-1 passes, ping-pong
+        u32 *dst = (res == m0) ? m1 : m0;
+        k_dilate_step<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(res, dst, g);
         CK_LAUNCH();
-        res = m1;
+        res = dst;
     }
     k_expand_mask<<<grid_for((i64)g.nwords * 32, 256, 8), 256, 0, st>>>(res, g, out01);
     CK_LAUNCH();

@@ -297,41 +297,24 @@ __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__
 // ===========================================================================
 // K1d: 2-D L1 dilation by k over axes (y, z) on the bitmask -- what the chamfer
 // distance transform + `dist > k -> 0` of _seg_utils.cpp:25-82,180-200 computes
-// for a 0/1 mask.  out(y, z) = OR_{|dy| <= k} zdil(in(y + dy), k - |dy|).
-// One thread per output word; the bitmask is L2 resident.  k <= 32.
+// for a 0/1 mask.  The L1 ball of radius k is the k-fold Minkowski sum of the
+// radius-1 diamond, and inside a rectangle every L1-shortest lattice path can be
+// chosen inside it, so k passes of the 5-point step below give the clipped
+// dilation exactly.  One thread per output word; the bitmask is L2 resident.
 // ===========================================================================
-__device__ __forceinline__ u32 zdil_word(u32 prev, u32 cur, u32 next, int r)
-{
-    // bits of `cur` row-word after smearing every set bit by +-r along z
-    u32 out = cur;
-    u64 lo = ((u64)cur << 32) | prev;   // cur in the high half: (lo >> (32 - s)) == (cur << s) | (prev >> (32 - s))
-    u64 hi = ((u64)next << 32) | cur;   // (hi >> s) low half == (cur >> s) | (next << (32 - s))
-    for (int s = 1; s <= r; ++s) {
-        out |= (u32)(lo >> (32 - s));
-        out |= (u32)(hi >> s);
-    }
-    return out;
-}
-
-__global__ void __launch_bounds__(256) k_dilate(const u32 *__restrict__ in, u32 *__restrict__ out, Geom g, int k)
+__global__ void __launch_bounds__(256) k_dilate_step(const u32 *__restrict__ in, u32 *__restrict__ out, Geom g)
 {
     const u32 tail = (g.nz & 31) ? ((1u << (g.nz & 31)) - 1u) : 0xFFFFFFFFu;
     for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < g.nwords; w += gridDim.x * blockDim.x) {
-        u32 row = w / g.wz;
-        u32 kw = w - row * g.wz;
-        u32 y = row % (u32)g.ny;
-        u32 acc = 0;
-        for (int dy = -k; dy <= k; ++dy) {
-            int yy = (int)y + dy;
-            if (yy < 0 || yy >= (int)g.ny) continue;
-            const u32 *r = in + (i64)(row + dy) * g.wz;  // same x, row index shifts by dy
-            u32 cur = r[kw];
-            u32 prev = kw > 0 ? r[kw - 1] : 0u;
-            u32 next = kw + 1 < g.wz ? r[kw + 1] : 0u;
-            if ((cur | prev | next) == 0) continue;
-            int rr = k - (dy < 0 ? -dy : dy);
-            acc |= zdil_word(prev, cur, next, rr);
-        }
+        u32 row, kw, x, y;
+        split_word(g, w, row, kw);
+        split_row(g, row, x, y);
+        const u32 cur = in[w];
+        const u32 prev = kw > 0 ? in[w - 1] : 0u;
+        const u32 next = kw + 1 < g.wz ? in[w + 1] : 0u;
+        u32 acc = cur | (cur << 1) | (prev >> 31) | (cur >> 1) | (next << 31);
+        if (y > 0) acc |= in[w - g.wz];
+        if (y + 1 < (u32)g.ny) acc |= in[w + g.wz];
         if (kw == g.wz - 1) acc &= tail;
         out[w] = acc;
     }
@@ -491,30 +474,48 @@ struct RunBaseDst {
 // foreground sectors) run one thread per ACTIVE word from this list, so every lane
 // of a warp has work (3 % foreground means ~10 % of the words are non-empty; a
 // thread-per-word grid over all words would run at ~2 active lanes per warp).
-// Order inside a block is raster order; blocks append with one atomicAdd each.
+// Order inside a block is raster order; blocks append with one atomicAdd each.  Also lists the non-empty words
+// on a tile border (the dilation variant; the plain path gets both lists from k_stream).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(SCAN_THREADS) k_compact_active(const u32 *__restrict__ mask, u32 nwords,
-                                                                 u32 *__restrict__ actw, Counts *cnt)
+                                                                 u32 *__restrict__ actw, u32 *__restrict__ bndw, Geom g,
+                                                                 TileGeom tg, Counts *cnt)
 {
     __shared__ u32 sm[33];
-    __shared__ u32 s_base;
+    __shared__ u32 s_base, s_bcount, s_bbase;
     for (u64 tile = blockIdx.x; tile * SCAN_TILE < nwords; tile += gridDim.x) {
+        if (threadIdx.x == 0) s_bcount = 0;
+        __syncthreads();
         const u64 i0 = tile * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
-        u32 flag[SCAN_ITEMS];
+        u32 flag[SCAN_ITEMS], bpos[SCAN_ITEMS];
         u32 v = 0;
 #pragma unroll
         for (int t = 0; t < SCAN_ITEMS; ++t) {
             flag[t] = (i0 + t < nwords) && (mask[i0 + t] != 0);
             v += flag[t];
+            bpos[t] = 0xFFFFFFFFu;
+            if (flag[t] && tg.tx) {      // non-empty word on a tile border of k_tile_ccl -> input of k_union_bnd
+                u32 row, k, x, y;
+                split_word(g, (u32)(i0 + t), row, k);
+                split_row(g, row, x, y);
+                if ((x && (x & (tg.tx - 1)) == 0) || (y && (y & (tg.ty - 1)) == 0)) bpos[t] = atomicAdd(&s_bcount, 1u);
+            }
         }
         u32 total;
         u32 ex = block_excl_scan(v, sm, &total);
-        if (threadIdx.x == 0) s_base = total ? (u32)atomicAdd((u64 *)&cnt->v[SYN_CNT_ACTIVE_WORDS], (u64)total) : 0u;
+        if (threadIdx.x == 0) {
+            s_base = total ? (u32)atomicAdd((u64 *)&cnt->v[SYN_CNT_ACTIVE_WORDS], (u64)total) : 0u;
+            const u32 nb = s_bcount;
+            s_bbase = nb ? (u32)atomicAdd((u64 *)&cnt->v[SYN_CNT_BND_WORDS], (u64)nb) : 0u;
+        }
         __syncthreads();
         ex += s_base;
+        const u32 bb = s_bbase;
 #pragma unroll
-        for (int t = 0; t < SCAN_ITEMS; ++t)
+        for (int t = 0; t < SCAN_ITEMS; ++t) {
             if (flag[t]) actw[ex++] = (u32)(i0 + t);
+            if (bpos[t] != 0xFFFFFFFFu) bndw[bb + bpos[t]] = (u32)(i0 + t);
+        }
         __syncthreads();
     }
 }
