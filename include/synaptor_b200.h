@@ -215,6 +215,21 @@ SYN_API int syn_merge_seg_tables(const int64_t *rows, int64_t n_rows, const uint
                                  int64_t *merged_out, uint32_t *fmap_out, int64_t *n_merged_dev, void *stream);
 
 /*
+ * syn_chunk_ccs_multilabel -- the `overlap_seg` variant of connected_components
+ * (synaptor/proc/seg/conncomps.py:24-28, reached through cc_task(..., overlap_seg=...),
+ * proc/tasks.py:41,64-67): `temp = zeros(uint64); temp[mask] = overlap_seg[mask]`, then a
+ * MULTI-LABEL 6-connected labelling of temp -- two face-adjacent voxels join only when they
+ * hold the same non-zero base id; voxels above threshold whose base id is 0 are background.
+ * Numbering, dust filter, table and counts exactly as syn_chunk_ccs (no dilation, no pair
+ * counting: the caller follows up with syn_count_overlaps for the `max_overlap` column).
+ * overlap_seg: device uint64 [nx][ny][nz].
+ */
+SYN_API int syn_chunk_ccs_multilabel(const float *pred, const uint64_t *overlap_seg, int64_t nx, int64_t ny, int64_t nz,
+                                     float thresh, int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out,
+                                     int64_t *seg_table, int64_t max_segs, void *workspace, int64_t workspace_bytes,
+                                     int64_t max_runs, int64_t *counts_host, void *stream);
+
+/*
  * Measurement hooks (no reference counterpart).
  * syn_launch_count   : kernels launched by this library in this process so far.
  * syn_profile_enable : 1 = syn_chunk_ccs records a CUDA event on its stream after every kernel and

@@ -34,6 +34,8 @@ SIGNATURES = {
     "syn_ccs_workspace_bytes": (_i64, [_i64] * 5),
     "syn_chunk_ccs": (_i32, [_vp, _i64, _i64, _i64, _f32, _i32, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp,
                              _i64, _vp, _i64, _i64, _vp, _vp]),
+    "syn_chunk_ccs_multilabel": (_i32, [_vp, _vp, _i64, _i64, _i64, _f32, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64,
+                                        _vp, _vp]),
     "syn_read_counts": (_i32, [_vp, _vp, _vp]),
     "syn_overlap_workspace_bytes": (_i64, [_i64] * 4),
     "syn_count_overlaps": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),

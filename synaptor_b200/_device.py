@@ -191,7 +191,8 @@ def default_capacities(shape):
 
 
 def chunk_ccs_device(pred, thresh, dust_thresh, connectivity=6, dil_k=0, offset=(0, 0, 0), base=None,
-                     stream=None, sync=True, max_runs=None, max_segs=None, max_pairs=None, out=None):
+                     stream=None, sync=True, max_runs=None, max_segs=None, max_pairs=None, out=None,
+                     overlap_seg=None):
     """
     Runs the fused chunk_ccs (+ chunk_overlaps when `base` is given) pipeline on
     CUDA tensors that are already resident.  `pred`: float32 [X,Y,Z] cuda tensor;
@@ -201,6 +202,8 @@ def chunk_ccs_device(pred, thresh, dust_thresh, connectivity=6, dil_k=0, offset=
     use read_counts() afterwards).
     `out`: optional ChunkResult from a previous call with the same shape to reuse
     its output buffers.
+    `overlap_seg`: int64-typed cuda tensor of uint64 ids -> the multi-label variant
+    (conncomps.py:24-28): voxels join only when they share a non-zero base id.
     """
     torch = _torch()
     L = C.lib()
@@ -234,14 +237,25 @@ def chunk_ccs_device(pred, thresh, dust_thresh, connectivity=6, dil_k=0, offset=
                     prow = torch.empty(max_pairs, dtype=torch.int32, device=device)
                     pcol = torch.empty(max_pairs, dtype=torch.int64, device=device)
                     pval = torch.empty(max_pairs, dtype=torch.int64, device=device)
-            rc = L.syn_chunk_ccs(
-                pred.data_ptr(), nx, ny, nz, ctypes.c_float(float(thresh)), int(connectivity), int(dil_k),
-                int(dust_thresh), ctypes.cast(off, ctypes.c_void_p), labels.data_ptr(), table.data_ptr(),
-                table.shape[0], base.data_ptr() if base is not None else None,
-                prow.data_ptr() if prow is not None else None, pcol.data_ptr() if pcol is not None else None,
-                pval.data_ptr() if pval is not None else None, prow.numel() if prow is not None else 0,
-                ws.data_ptr(), ws.numel(), max_runs,
-                counts.ctypes.data_as(ctypes.c_void_p) if sync else None, _stream_ptr(torch, stream))
+            if overlap_seg is not None:
+                assert base is None and overlap_seg.is_cuda and overlap_seg.dtype == torch.int64 \
+                    and overlap_seg.is_contiguous() and tuple(overlap_seg.shape) == (nx, ny, nz)
+                if int(connectivity) != 6 or int(dil_k) != 0:
+                    raise ValueError("cc_task(overlap_seg=...) is 6-connected and has no dilation (conncomps.py:28)")
+                rc = L.syn_chunk_ccs_multilabel(
+                    pred.data_ptr(), overlap_seg.data_ptr(), nx, ny, nz, ctypes.c_float(float(thresh)),
+                    int(dust_thresh), ctypes.cast(off, ctypes.c_void_p), labels.data_ptr(), table.data_ptr(),
+                    table.shape[0], ws.data_ptr(), ws.numel(), max_runs,
+                    counts.ctypes.data_as(ctypes.c_void_p) if sync else None, _stream_ptr(torch, stream))
+            else:
+                rc = L.syn_chunk_ccs(
+                    pred.data_ptr(), nx, ny, nz, ctypes.c_float(float(thresh)), int(connectivity), int(dil_k),
+                    int(dust_thresh), ctypes.cast(off, ctypes.c_void_p), labels.data_ptr(), table.data_ptr(),
+                    table.shape[0], base.data_ptr() if base is not None else None,
+                    prow.data_ptr() if prow is not None else None, pcol.data_ptr() if pcol is not None else None,
+                    pval.data_ptr() if pval is not None else None, prow.numel() if prow is not None else 0,
+                    ws.data_ptr(), ws.numel(), max_runs,
+                    counts.ctypes.data_as(ctypes.c_void_p) if sync else None, _stream_ptr(torch, stream))
         res = ChunkResult(labels, table, prow, pcol, pval, _counts_dict(counts) if sync else {}, ws)
         if rc == C.SYN_OK:
             return res

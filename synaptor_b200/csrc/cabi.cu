@@ -145,6 +145,7 @@ struct Workspace {
     u32 *tileflag;
     Counts *cnt;
     u32 *lmask, *omask, *runbase;
+    u32 *startw;                           // stored run-start words (multi-label variant only)
     u32 *actw;                             // compact list of non-empty mask words
     u32 *bndw;                             // non-empty words on a tile border
     u64 *scanstate;                        // 4 look-back state arrays + tickets, zeroed per call
@@ -165,7 +166,7 @@ struct Workspace {
 };
 
 
-void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, Workspace *w)
+void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, bool ml, Workspace *w)
 {
     size_t off = 0;
     auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += al(bytes); return p; };
@@ -194,6 +195,7 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     // ---- the rest is fully written before it is read ----
     w->lmask = (u32 *)take(nw * 4);
     w->omask = dilate ? (u32 *)take(nw * 4) : w->lmask;
+    w->startw = ml ? (u32 *)take(nw * 4) : nullptr;
     w->runbase = (u32 *)take(nw * 4);
     w->actw = (u32 *)take(nw * 4);
     w->bndw = (u32 *)take(nw * 4);
@@ -346,7 +348,7 @@ int64_t syn_ccs_workspace_bytes(int64_t nx, int64_t ny, int64_t nz, int64_t max_
     if (make_geom(nx, ny, nz, &g) != SYN_OK) return SYN_ERR_INVALID;
     if (max_runs < 1) max_runs = 1;
     Workspace w;
-    carve(nullptr, g, max_runs, max_pairs, true, &w);
+    carve(nullptr, g, max_runs, max_pairs, true, true, &w);
     return (int64_t)w.total;
 }
 
@@ -359,11 +361,16 @@ int syn_read_counts(const void *workspace, int64_t *counts_host, void *stream)
     return SYN_OK;
 }
 
-int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity, int dil_k,
-                  int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out, int64_t *seg_table,
-                  int64_t max_segs, const uint64_t *base_seg, uint32_t *pair_rows, uint64_t *pair_cols,
-                  int64_t *pair_counts, int64_t max_pairs, void *workspace, int64_t workspace_bytes,
-                  int64_t max_runs, int64_t *counts_host, void *stream)
+}  // extern "C"
+
+namespace {
+
+// `ml_base`: base segmentation of the multi-label variant (cc_task(overlap_seg=...), conncomps.py:24-28), else null
+int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity, int dil_k,
+                   int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out, int64_t *seg_table,
+                   int64_t max_segs, const uint64_t *base_seg, uint32_t *pair_rows, uint64_t *pair_cols,
+                   int64_t *pair_counts, int64_t max_pairs, void *workspace, int64_t workspace_bytes,
+                   int64_t max_runs, int64_t *counts_host, void *stream, const uint64_t *ml_base)
 {
     Geom g;
     int rc = make_geom(nx, ny, nz, &g);
@@ -379,8 +386,12 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         return fail(SYN_ERR_INVALID, "base_seg given without pair output arrays");
     if (!has_base) max_pairs = 0;
     const bool dilate = dil_k > 0;
+    const bool ml = ml_base != nullptr;
+    if (ml && (dilate || connectivity != 6 || has_base))
+        return fail(SYN_ERR_INVALID, "the multi-label variant is 6-connected, without dilation or pair counting");
     Workspace W;
-    carve((char *)workspace, g, max_runs, max_pairs, dilate, &W);
+    carve((char *)workspace, g, max_runs, max_pairs, dilate, ml, &W);
+    if (ml) W.tg = TileGeom{0, 0, 0, 0, 0, 0, 0};    // generic global path: no shared-memory tile pass
     if ((i64)W.total > workspace_bytes)
         return fail(SYN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %lld", W.total,
                     (long long)workspace_bytes);
@@ -397,7 +408,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     // it also produces the tiled run-id prefix and the active / border word lists.  Otherwise: plain threshold
     // kernel, and the generic output pass at the end. ---------------------------------------------------------
     const bool vec_in = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
-    const bool sector_out = (nz % 8 == 0) && vec_in && ((reinterpret_cast<uintptr_t>(labels_out) & 31) == 0) &&
+    const bool sector_out = !ml && (nz % 8 == 0) && vec_in && ((reinterpret_cast<uintptr_t>(labels_out) & 31) == 0) &&
                             (!has_base || (reinterpret_cast<uintptr_t>(base_seg) & 15) == 0);
     static const bool no_fuse = getenv("SYN_NO_FUSED_SCAN") != nullptr;
     const bool fused_scan = sector_out && !dilate && !no_fuse;
@@ -414,6 +425,11 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
 #undef SYN_STREAM
         CK_LAUNCH();
         PROF("stream");
+    } else if (ml) {
+        k_threshold_ml<<<wave_grid(k_threshold_ml, 256, div_up_u32(g.nwords, 8)), 256, 0, st>>>(
+            pred, (const u64 *)ml_base, W.omask, W.startw, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
+        CK_LAUNCH();
+        PROF("threshold_ml");
     } else {
         const i64 need = div_up_u32((u64)g.nchunks, 8 * 4);
         if (vec_in)
@@ -436,7 +452,8 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
         }
         PROF("dilate");
     }
-    const RunIdx R{W.runbase, fused_scan ? W.tilebase : nullptr, g.cpr};
+    const RunIdx R{W.runbase, fused_scan ? W.tilebase : nullptr, g.cpr, ml ? W.startw : nullptr,
+                   (const u64 *)ml_base};
     if (has_base) {      // (folding this into the streaming kernel cost it 10 % of its bandwidth: measured, reverted)
         k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
         CK_LAUNCH();
@@ -445,7 +462,7 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
 
     // --- scan #1: run ids (already done by the streaming kernel on the plain path) ----------------------
     if (!fused_scan) {
-        RunStartSrc src{W.lmask, g.nwords, g.wz};
+        RunStartSrc src{W.lmask, g.nwords, g.wz, ml ? W.startw : nullptr};
         rc = launch_scan<16>(W, 0, src, RunBaseDst{W.runbase}, g.nwords, &W.cnt->v[SYN_CNT_RUNS], st);
         if (rc != SYN_OK) return rc;
         PROF("run_scan");
@@ -510,10 +527,10 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     } else {
         const int grid = grid_for((i64)g.nchunks * 32 / 2 + 1, 256, 8);
         if (has_base)
-            k_write_labels<false, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
+            k_write_labels<false, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, R, W.runlabel, labels_out,
                                                                 bs, g, T, W.cnt);
         else
-            k_write_labels<false, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, W.runbase, W.runlabel, labels_out,
+            k_write_labels<false, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, R, W.runlabel, labels_out,
                                                                  bs, g, T, W.cnt);
         CK_LAUNCH();
         PROF("write_labels");
@@ -524,6 +541,32 @@ int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float t
     }
     if (g_prof_on) g_prof_valid = true;
     return finish_counts(W, (i64 *)counts_host, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int syn_chunk_ccs(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity, int dil_k,
+                  int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out, int64_t *seg_table,
+                  int64_t max_segs, const uint64_t *base_seg, uint32_t *pair_rows, uint64_t *pair_cols,
+                  int64_t *pair_counts, int64_t max_pairs, void *workspace, int64_t workspace_bytes,
+                  int64_t max_runs, int64_t *counts_host, void *stream)
+{
+    return chunk_ccs_impl(pred, nx, ny, nz, thresh, connectivity, dil_k, dust_thresh, offset_xyz, labels_out, seg_table,
+                          max_segs, base_seg, pair_rows, pair_cols, pair_counts, max_pairs, workspace, workspace_bytes,
+                          max_runs, counts_host, stream, nullptr);
+}
+
+int syn_chunk_ccs_multilabel(const float *pred, const uint64_t *overlap_seg, int64_t nx, int64_t ny, int64_t nz,
+                             float thresh, int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out,
+                             int64_t *seg_table, int64_t max_segs, void *workspace, int64_t workspace_bytes,
+                             int64_t max_runs, int64_t *counts_host, void *stream)
+{
+    if (!overlap_seg) return fail(SYN_ERR_INVALID, "null overlap_seg");
+    return chunk_ccs_impl(pred, nx, ny, nz, thresh, 6, 0, dust_thresh, offset_xyz, labels_out, seg_table, max_segs,
+                          nullptr, nullptr, nullptr, nullptr, 0, workspace, workspace_bytes, max_runs, counts_host,
+                          stream, overlap_seg);
 }
 
 int64_t syn_overlap_workspace_bytes(int64_t nx, int64_t ny, int64_t nz, int64_t max_pairs)
@@ -541,7 +584,7 @@ int syn_count_overlaps(const uint32_t *seg1, const uint64_t *seg2, int64_t nx, i
     if (!seg1 || !seg2 || !workspace || !pair_rows || !pair_cols || !pair_counts || max_pairs < 1)
         return fail(SYN_ERR_INVALID, "null pointer / bad capacity");
     Workspace W;
-    carve((char *)workspace, g, 1, max_pairs, true, &W);
+    carve((char *)workspace, g, 1, max_pairs, true, true, &W);
     if ((i64)W.total > workspace_bytes)
         return fail(SYN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %lld", W.total,
                     (long long)workspace_bytes);

@@ -102,11 +102,22 @@ struct RunIdx {
     const u32 *rb;
     const u32 *tb;
     u32 cpr;
+    // multi-label variant (conncomps.py:24-28): runs also break where the base id changes, so the run-start
+    // words are stored (startw) instead of derived from the mask, and runs of neighbouring rows are joined
+    // only when their base ids (read from mlbase) are equal.  Both null on the plain path.
+    const u32 *startw;
+    const u64 *mlbase;
     __device__ __forceinline__ u32 at(u32 w, u32 row, u32 k) const
     {
         u32 v = rb[w];
         if (tb) v += tb[(row * cpr + (k >> 2)) / TS_CHUNKS];
         return v;
+    }
+    // run-start bits of word w (its in-row index is k)
+    __device__ __forceinline__ u32 starts(const u32 *mask, u32 w, u32 k) const
+    {
+        if (startw) return startw[w];
+        return run_starts(mask[w], k ? (mask[w - 1] >> 31) : 0u);
     }
 };
 
@@ -295,6 +306,53 @@ __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__
 }
 
 // ===========================================================================
+// K1 of the multi-label variant (conncomps.py:24-28: temp[mask] = overlap_seg[mask]; label temp):
+// foreground = pred > thr AND base != 0; a z-run also ends where the base id changes.
+// Writes the mask word and the run-start word of every 32 voxels (one warp per word).
+// ===========================================================================
+__global__ void __launch_bounds__(256) k_threshold_ml(const float *__restrict__ pred, const u64 *__restrict__ base,
+                                                      u32 *__restrict__ mask, u32 *__restrict__ startw, Geom g,
+                                                      float thr, u64 *__restrict__ fg_count)
+{
+    const int lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    u32 nfg = 0;
+    for (u32 w = warp; w < g.nwords; w += nwarps) {
+        u32 row, k;
+        split_word(g, w, row, k);
+        const i64 z = (i64)k * 32 + lane;
+        bool f = false;
+        u64 b = 0;
+        if (z < g.nz) {
+            const i64 v = (i64)row * g.nz + z;
+            b = __ldcs(base + v);
+            f = (__ldcs(pred + v) > thr) && b != 0;
+        }
+        // predecessor along z: lane - 1, or (lane 0) the last voxel of the previous word of the row
+        u64 pb = __shfl_up_sync(SYN_FULL, b, 1);
+        bool pf = __shfl_up_sync(SYN_FULL, (int)f, 1) != 0;
+        if (lane == 0) {
+            pf = false;
+            if (k > 0) {
+                const i64 v = (i64)row * g.nz + z - 1;
+                pb = base[v];
+                pf = (pred[v] > thr) && pb != 0;
+            }
+        }
+        const bool st = f && !(pf && pb == b);
+        const u32 mw = __ballot_sync(SYN_FULL, f);
+        const u32 sw = __ballot_sync(SYN_FULL, st);
+        if (lane == 0) {
+            mask[w] = mw;
+            startw[w] = sw;
+            nfg += __popc(mw);
+        }
+    }
+    if (lane == 0 && nfg) atomicAdd(fg_count, (u64)nfg);
+}
+
+// ===========================================================================
 // K1d: 2-D L1 dilation by k over axes (y, z) on the bitmask -- what the chamfer
 // distance transform + `dist > k -> 0` of _seg_utils.cpp:25-82,180-200 computes
 // for a 0/1 mask.  The L1 ball of radius k is the k-fold Minkowski sum of the
@@ -437,10 +495,18 @@ __device__ __forceinline__ void store_prefix_u32(u32 *a, u64 i0, u64 n, u32 ex, 
 struct RunStartSrc {
     const u32 *mask;
     u32 nwords, wz;
+    const u32 *startw;     // multi-label variant: stored run-start words (else null)
     __device__ __forceinline__ u64 n() const { return nwords; }
     template <int N>
     __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
     {
+        if (startw) {
+            u32 m[N];
+            load_items_u32(startw, i0, n, m);
+#pragma unroll
+            for (int t = 0; t < N; ++t) item[t] = __popc(m[t]);
+            return;
+        }
         if (i0 >= n) {
 #pragma unroll
             for (int t = 0; t < N; ++t) item[t] = 0;
@@ -545,13 +611,13 @@ struct RowView {
     const u32 *mask;     // words of this row
     RunIdx R;            // run-start prefix
     u32 row, wz;
+    i64 nz;
     __device__ __forceinline__ u32 word(int k) const { return (k >= 0 && k < (int)wz) ? mask[k] : 0u; }
     // id of the run covering bit b (0..31) of word k; that bit must be set
     __device__ __forceinline__ u32 run_at(int k, int b) const
     {
-        u32 m = mask[k];
-        u32 carry = k ? (mask[k - 1] >> 31) : 0u;
-        return R.at(row * wz + (u32)k, row, (u32)k) + __popc(run_starts(m, carry) & mask_le((u32)b)) - 1u;
+        const u32 w = row * wz + (u32)k;
+        return R.at(w, row, (u32)k) + __popc(R.starts(mask - (size_t)row * wz, w, (u32)k) & mask_le((u32)b)) - 1u;
     }
 };
 
@@ -566,9 +632,16 @@ __device__ __forceinline__ void union_shifted(u32 *par, const RowView &A, const 
     u32 o = mA & nb;
     if (!o) return;
     u32 os = o & ~(o << 1);  // first bit of every overlap span (a span lies inside one run of A and one of B)
+    const bool ml = SHIFT == 0 && A.R.startw != nullptr;
+    if (ml)   // spans also break at the run starts of either row (base-id changes)
+        os |= o & (A.R.startw[A.row * A.wz + (u32)k] | A.R.startw[B.row * B.wz + (u32)k]);
     while (os) {
         int b = __ffs(os) - 1;
         os &= os - 1;
+        if (ml) {
+            const i64 z = (i64)k * 32 + b;
+            if (A.R.mlbase[(i64)A.row * A.nz + z] != A.R.mlbase[(i64)B.row * A.nz + z]) continue;
+        }
         u32 ga = A.run_at(k, b);
         int bb = b + SHIFT, kb = k;
         if (bb < 0) { bb = 31; kb = k - 1; }
@@ -595,7 +668,7 @@ __device__ __forceinline__ void union_rows_body(const u32 *__restrict__ mask, co
         split_word(g, w, row, kk);
         split_row(g, row, x, y);
         const int k = (int)kk;
-        RowView A{mask + (u64)row * g.wz, R, row, g.wz};
+        RowView A{mask + (u64)row * g.wz, R, row, g.wz, g.nz};
         bool do_y = true, do_x = true, do_dm = true, do_dp = true;   // (x,y-1) (x-1,y) (x-1,y-1) (x-1,y+1)
         if (tg.tx) {
             const u32 tX = x >> tg.txs, tY = y >> tg.tys;
@@ -609,26 +682,26 @@ __device__ __forceinline__ void union_rows_body(const u32 *__restrict__ mask, co
         }
         if (y > 0 && do_y) {
             u32 r2 = row - 1;
-            RowView B{mask + (u64)r2 * g.wz, R, r2, g.wz};
+            RowView B{mask + (u64)r2 * g.wz, R, r2, g.wz, g.nz};
             union_shifted<0>(par, A, B, k, m);
             if (CONN >= 18) { union_shifted<-1>(par, A, B, k, m); union_shifted<1>(par, A, B, k, m); }
         }
         if (x > 0) {
             u32 r2 = row - (u32)g.ny;
-            RowView B{mask + (u64)r2 * g.wz, R, r2, g.wz};
+            RowView B{mask + (u64)r2 * g.wz, R, r2, g.wz, g.nz};
             if (do_x) {
                 union_shifted<0>(par, A, B, k, m);
                 if (CONN >= 18) { union_shifted<-1>(par, A, B, k, m); union_shifted<1>(par, A, B, k, m); }
             }
             if (CONN >= 18 && y > 0 && do_dm) {
                 u32 r3 = r2 - 1;
-                RowView C{mask + (u64)r3 * g.wz, R, r3, g.wz};
+                RowView C{mask + (u64)r3 * g.wz, R, r3, g.wz, g.nz};
                 union_shifted<0>(par, A, C, k, m);
                 if (CONN == 26) { union_shifted<-1>(par, A, C, k, m); union_shifted<1>(par, A, C, k, m); }
             }
             if (CONN >= 18 && y + 1 < (u32)g.ny && do_dp) {
                 u32 r3 = r2 + 1;
-                RowView C{mask + (u64)r3 * g.wz, R, r3, g.wz};
+                RowView C{mask + (u64)r3 * g.wz, R, r3, g.wz, g.nz};
                 union_shifted<0>(par, A, C, k, m);
                 if (CONN == 26) { union_shifted<-1>(par, A, C, k, m); union_shifted<1>(par, A, C, k, m); }
             }
@@ -1244,16 +1317,16 @@ __device__ __forceinline__ void stats_body(const u32 *__restrict__ lmask, const 
         split_word(g, w, row, k);
         split_row(g, row, x, y);
         if (tg.tx && tileflag[(x >> tg.txs) * tg.tiles_y + (y >> tg.tys)] == 0) continue;
-        u32 carry = k ? (lmask[w - 1] >> 31) : 0u;
-        u32 starts = run_starts(m, carry);
+        u32 starts = R.starts(lmask, w, k);
         u32 rb = R.at(w, row, k);
-        u32 ps = m & ~(m << 1);  // piece starts (no carry: a continuing run still starts a piece here)
+        u32 ps = (m & ~(m << 1)) | starts;  // piece starts (a run continuing from the previous word starts a piece too)
         while (ps) {
             int b0 = __ffs(ps) - 1;
             ps &= ps - 1;
             u32 span = ~(m >> b0);                       // zero bits above the piece
             int len = span ? (__ffs(span) - 1) : 32;     // span==0 only when b0==0 and m is all ones
             if (len > 32 - b0) len = 32 - b0;
+            if (ps) len = min(len, __ffs(ps) - 1 - b0);  // (multi-label) the next run may start right behind
             u32 pm = (len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << b0;
             u32 bits = om & pm;
             if (!bits) continue;

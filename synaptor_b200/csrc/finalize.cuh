@@ -89,7 +89,7 @@ struct PairAcc {
 // ===========================================================================
 template <bool VEC, bool HAS_BASE, int UNROLL>
 __global__ void __launch_bounds__(256) k_write_labels(const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
-                                                      const u32 *__restrict__ runbase,
+                                                      RunIdx R,
                                                       const u32 *__restrict__ runlabel, u32 *__restrict__ labels,
                                                       const u64 *__restrict__ base, Geom g, PairTable T, Counts *cnt)
 {
@@ -138,9 +138,8 @@ __global__ void __launch_bounds__(256) k_write_labels(const u32 *__restrict__ lm
                 if (nib) {
                     const u32 w = widx[u];
                     const u32 kw = w % g.wz;
-                    const u32 carry = kw ? (lmask[w - 1] >> 31) : 0u;
-                    const u32 starts = run_starts(m[u], carry);
-                    const u32 rb = runbase[w];
+                    const u32 starts = R.starts(lmask, w, kw);
+                    const u32 rb = R.at(w, w / g.wz, kw);
                     u32 prev_run = 0xFFFFFFFFu, prev_lab = 0;
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
@@ -181,8 +180,8 @@ __global__ void __launch_bounds__(256) k_write_labels(const u32 *__restrict__ lm
                     u32 mm = lmask[w], oo = omask[w];
                     u32 lab = 0;
                     if ((oo >> lane) & 1u) {
-                        u32 carry = kw ? (lmask[w - 1] >> 31) : 0u;
-                        u32 run = runbase[w] + __popc(run_starts(mm, carry) & mask_le((u32)lane)) - 1u;
+                        (void)mm;
+                        u32 run = R.at(w, row, kw) + __popc(R.starts(lmask, w, kw) & mask_le((u32)lane)) - 1u;
                         lab = runlabel[run];
                     }
                     i64 v = (i64)row * g.nz + z;

@@ -13,7 +13,7 @@ def apply_chunk_id_maps(overlap_arr, chunk_id_maps):
         cs.append(np.asarray(ov.col, dtype=np.int64))
         vs.append(np.asarray(ov.data))
     if not rs:
-        return sp.coo_matrix(([], ([], [])))
+        return sp.coo_matrix((0, 0), dtype=np.int64)
     return sp.coo_matrix((np.concatenate(vs), (np.concatenate(rs), np.concatenate(cs))))
 
 
@@ -24,7 +24,7 @@ def consolidate_overlaps(overlap_mat_arr, dtype=np.uint64):
         r, c, v = sp.find(m)
         rs.append(r.astype(dtype)); cs.append(c.astype(dtype)); vs.append(v.astype(dtype))
     if not rs:
-        return sp.coo_matrix(([], ([], [])))
+        return sp.coo_matrix((0, 0), dtype=np.int64)
     full = sp.coo_matrix((np.concatenate(vs), (np.concatenate(rs), np.concatenate(cs))))
     full.sum_duplicates()
     return full

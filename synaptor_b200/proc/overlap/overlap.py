@@ -15,7 +15,8 @@ def find_max_overlaps(overlap_mat):
     c = np.asarray(overlap_mat.col)
     v = np.asarray(overlap_mat.data)
     if len(r) == 0:
-        return sparse.coo_matrix(([], ([], [])))
+        # (the reference's `coo_matrix(([], ([], [])))` raises on current scipy; an empty matrix is returned instead)
+        return sparse.coo_matrix((0, 0), dtype=np.int64)
     # stable sort by (row, -value) keeps entry order among equal values; first of each row wins
     order = np.lexsort((np.arange(len(r)), -v.astype(np.int64), r))
     rs = r[order]

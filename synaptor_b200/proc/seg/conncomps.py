@@ -11,7 +11,7 @@ import numpy as np
 from ... import _device as D
 
 
-def _run(d, thresh, dil_k, connectivity, dust=0):
+def _run(d, thresh, dil_k, connectivity, dust=0, overlap_seg=None):
     torch = D._torch()
     if not isinstance(d, torch.Tensor):
         d = np.asarray(d)
@@ -24,7 +24,12 @@ def _run(d, thresh, dil_k, connectivity, dust=0):
         t32 = np.float32(thresh)
     device = torch.device("cuda", torch.cuda.current_device())
     pred = D.to_device_f32(torch, d, device)
-    return D.chunk_ccs_device(pred, t32, dust, connectivity=connectivity, dil_k=dil_k)
+    ovl = None
+    if overlap_seg is not None:
+        if tuple(int(x) for x in overlap_seg.shape) != tuple(int(x) for x in pred.shape):
+            raise ValueError("overlap_seg and the prediction volume must have the same shape")
+        ovl = D.to_device_u64(torch, overlap_seg, device)
+    return D.chunk_ccs_device(pred, t32, dust, connectivity=connectivity, dil_k=dil_k, overlap_seg=ovl)
 
 
 def connected_components(d, thresh=0, overlap_seg=None, dtype=np.uint32, connectivity=6):
@@ -32,10 +37,10 @@ def connected_components(d, thresh=0, overlap_seg=None, dtype=np.uint32, connect
     Threshold `d > thresh` and label the connected components (default 6-connectivity,
     the reference's hard-coded choice; 18 and 26 are extensions).  Returns a
     C-contiguous array of `dtype` (default uint32).
+    With `overlap_seg` (conncomps.py:24-28) the labelling is multi-label: voxels above threshold join only
+    when they carry the same non-zero `overlap_seg` id; voxels whose id is 0 are background.
     """
-    if overlap_seg is not None:
-        raise NotImplementedError("connected_components(overlap_seg=...) (conncomps.py:24-28) is not built yet")
-    res = _run(d, thresh, 0, connectivity)
+    res = _run(d, thresh, 0, connectivity, overlap_seg=overlap_seg)
     if res is None:
         return np.zeros(np.asarray(d).shape, dtype=dtype)
     return res.labels_numpy().astype(dtype, copy=False)

@@ -63,9 +63,9 @@ def cc_task(desc_vol, cc_thresh, sz_thresh, offset=(0, 0, 0), overlap_seg=None, 
     Returns (ccs uint32 ndarray, {Face: [Continuation]}, DataFrame) exactly like the
     reference's cc_task (tasks.py:26-69).  `connectivity` and `dil_param` are
     extensions (the reference hard-codes 6 and has no dilation hook here).
+    With `overlap_seg` the labelling is the multi-label one of conncomps.py:24-28 (voxels join only
+    inside one non-zero base segment) and the table gets the `max_overlap` column (tasks.py:64-67).
     """
-    if overlap_seg is not None:
-        raise NotImplementedError("cc_task(overlap_seg=...) (multi-label CCL, tasks.py:64-67) is not built yet")
     say = print if verbose else (lambda *a, **k: None)
     start = time.time()
     say("Running connected components")
@@ -80,13 +80,26 @@ def cc_task(desc_vol, cc_thresh, sz_thresh, offset=(0, 0, 0), overlap_seg=None, 
     t32 = np.float32(cc_thresh) if isinstance(d, torch.Tensor) else D.float32_threshold(d.dtype, cc_thresh)
     device = torch.device("cuda", torch.cuda.current_device())
     pred = D.to_device_f32(torch, d, device)
+    ovl_dev = None
+    if overlap_seg is not None:
+        if tuple(int(x) for x in overlap_seg.shape) != shape:
+            raise ValueError(f"overlap_seg shape {tuple(overlap_seg.shape)} != prediction shape {shape}")
+        ovl_dev = D.to_device_u64(torch, overlap_seg, device)
     res = D.chunk_ccs_device(pred, t32, int(sz_thresh), connectivity=connectivity, dil_k=int(dil_param),
-                             offset=tuple(int(o) for o in offset))
+                             offset=tuple(int(o) for o in offset), overlap_seg=ovl_dev)
     say(f"Running connected components complete in {time.time() - start:.3f}s")
     t1 = time.time()
     say("Making seg info DataFrame")
     out = _materialise_cc(res, shape)
     say(f"Making seg info DataFrame complete in {time.time() - t1:.3f}s")
+    if overlap_seg is not None:
+        ccs, continuations, info = out
+        say("Adding overlapping seg to DataFrame")
+        t2 = time.time()
+        ovl_host = overlap_seg.cpu().numpy() if isinstance(overlap_seg, torch.Tensor) else np.asarray(overlap_seg)
+        info = overlap.add_overlapping_seg(info, ccs, ovl_host)
+        say(f"Adding overlapping seg to DataFrame complete in {time.time() - t2:.3f}s")
+        return ccs, continuations, info
     return out
 
 

@@ -238,6 +238,17 @@ def main():
                  dtype=np.float32).reshape(1, 1, -1)
     np.savez_compressed(os.path.join(HERE, "g6_threshold.npz"), d=t, thresh=0.3,
                         ccs=syn.proc.seg.connected_components(t, 0.3))
+    # ---- G7: cc_task(overlap_seg=...): multi-label labelling + max_overlap column (tasks.py:41,64-67) ----
+    pred7 = orc.synth_pred((24, 28, 40), seed=13, sigma=2.5, fg=0.25)
+    base7 = orc.synth_base((24, 28, 40), seed=14, block=5, bg=0.15)
+    ccs7, conts7, info7 = quiet(tasks.cc_task, pred7, 0.5, 6, offset=(5, 6, 7), overlap_seg=base7)
+    meta7, coords7 = flatten_conts(conts7)
+    np.savez_compressed(os.path.join(HERE, "g7_cc_task_overlap_seg.npz"), pred=pred7, base=base7, thresh=0.5, dust=6,
+                        offset=np.array([5, 6, 7]), ccs=ccs7, cont_meta=meta7, cont_coords=coords7,
+                        info_index=np.asarray(info7.index, dtype=np.int64),
+                        info_table=info7.to_numpy().astype(np.int64), info_columns=np.array(list(info7.columns)),
+                        plain_ncomp=int(syn.proc.seg.connected_components(pred7, 0.5).max()))
+    out["g7"] = (int(ccs7.max()), len(info7))
     print("golden written:", out)
 
 

@@ -133,6 +133,38 @@ def test_g6_threshold_golden(syn):
     assert np.array_equal(ccs, g["ccs"]), (ccs, g["ccs"])
 
 
+def test_g7_cc_task_overlap_seg_golden(syn):
+    g = gold("g7_cc_task_overlap_seg.npz")
+    ccs, conts, info = syn.proc.tasks.cc_task(g["pred"], float(g["thresh"]), int(g["dust"]),
+                                              offset=tuple(g["offset"].tolist()), overlap_seg=g["base"], verbose=False)
+    assert np.array_equal(ccs, g["ccs"]), first_diff(ccs, g["ccs"])
+    meta, coords = flatten_conts(conts)
+    assert np.array_equal(meta, g["cont_meta"]) and np.array_equal(coords, g["cont_coords"])
+    assert list(info.columns) == g["info_columns"].tolist() and info.index.name == "cleft_segid"
+    assert np.array_equal(np.asarray(info.index, dtype=np.int64), g["info_index"])
+    assert np.array_equal(info.to_numpy().astype(np.int64), g["info_table"])
+    lab = syn.proc.seg.connected_components(g["pred"], float(g["thresh"]), overlap_seg=g["base"])
+    want = orc.connected_components(g["pred"], float(g["thresh"]), overlap_seg=g["base"])
+    assert np.array_equal(lab, want), first_diff(lab, want)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 70), (3, 5, 7), (9, 11, 64), (16, 8, 129), (20, 24, 128), (12, 10, 260)])
+@pytest.mark.parametrize("block", [1, 3, 16])
+def test_multilabel_noise_vs_oracle(syn, shape, block):
+    """Multi-label labelling (overlap_seg) on noise at several densities; block = 1 makes nearly every voxel its
+    own base segment, block = 16 leaves long runs that break only rarely."""
+    rng = np.random.default_rng(hash((shape, block)) % (2 ** 32))
+    for p in (0.1, 0.5, 0.9, 1.0):
+        pred = rng.random(shape, dtype=np.float32)
+        base = orc.synth_base(shape, seed=int(p * 10) + block, block=block, bg=0.2)
+        want = orc.cc_task_c(pred, 1.0 - p, 3, offset=(1, 2, 3), overlap_seg=base)
+        got = syn.proc.tasks.cc_task(pred, 1.0 - p, 3, offset=(1, 2, 3), overlap_seg=base, verbose=False)
+        assert np.array_equal(got[0], want[0]), first_diff(got[0], want[0])
+        assert list(got[2].columns) == list(want[2].columns)
+        assert np.array_equal(np.asarray(got[2].index, dtype=np.int64), np.asarray(want[2].index, dtype=np.int64))
+        assert np.array_equal(got[2].to_numpy().astype(np.int64), want[2].to_numpy().astype(np.int64))
+
+
 # ----------------------------------------------------------------------------- random volumes vs the oracle
 SHAPES = [(1, 1, 1), (1, 1, 40), (3, 5, 7), (2, 3, 33), (9, 11, 64), (16, 8, 129), (7, 13, 131),
           (20, 24, 128), (33, 31, 100), (12, 10, 260), (40, 40, 36)]

@@ -130,3 +130,17 @@ def test_c_stats_match_np_flavour():
     ia, ta = table_of(a[2])
     ib, tb = table_of(b[2])
     assert np.array_equal(ia, ib) and np.array_equal(ta, tb)
+
+
+def test_g7_cc_task_overlap_seg():
+    """cc_task(overlap_seg=...) of the executed reference (multi-label labelling + max_overlap column)."""
+    g = gold("g7_cc_task_overlap_seg.npz")
+    ccs, conts, info = orc.cc_task_c(g["pred"], float(g["thresh"]), int(g["dust"]), offset=tuple(g["offset"].tolist()),
+                                     overlap_seg=g["base"])
+    assert int(g["plain_ncomp"]) < int(g["ccs"].max())          # the base segmentation really splits components
+    assert np.array_equal(ccs, g["ccs"])
+    meta, coords = flatten_conts(conts)
+    assert np.array_equal(meta, g["cont_meta"]) and np.array_equal(coords, g["cont_coords"])
+    assert list(info.columns) == g["info_columns"].tolist()
+    assert np.array_equal(np.asarray(info.index, dtype=np.int64), g["info_index"])
+    assert np.array_equal(info.to_numpy().astype(np.int64), g["info_table"])
