@@ -1,0 +1,155 @@
+"""
+On-disk formats of the chunk tasks on a LOCAL processing directory.
+
+Same file names, directory layout and CSV conventions as the reference's
+synaptor/proc/io (seginfo.py, overlap.py, idmap.py) over its local backend
+(synaptor/io/backends/local.py:47-56: `DataFrame.to_csv(index=True, header=True)`,
+`pd.read_csv(index_col=0)`), so the files written here are read by the untouched
+reference stages and vice versa.  Cloud / database back ends and the HDF5
+continuation files (h5py is not in this image) are out of scope.
+"""
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+
+from .. import colnames as cn
+from ...types.bbox import BBox3d
+from . import filenames as fn
+
+BBOX_REGEXP = re.compile("-?[0-9]+_-?[0-9]+_-?[0-9]+--?[0-9]+_-?[0-9]+_-?[0-9]+")
+_SPLIT = re.compile("(-?[0-9]+_-?[0-9]+_-?[0-9]+)-(-?[0-9]+_-?[0-9]+_-?[0-9]+)")
+
+
+# ---- chunk tags (synaptor/io/utils.py:40-47, 65-98) ---------------------------------------------
+def fname_chunk_tag(chunk_bounds):
+    """`x0_y0_z0-x1_y1_z1` of a BBox3d."""
+    lo, hi = chunk_bounds.min(), chunk_bounds.max()
+    return "{0}_{1}_{2}-{3}_{4}_{5}".format(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2])
+
+
+def bbox_from_tag(tag):
+    m = _SPLIT.search(tag)
+    assert m is not None, "split delimiter not found in tag"
+    beg = tuple(map(int, m.group(1).split("_")))
+    end = tuple(map(int, m.group(2).split("_")))
+    return BBox3d(beg, end)
+
+
+def bbox_from_fname(path):
+    m = BBOX_REGEXP.search(path)
+    assert m is not None, "bbox not found in path"
+    return bbox_from_tag(m.group(0))
+
+
+def read_dframe(path):
+    assert os.path.isfile(path)
+    return pd.read_csv(path, index_col=0)
+
+
+def write_dframe(dframe, path, header=True, index=True):
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    dframe.to_csv(path, index=index, header=header)
+
+
+# ---- segment info (synaptor/proc/io/seginfo.py:20-50, 110-130) -----------------------------------
+def chunk_info_fname(proc_url, chunk_bounds):
+    return os.path.join(proc_url, fn.seginfo_dirname, fn.seginfo_fmtstr.format(tag=fname_chunk_tag(chunk_bounds)))
+
+
+def write_chunk_seg_info(dframe, proc_url, chunk_bounds):
+    write_dframe(dframe, chunk_info_fname(proc_url, chunk_bounds))
+
+
+def read_chunk_seg_info(proc_url, chunk_bounds):
+    return read_dframe(chunk_info_fname(proc_url, chunk_bounds))
+
+
+def read_all_chunk_seg_infos(proc_url):
+    """Object array of DataFrames shaped like the chunk grid (lexicographic chunk order), and the directory."""
+    d = os.path.join(proc_url, fn.seginfo_dirname)
+    fnames = sorted(os.listdir(d), key=lambda f: bbox_from_fname(f).min())
+    return _grid_array({bbox_from_fname(f).min(): read_dframe(os.path.join(d, f)) for f in fnames}), d
+
+
+def write_merged_seg_info(dframe, proc_url):
+    write_dframe(dframe, os.path.join(proc_url, fn.merged_seginfo_fname))
+
+
+def read_merged_seg_info(proc_url):
+    return read_dframe(os.path.join(proc_url, fn.merged_seginfo_fname))
+
+
+def _grid_array(lookup):
+    """{chunk begin: object} -> object ndarray indexed by grid position (synaptor/io/utils.py:105-142)."""
+    keys = sorted(lookup)
+    xs, ys, zs = (sorted(set(k[a] for k in keys)) for a in range(3))
+    arr = np.empty((len(xs), len(ys), len(zs)), dtype=object)
+    for k in keys:
+        arr[xs.index(k[0]), ys.index(k[1]), zs.index(k[2])] = lookup[k]
+    return arr
+
+
+# ---- overlap matrices (synaptor/proc/io/overlap.py:19-60) ----------------------------------------
+def empty_matrix():
+    return sp.coo_matrix((0, 0), dtype=np.int64)
+
+
+def overlap_mat_from_dframe(df):
+    rs, cs, vs = list(df[cn.rows]), list(df[cn.cols]), list(df[cn.vals])
+    if len(rs) == 0 or len(cs) == 0 or len(vs) == 0:
+        return empty_matrix()
+    return sp.coo_matrix((vs, (rs, cs)))
+
+
+def chunk_overlap_fname(proc_url, chunk_bounds):
+    return os.path.join(proc_url, fn.overlaps_dirname, fn.overlaps_fmtstr.format(tag=fname_chunk_tag(chunk_bounds)))
+
+
+def write_chunk_overlap_mat(overlap_mat, chunk_bounds, proc_url):
+    rs, cs, vs = sp.find(overlap_mat)
+    write_dframe(pd.DataFrame({cn.rows: rs, cn.cols: cs, cn.vals: vs}), chunk_overlap_fname(proc_url, chunk_bounds))
+
+
+def read_chunk_overlap_mat(fname):
+    return overlap_mat_from_dframe(read_dframe(fname))
+
+
+def read_all_overlap_mats(proc_url):
+    d = os.path.join(proc_url, fn.overlaps_dirname)
+    fnames = sorted(os.listdir(d), key=lambda f: bbox_from_fname(f).min())
+    return _grid_array({bbox_from_fname(f).min(): read_chunk_overlap_mat(os.path.join(d, f)) for f in fnames}), d
+
+
+def write_max_overlaps(max_overlaps, proc_url):
+    """Sparse matrix of maximal overlaps -> max_overlaps.df, same three columns (proc/io/overlap.py:140-156; the
+    reference passes the file name where `header` belongs there -- the intended path is used here)."""
+    rs, cs, vs = sp.find(max_overlaps)
+    write_dframe(pd.DataFrame({cn.rows: rs, cn.cols: cs, cn.vals: vs}), os.path.join(proc_url, fn.max_overlaps_fname))
+
+
+# ---- id maps (synaptor/proc/io/idmap.py:19-37, 160-205) ------------------------------------------
+def cleft_map_fname(proc_url, chunk_bounds):
+    return os.path.join(proc_url, fn.idmap_dirname, fn.idmap_fmtstr.format(tag=fname_chunk_tag(chunk_bounds)))
+
+
+def make_dframe_from_dict(id_map):
+    df = pd.DataFrame(pd.Series(id_map), columns=[cn.dst_id])
+    df.index.name = cn.src_id
+    return df
+
+
+def write_chunk_id_map(id_map, proc_url, chunk_bounds):
+    write_dframe(make_dframe_from_dict(id_map), cleft_map_fname(proc_url, chunk_bounds))
+
+
+def write_chunk_id_maps(chunk_id_maps, chunk_bounds, proc_url):
+    for (id_map, bounds) in zip(chunk_id_maps.flat, chunk_bounds):
+        write_chunk_id_map(id_map, proc_url, bounds)
+
+
+def read_chunk_id_map(proc_url, chunk_bounds):
+    df = read_dframe(cleft_map_fname(proc_url, chunk_bounds))
+    return dict(zip(df.index, df[cn.dst_id]))

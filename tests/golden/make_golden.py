@@ -249,6 +249,28 @@ def main():
                         info_table=info7.to_numpy().astype(np.int64), info_columns=np.array(list(info7.columns)),
                         plain_ncomp=int(syn.proc.seg.connected_components(pred7, 0.5).max()))
     out["g7"] = (int(ccs7.max()), len(info7))
+    # ---- G8: on-disk formats of the chunk tasks written by the reference's own local writers -----------
+    import tempfile
+    import scipy.sparse as sp
+    from synaptor.proc import io as taskio
+    from synaptor.types.bbox import BBox3d
+    sys.modules.pop("zstandard", None)      # the stand-in for the absent module would confuse pandas' to_csv
+    with tempfile.TemporaryDirectory() as tmp:
+        bb = BBox3d((100, 200, 300), (148, 240, 336))
+        for sub in ("seg_infos", "overlaps", "id_maps"):
+            os.makedirs(os.path.join(tmp, sub))
+        taskio.write_chunk_seg_info(info, tmp, bb)
+        taskio.write_chunk_overlap_mat(ov, bb, tmp)
+        id_map = {int(k): int(k) + 1000 for k in list(info.index)[:7]}
+        taskio.write_chunk_id_map(id_map, tmp, bb)
+        files = {}
+        for (root, _, names) in os.walk(tmp):
+            for n in names:
+                files[os.path.relpath(os.path.join(root, n), tmp)] = open(os.path.join(root, n)).read()
+    np.savez_compressed(os.path.join(HERE, "g8_formats.npz"), names=np.array(sorted(files)),
+                        texts=np.array([files[k] for k in sorted(files)]), bbox=np.array(bb.astuple()),
+                        id_map_keys=np.array(list(id_map.keys())), id_map_vals=np.array(list(id_map.values())))
+    out["g8"] = sorted(files)
     print("golden written:", out)
 
 

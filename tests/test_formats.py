@@ -1,0 +1,65 @@
+"""
+On-disk formats of the chunk tasks: the files synaptor_b200.proc.io writes must be byte-identical
+to the ones the reference's own writers produced (tests/golden/g8_formats.npz, made by make_golden.py from the G1 /
+G2 outputs of the executed reference), and its readers must give the tables back.  CPU only.
+"""
+import os
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+
+from util import gold
+
+
+def _golden_files():
+    g = gold("g8_formats.npz")
+    return {str(n): str(t) for (n, t) in zip(g["names"], g["texts"])}, g
+
+
+def _g1_info():
+    g1 = gold("g1_cc_task.npz")
+    info = pd.DataFrame(g1["info_table"].astype(np.int64), index=g1["info_index"].astype(np.int64),
+                        columns=[str(c) for c in g1["info_columns"]])
+    info.index.name = "cleft_segid"
+    return info
+
+
+def test_writers_reproduce_reference_files(tmp_path):
+    from synaptor_b200.proc import io as taskio
+    from synaptor_b200.types.bbox import BBox3d
+    files, g = _golden_files()
+    bb = BBox3d(tuple(g["bbox"][:3].tolist()), tuple(g["bbox"][3:].tolist()))
+    assert taskio.fname_chunk_tag(bb) == "100_200_300-148_240_336"
+    assert taskio.bbox_from_fname("x/seg_info_100_200_300-148_240_336.df") == bb
+    taskio.write_chunk_seg_info(_g1_info(), str(tmp_path), bb)
+    g2 = gold("g2_overlap_task.npz")
+    ov = sp.coo_matrix((g2["data"], (g2["row"], g2["col"])), shape=tuple(g2["shape"].tolist()))
+    taskio.write_chunk_overlap_mat(ov, bb, str(tmp_path))
+    taskio.write_chunk_id_map(dict(zip(g["id_map_keys"].tolist(), g["id_map_vals"].tolist())), str(tmp_path), bb)
+    for (rel, want) in files.items():
+        got = open(os.path.join(tmp_path, rel)).read()
+        assert got == want, f"{rel} differs from the file the reference wrote"
+
+
+def test_readers_parse_reference_files(tmp_path):
+    from synaptor_b200.proc import io as taskio
+    from synaptor_b200.types.bbox import BBox3d
+    files, g = _golden_files()
+    for (rel, text) in files.items():
+        os.makedirs(os.path.dirname(os.path.join(tmp_path, rel)), exist_ok=True)
+        open(os.path.join(tmp_path, rel), "w").write(text)
+    bb = BBox3d(tuple(g["bbox"][:3].tolist()), tuple(g["bbox"][3:].tolist()))
+    info = taskio.read_chunk_seg_info(str(tmp_path), bb)
+    want = _g1_info()
+    assert info.index.name == "cleft_segid" and list(info.columns) == list(want.columns)
+    assert np.array_equal(info.to_numpy(), want.to_numpy()) and np.array_equal(info.index, want.index)
+    ov = taskio.read_chunk_overlap_mat(taskio.chunk_overlap_fname(str(tmp_path), bb))
+    g2 = gold("g2_overlap_task.npz")
+    ref = sp.coo_matrix((g2["data"], (g2["row"], g2["col"])), shape=tuple(g2["shape"].tolist()))
+    assert (ov.tocsr() != ref.tocsr()[:ov.shape[0], :ov.shape[1]]).nnz == 0 and ov.nnz == ref.nnz
+    assert taskio.read_chunk_id_map(str(tmp_path), bb) == dict(zip(g["id_map_keys"].tolist(), g["id_map_vals"].tolist()))
+    arr, _ = taskio.read_all_chunk_seg_infos(str(tmp_path))
+    assert arr.shape == (1, 1, 1) and len(arr[0, 0, 0]) == len(want)
+    mats, _ = taskio.read_all_overlap_mats(str(tmp_path))
+    assert mats.shape == (1, 1, 1) and mats[0, 0, 0].nnz == ref.nnz
