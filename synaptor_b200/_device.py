@@ -6,6 +6,7 @@ staging, streams); every computation happens in libsynaptor_b200.so, reached
 through ctypes (`_cabi`).  There is no CPU fallback anywhere in this module.
 """
 import ctypes
+import threading
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -28,7 +29,9 @@ def _stream_ptr(torch, stream=None):
 
 
 def _workspace(torch, device, nbytes):
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    # one workspace per (device, host thread): cc_overlap_tasks runs chunks on two threads at a time
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(),
+           threading.get_ident())
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         _ws_cache.pop(key, None)
@@ -45,9 +48,17 @@ def release_workspaces():
 _side_streams = {}
 
 
-def side_stream(torch, device, name):
-    """Per-device auxiliary torch streams ("in": H2D copies, "out": D2H copies) for the host-array entry points."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), name)
+# One chunk's input copies at a time: a host thread takes this permit before it queues its H2D copies and gives it
+# back when they have arrived.  Two chunks copying at once would share the link and finish together; one after the
+# other, chunk i's device work and results run under chunk i+1's copy.
+h2d_permit = threading.Semaphore(1)
+
+
+def side_stream(torch, device, name, shared=False):
+    """Per-device auxiliary torch streams ("in": H2D copies, "out": D2H copies) for the host-array entry points.
+    Per host thread unless `shared`."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), name,
+           0 if shared else threading.get_ident())
     s = _side_streams.get(key)
     if s is None:
         s = torch.cuda.Stream(device=device)
@@ -57,6 +68,43 @@ def side_stream(torch, device, name):
 
 def pinned_like(torch, t):
     return torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+
+
+# ---- pinned staging blocks for the label volume coming back ------------------------------------
+# A 512^3 label volume is a 537 MB pinned block.  cudaHostAlloc of that size takes ~200 ms, and torch's caching
+# host allocator does not reliably hand a just-freed block back under the multi-stream pattern of the pipelined
+# path (measured: stalls of 200 ms every few chunks), so the blocks are pooled here: a block goes back to the
+# pool when the numpy array that was returned to the caller is garbage collected.
+_pinned_pool = {}
+_pinned_lock = threading.Lock()
+_PINNED_POOL_MAX = 8
+
+
+def pinned_acquire(torch, shape, dtype):
+    key = (tuple(int(x) for x in shape), dtype)
+    with _pinned_lock:
+        free = _pinned_pool.get(key)
+        if free:
+            return free.pop()
+    return torch.empty(key[0], dtype=dtype, device="cpu", pin_memory=True)
+
+
+def pinned_release(host):
+    key = (tuple(host.shape), host.dtype)
+    with _pinned_lock:
+        free = _pinned_pool.setdefault(key, [])
+        if len(free) < _PINNED_POOL_MAX:
+            free.append(host)
+
+
+def pinned_numpy(host, view_dtype):
+    """numpy view of a pooled pinned block; the block returns to the pool when the array (and every view of it)
+    is gone."""
+    import weakref
+    arr = host.numpy().view(view_dtype)
+    owner = arr.base if arr.base is not None else arr
+    weakref.finalize(owner, pinned_release, host)
+    return arr
 
 
 def float32_threshold(dtype, thresh):
@@ -144,16 +192,16 @@ class ChunkResult:
     def labels_numpy(self):
         """D2H through pinned memory (torch's caching host allocator recycles the block)."""
         import torch
-        host = torch.empty(self.labels.shape, dtype=self.labels.dtype, device="cpu", pin_memory=True)
+        host = pinned_acquire(torch, self.labels.shape, self.labels.dtype)
         host.copy_(self.labels)
-        return host.numpy().view(np.uint32)
+        return pinned_numpy(host, np.uint32)
 
     def labels_numpy_async(self, stream):
         """Starts the D2H of the label volume on `stream` (after the work queued on the current stream);
         returns (pinned host tensor, event).  Synchronise the event before touching the array."""
         import torch
         cur = torch.cuda.current_stream()
-        host = torch.empty(self.labels.shape, dtype=self.labels.dtype, device="cpu", pin_memory=True)
+        host = pinned_acquire(torch, self.labels.shape, self.labels.dtype)
         stream.wait_stream(cur)
         with torch.cuda.stream(stream):
             host.copy_(self.labels, non_blocking=True)

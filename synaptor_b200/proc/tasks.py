@@ -46,7 +46,7 @@ def _materialise_cc(res, shape, between=None):
     info = seg.misc.seg_info_from_table(table[:, 0], table[:, 1:])
     extra = between() if between is not None else None
     ev.synchronize()
-    ccs = host.numpy().view(np.uint32).reshape(shape)
+    ccs = D.pinned_numpy(host, np.uint32).reshape(shape)
     if between is not None:
         return ccs, continuations, info, extra
     return ccs, continuations, info
@@ -138,25 +138,85 @@ def cc_overlap_task(desc_vol, base_segs, cc_thresh, sz_thresh, offset=(0, 0, 0),
     #   copy-out stream: label volume D2H, concurrent with the base H2D (PCIe is full duplex)
     s_main = torch.cuda.current_stream()
     s_in = D.side_stream(torch, device, "in")
-    s_in.wait_stream(s_main)
-    with torch.cuda.stream(s_in):
-        pred = D.to_device_f32(torch, d, device)
-        ev_pred = torch.cuda.Event()
-        ev_pred.record(s_in)
-        base = D.to_device_u64(torch, base_segs, device)
-        ev_base = torch.cuda.Event()
-        ev_base.record(s_in)
-    pred.record_stream(s_main)
-    base.record_stream(s_main)
-    s_main.wait_event(ev_pred)
-    res = D.chunk_ccs_device(pred, t32, int(sz_thresh), connectivity=connectivity, dil_k=int(dil_param), offset=off)
+    D.h2d_permit.acquire()              # one chunk's input copies at a time (see _device.h2d_permit)
+    released = [False]
 
-    def overlaps():
-        s_main.wait_event(ev_base)
-        return D.count_overlaps_device(res.labels, base)
+    def release():
+        if not released[0]:
+            released[0] = True
+            D.h2d_permit.release()
 
-    ccs, continuations, info, ov = _materialise_cc(res, shape, between=overlaps)
+    try:
+        s_in.wait_stream(s_main)
+        with torch.cuda.stream(s_in):
+            pred = D.to_device_f32(torch, d, device)
+            ev_pred = torch.cuda.Event()
+            ev_pred.record(s_in)
+            base = D.to_device_u64(torch, base_segs, device)
+            ev_base = torch.cuda.Event()
+            ev_base.record(s_in)
+        pred.record_stream(s_main)
+        base.record_stream(s_main)
+        s_main.wait_event(ev_pred)
+        res = D.chunk_ccs_device(pred, t32, int(sz_thresh), connectivity=connectivity, dil_k=int(dil_param),
+                                 offset=off)
+
+        def overlaps():
+            ev_base.synchronize()       # the base volume has arrived: the next chunk may start copying
+            release()
+            return D.count_overlaps_device(res.labels, base)
+
+        ccs, continuations, info, ov = _materialise_cc(res, shape, between=overlaps)
+    finally:
+        release()
     return ccs, continuations, info, _coo_from_result(ov)
+
+
+def cc_overlap_tasks(chunks, cc_thresh, sz_thresh, connectivity=6, dil_param=0, workers=2):
+    """
+    cc_overlap_task over a sequence of chunks, software-pipelined: `chunks` yields (desc_vol, base_segs) or
+    (desc_vol, base_segs, offset); results come back in order as (ccs, continuations, seg_info, overlap_mat).
+
+    One chunk is bound by its own host-to-device copy (1.6 GB for 512^3); everything else of the call -- the
+    device pipeline, the label volume coming back, building continuations / DataFrame / COO on the host -- can
+    run under the NEXT chunk's copy.  `workers` host threads (each with its own CUDA streams and workspace) take
+    chunks alternately, so the PCIe link stays busy with input copies back to back.
+    """
+    torch = D._torch()
+    device_index = torch.cuda.current_device()
+
+    def run(item):
+        d, b = item[0], item[1]
+        off = item[2] if len(item) > 2 else (0, 0, 0)
+        torch.cuda.set_device(device_index)
+        stream = D.side_stream(torch, torch.device("cuda", device_index), "main")
+        with torch.cuda.stream(stream):
+            out = cc_overlap_task(d, b, cc_thresh, sz_thresh, offset=off, connectivity=connectivity,
+                                  dil_param=dil_param)
+            stream.synchronize()
+        return out
+
+    pool = _worker_pool(max(1, int(workers)))
+    pending = []
+    for item in chunks:
+        pending.append(pool.submit(run, item))
+        if len(pending) >= workers:               # bounded look-ahead: at most `workers` chunks in flight
+            yield pending.pop(0).result()
+    for f in pending:
+        yield f.result()
+
+
+_pools = {}
+
+
+def _worker_pool(workers):
+    """Persistent worker threads: each keeps its CUDA streams, workspace and pinned staging blocks between calls."""
+    import concurrent.futures as cf
+    pool = _pools.get(workers)
+    if pool is None:
+        pool = cf.ThreadPoolExecutor(max_workers=workers, thread_name_prefix="synaptor_b200")
+        _pools[workers] = pool
+    return pool
 
 
 def _coo_from_result(res):

@@ -485,3 +485,22 @@ def test_merge_ccs_device_vs_oracle(syn, vshape, cshape):
     whole = orc.label_c(vol > 0.5, 6)[0]
     pairs = np.unique(np.stack([final[final != 0], whole[final != 0]], 1), axis=0)
     assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1]))
+
+
+def test_cc_overlap_tasks_pipelined(syn):
+    """The multi-chunk entry point gives, in order, exactly what cc_overlap_task gives per chunk."""
+    rng = np.random.default_rng(5)
+    chunks = []
+    for i in range(5):
+        shape = (24 + 8 * (i % 2), 32, 64)
+        pred = orc.synth_pred(shape, seed=20 + i, sigma=1.5, fg=0.08)
+        base = orc.synth_base(shape, seed=30 + i, block=8)
+        chunks.append((pred, base, (i, 2 * i, 3 * i)))
+    outs = list(syn.proc.tasks.cc_overlap_tasks(chunks, 0.5, 10))
+    assert len(outs) == len(chunks)
+    for ((pred, base, off), (ccs, conts, info, mat)) in zip(chunks, outs):
+        want_ccs, _, want_info = orc.cc_task_c(pred, 0.5, 10, offset=off)
+        assert np.array_equal(ccs, want_ccs), first_diff(ccs, want_ccs)
+        assert np.array_equal(info.to_numpy(), want_info.to_numpy())
+        r, c, v, shp = orc.count_overlaps_c(want_ccs, base)
+        assert mat.shape == shp and np.array_equal(mat.row, r) and np.array_equal(mat.col, c) and np.array_equal(mat.data, v)
