@@ -69,6 +69,18 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi needs a moment to start (longer on an 8-GPU box): do not enter the timed region before the
+        first sample has been written, or a 7 ms region is over before the sampler runs."""
+        t0 = time.time()
+        while self.proc is not None and time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -122,7 +134,7 @@ def cpu_baseline(nproc=None, shape=CPU_SAMPLE, reps=1):
     import multiprocessing as mp
     from oracle import oracle as orc
     cores = len(os.sched_getaffinity(0))
-    nproc = nproc or max(1, min(cores, 16))
+    nproc = nproc or max(1, cores)          # every host core the process may use: one reference-style task per core
     ctx = mp.get_context("fork")
     jobs = [(100 + i, shape) for i in range(nproc * reps)]
     with ctx.Pool(nproc) as pool:
@@ -248,6 +260,9 @@ def main():
 
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.wait_first_sample()
+    for _ in range(args.warmup):            # load already running when the timed steps start (clock samples)
+        res = step(res)
     launches0 = L.syn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -258,7 +273,6 @@ def main():
     barrier()
     launches = L.syn_launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     after = D.read_counts(res)
     assert after["errflags"] == 0 and after["kept"] == counts["kept"] and after["pairs"] == counts["pairs"], after
     # ---- cross-chunk merge_ccs exchange (config 4), timed on its own: NCCL all_gathers of counts, faces and
@@ -289,6 +303,10 @@ def main():
         C.check(L.syn_profile_enable(0))
         return acc
     stage_ms = profiled(1)
+    for _ in range(50):                     # ~35 ms more of the same step under the sampler (20 ms sampling period)
+        res = step(res)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
 
     # ---- e2e through the public API with pinned host buffers ---------------------------------------
     e2e = None
