@@ -315,9 +315,9 @@ def main():
         # one public call per chunk: pinned host arrays in (H2D inside), numpy / DataFrame / COO out (D2H + host
         # materialisation inside).  Warm-up in the steady-state pattern of the timed loop (the previous result is
         # still referenced while the next one is produced, so two pinned output blocks circulate).
-        # (synaptor_b200.proc.tasks.cc_overlap_tasks pipelines consecutive chunks over two host threads; measured
-        # steady state 32.5 ms per chunk against 33.9 ms here, but it needs a long warm-up to get there, so the
-        # bench keeps the plain call.)
+        # (synaptor_b200.proc.tasks.cc_overlap_tasks queues the next chunk's input copy ahead; tools/
+        # e2e_pipeline_probe.py measured 30.5 ms per chunk in its steady state against 33.2 ms here, but not
+        # reproducibly inside this short loop, so the bench keeps the plain call.)
         n_e2e = max(3, min(args.steps, 6))
         for _ in range(3):
             ccs, conts, info, mat = syn.proc.tasks.cc_overlap_task(pn, bn, THRESH, DUST, offset=offset)

@@ -48,12 +48,6 @@ def release_workspaces():
 _side_streams = {}
 
 
-# One chunk's input copies at a time: a host thread takes this permit before it queues its H2D copies and gives it
-# back when they have arrived.  Two chunks copying at once would share the link and finish together; one after the
-# other, chunk i's device work and results run under chunk i+1's copy.
-h2d_permit = threading.Semaphore(1)
-
-
 def side_stream(torch, device, name, shared=False):
     """Per-device auxiliary torch streams ("in": H2D copies, "out": D2H copies) for the host-array entry points.
     Per host thread unless `shared`."""
@@ -87,6 +81,17 @@ def pinned_acquire(torch, shape, dtype):
         if free:
             return free.pop()
     return torch.empty(key[0], dtype=dtype, device="cpu", pin_memory=True)
+
+
+def pinned_reserve(torch, shape, dtype, n):
+    """Makes sure `n` blocks of this shape are in the pool (cudaHostAlloc of a 512^3 label block takes ~0.3 s:
+    better before a pipelined run than in the middle of it)."""
+    key = (tuple(int(x) for x in shape), dtype)
+    with _pinned_lock:
+        have = len(_pinned_pool.get(key, []))
+    fresh = [torch.empty(key[0], dtype=dtype, device="cpu", pin_memory=True) for _ in range(max(0, n - have))]
+    for h in fresh:
+        pinned_release(h)
 
 
 def pinned_release(host):

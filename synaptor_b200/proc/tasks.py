@@ -136,87 +136,86 @@ def cc_overlap_task(desc_vol, base_segs, cc_thresh, sz_thresh, offset=(0, 0, 0),
     #   copy-in stream : pred H2D, then base H2D
     #   main stream    : chunk_ccs as soon as pred has arrived  ->  overlap counting once base has arrived
     #   copy-out stream: label volume D2H, concurrent with the base H2D (PCIe is full duplex)
+    ctx = _start_chunk(torch, device, d, base_segs)
+    return _finish_chunk(torch, ctx, shape, t32, sz_thresh, off, connectivity, dil_param)
+
+
+def _start_chunk(torch, device, d, base_segs):
+    """Queues the two input copies of a chunk on the copy-in stream; returns the device tensors and their events."""
     s_main = torch.cuda.current_stream()
     s_in = D.side_stream(torch, device, "in")
-    D.h2d_permit.acquire()              # one chunk's input copies at a time (see _device.h2d_permit)
-    released = [False]
+    s_in.wait_stream(s_main)
+    with torch.cuda.stream(s_in):
+        pred = D.to_device_f32(torch, d, device)
+        ev_pred = torch.cuda.Event()
+        ev_pred.record(s_in)
+        base = D.to_device_u64(torch, base_segs, device)
+        ev_base = torch.cuda.Event()
+        ev_base.record(s_in)
+    pred.record_stream(s_main)
+    base.record_stream(s_main)
+    return pred, base, ev_pred, ev_base
 
-    def release():
-        if not released[0]:
-            released[0] = True
-            D.h2d_permit.release()
 
-    try:
-        s_in.wait_stream(s_main)
-        with torch.cuda.stream(s_in):
-            pred = D.to_device_f32(torch, d, device)
-            ev_pred = torch.cuda.Event()
-            ev_pred.record(s_in)
-            base = D.to_device_u64(torch, base_segs, device)
-            ev_base = torch.cuda.Event()
-            ev_base.record(s_in)
-        pred.record_stream(s_main)
-        base.record_stream(s_main)
-        s_main.wait_event(ev_pred)
-        res = D.chunk_ccs_device(pred, t32, int(sz_thresh), connectivity=connectivity, dil_k=int(dil_param),
-                                 offset=off)
+def _finish_chunk(torch, ctx, shape, t32, sz_thresh, off, connectivity, dil_param):
+    pred, base, ev_pred, ev_base = ctx
+    s_main = torch.cuda.current_stream()
+    s_main.wait_event(ev_pred)
+    res = D.chunk_ccs_device(pred, t32, int(sz_thresh), connectivity=connectivity, dil_k=int(dil_param), offset=off)
 
-        def overlaps():
-            ev_base.synchronize()       # the base volume has arrived: the next chunk may start copying
-            release()
-            return D.count_overlaps_device(res.labels, base)
+    def overlaps():
+        s_main.wait_event(ev_base)
+        return D.count_overlaps_device(res.labels, base)
 
-        ccs, continuations, info, ov = _materialise_cc(res, shape, between=overlaps)
-    finally:
-        release()
+    ccs, continuations, info, ov = _materialise_cc(res, shape, between=overlaps)
     return ccs, continuations, info, _coo_from_result(ov)
 
 
-def cc_overlap_tasks(chunks, cc_thresh, sz_thresh, connectivity=6, dil_param=0, workers=2):
+def cc_overlap_tasks(chunks, cc_thresh, sz_thresh, connectivity=6, dil_param=0):
     """
     cc_overlap_task over a sequence of chunks, software-pipelined: `chunks` yields (desc_vol, base_segs) or
-    (desc_vol, base_segs, offset); results come back in order as (ccs, continuations, seg_info, overlap_mat).
+    (desc_vol, base_segs, offset) with host arrays; results come back in order as
+    (ccs, continuations, seg_info, overlap_mat), each identical to cc_overlap_task's.
 
-    One chunk is bound by its own host-to-device copy (1.6 GB for 512^3); everything else of the call -- the
-    device pipeline, the label volume coming back, building continuations / DataFrame / COO on the host -- can
-    run under the NEXT chunk's copy.  `workers` host threads (each with its own CUDA streams and workspace) take
-    chunks alternately, so the PCIe link stays busy with input copies back to back.
+    One chunk is bound by its own host-to-device copy (1.6 GB for 512^3).  Here the input copies of chunk i+1 are
+    queued (asynchronously, on the copy-in stream) BEFORE chunk i is finished, so chunk i's device pipeline, its
+    label volume coming back and the host-side construction of continuations / DataFrame / COO all run under the
+    next chunk's copy: the PCIe link carries input copies back to back.  Single host thread; two chunks' device
+    buffers alive at a time.
     """
     torch = D._torch()
-    device_index = torch.cuda.current_device()
+    device = torch.device("cuda", torch.cuda.current_device())
 
-    def run(item):
-        d, b = item[0], item[1]
-        off = item[2] if len(item) > 2 else (0, 0, 0)
-        torch.cuda.set_device(device_index)
-        stream = D.side_stream(torch, torch.device("cuda", device_index), "main")
-        with torch.cuda.stream(stream):
-            out = cc_overlap_task(d, b, cc_thresh, sz_thresh, offset=off, connectivity=connectivity,
-                                  dil_param=dil_param)
-            stream.synchronize()
-        return out
+    def start(item):
+        d = np.asarray(item[0])
+        shape = tuple(int(x) for x in d.shape)
+        off = tuple(int(o) for o in item[2]) if len(item) > 2 else (0, 0, 0)
+        if 0 in shape or isinstance(item[1], torch.Tensor):
+            return ("plain", item, off)
+        t32 = D.float32_threshold(d.dtype, cc_thresh)
+        return ("piped", _start_chunk(torch, device, d, item[1]), shape, t32, off)
 
-    pool = _worker_pool(max(1, int(workers)))
-    pending = []
+    def finish(st):
+        if st[0] == "plain":
+            return cc_overlap_task(st[1][0], st[1][1], cc_thresh, sz_thresh, offset=st[2], connectivity=connectivity,
+                                   dil_param=dil_param)
+        _, ctx, shape, t32, off = st
+        return _finish_chunk(torch, ctx, shape, t32, sz_thresh, off, connectivity, dil_param)
+
+    prev = None
+    reserved = False
     for item in chunks:
-        pending.append(pool.submit(run, item))
-        if len(pending) >= workers:               # bounded look-ahead: at most `workers` chunks in flight
-            yield pending.pop(0).result()
-    for f in pending:
-        yield f.result()
-
-
-_pools = {}
-
-
-def _worker_pool(workers):
-    """Persistent worker threads: each keeps its CUDA streams, workspace and pinned staging blocks between calls."""
-    import concurrent.futures as cf
-    pool = _pools.get(workers)
-    if pool is None:
-        pool = cf.ThreadPoolExecutor(max_workers=workers, thread_name_prefix="synaptor_b200")
-        _pools[workers] = pool
-    return pool
+        if not reserved:                  # pinned blocks for the label volumes that will be alive at once
+            reserved = True
+            shp = tuple(int(x) for x in np.asarray(item[0]).shape)
+            if len(shp) == 3 and 0 not in shp:
+                D.pinned_reserve(torch, shp, torch.int32, 4)
+        cur = start(item)                 # queue this chunk's input copies first ...
+        if prev is not None:
+            yield finish(prev)            # ... then finish the previous chunk under them
+        prev = cur
+    if prev is not None:
+        yield finish(prev)
 
 
 def _coo_from_result(res):

@@ -51,7 +51,7 @@ def timed_empty(*a, **k):
 
 torch.empty = timed_empty
 workers = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-for _ in T.cc_overlap_tasks([(pn, bn)] * 6, 0.5, 100, workers=workers):
+for _ in T.cc_overlap_tasks([(pn, bn)] * 6, 0.5, 100):
     pass
 torch.cuda.synchronize()
 for rep in range(3):
@@ -59,7 +59,7 @@ for rep in range(3):
     n = 12
     t0 = time.perf_counter()
     ts = []
-    for out in T.cc_overlap_tasks([(pn, bn)] * n, 0.5, 100, workers=workers):
+    for out in T.cc_overlap_tasks([(pn, bn)] * n, 0.5, 100):
         ccs, conts, info, mat = out
         ts.append(time.perf_counter() - t0)
     torch.cuda.synchronize()
