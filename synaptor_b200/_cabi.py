@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsynaptor_b200.so")
+# SYNAPTOR_B200_LIB: another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("SYNAPTOR_B200_LIB") or os.path.join(_HERE, "libsynaptor_b200.so")
 
 SYN_OK = 0
 SYN_ERR_INVALID = -1

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <cstdint>
@@ -416,12 +417,20 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
     PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap ? W.paircap - 1 : 0, W.cnt};
     if (sector_out) {
         const i64 ntiles = ((i64)g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
-#define SYN_STREAM(HB, FS)                                                                                         \
-    k_stream<HB, FS><<<wave_grid(k_stream<HB, FS>, TS_THREADS, ntiles), TS_THREADS, 0, st>>>(                      \
+        static const int stream_ctas = getenv("SYN_STREAM_CTAS") ? atoi(getenv("SYN_STREAM_CTAS")) : 0;   // per SM; 0 = occupancy
+        static const bool no_tma = getenv("SYN_NO_TMA") != nullptr;
+        // base ids by TMA bulk copies into shared memory when chunk c starts at voxel 128 c (nz % 128 == 0)
+        const bool tma = has_base && !no_tma && (nz % 128 == 0);
+#define SYN_STREAM(HB, FS, TM)                                                                                     \
+    k_stream<HB, FS, TM><<<stream_ctas > 0 ? (int)std::min<i64>((i64)stream_ctas * sm_count(), ntiles)             \
+                                           : wave_grid(k_stream<HB, FS, TM>, TS_THREADS, ntiles,                   \
+                                                       TM ? TS_TMA_SMEM : 0),                                      \
+                           TS_THREADS, TM ? TS_TMA_SMEM : 0, st>>>(                                                \
         pred, bs, labels_out, W.omask, W.runbase, W.tileagg, W.tilebase, W.actw, W.bndw, g, W.tg, thresh, W.cnt,   \
         (u32)max_runs)
-        if (has_base) { if (fused_scan) SYN_STREAM(true, true); else SYN_STREAM(true, false); }
-        else { if (fused_scan) SYN_STREAM(false, true); else SYN_STREAM(false, false); }
+        if (tma) { if (fused_scan) SYN_STREAM(true, true, true); else SYN_STREAM(true, false, true); }
+        else if (has_base) { if (fused_scan) SYN_STREAM(true, true, false); else SYN_STREAM(true, false, false); }
+        else { if (fused_scan) SYN_STREAM(false, true, false); else SYN_STREAM(false, false, false); }
 #undef SYN_STREAM
         CK_LAUNCH();
         PROF("stream");
