@@ -1041,6 +1041,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     {
         u32 rb = ex & 0xFFFFu, ab = ex >> 16;
         u32 jj = jj0, xl = xl0, yl = yl0, k = k0;
+        const bool one_seg = (segw & 3u) == 0;           // the thread's four words lie in one x-slab segment
 #pragma unroll
         for (int q = 0; q < TILE_WPT; ++q) {
             if (i0 + q < ntw) {
@@ -1051,7 +1052,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
                     if (m[q]) {
                         s_st[i0 + q] = st[q];
                         s_act[ab++] = (i0 + q) | (k << 11) | (yl << 21) | (xl << 27);
-                        for (u32 r = 0; r < n; ++r) s_segof[rb + r] = (unsigned char)xl;   // no search in the flatten
+                        if (!one_seg)
+                            for (u32 r = 0; r < n; ++r) { s_segof[rb + r] = (unsigned char)xl; s_par[rb + r] = rb + r; }
                     }
                 }
                 rb += n;
@@ -1059,10 +1061,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
                 if (++jj == segw) { jj = 0; yl = 0; ++xl; }
             }
         }
+        if (!dense && one_seg) {
+            // parent = self and x-slab of every run of my words: ONE loop over the thread's runs (usually 0-2)
+            const u32 r0 = ex & 0xFFFFu;
+            for (u32 r = r0; r < rb; ++r) { s_segof[r] = (unsigned char)xl0; s_par[r] = r; }
+        }
     }
     if (threadIdx.x == 0) s_segoff[vx] = nloc;
-    if (!dense)
-        for (u32 i = threadIdx.x; i < nloc; i += blockDim.x) s_par[i] = i;
     __syncthreads();
     if (threadIdx.x < vx) s_delta[threadIdx.x] = segbase - s_segoff[threadIdx.x];
     if (dense) {
