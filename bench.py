@@ -40,9 +40,9 @@ BYTES_PER_VOXEL_PIPELINE = 16   # 4 B pred read + 4 B label write + 8 B base rea
 BYTES_PER_VOXEL_STREAM_KERNEL = 16  # k_stream: 4 B pred read + 8 B base read + 4 B label (zero-fill) write
 CPU_SAMPLE = (256, 256, 256)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_stream launch on the 512^3 workload (ncu --set full,
-# profiles/r01h_top_summary.txt: 1.610975 GB read + 477.26 MB written; the algorithmic 16 B/voxel are 2.147 GB --
-# the foreground sectors are not zero-filled by this kernel)
-STREAM_TRAFFIC_512 = 2088233752
+# profiles/r01j_top_summary.txt: 1.610879 GB read + 490.25 MB written in 324.6 us; the algorithmic 16 B/voxel are
+# 2.147 GB -- the foreground sectors are not zero-filled by this kernel)
+STREAM_TRAFFIC_512 = 2101131544
 
 
 def peaks():
@@ -359,7 +359,7 @@ def main():
                        "l2": "inputs (1.6 GB/step) exceed the 126 MB L2; no flush needed",
                        "components": counts["components"], "kept": counts["kept"], "pairs": counts["pairs"],
                        "runs": counts["runs"], "fg_voxels": counts["fg_voxels"], "merged_segments": n_merged},
-            "roofline": {"bound": "hbm", "kernel": "k_stream<base,scan> (pred + base read, threshold, label zero-fill, run prefix)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_stream<base,scan,tma> (pred + base read [base by TMA bulk copies], threshold, label zero-fill, run prefix)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": STREAM_TRAFFIC_512 if shape == (512, 512, 512) else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL_STREAM_KERNEL, "kernel_ms": wl_ms,
