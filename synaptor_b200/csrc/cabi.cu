@@ -419,18 +419,21 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
         const i64 ntiles = ((i64)g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
         static const int stream_ctas = getenv("SYN_STREAM_CTAS") ? atoi(getenv("SYN_STREAM_CTAS")) : 0;   // per SM; 0 = occupancy
         static const bool no_tma = getenv("SYN_NO_TMA") != nullptr;
-        // base ids by TMA bulk copies into shared memory when chunk c starts at voxel 128 c (nz % 128 == 0)
-        const bool tma = has_base && !no_tma && (nz % 128 == 0);
-#define SYN_STREAM(HB, FS, TM)                                                                                     \
-    k_stream<HB, FS, TM><<<stream_ctas > 0 ? (int)std::min<i64>((i64)stream_ctas * sm_count(), ntiles)             \
-                                           : wave_grid(k_stream<HB, FS, TM>, TS_THREADS, ntiles,                   \
-                                                       TM ? TS_TMA_SMEM : 0),                                      \
-                           TS_THREADS, TM ? TS_TMA_SMEM : 0, st>>>(                                                \
+        static const bool all_tma = getenv("SYN_ALL_TMA") != nullptr;    // A/B: predictions by TMA on the fused path too
+        // bulk copies into shared memory need chunk c to start at voxel 128 c (nz % 128 == 0)
+        const bool tma = !no_tma && (nz % 128 == 0);
+#define SYN_STREAM(HB, FS, TB, TP, NST)                                                                            \
+    k_stream<HB, FS, TB, TP, NST><<<stream_ctas > 0 ? (int)std::min<i64>((i64)stream_ctas * sm_count(), ntiles)    \
+                                                   : wave_grid(k_stream<HB, FS, TB, TP, NST>, TS_THREADS, ntiles,  \
+                                                               NST * ts_stage_bytes(TP, TB)),                      \
+                                   TS_THREADS, NST * ts_stage_bytes(TP, TB), st>>>(                                \
         pred, bs, labels_out, W.omask, W.runbase, W.tileagg, W.tilebase, W.actw, W.bndw, g, W.tg, thresh, W.cnt,   \
         (u32)max_runs)
-        if (tma) { if (fused_scan) SYN_STREAM(true, true, true); else SYN_STREAM(true, false, true); }
-        else if (has_base) { if (fused_scan) SYN_STREAM(true, true, false); else SYN_STREAM(true, false, false); }
-        else { if (fused_scan) SYN_STREAM(false, true, false); else SYN_STREAM(false, false, false); }
+        if (has_base && tma && all_tma) { if (fused_scan) SYN_STREAM(true, true, true, true, 2); else SYN_STREAM(true, false, true, true, 2); }
+        else if (has_base && tma) { if (fused_scan) SYN_STREAM(true, true, true, false, 2); else SYN_STREAM(true, false, true, false, 2); }
+        else if (has_base) { if (fused_scan) SYN_STREAM(true, true, false, false, 1); else SYN_STREAM(true, false, false, false, 1); }
+        else if (tma) { if (fused_scan) SYN_STREAM(false, true, false, true, 4); else SYN_STREAM(false, false, false, true, 4); }
+        else { if (fused_scan) SYN_STREAM(false, true, false, false, 1); else SYN_STREAM(false, false, false, false, 1); }
 #undef SYN_STREAM
         CK_LAUNCH();
         PROF("stream");

@@ -133,19 +133,21 @@ struct RunIdx {
 //   bndw[]      non-empty words on a tile border of k_tile_ccl (the input of k_union_bnd)
 // No dependence between CTAs: 16 B/voxel of pure streaming.
 // ===========================================================================
-// TMA_BASE (needs nz % 128 == 0, i.e. chunk c starts at voxel 128 c): the base ids -- two thirds of the bytes
-// read, and only needed for a max() -- do not pass through registers: thread 0 issues one 32 KB cp.async.bulk per
-// quarter tile into a ring of TS_NSTAGE shared-memory stages, TS_NSTAGE - 1 quarter tiles ahead (also across the
-// scan phase and the tile boundary), and the CTA reduces each stage from shared memory when its mbarrier flips.
-#ifndef TS_NSTAGE_DEF
-#define TS_NSTAGE_DEF 2      // measured: 2 stages (3 CTAs/SM) 345 us, 3 stages (2 CTAs/SM) 356 us, 4 stages (1 CTA/SM) 532 us
-#endif
-constexpr int TS_NSTAGE = TS_NSTAGE_DEF;
-constexpr int TS_QCHUNKS = TS_CHUNKS / 4;                      // chunks per quarter tile (one bulk copy)
-constexpr int TS_STAGE_BYTES = TS_QCHUNKS * 128 * 8;           // 32 KB of base ids
-constexpr size_t TS_TMA_SMEM = (size_t)TS_NSTAGE * TS_STAGE_BYTES;
+// TMA_BASE / TMA_PRED (need nz % 128 == 0, i.e. chunk c starts at voxel 128 c): the stream does not pass through
+// registers.  Thread 0 issues one cp.async.bulk per quarter tile and array (32 KB of base ids, 16 KB of predictions)
+// into a ring of NST shared-memory stages, NST - 1 quarter tiles ahead (also across the scan phase and the tile
+// boundary); the CTA consumes a stage from shared memory when its mbarrier flips.  The bytes in flight then live
+// in shared memory, which is what this kernel is short of (1 / 2 / 3 CTAs per SM = 585 / 406 /
+// 364 us with register loads).  Base ids -- two thirds of the bytes read, only needed for a max() -- gain most.
+constexpr int TS_QCHUNKS = TS_CHUNKS / 4;                      // chunks per quarter tile (one bulk copy per array)
+constexpr int TS_PRED_BYTES = TS_QCHUNKS * 128 * 4;            // 16 KB of predictions
+constexpr int TS_BASE_BYTES = TS_QCHUNKS * 128 * 8;            // 32 KB of base ids
+__host__ __device__ constexpr size_t ts_stage_bytes(bool tma_pred, bool tma_base)
+{
+    return (tma_pred ? TS_PRED_BYTES : 0) + (tma_base ? TS_BASE_BYTES : 0);
+}
 
-template <bool HAS_BASE, bool FUSE_SCAN, bool TMA_BASE>
+template <bool HAS_BASE, bool FUSE_SCAN, bool TMA_BASE, bool TMA_PRED, int NST>
 __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__ pred, const u64 *__restrict__ base,
                                                        u32 *__restrict__ labels, u32 *__restrict__ mask,
                                                        u32 *__restrict__ rb, u32 *__restrict__ tileagg,
@@ -153,8 +155,11 @@ __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__
                                                        u32 *__restrict__ bndw, Geom g, TileGeom tg, float thr,
                                                        Counts *cnt, u32 max_runs)
 {
-    extern __shared__ __align__(128) unsigned char s_stage[];    // TMA_BASE: TS_NSTAGE stages of base ids
-    __shared__ __align__(8) u64 s_mbar[TS_NSTAGE];
+    constexpr bool TMA = TMA_BASE || TMA_PRED;
+    constexpr size_t STAGE = ts_stage_bytes(TMA_PRED, TMA_BASE);
+    constexpr size_t BASE_OFF = TMA_PRED ? TS_PRED_BYTES : 0;    // stage layout: [predictions][base ids]
+    extern __shared__ __align__(128) unsigned char s_stage[];    // TMA: NST stages
+    __shared__ __align__(8) u64 s_mbar[NST];
     __shared__ u32 s_m[TS_SLOTS + 1];   // s_m[0]: the word before the tile's first slot; slot s at s_m[s + 1]
     __shared__ u32 sm[33];
     __shared__ u32 s_bcount, s_abase, s_bbase;
@@ -162,26 +167,28 @@ __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__
     const u32 ntiles = (g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
     u32 nfg = 0;
     u64 bmax = 0;
-    u32 qi = 0;                          // this CTA's quarter-tile counter (TMA_BASE)
+    u32 qi = 0;                          // this CTA's quarter-tile counter (TMA)
     // quarter tile #q of this CTA: tile blockIdx.x + (q / 4) * gridDim.x, chunks [.. + (q % 4) * 32, + 32)
-    auto issue_base = [&](u32 q) {       // thread 0 only
+    auto issue = [&](u32 q) {            // thread 0 only
         const u64 tile = (u64)blockIdx.x + (u64)(q >> 2) * gridDim.x;
         if (tile >= ntiles) return;
         const u64 chunk = tile * TS_CHUNKS + (u64)(q & 3u) * TS_QCHUNKS;
         if (chunk >= g.nchunks) return;
         const u32 nch = (u32)min((u64)TS_QCHUNKS, (u64)g.nchunks - chunk);
-        const u32 stage = q % TS_NSTAGE;
-        mbar_expect_tx(&s_mbar[stage], nch * 1024u);
-        bulk_g2s(s_stage + (size_t)stage * TS_STAGE_BYTES, base + chunk * 128, nch * 1024u, &s_mbar[stage]);
+        const u32 stage = q % NST;
+        unsigned char *dst = s_stage + (size_t)stage * STAGE;
+        mbar_expect_tx(&s_mbar[stage], nch * ((TMA_PRED ? 512u : 0u) + (TMA_BASE ? 1024u : 0u)));
+        if (TMA_PRED) bulk_g2s(dst, pred + chunk * 128, nch * 512u, &s_mbar[stage]);
+        if (TMA_BASE) bulk_g2s(dst + BASE_OFF, base + chunk * 128, nch * 1024u, &s_mbar[stage]);
     };
-    if (TMA_BASE) {
+    if (TMA) {
         if (threadIdx.x == 0) {
-            for (int s = 0; s < TS_NSTAGE; ++s) mbar_init(&s_mbar[s], 1);
+            for (int s = 0; s < NST; ++s) mbar_init(&s_mbar[s], 1);
             mbar_init_fence();
         }
         __syncthreads();
         if (threadIdx.x == 0)
-            for (u32 q = 0; q + 1 < TS_NSTAGE; ++q) issue_base(q);
+            for (u32 q = 0; q + 1 < (u32)NST; ++q) issue(q);
     }
     for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const u32 cbase = tile * TS_CHUNKS;
@@ -192,7 +199,10 @@ __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__
             // warp w handles chunks it * 32 + w * 4 .. + 3 of the tile (a quarter tile per iteration and CTA)
             const u32 cl0 = (u32)it * TS_QCHUNKS + (u32)wid * 4;      // chunk index inside the tile
             const u32 c0 = cbase + cl0;
-            if (TMA_BASE && threadIdx.x == 0) issue_base(qi + TS_NSTAGE - 1);
+            if (TMA && threadIdx.x == 0) issue(qi + NST - 1);
+            const unsigned char *stg = s_stage + (size_t)(qi % NST) * STAGE;
+            const bool qvalid = (u64)cbase + (u64)it * TS_QCHUNKS < g.nchunks;
+            if (TMA_PRED && qvalid) mbar_wait(&s_mbar[qi % NST], (qi / NST) & 1u);     // predictions of this quarter tile
             float4 v[4];
             ulonglong2 b01[4], b23[4];
             bool ok[4];
@@ -209,7 +219,8 @@ __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (HAS_BASE && !TMA_BASE) { b01[u] = make_ulonglong2(0, 0); b23[u] = make_ulonglong2(0, 0); }
                 if (ok[u]) {
-                    v[u] = __ldcs(reinterpret_cast<const float4 *>(pred + vox[u]));
+                    if (TMA_PRED) v[u] = *reinterpret_cast<const float4 *>(stg + ((size_t)(wid * 4 + u) * 128 + 4 * lane) * 4);
+                    else v[u] = __ldcs(reinterpret_cast<const float4 *>(pred + vox[u]));
                     if (HAS_BASE && !TMA_BASE) {
                         const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(base + vox[u]);
                         b01[u] = __ldcs(bp);
@@ -238,13 +249,12 @@ __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__
                 }
                 if (HAS_BASE && !TMA_BASE) bmax = max(bmax, max(max(b01[u].x, b01[u].y), max(b23[u].x, b23[u].y)));
             }
-            if (TMA_BASE) {
-                const u64 chunk = (u64)cbase + (u64)it * TS_QCHUNKS;
-                if (chunk < g.nchunks) {
-                    const u32 stage = qi % TS_NSTAGE;
-                    mbar_wait(&s_mbar[stage], (qi / TS_NSTAGE) & 1u);
+            if (TMA) {
+                if (TMA_BASE && qvalid) {
+                    if (!TMA_PRED) mbar_wait(&s_mbar[qi % NST], (qi / NST) & 1u);
+                    const u64 chunk = (u64)cbase + (u64)it * TS_QCHUNKS;
                     const u32 n16 = (u32)min((u64)TS_QCHUNKS, (u64)g.nchunks - chunk) * 64u;   // 16-byte units
-                    const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(s_stage + (size_t)stage * TS_STAGE_BYTES);
+                    const ulonglong2 *sp = reinterpret_cast<const ulonglong2 *>(stg + BASE_OFF);
 #pragma unroll 4
                     for (u32 j = threadIdx.x; j < n16; j += TS_THREADS) {
                         const ulonglong2 b = sp[j];
