@@ -181,7 +181,10 @@ def test_random_noise_vs_oracle(syn, shape, conn):
 
 # shapes with nz % 8 == 0 take the streaming / sector path (k_stream, k_sector_labels); (16, 32, 512) holds
 # exactly one 2048-word tile of the shared-memory labelling pass, the larger ones several tiles and tile borders
-SECTOR_SHAPES = [(16, 32, 512), (20, 40, 256), (9, 70, 96), (33, 17, 64), (5, 6, 8), (40, 24, 1032)]
+# nz % 128 == 0 additionally takes the TMA stage ring of k_stream; (3, 7, 128) and (5, 13, 384) end in a partial
+# quarter tile (21 and 195 chunks), (20, 40, 256) in a half tile
+SECTOR_SHAPES = [(16, 32, 512), (20, 40, 256), (9, 70, 96), (33, 17, 64), (5, 6, 8), (40, 24, 1032), (3, 7, 128),
+                 (5, 13, 384)]
 
 
 @pytest.mark.parametrize("shape", SECTOR_SHAPES)
@@ -203,7 +206,7 @@ def test_sector_path_noise_vs_oracle(syn, shape, conn):
         assert flagged > 0, "the dense / many-roots fallbacks were never taken"
 
 
-@pytest.mark.parametrize("shape", [(16, 32, 512), (24, 40, 128)])
+@pytest.mark.parametrize("shape", [(16, 32, 512), (24, 40, 128), (3, 7, 128), (5, 13, 384), (9, 70, 96)])
 def test_sector_path_fused_overlap_noise(syn, shape):
     rng = np.random.default_rng(99)
     for p in (0.06, 0.5):
