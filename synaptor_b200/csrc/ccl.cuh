@@ -491,6 +491,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_1p(Src src, Dst dst, vola
         if (blockIdx.x == 0 && threadIdx.x == 0 && total_out) *total_out = 0;
         return;
     }
+    // When the grid covers all tiles, the CTAs beyond the (device-side) tile count leave at once instead of queueing
+    // on the ticket only to find out that there is no work: hundreds of same-address atomics were a fixed ~5 us per
+    // scan.  The tickets themselves stay: a CTA then only ever waits on CTAs that are already running, whatever else
+    // shares the GPU (a second pipeline on another stream, for instance).
+    const bool one_each = gridDim.x >= ntiles;
+    if (one_each && blockIdx.x >= ntiles) return;
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
         __syncthreads();
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_1p(Src src, Dst dst, vola
         __syncthreads();
         ex += s_prefix;
         dst.store(i0, n, ex, item);
-        if (gridDim.x >= ntiles) break;   // one tile per CTA: no second ticket round trip
+        if (one_each) break;               // one tile per CTA: no second ticket round trip
         __syncthreads();   // s_tile / s_prefix are rewritten in the next round
     }
 }
