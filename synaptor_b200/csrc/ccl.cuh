@@ -1321,23 +1321,36 @@ struct RootFlagSrc {  // flattens while flagging
     template <int N>
     __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
     {
-        u32 p[N], q[N];
+        u32 p[N], x[N], r[N];
         load_items_u32(par, i0, n, p);
-        // second hop for all items at once (independent loads); most runs are roots or children of a root
+        // walk all N chains in lockstep, one hop per round: the loads of a round are independent of each other
+        // (most runs are roots or children of a root; a component spanning several tiles needs 2-4 hops)
 #pragma unroll
         for (int t = 0; t < N; ++t) {
             const u32 g = (u32)(i0 + t);
-            q[t] = (i0 + t < n && p[t] != g) ? ldcg_u32(par + p[t]) : p[t];
+            const bool valid = i0 + t < n;
+            x[t] = valid ? p[t] : 0u;
+            r[t] = (valid && p[t] != g) ? ldcg_u32(par + p[t]) : x[t];
+        }
+        bool pending = true;
+        while (pending) {
+            pending = false;
+#pragma unroll
+            for (int t = 0; t < N; ++t) {
+                if (r[t] != x[t]) {
+                    x[t] = r[t];
+                    r[t] = ldcg_u32(par + x[t]);
+                    pending = true;
+                }
+            }
         }
 #pragma unroll
         for (int t = 0; t < N; ++t) {
             item[t] = 0;
             if (i0 + t < n) {
                 const u32 g = (u32)(i0 + t);
-                u32 x = p[t], r = q[t];
-                while (r != x) { x = r; r = ldcg_u32(par + x); }
-                if (x != p[t]) par[g] = x;    // flatten (a concurrent reader sees the old ancestor or the root)
-                item[t] = (x == g);
+                if (x[t] != p[t]) par[g] = x[t];    // flatten (a concurrent reader sees the old ancestor or the root)
+                item[t] = (x[t] == g);
             }
         }
     }
