@@ -215,6 +215,18 @@ SYN_API int syn_merge_seg_tables(const int64_t *rows, int64_t n_rows, const uint
                                  int64_t *merged_out, uint32_t *fmap_out, int64_t *n_merged_dev, void *stream);
 
 /*
+ * syn_merge_overlaps -- proc/tasks.py:300-311 (merge_overlaps_task: consolidate_overlaps,
+ * overlap/merge/merge_overlaps.py:24-40, then find_max_overlaps, overlap/overlap.py:15-28).
+ * rows / cols / counts: device arrays of n (label, base id, voxel count) triples of all chunks,
+ * labels already in merged global ids (< n_ids; 0 = dropped, ignored).  Duplicates are summed;
+ * argcol_out[id] = base id with the largest total for that label (ties: the smallest base id, the
+ * first strict maximum of the (row, col)-sorted consolidated matrix), maxval_out[id] = that total
+ * (0 and all-ones argcol where a label has no overlap).  Dense arrays of n_ids entries.
+ */
+SYN_API int syn_merge_overlaps(const uint32_t *rows, const uint64_t *cols, const int64_t *counts, int64_t n,
+                               int64_t n_ids, uint64_t *argcol_out, int64_t *maxval_out, void *stream);
+
+/*
  * syn_chunk_ccs_multilabel -- the `overlap_seg` variant of connected_components
  * (synaptor/proc/seg/conncomps.py:24-28, reached through cc_task(..., overlap_seg=...),
  * proc/tasks.py:41,64-67): `temp = zeros(uint64); temp[mask] = overlap_seg[mask]`, then a

@@ -745,6 +745,35 @@ int syn_unique_u64(const uint64_t *vals, int64_t n, uint64_t *out, int64_t cap, 
 }
 
 
+int syn_merge_overlaps(const uint32_t *rows, const uint64_t *cols, const int64_t *counts, int64_t n, int64_t n_ids,
+                       uint64_t *argcol_out, int64_t *maxval_out, void *stream)
+{
+    if (n < 0 || n_ids < 0 || (n > 0 && (!rows || !cols || !counts)) || (n_ids > 0 && (!argcol_out || !maxval_out)))
+        return fail(SYN_ERR_INVALID, "bad arguments");
+    if (n_ids == 0) return SYN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_mo_init<<<grid_for(n_ids, 256, 8), 256, 0, st>>>((u64 *)argcol_out, (i64 *)maxval_out, n_ids);
+    CK_LAUNCH();
+    if (n == 0) return SYN_OK;
+    const u32 cap = pow2_at_least(2 * n);
+    char *buf = nullptr;
+    CK(cudaMallocAsync(&buf, (size_t)cap * (sizeof(PairKey) + 16) + sizeof(Counts), st));
+    PairTable T{(PairKey *)buf, (u64 *)(buf + (size_t)cap * sizeof(PairKey)),
+                (u64 *)(buf + (size_t)cap * (sizeof(PairKey) + 8)), cap - 1,
+                (Counts *)(buf + (size_t)cap * (sizeof(PairKey) + 16))};
+    CK(cudaMemsetAsync(T.cnt, 0, sizeof(Counts), st));
+    k_pair_table_init<<<grid_for(cap, 256, 8), 256, 0, st>>>(T);
+    CK_LAUNCH();
+    k_mo_insert<<<grid_for(n, 256, 8), 256, 0, st>>>(rows, (const u64 *)cols, (const i64 *)counts, n, T);
+    CK_LAUNCH();
+    k_mo_rowmax<<<grid_for(cap, 256, 8), 256, 0, st>>>(T, (i64 *)maxval_out, n_ids);
+    CK_LAUNCH();
+    k_mo_rowarg<<<grid_for(cap, 256, 8), 256, 0, st>>>(T, (const i64 *)maxval_out, (u64 *)argcol_out, n_ids);
+    CK_LAUNCH();
+    CK(cudaFreeAsync(buf, st));
+    return SYN_OK;
+}
+
 long long syn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int syn_profile_enable(int on)

@@ -477,4 +477,48 @@ __global__ void __launch_bounds__(256) k_pair_emit(PairTable T, const u32 *__res
     }
 }
 
+// ---------------------------------------------------------------------------
+// merge_overlaps (proc/tasks.py:300-311, overlap/merge/merge_overlaps.py:24-40, overlap.py:15-28): the chunks'
+// (label, base id, count) triples, labels already in merged global ids, are summed per pair in the pair table;
+// per label the base id with the largest total wins, ties go to the smallest base id (the consolidated matrix is
+// sorted by (row, col) and find_max_overlaps keeps the first strict maximum).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mo_insert(const u32 *__restrict__ rows, const u64 *__restrict__ cols,
+                                                   const i64 *__restrict__ counts, i64 n, PairTable T)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const u32 r = rows[i];
+        const i64 c = counts[i];
+        if (r == 0 || c <= 0) continue;          // label 0 = dropped by the merge (size threshold)
+        pair_insert(T, r, cols[i], (u32)c, (u64)i);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mo_init(u64 *__restrict__ argcol, i64 *__restrict__ maxval, i64 n_ids)
+{
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n_ids; i += (i64)gridDim.x * blockDim.x) {
+        argcol[i] = ~0ull;
+        maxval[i] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mo_rowmax(PairTable T, i64 *__restrict__ maxval, i64 n_ids)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.capmask; i += gridDim.x * blockDim.x) {
+        const PairKey k = T.keys[i];
+        if (k.label == ~0ull || (i64)k.label >= n_ids) continue;
+        atomicMax((u64 *)maxval + k.label, T.count[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mo_rowarg(PairTable T, const i64 *__restrict__ maxval,
+                                                   u64 *__restrict__ argcol, i64 n_ids)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.capmask; i += gridDim.x * blockDim.x) {
+        const PairKey k = T.keys[i];
+        if (k.label == ~0ull || (i64)k.label >= n_ids) continue;
+        if ((i64)T.count[i] == maxval[k.label]) atomicMin(argcol + k.label, k.base);
+    }
+}
+
 }  // namespace syn

@@ -98,6 +98,18 @@ class DeviceOps:
     def union_min_map(self, edges, n_edges, n_ids):
         return self.D.union_min_map_device(edges, n_edges, n_ids)
 
+    def merge_overlaps(self, rows, cols, counts, n_ids):
+        import ctypes
+        from . import _cabi as C
+        torch = self.torch
+        argcol = torch.empty(max(int(n_ids), 1), dtype=torch.int64, device=rows.device)
+        maxval = torch.empty(max(int(n_ids), 1), dtype=torch.int64, device=rows.device)
+        with torch.cuda.device(rows.device):
+            C.check(C.lib().syn_merge_overlaps(rows.data_ptr(), cols.data_ptr(), counts.data_ptr(), int(rows.numel()),
+                                               int(n_ids), argcol.data_ptr(), maxval.data_ptr(),
+                                               self.D._stream_ptr(torch)))
+        return argcol, maxval
+
     def merge_tables(self, rows, n_rows, gmap, size_thr):
         import ctypes
         from . import _cabi as C
@@ -225,3 +237,54 @@ def merge_ccs_device(results, grid, rank=None, world=None, size_thr=0, group=Non
             ops.relabel(r.labels, lut)
     n_merged = int(n_merged_dev.cpu()[0])
     return MergeResult(merged[:n_merged], n_merged, base, fmap, final_luts, int(n_edges.cpu()[0]))
+
+
+def merge_overlaps_device(results, merge, rank=None, world=None, group=None, ops=None):
+    """
+    merge_overlaps_task (proc/tasks.py:300-311) for chunks resident on one or several GPUs, after
+    merge_ccs_device: `results` are THIS rank's ChunkResults of the fused pass (pair_rows / pair_cols / pair_vals
+    = the chunk's overlap triples in chunk-local labels, counts["pairs"]), `merge` the MergeResult (chunk_luts:
+    chunk-local label -> merged global id, 0 = dropped).  One all_gather of the (padded) triples, then every rank
+    sums duplicates and takes the arg-max base id per merged cleft on the device (syn_merge_overlaps).
+    Returns {merged cleft id: (base id, voxel count)} as three numpy arrays (ids ascending, base ids, counts).
+    Collective: every rank of `group` must call it.
+    """
+    import torch
+    import torch.distributed as dist
+    ops = ops or DeviceOps()
+    if not isinstance(results, (list, tuple)):
+        results = [results]
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if world > 1 else 0
+    device = results[0].labels.device
+    rows_l, cols_l, vals_l = [], [], []
+    for (r, lut) in zip(results, merge.chunk_luts):
+        n = int(r.counts["pairs"])
+        rows = r.pair_rows[:n].clone()
+        ops.relabel(rows, lut)                       # chunk-local label -> merged global id (0 = dropped)
+        rows_l.append(rows)
+        cols_l.append(r.pair_cols[:n])
+        vals_l.append(r.pair_vals[:n])
+    rows = torch.cat(rows_l) if rows_l else torch.zeros(0, dtype=torch.int32, device=device)
+    cols = torch.cat(cols_l) if cols_l else torch.zeros(0, dtype=torch.int64, device=device)
+    vals = torch.cat(vals_l) if vals_l else torch.zeros(0, dtype=torch.int64, device=device)
+    if world > 1:
+        n_local = torch.tensor([rows.numel()], dtype=torch.int64, device=device)
+        n_all = _all_gather(torch, dist, n_local, world, group).cpu().numpy().reshape(-1)
+        cap = int(n_all.max()) if len(n_all) else 0
+        packed = torch.zeros((max(cap, 1), 3), dtype=torch.int64, device=device)    # zero rows are ignored
+        if rows.numel():
+            packed[:rows.numel(), 0] = rows.to(torch.int64) & 0xFFFFFFFF
+            packed[:rows.numel(), 1] = cols
+            packed[:rows.numel(), 2] = vals
+        allp = _all_gather(torch, dist, packed, world, group).reshape(-1, 3)
+        rows = allp[:, 0].to(torch.int32).contiguous()
+        cols = allp[:, 1].contiguous()
+        vals = allp[:, 2].contiguous()
+    n_ids = int(merge.fmap.numel())
+    argcol, maxval = ops.merge_overlaps(rows, cols, vals, n_ids)
+    mv = maxval.cpu().numpy()[:n_ids]
+    ids = np.nonzero(mv > 0)[0]
+    return ids.astype(np.int64), argcol.cpu().numpy().view(np.uint64)[ids], mv[ids]

@@ -454,6 +454,7 @@ def test_merge_ccs_device_vs_oracle(syn, vshape, cshape):
     from synaptor_b200 import _device as D
     from synaptor_b200 import multi
     vol = orc.synth_pred(vshape, seed=11, sigma=2.0, fg=0.10)
+    base_vol = orc.synth_base(vshape, seed=12, block=5, bg=0.1)
     grid = tuple(v // c for (v, c) in zip(vshape, cshape))
     dev = torch.device("cuda", torch.cuda.current_device())
     results, chunks = [], []
@@ -463,7 +464,9 @@ def test_merge_ccs_device_vs_oracle(syn, vshape, cshape):
         beg = tuple(a * b for (a, b) in zip(gi, cshape))
         sl = tuple(slice(b, b + c) for (b, c) in zip(beg, cshape))
         sub = np.ascontiguousarray(vol[sl])
-        res = D.chunk_ccs_device(torch.from_numpy(sub).to(dev), np.float32(0.5), 10, offset=beg)
+        bsub = np.ascontiguousarray(base_vol[sl])
+        res = D.chunk_ccs_device(torch.from_numpy(sub).to(dev), np.float32(0.5), 10, offset=beg,
+                                 base=torch.from_numpy(bsub.view(np.int64)).to(dev))
         ccs, conts, info = orc.cc_task_c(sub, 0.5, 10, offset=beg)
         assert np.array_equal(res.labels_numpy(), ccs)
         results.append(res)
@@ -473,6 +476,19 @@ def test_merge_ccs_device_vs_oracle(syn, vshape, cshape):
     # the oracle pads faces to (two largest dims); axis order inside a face is (smaller axis index, larger)
     merged, id_maps = orc.merge_ccs_task(cont_arr, info_arr, 15, (max(cshape), max(cshape)))
     out = multi.merge_ccs_device(results, grid, rank=0, world=1, size_thr=15)
+    # merge_overlaps_task on the device (proc/tasks.py:300-311): arg-max base segment per merged cleft
+    ids, cols, vals = multi.merge_overlaps_device(results, out, rank=0, world=1)
+    tot = {}
+    for (gi, sl, ccs) in chunks:
+        fin = orc.remap_ids(ccs.copy(), id_maps[gi])
+        r, c, v, _ = orc.count_overlaps_c(fin, np.ascontiguousarray(base_vol[sl]))
+        for (a, b, n) in zip(r.tolist(), c.tolist(), v.tolist()):
+            tot[(a, b)] = tot.get((a, b), 0) + n
+    best = {}
+    for ((a, b), n) in sorted(tot.items()):
+        if a not in best or n > best[a][1]:
+            best[a] = (b, n)
+    assert {int(i): (int(c), int(v)) for (i, c, v) in zip(ids, cols, vals)} == best
     got = {int(r[0]): r[1:].tolist() for r in out.merged_table.cpu().numpy()}
     assert set(got) == set(merged) and out.n_merged == len(merged)
     for (k, row) in merged.items():

@@ -64,6 +64,21 @@ class NumpyOps:
                 par[max(ra, rb)] = min(ra, rb)
         return torch.from_numpy(np.array([find(i) for i in range(n_ids)], dtype=np.uint32).view(np.int32))
 
+    def merge_overlaps(self, rows, cols, counts, n_ids):
+        r = rows.numpy().view(np.uint32).astype(np.int64)
+        c = cols.numpy().view(np.uint64)
+        v = counts.numpy()
+        tot = {}
+        for (a, b, n) in zip(r.tolist(), c.tolist(), v.tolist()):
+            if a and n > 0:
+                tot[(a, b)] = tot.get((a, b), 0) + n
+        arg = np.full(max(n_ids, 1), np.iinfo(np.uint64).max, dtype=np.uint64)
+        mx = np.zeros(max(n_ids, 1), dtype=np.int64)
+        for ((a, b), n) in sorted(tot.items()):
+            if n > mx[a]:
+                mx[a], arg[a] = n, b
+        return torch.from_numpy(arg.view(np.int64)), torch.from_numpy(mx)
+
     def merge_tables(self, rows, n_rows, gmap, size_thr):
         g = gmap.numpy().view(np.uint32)
         r = rows.numpy()
@@ -93,10 +108,32 @@ def make_chunks(vol, cshape, thresh, dust):
     return grid, chunks
 
 
-def to_result(ccs, table):
-    return SimpleNamespace(labels=torch.from_numpy(ccs.view(np.int32).copy()),
-                           seg_table=torch.from_numpy(table.copy()),
-                           counts={"kept": len(table), "max_label": int(ccs.max())})
+def to_result(ccs, table, base=None):
+    res = SimpleNamespace(labels=torch.from_numpy(ccs.view(np.int32).copy()),
+                          seg_table=torch.from_numpy(table.copy()),
+                          counts={"kept": len(table), "max_label": int(ccs.max())})
+    if base is not None:
+        r, c, v, _ = orc.count_overlaps_c(ccs, base)
+        res.pair_rows = torch.from_numpy(r.astype(np.uint32).view(np.int32).copy())
+        res.pair_cols = torch.from_numpy(c.astype(np.uint64).view(np.int64).copy())
+        res.pair_vals = torch.from_numpy(v.astype(np.int64).copy())
+        res.counts["pairs"] = len(r)
+    return res
+
+
+def oracle_max_overlaps(vshape, chunks, id_maps, base):
+    """merge_overlaps_task on the remapped chunk volumes: {merged id: (base id, count)}."""
+    tot = {}
+    for (gi, sl, ccs, _, _, _) in chunks:
+        final = orc.remap_ids(ccs.copy(), id_maps[gi])
+        r, c, v, _ = orc.count_overlaps_c(final, np.ascontiguousarray(base[sl]))
+        for (a, b, n) in zip(r.tolist(), c.tolist(), v.tolist()):
+            tot[(a, b)] = tot.get((a, b), 0) + n
+    best = {}
+    for ((a, b), n) in sorted(tot.items()):          # (row, col) order of the consolidated matrix; first strict max
+        if a not in best or n > best[a][1]:
+            best[a] = (b, n)
+    return best
 
 
 def oracle_merge(grid, chunks, size_thr, face_shape):
@@ -117,11 +154,13 @@ def _worker(rank, world, port, q):
         grid, chunks = make_chunks(vol, cshape, 0.5, 6)
         owners = multi.chunk_owners(grid, world)
         mine = [i for i in range(len(chunks)) if owners[i] == rank]
-        results = [to_result(chunks[i][2], chunks[i][5]) for i in mine]
+        base = orc.synth_base(vol.shape, seed=22, block=6, bg=0.1)
+        results = [to_result(chunks[i][2], chunks[i][5], np.ascontiguousarray(base[chunks[i][1]])) for i in mine]
         res = multi.merge_ccs_device(results, grid, rank=rank, world=world, size_thr=10, ops=NumpyOps())
+        mo = multi.merge_overlaps_device(results, res, rank=rank, world=world, ops=NumpyOps())
         out = {"rank": rank, "merged": res.merged_table.numpy(), "labels": {i: r.labels.numpy().view(np.uint32)
                                                                             for (i, r) in zip(mine, results)},
-               "base": res.id_base, "n_edges": res.n_edges}
+               "base": res.id_base, "n_edges": res.n_edges, "max_overlaps": mo}
         q.put(out)
     finally:
         dist.destroy_process_group()
@@ -165,6 +204,13 @@ def test_merge_plumbing_world2_gloo():
     for (i, (gi, sl, ccs, _, _, _)) in enumerate(chunks):
         want = orc.remap_ids(ccs.copy(), id_maps[gi])
         assert np.array_equal(labels[i], want)
+    # merge_overlaps: every rank holds the same arg-max table, equal to the oracle's on the remapped volumes
+    base = orc.synth_base(vol.shape, seed=22, block=6, bg=0.1)
+    want_mo = oracle_max_overlaps(vol.shape, chunks, id_maps, base)
+    for o in outs:
+        ids, cols, vals = o["max_overlaps"]
+        got_mo = {int(i): (int(c), int(v)) for (i, c, v) in zip(ids, cols, vals)}
+        assert got_mo == want_mo
 
 
 def test_plan_helpers():
