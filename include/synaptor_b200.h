@@ -244,15 +244,14 @@ SYN_API int syn_chunk_ccs_multilabel(const float *pred, const uint64_t *overlap_
 /*
  * Measurement hooks (no reference counterpart).
  * syn_launch_count   : kernels launched by this library in this process so far.
- * syn_profile_enable : 1 = syn_chunk_ccs records a CUDA event on its stream after every kernel and
- *                      runs the dense fill serially (clean per-kernel times); 2 = the same marks
- *                      with the side-stream overlap left on; 0 = off.  Not thread-safe; for bench.py.
+ * syn_profile_enable : non-zero = syn_chunk_ccs records a CUDA event on its stream after every kernel;
+ *                      0 = off.  Not thread-safe; for bench.py.
  * syn_profile_read   : synchronises on the last recorded call and returns the number K of
  *                      intervals (<= SYN_PROF_MAX), stage_ms[i] = elapsed ms of interval i.
  * syn_profile_name   : name of interval i of the last recorded call = the kernel that ended it
- *                      ("threshold_runs", "dense_fill", "tile_ccl", "union_bnd", "flatten_rank",
- *                      "stats_merge", "dust_table", "run_labels", "sector_labels", "pair_mark",
- *                      "pair_scan", "pair_emit", "join_dense", ...).
+ *                      ("stream", "pair_init", "tile_ccl", "union_bnd", "flatten_rank", "stats_merge",
+ *                      "dust_table", "run_labels", "sector_labels", "pair_count", "pair_bucket_scan",
+ *                      "pair_scatter", "pair_emit"; other names on the generic / dilation path).
  */
 #define SYN_PROF_MAX 40
 SYN_API long long syn_launch_count(void);

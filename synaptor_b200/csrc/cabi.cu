@@ -48,7 +48,6 @@ std::atomic<long long> g_launches{0};
 // ended at mark i + 1.
 constexpr int PROF_MAX = 40;
 bool g_prof_on = false;
-bool g_prof_overlap = false;   // syn_profile_enable(2): keep the side-stream overlap while recording events
 cudaEvent_t g_prof_ev[PROF_MAX];
 const char *g_prof_name[PROF_MAX];
 int g_prof_n = 0;
@@ -783,7 +782,6 @@ int syn_profile_enable(int on)
         g_prof_created = true;
     }
     g_prof_on = on != 0;
-    g_prof_overlap = on == 2;
     g_prof_valid = false;
     g_prof_n = 0;
     return SYN_OK;
