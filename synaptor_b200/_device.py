@@ -456,4 +456,8 @@ def unique_u64_device(vals, cap=1 << 16, stream=None):
         n = int(cnt.cpu()[0])
         if n <= cap:
             return np.sort(out[:n].cpu().numpy().view(np.uint64))
-        cap = max(n, cap * 4)
+        # overflow.  The count is only a lower bound of the need once the hash table filled up (every failed
+        # insert adds cap + 1 to it), so it is trusted only when it is plausible; the need never exceeds the
+        # number of elements.
+        total = int(flat.numel())
+        cap = min(total, max(cap * 4, n if n <= total else 0))

@@ -523,3 +523,14 @@ def test_cc_overlap_tasks_pipelined(syn):
         assert np.array_equal(info.to_numpy(), want_info.to_numpy())
         r, c, v, shp = orc.count_overlaps_c(want_ccs, base)
         assert mat.shape == shp and np.array_equal(mat.row, r) and np.array_equal(mat.col, c) and np.array_equal(mat.data, v)
+
+
+def test_unique_ids_many_distinct(syn):
+    """More distinct uint64 ids than the first table guess (the hash table fills up and the call must grow it
+    sensibly: the overflow count it reports is not the number of distinct ids)."""
+    rng = np.random.default_rng(8)
+    seg = rng.integers(1, 2 ** 40, size=(30, 40, 200), dtype=np.uint64)
+    seg[rng.random(seg.shape) < 0.1] = 0
+    got = syn.seg_utils.nonzero_unique_ids(seg)
+    want = np.unique(seg)
+    assert np.array_equal(got, want[want != 0])
