@@ -33,7 +33,8 @@ for case in range(ncases):
         else rng.random(shape, dtype=np.float32) + np.float32(p - 0.5)
     dust = int(rng.choice([0, 1, 5, 50]))
     off = tuple(int(v) for v in rng.integers(-50, 50, size=3))
-    mode = rng.choice(["cc", "cc26", "cc18", "fused", "dil", "ml"], p=[0.25, 0.1, 0.05, 0.35, 0.1, 0.15])
+    mode = rng.choice(["cc", "cc26", "cc18", "fused", "dil", "ml", "host", "utils", "merge"],
+                      p=[0.15, 0.08, 0.04, 0.25, 0.08, 0.1, 0.1, 0.1, 0.1])
     base = orc.synth_base(shape, seed=int(rng.integers(1 << 30)), block=int(rng.choice([1, 2, 4, 9])), bg=0.2)
     try:
         if mode == "fused":
@@ -43,6 +44,55 @@ for case in range(ncases):
             ok = np.array_equal(got[0], want[0]) and np.array_equal(got[2].to_numpy(), want[2].to_numpy()) and \
                 got[3].shape == shp and np.array_equal(got[3].row, r) and np.array_equal(got[3].col, c) and \
                 np.array_equal(got[3].data, v)
+        elif mode == "host":       # host arrays in: pipelined copies + standalone overlap counter; F-order prediction
+            pf = np.asfortranarray(pred) if rng.random() < 0.5 else pred
+            got = T.cc_overlap_task(pf, base, 0.5, dust, offset=off)
+            want = orc.cc_task_c(pred, 0.5, dust, offset=off)
+            r, c, v, shp = orc.count_overlaps_c(want[0], base)
+            ok = np.array_equal(got[0], want[0]) and np.array_equal(got[2].to_numpy(), want[2].to_numpy()) and \
+                got[3].shape == shp and np.array_equal(got[3].row, r) and np.array_equal(got[3].col, c) and \
+                np.array_equal(got[3].data, v)
+        elif mode == "utils":      # seg_utils on an arbitrary label volume
+            seg = orc.cc_task_c(pred, 0.5, 0)[0]
+            seg[seg != 0] = (seg[seg != 0] * 7919) % 100003 + 1          # non-contiguous ids
+            su = syn.seg_utils
+            sz = su.segment_sizes(seg)
+            wsz = orc.segment_sizes_np(seg)
+            ok = {int(k): int(v) for (k, v) in sz.items()} == {int(k): int(v) for (k, v) in wsz.items()}
+            cm, wcm = su.centers_of_mass(seg, offset=off), orc.centers_of_mass_np(seg, offset=off)
+            ok = ok and {int(k): tuple(int(x) for x in v) for (k, v) in cm.items()} == \
+                {int(k): tuple(int(x) for x in v) for (k, v) in wcm.items()}
+            bb, wbb = su.bounding_boxes(seg, offset=off), orc.bounding_boxes_np(seg, offset=off)
+            ok = ok and {int(k): tuple(v.astuple()) for (k, v) in bb.items()} == \
+                {int(k): tuple(int(x) for x in v) for (k, v) in wbb.items()}
+            fs, fsz = su.filter_segs_by_size(seg, max(dust, 1))
+            wfs, wfsz = orc.filter_segs_by_size_np(seg, max(dust, 1))
+            ok = ok and np.array_equal(fs, wfs)
+        elif mode == "merge":      # chunked pipeline + device merge + remap vs the oracle's merge_ccs_task
+            from synaptor_b200 import _device as D
+            from synaptor_b200 import multi
+            cs = tuple(max(1, s // int(rng.choice([1, 2]))) for s in shape)
+            vs = tuple((s // c) * c for (s, c) in zip(shape, cs))
+            vol = np.ascontiguousarray(pred[:vs[0], :vs[1], :vs[2]])
+            grid = tuple(v // c for (v, c) in zip(vs, cs))
+            cont_arr, info_arr = np.empty(grid, dtype=object), np.empty(grid, dtype=object)
+            results, chunks = [], []
+            for gi in np.ndindex(grid):
+                beg = tuple(a * b for (a, b) in zip(gi, cs))
+                sl = tuple(slice(b, b + c) for (b, c) in zip(beg, cs))
+                sub = np.ascontiguousarray(vol[sl])
+                results.append(D.chunk_ccs_device(torch.from_numpy(sub).cuda(), np.float32(0.5), dust, offset=beg))
+                ccs, conts, info = orc.cc_task_c(sub, 0.5, dust, offset=beg)
+                chunks.append((gi, sl, ccs))
+                cont_arr[gi], info_arr[gi] = conts, info
+            fs2 = tuple(sorted(cs)[1:])
+            merged, id_maps = orc.merge_ccs_task(cont_arr, info_arr, dust + 3, (max(cs), max(cs)))
+            out = multi.merge_ccs_device(results, grid, rank=0, world=1, size_thr=dust + 3)
+            gotm = {int(r[0]): r[1:].tolist() for r in out.merged_table.cpu().numpy()}
+            ok = set(gotm) == set(merged) and all(gotm[k][0] == merged[k][0] and gotm[k][4:] == merged[k][4:]
+                                                  for k in merged)
+            for ((gi, sl, ccs), res) in zip(chunks, results):
+                ok = ok and np.array_equal(res.labels_numpy(), orc.remap_ids(ccs.copy(), id_maps[gi]))
         elif mode == "ml":
             got = T.cc_task(pred, 0.5, dust, offset=off, overlap_seg=base, verbose=False)
             want = orc.cc_task_c(pred, 0.5, dust, offset=off, overlap_seg=base)
