@@ -75,3 +75,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(d, f)).read()
                 assert "oracle" not in text.lower(), f"{os.path.join(d, f)} mentions the oracle"
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/synaptor_b200.h is the drop-in boundary: it must compile as C99 (and as C++) on its own."""
+    import shutil
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "synaptor_b200.h"\nint main(void) { return syn_version() > 0 ? 0 : 1; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    if shutil.which("gcc"):
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                               "-I", inc, str(src)])
+    if shutil.which("g++"):
+        subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)])
