@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the plain syn_chunk_ccs call, not its CUDA graph")
     ap.add_argument("--chunk", type=int, nargs=3, default=list(CHUNK))
     args = ap.parse_args()
     if args.impl == "reference":
@@ -251,29 +252,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The timed steps replay ONE captured CUDA graph of the syn_chunk_ccs call (D.ChunkPipeline: stream capture of
+    # the same C-ABI call on the resident input tensors; 13 kernels + 1 memset per replay) -- what a production loop
+    # over equally shaped chunks does.  --no-graph times the plain call instead.
+    pipe = None if args.no_graph else D.ChunkPipeline(shape, DUST, thresh=THRESH, connectivity=CONN, offset=offset,
+                                                      device=dev, pred=pred, base=base)
     # first call sizes the buffers (sync=True grows capacities if needed)
     res = D.chunk_ccs_device(pred, t32, DUST, connectivity=CONN, base=base, offset=offset, sync=True)
     counts = dict(res.counts)
-    for _ in range(args.warmup):
-        res = step(res)
-    barrier()
+    run_stream = pipe.stream if pipe is not None else torch.cuda.current_stream()
+    if pipe is not None:
+        pipe.run()
+        assert pipe.counts()["kept"] == counts["kept"]
+
+    def timed_step():
+        if pipe is not None:
+            pipe.graph.replay()
+        else:
+            step(res)
 
     sampler = ClockSampler(local)
     sampler.start()
     sampler.wait_first_sample()
-    for _ in range(args.warmup):            # load already running when the timed steps start (clock samples)
-        res = step(res)
-    launches0 = L.syn_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        res = step(res)
-    e1.record()
-    barrier()
-    launches = L.syn_launch_count() - launches0
+    with torch.cuda.stream(run_stream):
+        for _ in range(2 * args.warmup):        # load already running when the timed steps start (clock samples)
+            timed_step()
+        launches0 = L.syn_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            timed_step()
+        e1.record()
+        barrier()
+    launches = (args.steps * pipe.launches_per_run) if pipe is not None else (L.syn_launch_count() - launches0)
     ms_total = e0.elapsed_time(e1)
-    after = D.read_counts(res)
+    after = pipe.counts() if pipe is not None else D.read_counts(res)
     assert after["errflags"] == 0 and after["kept"] == counts["kept"] and after["pairs"] == counts["pairs"], after
     # ---- cross-chunk merge_ccs exchange (config 4), timed on its own: NCCL all_gathers of counts, faces and
     # tables + device union-find + LUT remap of every rank's label volume.  Not part of the headline metric
@@ -355,6 +369,7 @@ def main():
             "config": {"workload": f"configs[1]: chunk_ccs+chunk_overlaps {shape[0]}x{shape[1]}x{shape[2]} per GPU, "
                                    "float32 pred (sigma 2, fg 3%), thr 0.5, 6-conn, dust 100, uint64 base (32^3 blocks)",
                        "chunks_per_gpu": 1, "grid": list(grid), "merge_ccs_in_step": False,
+                       "cuda_graph": pipe is not None,
                        "merge_ccs_ms_separate": merge_ms,
                        "l2": "inputs (1.6 GB/step) exceed the 126 MB L2; no flush needed",
                        "components": counts["components"], "kept": counts["kept"], "pairs": counts["pairs"],

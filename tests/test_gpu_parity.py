@@ -534,3 +534,29 @@ def test_unique_ids_many_distinct(syn):
     got = syn.seg_utils.nonzero_unique_ids(seg)
     want = np.unique(seg)
     assert np.array_equal(got, want[want != 0])
+
+
+def test_chunk_pipeline_graph_replay(syn):
+    """ChunkPipeline: the captured CUDA graph gives, chunk after chunk, what the eager call gives -- including
+    after a chunk that overflows the capacities sized on the first one."""
+    import torch
+    from synaptor_b200 import _device as D
+    shape = (16, 32, 512)
+    pipe = D.ChunkPipeline(shape, dust_thresh=5, offset=(1, 2, 3))
+    rng = np.random.default_rng(4)
+    for (i, p) in enumerate((0.02, 0.05, 0.6, 0.03)):          # 0.6: far more runs / pairs than the first chunk
+        pred = rng.random(shape, dtype=np.float32) + np.float32(p - 0.5)      # foreground fraction p at threshold 0.5
+        base = orc.synth_base(shape, seed=40 + i, block=8)
+        pipe.pred.copy_(torch.from_numpy(pred))
+        pipe.base.copy_(torch.from_numpy(base.view(np.int64)))
+        res = pipe.run()
+        c = pipe.counts()
+        res = pipe.result
+        want_ccs, _, want_info = orc.cc_task_c(pred, 0.5, 5, offset=(1, 2, 3))
+        assert np.array_equal(res.labels_numpy(), want_ccs), first_diff(res.labels_numpy(), want_ccs)
+        assert c["kept"] == len(want_info)
+        assert np.array_equal(res.table_numpy()[:, 1:], want_info.to_numpy())
+        r, cc, v, _ = orc.count_overlaps_c(want_ccs, base)
+        gr, gc, gv = res.pairs_numpy()
+        assert np.array_equal(gr, r) and np.array_equal(gc, cc.astype(np.uint64)) and np.array_equal(gv, v)
+    assert pipe.launches_per_run >= 10
