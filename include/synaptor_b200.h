@@ -215,6 +215,23 @@ SYN_API int syn_merge_seg_tables(const int64_t *rows, int64_t n_rows, const uint
                                  int64_t *merged_out, uint32_t *fmap_out, int64_t *n_merged_dev, void *stream);
 
 /*
+ * syn_merge_ccs_grid -- the device half of merge_ccs_task (proc/tasks.py:72-122) for a whole chunk grid in ONE
+ * call: edges over every interior face pair (merge_ccs.py:69-128), union-find to the smallest id
+ * (proc/utils.py:39-86), rows of all chunks in global id order (assign_ids.py:8-25), merged table + size threshold
+ * (merge_df.py:13-68).  faces_all: uint32 [n_slots][facebuf], the six faces of every chunk ALREADY in global ids,
+ * face order (axis 0 hi, axis 0 lo, axis 1 hi, ...), facebuf = 2 (ny nz + nx nz + nx ny); tables_all: int64
+ * [n_slots][maxk][SYN_SEG_NCOLS]; slot_of_chunk / kept: HOST arrays over the chunks in np.ndindex order (where a
+ * chunk's data sits in the gathered buffers, and its row count); grid_xyz / shape_xyz: HOST int64[3].
+ * Outputs as syn_union_min_map (gmap_out [total+1]) and syn_merge_seg_tables; edges_scratch uint32
+ * [max_edges][2], rows_scratch int64 [total][SYN_SEG_NCOLS].
+ */
+SYN_API int syn_merge_ccs_grid(const uint32_t *faces_all, const int64_t *tables_all, const int64_t *kept,
+                               const int64_t *slot_of_chunk, const int64_t *grid_xyz, const int64_t *shape_xyz,
+                               int64_t maxk, int64_t size_thr, uint32_t *edges_scratch, int64_t max_edges,
+                               unsigned long long *n_edges_dev, uint32_t *gmap_out, int64_t *rows_scratch,
+                               int64_t *merged_out, uint32_t *fmap_out, int64_t *n_merged_dev, void *stream);
+
+/*
  * syn_merge_overlaps -- proc/tasks.py:300-311 (merge_overlaps_task: consolidate_overlaps,
  * overlap/merge/merge_overlaps.py:24-40, then find_max_overlaps, overlap/overlap.py:15-28).
  * rows / cols / counts: device arrays of n (label, base id, voxel count) triples of all chunks,

@@ -50,6 +50,8 @@ SIGNATURES = {
     "syn_unique_u64": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "syn_ids_to_lut": (_i32, [_vp, _i64, _i64, ctypes.c_uint32, _vp, _i64, _vp]),
     "syn_merge_seg_tables": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "syn_merge_ccs_grid": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp]),
     "syn_merge_overlaps": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "syn_launch_count": (ctypes.c_longlong, []),
     "syn_profile_enable": (_i32, [_i32]),

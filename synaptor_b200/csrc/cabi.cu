@@ -744,6 +744,69 @@ int syn_unique_u64(const uint64_t *vals, int64_t n, uint64_t *out, int64_t cap, 
 }
 
 
+int syn_merge_ccs_grid(const uint32_t *faces_all, const int64_t *tables_all, const int64_t *kept,
+                       const int64_t *slot_of_chunk, const int64_t *grid_xyz, const int64_t *shape_xyz, int64_t maxk,
+                       int64_t size_thr, uint32_t *edges_scratch, int64_t max_edges, unsigned long long *n_edges_dev,
+                       uint32_t *gmap_out, int64_t *rows_scratch, int64_t *merged_out, uint32_t *fmap_out,
+                       int64_t *n_merged_dev, void *stream)
+{
+    if (!faces_all || !tables_all || !kept || !slot_of_chunk || !grid_xyz || !shape_xyz || !edges_scratch ||
+        !n_edges_dev || !gmap_out || !fmap_out || !n_merged_dev || maxk < 1 || max_edges < 1)
+        return fail(SYN_ERR_INVALID, "bad arguments");
+    const i64 gx = grid_xyz[0], gy = grid_xyz[1], gz = grid_xyz[2];
+    const i64 nx = shape_xyz[0], ny = shape_xyz[1], nz = shape_xyz[2];
+    if (gx < 1 || gy < 1 || gz < 1 || nx < 1 || ny < 1 || nz < 1) return fail(SYN_ERR_INVALID, "bad grid / shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    // face buffer of one chunk: (axis 0 hi, axis 0 lo, axis 1 hi, axis 1 lo, axis 2 hi, axis 2 lo), continuation.py:57-59
+    const i64 fsz[3] = {ny * nz, nx * nz, nx * ny};
+    i64 foff[6], facebuf = 0;
+    for (int f = 0; f < 6; ++f) { foff[f] = facebuf; facebuf += fsz[f / 2]; }
+    const i64 nchunks = gx * gy * gz;
+    i64 total = 0;
+    for (i64 i = 0; i < nchunks; ++i) {
+        if (kept[i] < 0 || kept[i] > maxk) return fail(SYN_ERR_INVALID, "kept[%lld] out of range", (long long)i);
+        total += kept[i];
+    }
+    CK(cudaMemsetAsync(n_edges_dev, 0, 8, st));
+    // edges of every interior face pair: the hi face of a chunk against the lo face of its +1 neighbour
+    // (merge_ccs.py:69-114 visits exactly these pairs)
+    for (i64 cx = 0; cx < gx; ++cx)
+        for (i64 cy = 0; cy < gy; ++cy)
+            for (i64 cz = 0; cz < gz; ++cz) {
+                const i64 here = (cx * gy + cy) * gz + cz;
+                const i64 idx[3] = {cx, cy, cz}, g3[3] = {gx, gy, gz};
+                for (int axis = 0; axis < 3; ++axis) {
+                    if (idx[axis] == g3[axis] - 1) continue;
+                    i64 o[3] = {cx, cy, cz};
+                    o[axis] += 1;
+                    const i64 there = (o[0] * gy + o[1]) * gz + o[2];
+                    const u32 *fa = faces_all + slot_of_chunk[here] * facebuf + foff[2 * axis];        // hi face
+                    const u32 *fb = faces_all + slot_of_chunk[there] * facebuf + foff[2 * axis + 1];   // lo face
+                    k_face_pair_edges<<<grid_for(fsz[axis], 256, 8), 256, 0, st>>>(fa, fb, fsz[axis], edges_scratch,
+                                                                                  max_edges, n_edges_dev);
+                    CK_LAUNCH();
+                }
+            }
+    // union-find to the smallest id
+    const i64 n_ids = total + 1;
+    k_iota_u32<<<grid_for(n_ids, 256, 8), 256, 0, st>>>(gmap_out, n_ids);
+    CK_LAUNCH();
+    k_union_edges<<<grid_for(max_edges, 256, 8), 256, 0, st>>>(edges_scratch, n_edges_dev, max_edges, n_ids, gmap_out);
+    CK_LAUNCH();
+    k_flatten<<<grid_for(n_ids, 256, 8), 256, 0, st>>>(gmap_out, n_ids);
+    CK_LAUNCH();
+    // the table rows of all chunks in global id order (assign_ids.py:8-25: chunk after chunk, rows in table order)
+    if (total > 0 && !rows_scratch) return fail(SYN_ERR_INVALID, "rows_scratch missing");
+    i64 base = 0;
+    for (i64 i = 0; i < nchunks; ++i) {
+        if (kept[i])
+            CK(cudaMemcpyAsync(rows_scratch + base * SYN_SEG_NCOLS, tables_all + slot_of_chunk[i] * maxk * SYN_SEG_NCOLS,
+                               (size_t)kept[i] * SYN_SEG_NCOLS * 8, cudaMemcpyDeviceToDevice, st));
+        base += kept[i];
+    }
+    return syn_merge_seg_tables(rows_scratch, total, gmap_out, size_thr, merged_out, fmap_out, n_merged_dev, stream);
+}
+
 int syn_merge_overlaps(const uint32_t *rows, const uint64_t *cols, const int64_t *counts, int64_t n, int64_t n_ids,
                        uint64_t *argcol_out, int64_t *maxval_out, void *stream)
 {

@@ -98,6 +98,32 @@ class DeviceOps:
     def union_min_map(self, edges, n_edges, n_ids):
         return self.D.union_min_map_device(edges, n_edges, n_ids)
 
+    def merge_grid(self, faces_all, tables_all, kept, slots, grid, shape, maxk, size_thr, total, max_edges):
+        """Everything between the exchanges and the LUT composition in one C call (syn_merge_ccs_grid)."""
+        import ctypes
+        from . import _cabi as C
+        torch = self.torch
+        device = faces_all.device
+        edges = torch.empty((max_edges, 2), dtype=torch.int32, device=device)
+        n_edges = torch.empty(1, dtype=torch.int64, device=device)
+        gmap = torch.empty(total + 1, dtype=torch.int32, device=device)
+        rows = torch.empty((max(total, 1), C.SEG_NCOLS), dtype=torch.int64, device=device)
+        merged = torch.empty((max(total, 1), C.SEG_NCOLS), dtype=torch.int64, device=device)
+        fmap = torch.empty(total + 1, dtype=torch.int32, device=device)
+        n_merged = torch.zeros(1, dtype=torch.int64, device=device)
+        kept_h = np.ascontiguousarray(kept, dtype=np.int64)
+        slots_h = np.ascontiguousarray(slots, dtype=np.int64)
+        grid_h = np.asarray(grid, dtype=np.int64)
+        shape_h = np.asarray(shape, dtype=np.int64)
+        vp = ctypes.c_void_p
+        with torch.cuda.device(device):
+            C.check(C.lib().syn_merge_ccs_grid(
+                faces_all.data_ptr(), tables_all.data_ptr(), kept_h.ctypes.data_as(vp), slots_h.ctypes.data_as(vp),
+                grid_h.ctypes.data_as(vp), shape_h.ctypes.data_as(vp), int(maxk), int(size_thr), edges.data_ptr(),
+                int(max_edges), n_edges.data_ptr(), gmap.data_ptr(), rows.data_ptr(), merged.data_ptr(),
+                fmap.data_ptr(), n_merged.data_ptr(), self.D._stream_ptr(torch)))
+        return merged, fmap, n_merged, n_edges
+
     def merge_overlaps(self, rows, cols, counts, n_ids):
         import ctypes
         from . import _cabi as C
@@ -209,24 +235,31 @@ def merge_ccs_device(results, grid, rank=None, world=None, size_thr=0, group=Non
     faces_all = _all_gather(torch, dist, torch.stack(faces_local), world, group)     # [world, per_rank, facebuf]
     tables_all = _all_gather(torch, dist, torch.stack(tables_local), world, group)   # [world, per_rank, maxk, 11]
 
-    def chunk_faces(i):
-        return faces_all[owners[i], i // world]
-
-    # ---- every rank: edges over the interior faces, union-find to the smallest id ---------------------
     pairs = interior_face_pairs(grid)
     cap = max(1024, sum(sizes[sa] for (_, sa, _, _) in pairs))
-    edges = torch.empty((cap, 2), dtype=torch.int32, device=device)
-    n_edges = torch.zeros(1, dtype=torch.int64, device=device)
-    for (ia, sa, ib, sb) in pairs:
-        fa = chunk_faces(ia)[offs[sa]:offs[sa] + sizes[sa]]
-        fb = chunk_faces(ib)[offs[sb]:offs[sb] + sizes[sb]]
-        ops.face_pair_edges(fa, fb, edges, n_edges)
-    gmap = ops.union_min_map(edges, n_edges, total + 1)
+    if hasattr(ops, "merge_grid"):
+        # ---- every rank: one C call -- edges over the interior faces, union-find to the smallest id, rows in
+        # global id order, merged table + size threshold (identical inputs, deterministic => identical results)
+        slots = [owners[i] * per_rank + i // world for i in range(nchunks)]
+        merged, fmap, n_merged_dev, n_edges = ops.merge_grid(faces_all.contiguous(), tables_all.contiguous(), kept, slots,
+                                                             grid, shape, max(maxk, 1), size_thr, total, cap)
+    else:
+        def chunk_faces(i):
+            return faces_all[owners[i], i // world]
 
-    # ---- merged table + size threshold ------------------------------------------------------------
-    rows = torch.cat([tables_all[owners[i], i // world, :int(kept[i])] for i in range(nchunks)]) if total else \
-        torch.zeros((0, results[0].seg_table.shape[1]), dtype=torch.int64, device=device)
-    merged, fmap, n_merged_dev = ops.merge_tables(rows, total, gmap, size_thr)
+        # ---- every rank: edges over the interior faces, union-find to the smallest id ---------------------
+        edges = torch.empty((cap, 2), dtype=torch.int32, device=device)
+        n_edges = torch.zeros(1, dtype=torch.int64, device=device)
+        for (ia, sa, ib, sb) in pairs:
+            fa = chunk_faces(ia)[offs[sa]:offs[sa] + sizes[sa]]
+            fb = chunk_faces(ib)[offs[sb]:offs[sb] + sizes[sb]]
+            ops.face_pair_edges(fa, fb, edges, n_edges)
+        gmap = ops.union_min_map(edges, n_edges, total + 1)
+
+        # ---- merged table + size threshold ------------------------------------------------------------
+        rows = torch.cat([tables_all[owners[i], i // world, :int(kept[i])] for i in range(nchunks)]) if total else \
+            torch.zeros((0, results[0].seg_table.shape[1]), dtype=torch.int64, device=device)
+        merged, fmap, n_merged_dev = ops.merge_tables(rows, total, gmap, size_thr)
 
     # ---- local: compose chunk LUT with the final map, relabel the volumes in place ---------------------
     final_luts = []
