@@ -121,7 +121,7 @@ u32 pow2_at_least(i64 v)
 // workspace carving (must match syn_ccs_workspace_bytes)
 TileGeom make_tiles(const Geom &g)
 {
-    TileGeom t{0, 0, 0, 0, 0, 0, 0};
+    TileGeom t{0, 0, 0, 0, 0, 0, 0, 0};
     if (g.wz > TILE_WORDS / 2) return t;          // one row already fills a tile: no shared-memory pass
     u32 rpt = TILE_WORDS / g.wz;                    // rows per tile, >= 2
     u32 ty = 1;
@@ -325,6 +325,13 @@ int launch_union(const Workspace &W, const Geom &g, RunIdx R, bool bnd_list, i64
             W.lmask, R, W.par, g, W.tg, W.bndw, W.tileflag, W.actw, W.cnt);
         CK_LAUNCH();
         PROF("union_bnd");
+    } else if (bnd_list) {
+        // 18 / 26 connectivity: the border-word list (incl. the rows whose diagonal neighbours cross a tile border)
+        k_union_bnd_diag<CONN == 6 ? 18 : CONN><<<wave_grid(k_union_bnd_diag<CONN == 6 ? 18 : CONN>, 256,
+                                                            div_up_u32(g.nwords, 256 * 4)), 256, 0, st>>>(
+            W.lmask, R, W.par, g, W.tg, W.bndw, W.tileflag, W.actw, W.cnt);
+        CK_LAUNCH();
+        PROF("union_bnd_diag");
     } else {
         k_union_rows<CONN><<<wave_grid(k_union_rows<CONN>, 256, div_up_u32(g.nwords, 256)), 256, 0, st>>>(
             W.lmask, R, W.par, g, W.tg, W.tileflag, W.actw, W.cnt);
@@ -391,7 +398,8 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
         return fail(SYN_ERR_INVALID, "the multi-label variant is 6-connected, without dilation or pair counting");
     Workspace W;
     carve((char *)workspace, g, max_runs, max_pairs, dilate, ml, &W);
-    if (ml) W.tg = TileGeom{0, 0, 0, 0, 0, 0, 0};    // generic global path: no shared-memory tile pass
+    if (ml) W.tg = TileGeom{0, 0, 0, 0, 0, 0, 0, 0};
+    W.tg.diag = connectivity > 6;    // generic global path: no shared-memory tile pass
     if ((i64)W.total > workspace_bytes)
         return fail(SYN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %lld", W.total,
                     (long long)workspace_bytes);
@@ -492,8 +500,8 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
     // --- unions ------------------------------------------------------------------------------
     const bool bnd_list = W.tg.tx != 0;   // both producers of the active-word list also list the border words
     if (connectivity == 6) rc = launch_union<6>(W, g, R, bnd_list, max_runs, st);
-    else if (connectivity == 18) rc = launch_union<18>(W, g, R, false, max_runs, st);
-    else rc = launch_union<26>(W, g, R, false, max_runs, st);
+    else if (connectivity == 18) rc = launch_union<18>(W, g, R, bnd_list, max_runs, st);
+    else rc = launch_union<26>(W, g, R, bnd_list, max_runs, st);
     if (rc != SYN_OK) return rc;
 
     // --- scan #2: flatten + canonical rank -----------------------------------------------------

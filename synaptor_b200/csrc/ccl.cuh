@@ -121,6 +121,14 @@ struct RunIdx {
     }
 };
 
+// a row whose unions with already-visited neighbour rows cross a tile border of k_tile_ccl
+__device__ __forceinline__ bool tile_border_row(const TileGeom &tg, u32 x, u32 y, u32 ny)
+{
+    if (!tg.tx) return false;
+    if ((x && (x & (tg.tx - 1)) == 0) || (y && (y & (tg.ty - 1)) == 0)) return true;
+    return tg.diag && x && y + 1 < ny && ((y + 1) & (tg.ty - 1)) == 0;      // (x-1, y+1) lies in the next y-tile
+}
+
 // ===========================================================================
 // K1 (sector mode, nz % 8 == 0): ONE streaming pass over the dense inputs, at HBM speed:
 //   pred (4 B/voxel read)   -> mask[w]    the foreground bits
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(TS_THREADS) k_stream(const float *__restrict__
             const u32 kc = cok ? c - row * g.cpr : 0;
             u32 x, y;
             split_row(g, row, x, y);
-            const bool border = tg.tx && ((x && (x & (tg.tx - 1)) == 0) || (y && (y & (tg.ty - 1)) == 0));
+            const bool border = tile_border_row(tg, x, y, (u32)g.ny);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const u32 s = 2 * threadIdx.x + q;
@@ -633,7 +641,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_compact_active(const u32 *__re
                 u32 row, k, x, y;
                 split_word(g, (u32)(i0 + t), row, k);
                 split_row(g, row, x, y);
-                if ((x && (x & (tg.tx - 1)) == 0) || (y && (y & (tg.ty - 1)) == 0)) bpos[t] = atomicAdd(&s_bcount, 1u);
+                if (tile_border_row(tg, x, y, (u32)g.ny)) bpos[t] = atomicAdd(&s_bcount, 1u);
             }
         }
         u32 total;
@@ -722,16 +730,18 @@ __device__ __forceinline__ void union_shifted(u32 *par, const RowView &A, const 
 
 // With tiling enabled (tg.tx != 0) a pair of rows inside one tile was already joined by K2 and is
 // skipped here unless that tile was flagged as too dense.
-// BND_DONE: the tile borders are joined by k_union_bnd; only flagged tiles are left (usually none).
-template <int CONN, bool BND_DONE>
+// MODE 0: every active word, borders and flagged tiles (no border list: non-tiled geometry).
+// MODE 1: the words of the border list, borders only.
+// MODE 2: every active word, flagged tiles only (tiles the shared-memory pass had to leave; usually none).
+template <int CONN, int MODE>
 __device__ __forceinline__ void union_rows_body(const u32 *__restrict__ mask, const RunIdx &R, u32 *par, const Geom &g,
                                                 const TileGeom &tg, const u32 *__restrict__ tileflag,
-                                                const u32 *__restrict__ actw, const Counts *cnt)
+                                                const u32 *__restrict__ words, const Counts *cnt)
 {
-    if (BND_DONE && cnt->v[SYN_CNT_FLAGGED_TILES] == 0) return;
-    const u32 nact = (u32)cnt->v[SYN_CNT_ACTIVE_WORDS];
+    if (MODE == 2 && cnt->v[SYN_CNT_FLAGGED_TILES] == 0) return;
+    const u32 nact = (u32)cnt->v[MODE == 1 ? SYN_CNT_BND_WORDS : SYN_CNT_ACTIVE_WORDS];
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nact; i += gridDim.x * blockDim.x) {
-        const u32 w = actw[i];
+        const u32 w = words[i];
         u32 m = mask[w];
         u32 row, kk, x, y;
         split_word(g, w, row, kk);
@@ -743,10 +753,12 @@ __device__ __forceinline__ void union_rows_body(const u32 *__restrict__ mask, co
             const u32 tX = x >> tg.txs, tY = y >> tg.tys;
             const bool dense = tileflag[tX * tg.tiles_y + tY] != 0;
             const bool xb = (x & (tg.tx - 1)) == 0, yb = (y & (tg.ty - 1)) == 0, ye = ((y + 1) & (tg.ty - 1)) == 0;
-            do_y = dense || (!BND_DONE && yb);
-            do_x = dense || (!BND_DONE && xb);
-            do_dm = dense || xb || yb;
-            do_dp = dense || xb || ye;
+            // a flagged tile's own rows are all done in MODE 0 / 2; its border rows need nothing extra in MODE 1
+            const bool in = MODE != 1 && dense, bd = MODE != 2;
+            do_y = in || (bd && yb);
+            do_x = in || (bd && xb);
+            do_dm = in || (bd && (xb || yb));
+            do_dp = in || (bd && (xb || ye));
             if (!(do_y || do_x || do_dm || do_dp)) continue;
         }
         if (y > 0 && do_y) {
@@ -784,7 +796,7 @@ __global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask
                                                     const Counts *cnt)
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
-    union_rows_body<CONN, false>(mask, R, par, g, tg, tileflag, actw, cnt);
+    union_rows_body<CONN, 0>(mask, R, par, g, tg, tileflag, actw, cnt);
 }
 
 
@@ -1243,7 +1255,7 @@ __global__ void __launch_bounds__(256) k_union_bnd(const u32 *__restrict__ mask,
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
     // tiles the shared-memory pass had to leave (too many runs; normally none): every row pair inside them
-    union_rows_body<6, true>(mask, R, par, g, tg, tileflag, actw, cnt);
+    union_rows_body<6, 2>(mask, R, par, g, tg, tileflag, actw, cnt);
     const u32 nb = (u32)cnt->v[SYN_CNT_BND_WORDS];
     const int lane = threadIdx.x & 31;
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1300,6 +1312,99 @@ __global__ void __launch_bounds__(256) k_union_bnd(const u32 *__restrict__ mask,
                 const u32 ga = rb_o + __popc(st_o & mask_le(b)) - 1u;
                 const u32 gb = R.at(wB, rowB, k_o) + __popc(run_starts(mB, carryB) & mask_le(b)) - 1u;
                 uf_union(par, ga, gb);
+            }
+        }
+    }
+}
+
+// 18 / 26 connectivity: the same lane-per-span scheme, one neighbour direction after the other.  A direction =
+// (neighbour row, z shift): rows (x, y-1), (x-1, y) with shifts 0 / -1 / +1, rows (x-1, y-1), (x-1, y+1) with
+// shift 0 (18) and -1 / +1 (26).  A word takes part in a direction when that row pair crosses a tile border.
+template <int CONN>
+__global__ void __launch_bounds__(256) k_union_bnd_diag(const u32 *__restrict__ mask, RunIdx R, u32 *par, Geom g,
+                                                        TileGeom tg, const u32 *__restrict__ bndw,
+                                                        const u32 *__restrict__ tileflag, const u32 *__restrict__ actw,
+                                                        const Counts *cnt)
+{
+    if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
+    union_rows_body<CONN, 2>(mask, R, par, g, tg, tileflag, actw, cnt);      // flagged tiles (normally none)
+    const u32 nb = (u32)cnt->v[SYN_CNT_BND_WORDS];
+    const int lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int ny = (int)g.ny, wz = (int)g.wz;
+    constexpr int NDIR = CONN == 26 ? 12 : 8;
+    for (u32 a0 = warp * 32; a0 < nb; a0 += nwarps * 32) {
+        const u32 a = a0 + lane;
+        u32 w = 0, m = 0, starts = 0, rb = 0, k = 0, row = 0, x = 0, y = 0;
+        bool xb = false, yb = false, ye = false;
+        if (a < nb) {
+            w = bndw[a];
+            m = mask[w];
+            split_word(g, w, row, k);
+            split_row(g, row, x, y);
+            xb = (x & (tg.tx - 1)) == 0;
+            yb = (y & (tg.ty - 1)) == 0;
+            ye = ((y + 1) & (tg.ty - 1)) == 0;
+            starts = run_starts(m, k ? (mask[w - 1] >> 31) : 0u);
+            rb = R.at(w, row, k);
+        }
+#pragma unroll 1
+        for (int d = 0; d < NDIR; ++d) {
+            // direction table: d 0-2 (x, y-1) shifts 0,-1,+1; 3-5 (x-1, y); 6 (x-1, y-1) 0; 7 (x-1, y+1) 0;
+            // 8, 9 (x-1, y-1) -1,+1; 10, 11 (x-1, y+1) -1,+1
+            int drow, shift;
+            bool use;
+            if (d < 3) { drow = -1; shift = d == 0 ? 0 : (d == 1 ? -1 : 1); use = y > 0 && yb; }
+            else if (d < 6) { drow = -ny; shift = d == 3 ? 0 : (d == 4 ? -1 : 1); use = x > 0 && xb; }
+            else {
+                const bool minus = d == 6 || d == 8 || d == 9;       // (x-1, y-1), else (x-1, y+1)
+                drow = -ny + (minus ? -1 : 1);
+                shift = d < 8 ? 0 : ((d & 1) ? 1 : -1);
+                use = x > 0 && (minus ? (y > 0 && (xb || yb)) : ((int)y + 1 < ny && (xb || ye)));
+            }
+            u32 os = 0;
+            if (a < nb && use && m) {
+                const u32 *B = mask + (i64)((int)row + drow) * wz;
+                const u32 cur = B[k];
+                u32 nbw;   // bit b set <=> the neighbour row has bit (b + shift) set
+                if (shift == 0) nbw = cur;
+                else if (shift < 0) nbw = (cur << 1) | (k > 0 ? (B[k - 1] >> 31) : 0u);
+                else nbw = (cur >> 1) | ((int)k + 1 < wz ? (B[k + 1] << 31) : 0u);
+                const u32 o = m & nbw;
+                os = o & ~(o << 1);
+            }
+            const u32 n = __popc(os);
+            const u32 incl = warp_incl_scan(n, lane);
+            const u32 excl = incl - n;
+            const u32 total = __shfl_sync(SYN_FULL, incl, 31);
+            for (u32 r0 = 0; r0 < total; r0 += 32) {
+                const u32 j = r0 + lane;
+                int o = 0;
+#pragma unroll
+                for (int s = 16; s; s >>= 1) {
+                    const u32 e = __shfl_sync(SYN_FULL, excl, (o + s) & 31);
+                    if (e <= j) o += s;
+                }
+                const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
+                const u32 os_o = __shfl_sync(SYN_FULL, os, o);
+                const u32 st_o = __shfl_sync(SYN_FULL, starts, o);
+                const u32 rb_o = __shfl_sync(SYN_FULL, rb, o);
+                const u32 k_o = __shfl_sync(SYN_FULL, k, o);
+                const u32 row_o = __shfl_sync(SYN_FULL, row, o);
+                if (j < total) {
+                    const u32 b = select_bit(os_o, j - e_o);
+                    const u32 ga = rb_o + __popc(st_o & mask_le(b)) - 1u;
+                    const u32 rowB = (u32)((int)row_o + drow);
+                    int bb = (int)b + shift, kb = (int)k_o;
+                    if (bb < 0) { bb = 31; --kb; }
+                    else if (bb > 31) { bb = 0; ++kb; }
+                    const u32 wB = rowB * g.wz + (u32)kb;
+                    const u32 mB = mask[wB];
+                    const u32 carryB = kb ? (mask[wB - 1] >> 31) : 0u;
+                    const u32 gb = R.at(wB, rowB, (u32)kb) + __popc(run_starts(mB, carryB) & mask_le((u32)bb)) - 1u;
+                    uf_union(par, ga, gb);
+                }
             }
         }
     }

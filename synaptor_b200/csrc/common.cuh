@@ -59,6 +59,7 @@ struct TileGeom {
     u32 tiles_x, tiles_y;
     u32 ntiles;
     u32 txs, tys;        // log2(tx), log2(ty)
+    u32 diag;            // 18 / 26 connectivity: the last row of a tile (y + 1 on a tile border) is a border row too
 };
 
 // per-component accumulator, one 64-byte record (two 32 B sectors)
