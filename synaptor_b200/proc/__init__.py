@@ -3,6 +3,7 @@ from . import colnames
 from . import seg
 from . import overlap
 from . import utils
+from . import hashing
 
 from . import tasks
 from .tasks import cc_task
@@ -10,3 +11,4 @@ from .tasks import merge_ccs_task
 from .tasks import remap_ids_task
 from .tasks import overlap_task
 from .tasks import merge_overlaps_task
+from .tasks import match_continuations_task, seg_graph_cc_task, merge_seginfo_task

@@ -15,8 +15,14 @@ seg_info_cols = size_cols + centroid_cols + bbox_cols
 
 src_id = "src_id"
 dst_id = "dst_id"
+dst_id_hash = "dst_id_hash"
 
 ovl_segid = "max_overlap"
 rows = "row_id"
 cols = "col_id"
 vals = "vals"
+
+contin_filename = "filename"
+facehash = "facehash"
+graph_id1 = "graph_id1"
+graph_id2 = "graph_id2"

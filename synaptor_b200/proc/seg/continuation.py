@@ -8,6 +8,7 @@ Python loop.
 import numpy as np
 
 from ... import _device as D
+from .. import hashing
 
 
 class Continuation(object):
@@ -116,3 +117,18 @@ def extract_all_continuations(seg):
             return {f: [] for f in Face.all_faces()}, set()
         dev = D.to_device_u32(torch, seg, torch.device("cuda", torch.cuda.current_device()))
     return continuations_from_faces(faces_from_device(dev))
+
+
+def hash_chunk_faces(chunk_begin, chunk_end, maxval):
+    """
+    {Face: bucket below maxval} such that the two faces on either side of a chunk boundary
+    share a bucket (continuation.py:136-153): the key is the chunk's end corner with, for a
+    low face, the face axis replaced by the chunk's begin, plus the axis.
+    """
+    face_hashes = dict()
+    for face in Face.all_faces():
+        corner = list(chunk_end)
+        if not face.hi_index:
+            corner[face.axis] = chunk_begin[face.axis]
+        face_hashes[face] = hashing.hashval((corner[0], corner[1], corner[2], face.axis), maxval=maxval)
+    return face_hashes

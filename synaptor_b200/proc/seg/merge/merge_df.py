@@ -16,7 +16,8 @@ def add_new_ids(seginfo_df, mapping, new_id_colname="new_ids"):
 
 
 def merge_seginfo_df(seginfo_df, new_id_colname="new_ids"):
-    ids = np.asarray(seginfo_df.index, dtype=np.int64)
+    # ids: the cleft_segid column when the frame carries one (tables read back from a store), else the index
+    ids = np.asarray(seginfo_df[cn.seg_id] if cn.seg_id in seginfo_df.columns else seginfo_df.index, dtype=np.int64)
     new = seginfo_df[new_id_colname].to_numpy(dtype=np.float64)
     dst = np.where(np.isnan(new), ids, np.nan_to_num(new)).astype(np.int64)
     tab = seginfo_df[cn.seg_info_cols].to_numpy(dtype=np.int64)

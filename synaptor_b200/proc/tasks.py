@@ -10,6 +10,8 @@ import numpy as np
 from .. import _device as D
 from .. import seg_utils
 from . import colnames as cn
+from . import hashing
+from . import utils
 from . import overlap
 from . import seg
 from .seg import continuation as cont_mod
@@ -246,6 +248,48 @@ def merge_ccs_task(cont_info_arr, cleft_info_arr, size_thr, max_face_shape, enfo
     chunk_id_maps = timed("Updating chunk id maps (for size thresholding)", seg.merge.update_chunk_id_maps,
                           chunk_id_maps, size_thr_map)
     return cons_cleft_info, chunk_id_maps
+
+
+def match_continuations_task(contins1, contins2, max_face_shape=(1024, 1024), id_map1=None, id_map2=None):
+    """
+    One unit of the merge sharded by face hash (tasks.py:125-138): the continuations of the two
+    facing faces of a chunk boundary -> list of (id here, id there) graph edges.  The id maps
+    (chunk id -> global id) are applied to the continuations in place first, as in the reference.
+    """
+    if id_map1 is not None:
+        seg.merge.apply_id_map(contins1, id_map1)
+    if id_map2 is not None:
+        seg.merge.apply_id_map(contins2, id_map2)
+    return timed("Matching continuations", seg.merge.match_continuations, contins1, contins2,
+                 face_shape=max_face_shape)
+
+
+def seg_graph_cc_task(graph_edges, hashmax, all_ids):
+    """
+    Components of the gathered edge graph -> DataFrame (src_id, dst_id, dst_id_hash): every id of
+    all_ids mapped to the smallest id of its component, and the bucket of the target id that
+    shards the table merge (tasks.py:141-163).
+    """
+    ccs = timed("Finding connected components", utils.find_connected_components, graph_edges)
+    seg_merge_map = timed("Making seg merge_map", utils.make_id_map, ccs)
+    seg_merge_map = timed("Expanding mapping to include all ids", seg.merge.expand_id_map, seg_merge_map, all_ids)
+    seg_merge_df = timed("Making map dataframe", merge_misc.make_map_dframe, seg_merge_map)
+    return timed("Hashing dst id", hashing.add_hashed_index, seg_merge_df, [cn.dst_id], hashmax,
+                 indexname=cn.dst_id_hash)
+
+
+def merge_seginfo_task(seginfo_dframe, szthresh=None):
+    """
+    Table merge of one dst-hash bucket (tasks.py:166-180): rows carrying a dst_id column ->
+    (merged table, {dropped id: 0} or None).
+    """
+    merged_df = timed("Merging seginfo dataframe", seg.merge.merge_seginfo_df, seginfo_dframe,
+                      new_id_colname=cn.dst_id)
+    szthresh_map = None
+    if szthresh is not None:
+        szthresh_map = timed("Enforcing size threshold over merged ccs", seg.merge.enforce_size_threshold,
+                             merged_df, szthresh)
+    return merged_df, szthresh_map
 
 
 def merge_overlaps_task(overlaps_arr):

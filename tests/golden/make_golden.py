@@ -271,6 +271,66 @@ def main():
                         texts=np.array([files[k] for k in sorted(files)]), bbox=np.array(bb.astuple()),
                         id_map_keys=np.array(list(id_map.keys())), id_map_vals=np.array(list(id_map.values())))
     out["g8"] = sorted(files)
+    # ---- G9: merge sharded by hash: hashval / hash_chunk_faces, match_continuations_task per face pair,
+    #          seg_graph_cc_task, merge_seginfo_task per dst-hash bucket (tasks.py:125-180) -----------------
+    import collections
+    import collections.abc
+    collections.Iterable = collections.abc.Iterable      # proc/hashing.py:33 predates its removal (python 3.10)
+    import pandas as pd
+    from synaptor.proc import hashing as ref_hashing
+    from synaptor.proc import colnames as rcn
+    from synaptor.proc.seg.continuation import Face, hash_chunk_faces
+    hash_in = [(0, 0, 0, 0), (1024, 2048, 256, 2), (20, 18, 16, 1), (7,), (123456789012, 5, 3, 0)]
+    hash_scalar_in = [0, 1, 17, 99999, 2 ** 40 + 3]
+    hashmax9 = 5
+    hv = [ref_hashing.hashval(v, 1000) for v in hash_in]
+    hs = [ref_hashing.hashval(v, 7) for v in hash_scalar_in]
+    fh = {}
+    for (gi, bb) in zip(np.ndindex(grid), boxes):
+        d9 = hash_chunk_faces(tuple(bb.min()), tuple(bb.max()), 64)
+        fh[gi] = [d9[f] for f in Face.all_faces()]
+    cont9 = np.empty(grid, dtype=object)
+    info9 = np.empty(grid, dtype=object)
+    for (gi, bb) in zip(np.ndindex(grid), boxes):
+        _, ct, inf = quiet(tasks.cc_task, np.ascontiguousarray(vol[bb.index()]), 0.5, 10, offset=tuple(bb.min()))
+        cont9[gi], info9[gi] = ct, inf
+    full9, maps9 = syn.proc.seg.merge.assign_unique_ids_serial(info9)
+    edges9 = []
+    for gi in np.ndindex(grid):
+        for axis in range(3):
+            if gi[axis] == grid[axis] - 1:
+                continue
+            gj = list(gi)
+            gj[axis] += 1
+            gj = tuple(gj)
+            edges9.extend(quiet(tasks.match_continuations_task, cont9[gi][Face(axis, True)],
+                                cont9[gj][Face(axis, False)], max_face_shape=(20, 18),
+                                id_map1=maps9[gi], id_map2=maps9[gj]))
+    all_ids9 = list(full9.index)
+    mdf9 = quiet(tasks.seg_graph_cc_task, edges9, hashmax9, all_ids9)
+    mapping9 = dict(zip(mdf9[rcn.src_id], mdf9[rcn.dst_id]))
+    hashes9 = dict(zip(mdf9[rcn.src_id], mdf9[rcn.dst_id_hash]))
+    full9[rcn.dst_id] = full9.index.map(mapping9)
+    b_idx, b_tab, b_hash, dropped = [], [], [], []
+    for h in range(hashmax9):
+        part = full9[[hashes9[i] == h for i in full9.index]].copy()
+        if len(part) == 0:
+            continue
+        mg, szm = quiet(tasks.merge_seginfo_task, part, szthresh=15)
+        i9, t9 = df_to_arrays(mg)
+        b_idx.append(i9); b_tab.append(t9); b_hash.append(np.full(len(i9), h)); dropped.extend(szm.keys())
+    np.savez_compressed(os.path.join(HERE, "g9_hashed_merge.npz"),
+                        hash_in=np.array([",".join(map(str, v)) for v in hash_in]), hash_out=np.array(hv),
+                        hash_scalar_in=np.array(hash_scalar_in, dtype=np.int64), hash_scalar_out=np.array(hs),
+                        face_hashes=np.array([fh[gi] for gi in np.ndindex(grid)]),
+                        chunk_begin=np.array([bb.min() for bb in boxes]), chunk_end=np.array([bb.max() for bb in boxes]),
+                        edges=np.array(sorted(set((int(a), int(b)) for (a, b) in edges9)), dtype=np.int64).reshape(-1, 2),
+                        map_src=mdf9[rcn.src_id].to_numpy(dtype=np.int64), map_dst=mdf9[rcn.dst_id].to_numpy(dtype=np.int64),
+                        map_hash=mdf9[rcn.dst_id_hash].to_numpy(dtype=np.int64), hashmax=hashmax9,
+                        merged_index=np.concatenate(b_idx), merged_table=np.concatenate(b_tab),
+                        merged_hash=np.concatenate(b_hash), merged_columns=np.array(list(mg.columns)),
+                        dropped=np.array(sorted(int(d) for d in dropped), dtype=np.int64), size_thr=15)
+    out["g9"] = (len(edges9), len(mdf9), int(sum(len(x) for x in b_idx)), len(dropped))
     print("golden written:", out)
 
 

@@ -63,3 +63,27 @@ def test_readers_parse_reference_files(tmp_path):
     assert arr.shape == (1, 1, 1) and len(arr[0, 0, 0]) == len(want)
     mats, _ = taskio.read_all_overlap_mats(str(tmp_path))
     assert mats.shape == (1, 1, 1) and mats[0, 0, 0].nnz == ref.nnz
+
+
+def test_g9_hashing_golden():
+    """hashval / hash_chunk_faces / add_hashed_index against values produced by the reference (proc/hashing.py)."""
+    from synaptor_b200.proc import hashing
+    from synaptor_b200.proc.seg.continuation import Face, hash_chunk_faces
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "g9_hashed_merge.npz"))
+    for (text, want) in zip(g["hash_in"].tolist(), g["hash_out"].tolist()):
+        assert hashing.hashval(tuple(int(x) for x in text.split(",")), 1000) == want
+    for (v, want) in zip(g["hash_scalar_in"].tolist(), g["hash_scalar_out"].tolist()):
+        assert hashing.hashval(v, 7) == want
+    for (b, e, want) in zip(g["chunk_begin"].tolist(), g["chunk_end"].tolist(), g["face_hashes"].tolist()):
+        d = hash_chunk_faces(tuple(b), tuple(e), 64)
+        assert [d[f] for f in Face.all_faces()] == want
+    # faces on either side of an interior boundary share a bucket
+    lo = hash_chunk_faces((0, 0, 0), (20, 18, 16), 1 << 20)
+    hi = hash_chunk_faces((20, 0, 0), (40, 18, 16), 1 << 20)
+    assert lo[Face(0, True)] == hi[Face(0, False)]
+    import pandas as pd
+    df = pd.DataFrame({"dst_id": g["map_dst"]})
+    df = hashing.add_hashed_index(df, ["dst_id"], int(g["hashmax"]), indexname="dst_id_hash")
+    assert df["dst_id_hash"].tolist() == g["map_hash"].tolist()
+    df2 = pd.DataFrame({"a": [1.0, np.nan], "b": [2, 3]})
+    assert hashing.add_hashed_index(df2, ["a"], 9, null_fillval=-1)["hashed_index"].tolist()[1] == -1

@@ -117,6 +117,56 @@ def test_g4_merge_golden(syn):
     assert np.array_equal(final, g["final"]), first_diff(final, g["final"])
 
 
+def test_g9_hashed_merge_golden(syn):
+    """Merge sharded by hash (tasks.py:125-180) against the executed reference: same edges, map, buckets, tables."""
+    g, g4 = gold("g9_hashed_merge.npz"), gold("g4_merge_ccs.npz")
+    cn, tasks, Face = syn.proc.colnames, syn.proc.tasks, syn.proc.seg.Face
+    vol = g4["vol"]
+    boxes = syn.chunk_bboxes(vol.shape, tuple(g4["chunk_shape"].tolist()))
+    grid = (2, 2, 2)
+    cont_arr = np.empty(grid, dtype=object)
+    info_arr = np.empty(grid, dtype=object)
+    for (gi, bb) in zip(np.ndindex(grid), boxes):
+        _, cont_arr[gi], info_arr[gi] = tasks.cc_task(np.ascontiguousarray(vol[bb.index()]), 0.5, 10,
+                                                      offset=tuple(bb.min()), verbose=False)
+    full, maps = syn.proc.seg.merge.assign_unique_ids_serial(info_arr)
+    mfs = tuple(g4["max_face_shape"].tolist())
+    edges = []
+    for gi in np.ndindex(grid):
+        for axis in range(3):
+            if gi[axis] == grid[axis] - 1:
+                continue
+            gj = tuple(v + (a == axis) for (a, v) in enumerate(gi))
+            edges.extend(tasks.match_continuations_task(cont_arr[gi][Face(axis, True)], cont_arr[gj][Face(axis, False)],
+                                                        max_face_shape=mfs, id_map1=maps[gi], id_map2=maps[gj]))
+    assert sorted(set((int(a), int(b)) for (a, b) in edges)) == [tuple(e) for e in g["edges"].tolist()]
+    hashmax = int(g["hashmax"])
+    mdf = tasks.seg_graph_cc_task(edges, hashmax, list(full.index))
+    assert list(mdf.columns) == [cn.src_id, cn.dst_id, cn.dst_id_hash]
+    got = {int(a): (int(b), int(h)) for (a, b, h) in zip(mdf[cn.src_id], mdf[cn.dst_id], mdf[cn.dst_id_hash])}
+    want = {int(a): (int(b), int(h)) for (a, b, h) in zip(g["map_src"], g["map_dst"], g["map_hash"])}
+    assert got == want
+    full[cn.dst_id] = full.index.map({k: v[0] for (k, v) in got.items()})
+    gold_rows = {int(i): (int(h), r.astype(np.int64)) for (i, h, r) in
+                 zip(g["merged_index"], g["merged_hash"], g["merged_table"])}
+    seen, dropped = set(), []
+    for h in range(hashmax):
+        part = full[[got[int(i)][1] == h for i in full.index]].copy()
+        if len(part) == 0:
+            continue
+        merged, szmap = tasks.merge_seginfo_task(part, szthresh=int(g["size_thr"]))
+        assert all(v == 0 for v in szmap.values())
+        dropped.extend(int(k) for k in szmap)
+        midx, mtab = table_of(merged)
+        for (k, row) in zip(midx.tolist(), mtab):
+            gh, gr = gold_rows[k]
+            assert gh == h and row[0] == gr[0] and np.array_equal(row[4:], gr[4:])
+            assert np.all(np.abs(row[1:4] - gr[1:4]) <= 1)
+            seen.add(k)
+    assert seen == set(gold_rows) and sorted(dropped) == g["dropped"].tolist()
+    assert tasks.merge_seginfo_task(full.copy())[1] is None
+
+
 def test_g5_centroids_golden(syn):
     g = gold("g5_centroids.npz")
     c = syn.centers_of_mass(g["seg"])
