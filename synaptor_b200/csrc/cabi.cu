@@ -439,7 +439,15 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
         if (has_base && tma && all_tma) { if (fused_scan) SYN_STREAM(true, true, true, true, 2); else SYN_STREAM(true, false, true, true, 2); }
         else if (has_base && tma) { if (fused_scan) SYN_STREAM(true, true, true, false, 2); else SYN_STREAM(true, false, true, false, 2); }
         else if (has_base) { if (fused_scan) SYN_STREAM(true, true, false, false, 1); else SYN_STREAM(true, false, false, false, 1); }
-        else if (tma) { if (fused_scan) SYN_STREAM(false, true, false, true, 4); else SYN_STREAM(false, false, false, true, 4); }
+        else if (tma && fused_scan) {
+            // predictions through a deeper ring on large volumes: 6 x 16 KB stages, 2 CTAs/SM (512^3: 206 -> 198 us,
+            // 1024^3: 1560 -> 1469 us); small volumes keep 4 stages and 3 CTAs/SM (256^3: 34 vs 39 us)
+            static const int nb_nst = getenv("SYN_NB_NST") ? atoi(getenv("SYN_NB_NST")) : 0;      // A/B override
+            const int nst = nb_nst ? nb_nst : (ntiles >= 4096 ? 6 : 4);
+            if (nst == 6) SYN_STREAM(false, true, false, true, 6);
+            else SYN_STREAM(false, true, false, true, 4);
+        }
+        else if (tma) SYN_STREAM(false, false, false, true, 4);
         else { if (fused_scan) SYN_STREAM(false, true, false, false, 1); else SYN_STREAM(false, false, false, false, 1); }
 #undef SYN_STREAM
         CK_LAUNCH();
