@@ -1554,10 +1554,47 @@ __global__ void __launch_bounds__(256) k_stats_merge(const TileRec *__restrict__
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
     const u64 n = (u64)cnt->v[SYN_CNT_TILE_RECORDS];
-    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        const TileRec r = recs[i];
+    // A component that spans thousands of tiles (dilation) would serialise thousands of same-address atomics in L2.
+    // Each CTA therefore picks ONE candidate -- the component of the largest record among its first 256 -- and sums
+    // that component's records in shared memory; everything else goes straight to the global accumulators.
+    __shared__ unsigned long long s_best;            // size << 32 | component of the CTA's largest first-round record
+    __shared__ unsigned long long s_acc[4];          // size, sx, sy, sz of the candidate
+    __shared__ u32 s_box[6];
+    if (threadIdx.x == 0) {
+        s_best = 0;
+        s_acc[0] = s_acc[1] = s_acc[2] = s_acc[3] = 0;
+        s_box[0] = s_box[1] = s_box[2] = 0xFFFFFFFFu;
+        s_box[3] = s_box[4] = s_box[5] = 0;
+    }
+    __syncthreads();
+    bool first = true;
+    u32 cand = 0xFFFFFFFFu;
+    for (u64 i0 = blockIdx.x * (u64)blockDim.x; i0 < n; i0 += (u64)gridDim.x * blockDim.x) {
+        const u64 i = i0 + threadIdx.x;
+        TileRec r;
+        r.size = 0;
+        u32 c = 0;
+        if (i < n) {
+            r = recs[i];
+            if (r.size) c = rank[par[r.root]];
+        }
+        if (first) {
+            if (r.size >= 64) atomicMax(&s_best, ((unsigned long long)r.size << 32) | c);
+            __syncthreads();
+            cand = s_best ? (u32)s_best : 0xFFFFFFFFu;
+            first = false;
+        }
         if (r.size == 0) continue;
-        CompStat *s = stat + rank[par[r.root]];
+        if (c == cand) {
+            atomicAdd(&s_acc[0], (unsigned long long)r.size);
+            atomicAdd(&s_acc[1], (unsigned long long)r.sx);
+            atomicAdd(&s_acc[2], (unsigned long long)r.sy);
+            atomicAdd(&s_acc[3], (unsigned long long)r.sz);
+            atomicMin(&s_box[0], r.minx); atomicMin(&s_box[1], r.miny); atomicMin(&s_box[2], r.minz);
+            atomicMax(&s_box[3], r.maxx); atomicMax(&s_box[4], r.maxy); atomicMax(&s_box[5], r.maxz);
+            continue;
+        }
+        CompStat *s = stat + c;
         atomicAdd(&s->size, (u64)r.size);
         atomicAdd(&s->sx, r.sx);
         atomicAdd(&s->sy, r.sy);
@@ -1568,6 +1605,16 @@ __global__ void __launch_bounds__(256) k_stats_merge(const TileRec *__restrict__
         if (r.maxx > ldcg_u32(&s->maxx)) atomicMax(&s->maxx, r.maxx);
         if (r.maxy > ldcg_u32(&s->maxy)) atomicMax(&s->maxy, r.maxy);
         if (r.maxz > ldcg_u32(&s->maxz)) atomicMax(&s->maxz, r.maxz);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_acc[0]) {
+        CompStat *s = stat + (u32)s_best;
+        atomicAdd(&s->size, (u64)s_acc[0]);
+        atomicAdd(&s->sx, (u64)s_acc[1]);
+        atomicAdd(&s->sy, (u64)s_acc[2]);
+        atomicAdd(&s->sz, (u64)s_acc[3]);
+        atomicMin(&s->minx, s_box[0]); atomicMin(&s->miny, s_box[1]); atomicMin(&s->minz, s_box[2]);
+        atomicMax(&s->maxx, s_box[3]); atomicMax(&s->maxy, s_box[4]); atomicMax(&s->maxz, s_box[5]);
     }
     stats_body(lmask, omask, R, par, rank, stat, g, tg, tileflag, actw, cnt);
 }
