@@ -871,15 +871,19 @@ __device__ __forceinline__ u32 select_bit_small(u32 w, u32 n)
 // prefix sum turns the 32 counts into a work list, and the lanes then take the spans one each (owner by
 // shuffle binary search, span start by select_bit) and perform the unions with uniform control flow.
 // Used for 18 / 26 connectivity (6-connectivity has the combined pass below).
-template <int SHIFT>
-__device__ __forceinline__ void tile_pass(const u32 *s_mask, const unsigned short *s_rb, const u32 *s_st, u32 *s_par,
-                                          const u32 *s_act, u32 nact, u32 wz, u32 vy, u32 dxl, int dyl, int off)
+template <bool SHIFTED>
+__device__ __forceinline__ void tile_pass_row(const u32 *s_mask, const unsigned short *s_rb, const u32 *s_st,
+                                              u32 *s_par, const u32 *s_act, u32 nact, u32 wz, u32 vy, u32 dxl, int dyl,
+                                              int off)
 {
     const int lane = threadIdx.x & 31;
     const u32 wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     for (u32 a0 = wib * 32; a0 < nact; a0 += nwb * 32) {
         const u32 a = a0 + lane;
-        u32 os = 0, i = 0;
+        // os0: starts of the direct overlap spans; os1 / os2: the diagonal contacts that are NOT implied by a direct
+        // overlap -- a run of this row starting at bit b where a neighbour run ends at b - 1, and a run ending at b
+        // where a neighbour run starts at b + 1 (any other z-diagonal contact means the two runs overlap)
+        u32 os0 = 0, os1 = 0, os2 = 0, i = 0;
         if (a < nact) {
             const u32 e = s_act[a];
             i = e & 2047u;
@@ -888,15 +892,20 @@ __device__ __forceinline__ void tile_pass(const u32 *s_mask, const unsigned shor
             const u32 xl = e >> 27;
             if (xl >= dxl && yl + dyl >= 0 && yl + dyl < (int)vy) {
                 const int iB = (int)i + off;
-                u32 nb;
-                if (SHIFT == 0) nb = s_mask[iB];
-                else if (SHIFT < 0) nb = (s_mask[iB] << 1) | (k > 0 ? (s_mask[iB - 1] >> 31) : 0u);
-                else nb = (s_mask[iB] >> 1) | (k + 1 < wz ? (s_mask[iB + 1] << 31) : 0u);
-                const u32 o = s_mask[i] & nb;
-                os = o & ~(o << 1);
+                const u32 m = s_mask[i], cur = s_mask[iB];
+                const u32 o = m & cur;
+                os0 = o & ~(o << 1);
+                if (SHIFTED) {
+                    const bool more = k + 1 < wz;
+                    const u32 shl = (cur << 1) | (k > 0 ? (s_mask[iB - 1] >> 31) : 0u);
+                    const u32 shr = (cur >> 1) | (more ? (s_mask[iB + 1] << 31) : 0u);
+                    const u32 ends = m & ~((m >> 1) | (more ? (s_mask[i + 1] << 31) : 0u));
+                    os1 = s_st[i] & shl & ~cur;
+                    os2 = ends & shr & ~cur;
+                }
             }
         }
-        const u32 n = __popc(os);
+        const u32 n = __popc(os0) + __popc(os1) + __popc(os2);
         const u32 incl = warp_incl_scan(n, lane);
         const u32 excl = incl - n;
         const u32 total = __shfl_sync(SYN_FULL, incl, 31);
@@ -909,12 +918,21 @@ __device__ __forceinline__ void tile_pass(const u32 *s_mask, const unsigned shor
                 if (e <= j) o += s;
             }
             const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
-            const u32 os_o = __shfl_sync(SYN_FULL, os, o);
+            const u32 os0_o = __shfl_sync(SYN_FULL, os0, o);
+            const u32 os1_o = SHIFTED ? __shfl_sync(SYN_FULL, os1, o) : 0u;
+            const u32 os2_o = SHIFTED ? __shfl_sync(SYN_FULL, os2, o) : 0u;
             const u32 i_o = __shfl_sync(SYN_FULL, i, o);
             if (j < total) {
-                const u32 b = select_bit(os_o, j - e_o);
+                u32 idx = j - e_o, os_o = os0_o;
+                int shift = 0;
+                if (SHIFTED) {
+                    const u32 n0 = __popc(os0_o), n1 = __popc(os1_o);
+                    if (idx >= n0 + n1) { idx -= n0 + n1; os_o = os2_o; shift = 1; }
+                    else if (idx >= n0) { idx -= n0; os_o = os1_o; shift = -1; }
+                }
+                const u32 b = select_bit(os_o, idx);
                 const u32 ga = (u32)s_rb[i_o] + __popc(s_st[i_o] & mask_le(b)) - 1u;
-                int iB = (int)i_o + off, bb = (int)b + SHIFT;
+                int iB = (int)i_o + off, bb = (int)b + shift;
                 if (bb < 0) { bb = 31; --iB; }
                 else if (bb > 31) { bb = 0; ++iB; }
                 const u32 gb = (u32)s_rb[iB] + __popc(s_st[iB] & mask_le((u32)bb)) - 1u;
@@ -1127,21 +1145,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
     if (CONN == 6) {
         tile_pass6(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, segw);
     } else {
-        // (x, y-1) and (x-1, y): face neighbours; the remaining rows / shifts only for 18 / 26
-        tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
-        tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
-        tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
-        tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
-        tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
-        tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
-        tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
-        tile_pass<0>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
-        if (CONN == 26) {
-            tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
-            tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
-            tile_pass<-1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
-            tile_pass<1>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
-        }
+        // one pass per neighbour row: (x, y-1) and (x-1, y) with their z-diagonals, (x-1, y-1) and (x-1, y+1) with
+        // (26) or without (18) theirs
+        tile_pass_row<true>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 0, -1, -wz);
+        tile_pass_row<true>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 0, -sg);
+        tile_pass_row<CONN == 26>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, -1, -sg - wz);
+        tile_pass_row<CONN == 26>(s_mask, s_rb, s_st, s_par, s_act, nact, g.wz, vy, 1, 1, -sg + wz);
     }
     __syncthreads();
     SYN_TIMER_MARK(cnt, 3);   // unions
@@ -1317,9 +1326,9 @@ __global__ void __launch_bounds__(256) k_union_bnd(const u32 *__restrict__ mask,
     }
 }
 
-// 18 / 26 connectivity: the same lane-per-span scheme, one neighbour direction after the other.  A direction =
-// (neighbour row, z shift): rows (x, y-1), (x-1, y) with shifts 0 / -1 / +1, rows (x-1, y-1), (x-1, y+1) with
-// shift 0 (18) and -1 / +1 (26).  A word takes part in a direction when that row pair crosses a tile border.
+// 18 / 26 connectivity: the same lane-per-span scheme, one neighbour ROW after the other, the z shifts of a row
+// together: rows (x, y-1), (x-1, y) with shifts 0 / -1 / +1, rows (x-1, y-1), (x-1, y+1) with shift 0 (18) and
+// 0 / -1 / +1 (26).  A word takes part for a row when that row pair crosses a tile border.
 template <int CONN>
 __global__ void __launch_bounds__(256) k_union_bnd_diag(const u32 *__restrict__ mask, RunIdx R, u32 *par, Geom g,
                                                         TileGeom tg, const u32 *__restrict__ bndw,
@@ -1333,10 +1342,9 @@ __global__ void __launch_bounds__(256) k_union_bnd_diag(const u32 *__restrict__ 
     const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u32 nwarps = (gridDim.x * blockDim.x) >> 5;
     const int ny = (int)g.ny, wz = (int)g.wz;
-    constexpr int NDIR = CONN == 26 ? 12 : 8;
     for (u32 a0 = warp * 32; a0 < nb; a0 += nwarps * 32) {
         const u32 a = a0 + lane;
-        u32 w = 0, m = 0, starts = 0, rb = 0, k = 0, row = 0, x = 0, y = 0;
+        u32 w = 0, m = 0, starts = 0, ends = 0, rb = 0, k = 0, row = 0, x = 0, y = 0;
         bool xb = false, yb = false, ye = false;
         if (a < nb) {
             w = bndw[a];
@@ -1347,34 +1355,34 @@ __global__ void __launch_bounds__(256) k_union_bnd_diag(const u32 *__restrict__ 
             yb = (y & (tg.ty - 1)) == 0;
             ye = ((y + 1) & (tg.ty - 1)) == 0;
             starts = run_starts(m, k ? (mask[w - 1] >> 31) : 0u);
+            ends = m & ~((m >> 1) | ((int)k + 1 < wz ? (mask[w + 1] << 31) : 0u));
             rb = R.at(w, row, k);
         }
 #pragma unroll 1
-        for (int d = 0; d < NDIR; ++d) {
-            // direction table: d 0-2 (x, y-1) shifts 0,-1,+1; 3-5 (x-1, y); 6 (x-1, y-1) 0; 7 (x-1, y+1) 0;
-            // 8, 9 (x-1, y-1) -1,+1; 10, 11 (x-1, y+1) -1,+1
-            int drow, shift;
+        for (int nr = 0; nr < 4; ++nr) {
+            // neighbour rows: 0 (x, y-1), 1 (x-1, y): z shifts 0, -1, +1;  2 (x-1, y-1), 3 (x-1, y+1): shift 0 (18),
+            // 0, -1, +1 (26).  The spans of all shifts of a row go through ONE prefix sum / search.
+            int drow;
             bool use;
-            if (d < 3) { drow = -1; shift = d == 0 ? 0 : (d == 1 ? -1 : 1); use = y > 0 && yb; }
-            else if (d < 6) { drow = -ny; shift = d == 3 ? 0 : (d == 4 ? -1 : 1); use = x > 0 && xb; }
-            else {
-                const bool minus = d == 6 || d == 8 || d == 9;       // (x-1, y-1), else (x-1, y+1)
-                drow = -ny + (minus ? -1 : 1);
-                shift = d < 8 ? 0 : ((d & 1) ? 1 : -1);
-                use = x > 0 && (minus ? (y > 0 && (xb || yb)) : ((int)y + 1 < ny && (xb || ye)));
-            }
-            u32 os = 0;
+            if (nr == 0) { drow = -1; use = y > 0 && yb; }
+            else if (nr == 1) { drow = -ny; use = x > 0 && xb; }
+            else if (nr == 2) { drow = -ny - 1; use = x > 0 && y > 0 && (xb || yb); }
+            else { drow = -ny + 1; use = x > 0 && (int)y + 1 < ny && (xb || ye); }
+            const bool shifted = CONN == 26 || nr < 2;
+            u32 os0 = 0, os1 = 0, os2 = 0;
             if (a < nb && use && m) {
                 const u32 *B = mask + (i64)((int)row + drow) * wz;
                 const u32 cur = B[k];
-                u32 nbw;   // bit b set <=> the neighbour row has bit (b + shift) set
-                if (shift == 0) nbw = cur;
-                else if (shift < 0) nbw = (cur << 1) | (k > 0 ? (B[k - 1] >> 31) : 0u);
-                else nbw = (cur >> 1) | ((int)k + 1 < wz ? (B[k + 1] << 31) : 0u);
-                const u32 o = m & nbw;
-                os = o & ~(o << 1);
+                const u32 o = m & cur;
+                os0 = o & ~(o << 1);
+                if (shifted) {
+                    // the diagonal contacts not implied by a direct overlap: a run starting at b where a neighbour
+                    // run ends at b - 1, a run ending at b where a neighbour run starts at b + 1
+                    os1 = starts & ((cur << 1) | (k > 0 ? (B[k - 1] >> 31) : 0u)) & ~cur;
+                    os2 = ends & ((cur >> 1) | ((int)k + 1 < wz ? (B[k + 1] << 31) : 0u)) & ~cur;
+                }
             }
-            const u32 n = __popc(os);
+            const u32 n = __popc(os0) + __popc(os1) + __popc(os2);
             const u32 incl = warp_incl_scan(n, lane);
             const u32 excl = incl - n;
             const u32 total = __shfl_sync(SYN_FULL, incl, 31);
@@ -1387,13 +1395,20 @@ __global__ void __launch_bounds__(256) k_union_bnd_diag(const u32 *__restrict__ 
                     if (e <= j) o += s;
                 }
                 const u32 e_o = __shfl_sync(SYN_FULL, excl, o);
-                const u32 os_o = __shfl_sync(SYN_FULL, os, o);
+                const u32 os0_o = __shfl_sync(SYN_FULL, os0, o);
+                const u32 os1_o = __shfl_sync(SYN_FULL, os1, o);
+                const u32 os2_o = __shfl_sync(SYN_FULL, os2, o);
                 const u32 st_o = __shfl_sync(SYN_FULL, starts, o);
                 const u32 rb_o = __shfl_sync(SYN_FULL, rb, o);
                 const u32 k_o = __shfl_sync(SYN_FULL, k, o);
                 const u32 row_o = __shfl_sync(SYN_FULL, row, o);
                 if (j < total) {
-                    const u32 b = select_bit(os_o, j - e_o);
+                    u32 idx = j - e_o, os_o = os0_o;
+                    int shift = 0;
+                    const u32 n0 = __popc(os0_o), n1 = __popc(os1_o);
+                    if (idx >= n0 + n1) { idx -= n0 + n1; os_o = os2_o; shift = 1; }
+                    else if (idx >= n0) { idx -= n0; os_o = os1_o; shift = -1; }
+                    const u32 b = select_bit(os_o, idx);
                     const u32 ga = rb_o + __popc(st_o & mask_le(b)) - 1u;
                     const u32 rowB = (u32)((int)row_o + drow);
                     int bb = (int)b + shift, kb = (int)k_o;
