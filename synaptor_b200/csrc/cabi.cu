@@ -398,14 +398,12 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
         return fail(SYN_ERR_INVALID, "the multi-label variant is 6-connected, without dilation or pair counting");
     Workspace W;
     carve((char *)workspace, g, max_runs, max_pairs, dilate, ml, &W);
-    if (ml) W.tg = TileGeom{0, 0, 0, 0, 0, 0, 0, 0};
-    W.tg.diag = connectivity > 6;    // generic global path: no shared-memory tile pass
+    if (ml) W.tg = TileGeom{0, 0, 0, 0, 0, 0, 0, 0};     // generic global path: no shared-memory tile pass
+    W.tg.diag = connectivity > 6;                        // rows with diagonal neighbours across a tile border
     if ((i64)W.total > workspace_bytes)
         return fail(SYN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %lld", W.total,
                     (long long)workspace_bytes);
     cudaStream_t st = (cudaStream_t)stream;
-    const int sms = sm_count();
-    (void)sms;
 
     CK(cudaMemsetAsync(workspace, 0, W.zero_bytes, st));     // counters, scan state, tile flags, pair buckets
     g_prof_n = 0;

@@ -305,15 +305,6 @@ __global__ void __launch_bounds__(32 * SL_WARPS) k_sector_labels(const u32 *__re
             const i64 vox = (i64)row * g.nz + (i64)kw * 32 + q8;
             const u32 ob = (om_o >> q8) & 0xFFu;               // voxels that receive a label
             const u32 mb = (m_o >> q8) & 0xFFu;                // labelled mask (differs from ob only with dilation)
-            // base ids of the foreground voxels: up to four 16-byte loads, issued before the label lookups
-            ulonglong2 bq[4];
-            if (HAS_BASE) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    bq[u] = make_ulonglong2(0, 0);
-                    if ((ob >> (2 * u)) & 3u) bq[u] = __ldcs(reinterpret_cast<const ulonglong2 *>(base + vox) + u);
-                }
-            }
             // pieces of runs inside the byte (<= 4) and their labels
             const u32 ps = mb & ~(mb << 1) & 0xFFu;
             u32 plab[4];
@@ -327,6 +318,17 @@ __global__ void __launch_bounds__(32 * SL_WARPS) k_sector_labels(const u32 *__re
                         rest &= rest - 1;
                         plab[p] = runlabel[rb_o + __popc(st_o & mask_le(q8 + t)) - 1u];
                     }
+                }
+            }
+            // base ids of the foreground voxels: up to four 16-byte loads -- only for a sector that keeps a label
+            // (the sectors of dust components, a large share of all foreground sectors, need none)
+            ulonglong2 bq[4];
+            if (HAS_BASE) {
+                const bool any = (plab[0] | plab[1] | plab[2] | plab[3]) != 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    bq[u] = make_ulonglong2(0, 0);
+                    if (any && ((ob >> (2 * u)) & 3u)) bq[u] = __ldcs(reinterpret_cast<const ulonglong2 *>(base + vox) + u);
                 }
             }
             u32 lab[8];
