@@ -41,10 +41,12 @@ def _materialise_cc(res, shape, between=None):
     can overlap it) and its result is appended.
     """
     torch = D._torch()
-    host, ev = res.labels_numpy_async(D.side_stream(torch, res.labels.device, "out"))
+    # the small copies first: the D2H engine serves requests in order, so behind the 0.5 GB label copy the faces
+    # would arrive ~10 ms later and the host work below would end up after the copies instead of under them
     faces = cont_mod.faces_from_device(res.labels)
-    continuations, _ = cont_mod.continuations_from_faces(faces)     # ~10 ms of host work, hidden under the copies
     table = res.table_numpy()
+    host, ev = res.labels_numpy_async(D.side_stream(torch, res.labels.device, "out"))
+    continuations, _ = cont_mod.continuations_from_faces(faces)     # ~10 ms of host work, hidden under the copies
     info = seg.misc.seg_info_from_table(table[:, 0], table[:, 1:])
     extra = between() if between is not None else None
     ev.synchronize()
