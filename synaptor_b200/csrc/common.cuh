@@ -199,6 +199,14 @@ __device__ __forceinline__ void uf_union(u32 *par, u32 a, u32 b)
 // TMA bulk copy global -> shared with mbarrier completion (cp.async.bulk, sm_90+): the in-flight bytes live in
 // shared memory instead of registers, so a streaming kernel can keep far more of them outstanding.
 // ---------------------------------------------------------------------------
+// 256-bit global store (sm_100: STG.256).  The address must be 32-byte aligned.
+__device__ __forceinline__ void st_256(u32 *p, const u32 (&v)[8])
+{
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count)

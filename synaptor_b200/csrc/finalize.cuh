@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(256) k_write_labels(const u32 *__restrict__ lm
 // stages the per-word data in its slice of shared memory and writes one entry per non-empty byte into a SECTOR
 // LIST; the lanes then walk the list 32 sectors at a time, ONE LANE PER SECTOR, with no search.  A sector holds
 // at most 4 pieces of runs: their labels are fetched together, the (at most 8) base ids of the foreground voxels
-// too, then the whole 32-byte sector is stored and the (label, base) groups go to the pair table.
+// too, then the whole 32-byte sector is stored (one 256-bit store) and the (label, base)
+// groups go to the pair table.
 constexpr int SL_WPL = 4;                   // words per lane per batch
 constexpr int SL_BATCH = 32 * SL_WPL;
 constexpr int SL_WARPS = 8;
@@ -338,9 +339,7 @@ __global__ void __launch_bounds__(32 * SL_WARPS) k_sector_labels(const u32 *__re
                 const u32 l = pi <= 1 ? plab[0] : pi == 2 ? plab[1] : pi == 3 ? plab[2] : plab[3];
                 lab[t] = ((ob >> t) & 1u) ? l : 0u;
             }
-            uint4 *lp = reinterpret_cast<uint4 *>(labels + vox);
-            lp[0] = make_uint4(lab[0], lab[1], lab[2], lab[3]);
-            lp[1] = make_uint4(lab[4], lab[5], lab[6], lab[7]);
+            st_256(labels + vox, lab);
             if (HAS_BASE) {
                 const u64 bv[8] = {bq[0].x, bq[0].y, bq[1].x, bq[1].y, bq[2].x, bq[2].y, bq[3].x, bq[3].y};
                 const u64 pos0 = (u64)w_o * 32 + q8;
