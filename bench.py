@@ -329,9 +329,6 @@ def main():
         # one public call per chunk: pinned host arrays in (H2D inside), numpy / DataFrame / COO out (D2H + host
         # materialisation inside).  Warm-up in the steady-state pattern of the timed loop (the previous result is
         # still referenced while the next one is produced, so two pinned output blocks circulate).
-        # (synaptor_b200.proc.tasks.cc_overlap_tasks queues the next chunk's input copy ahead; tools/
-        # e2e_pipeline_probe.py measured 30.5 ms per chunk in its steady state against 33.2 ms here, but not
-        # reproducibly inside this short loop, so the bench keeps the plain call.)
         n_e2e = max(3, min(args.steps, 6))
         for _ in range(3):
             ccs, conts, info, mat = syn.proc.tasks.cc_overlap_task(pn, bn, THRESH, DUST, offset=offset)
@@ -342,10 +339,22 @@ def main():
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / n_e2e
         assert len(info) == counts["kept"] and mat.nnz == counts["pairs"]
+        # the same chunks through the generator form of the call (cc_overlap_tasks: the next chunk's input copies
+        # are queued before the previous chunk is finished, so the PCIe link carries inputs back to back);
+        # reported next to the per-call figure, which stays the headline e2e value
+        for out in syn.proc.tasks.cc_overlap_tasks(((pn, bn, offset) for _ in range(3)), THRESH, DUST):
+            ccs, conts, info, mat = out
+        barrier()
+        t0 = time.perf_counter()
+        for out in syn.proc.tasks.cc_overlap_tasks(((pn, bn, offset) for _ in range(n_e2e)), THRESH, DUST):
+            ccs, conts, info, mat = out
+        torch.cuda.synchronize()
+        e2e_piped_s = (time.perf_counter() - t0) / n_e2e
+        assert len(info) == counts["kept"] and mat.nnz == counts["pairs"]
         h2d = pred_pin.numel() * 4 + base_pin.numel() * 8
         d2h = ccs.nbytes + len(info) * 11 * 8 + mat.nnz * 20 + sum(
             2 * (shape[(a + 1) % 3] * shape[(a + 2) % 3]) * 4 for a in range(3))
-        e2e = {"seconds": e2e_s, "h2d": h2d, "d2h": d2h, "n": n_e2e}
+        e2e = {"seconds": e2e_s, "h2d": h2d, "d2h": d2h, "n": n_e2e, "piped_seconds": e2e_piped_s}
 
     # ---- reduce over ranks --------------------------------------------------------------------------
     ms_max = ms_total
@@ -388,6 +397,7 @@ def main():
             line["e2e"] = {"value": world * nvox / e2e_s_max / 1e9, "unit": "Gvoxel/s",
                            "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                            "ms_per_step": e2e_s_max * 1e3, "chunks": int(e2e["n"]),
+                           "ms_per_step_generator_call_rank0": e2e["piped_seconds"] * 1e3,
                            "api": "synaptor_b200.proc.tasks.cc_overlap_task (one call per chunk; pinned host arrays in, "
                                   "numpy / DataFrame / COO out)"}
         if not args.no_cpu_baseline and world == 1:
