@@ -40,9 +40,9 @@ BYTES_PER_VOXEL_PIPELINE = 16   # 4 B pred read + 4 B label write + 8 B base rea
 BYTES_PER_VOXEL_STREAM_KERNEL = 16  # k_stream: 4 B pred read + 8 B base read + 4 B label (zero-fill) write
 CPU_SAMPLE = (256, 256, 256)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_stream launch on the 512^3 workload (ncu --set full,
-# profiles/r01k_top_summary.txt: 1.610693 GB read + 491.19 MB written in 326.6 us; the algorithmic 16 B/voxel are
+# profiles/r01m_top_summary.txt: 1.610673 GB read + 491.01 MB written in 331.9 us (under ncu); the algorithmic 16 B/voxel are
 # 2.147 GB -- the foreground sectors are not zero-filled by this kernel)
-STREAM_TRAFFIC_512 = 2101881736
+STREAM_TRAFFIC_512 = 2101686120
 
 
 def peaks():
