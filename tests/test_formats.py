@@ -87,3 +87,39 @@ def test_g9_hashing_golden():
     assert df["dst_id_hash"].tolist() == g["map_hash"].tolist()
     df2 = pd.DataFrame({"a": [1.0, np.nan], "b": [2, 3]})
     assert hashing.add_hashed_index(df2, ["a"], 9, null_fillval=-1)["hashed_index"].tolist()[1] == -1
+
+
+def test_g9_merge_seginfo_task_host():
+    """merge_seginfo_task (host-only part of the merge sharded by hash, tasks.py:166-180) per dst-hash bucket."""
+    from synaptor_b200.proc import tasks, colnames as cn
+    from synaptor_b200.proc.seg import merge
+    g, g4 = gold("g9_hashed_merge.npz"), gold("g4_merge_ccs.npz")
+    grid = (2, 2, 2)
+    info = np.empty(grid, dtype=object)
+    for (i, gi) in enumerate(np.ndindex(grid)):
+        t = g4[f"chunk_table_{i}"]
+        df = pd.DataFrame(t[:, 1:], index=t[:, 0], columns=cn.seg_info_cols)
+        df.index.name = cn.seg_id
+        info[gi] = df
+    full, _ = merge.assign_unique_ids_serial(info)
+    dst = dict(zip(g["map_src"].tolist(), g["map_dst"].tolist()))
+    bucket = dict(zip(g["map_src"].tolist(), g["map_hash"].tolist()))
+    full[cn.dst_id] = full.index.map(dst)
+    want = {int(i): (int(h), r.astype(np.int64)) for (i, h, r) in zip(g["merged_index"], g["merged_hash"], g["merged_table"])}
+    seen, dropped = set(), []
+    for h in range(int(g["hashmax"])):
+        part = full[[bucket[int(i)] == h for i in full.index]].copy()
+        if len(part) == 0:
+            continue
+        merged, szmap = tasks.merge_seginfo_task(part, szthresh=int(g["size_thr"]))
+        dropped += [int(k) for k in szmap]
+        for (k, row) in zip(merged.index.tolist(), merged.to_numpy(dtype=np.int64)):
+            gh, gr = want[int(k)]
+            assert gh == h and row[0] == gr[0] and np.array_equal(row[4:], gr[4:])
+            assert np.all(np.abs(row[1:4] - gr[1:4]) <= 1)     # float64 weighted mean, truncated
+            seen.add(int(k))
+    assert seen == set(want) and sorted(dropped) == g["dropped"].tolist()
+    # a frame that carries cleft_segid as a column (read back from a store) merges the same way
+    part = full.reset_index()
+    m2, none = tasks.merge_seginfo_task(part)
+    assert none is None and len(m2) == len(set(dst.values()))
