@@ -331,6 +331,38 @@ def main():
                         merged_hash=np.concatenate(b_hash), merged_columns=np.array(list(mg.columns)),
                         dropped=np.array(sorted(int(d) for d in dropped), dtype=np.int64), size_thr=15)
     out["g9"] = (len(edges9), len(mdf9), int(sum(len(x) for x in b_idx)), len(dropped))
+    # ---- G10: the seg_utils functions of the path, executed standalone (describe.py / filtering.py / relabel.py /
+    #           overlap.py with orig_ids False and True) on a volume with non-dense ids ----------------------------
+    su = syn.seg_utils
+    seg10 = quiet(syn.proc.seg.connected_components, orc.synth_pred((26, 30, 44), seed=31, sigma=1.5, fg=0.15), 0.5)
+    seg10[seg10 == 3] = 900
+    seg10[seg10 == 7] = 70000
+    base10 = orc.synth_base(seg10.shape, seed=32, block=7, bg=0.2)
+    sz10 = su.segment_sizes(seg10)
+    com10 = su.centers_of_mass(seg10, offset=(3, 4, 5))
+    bb10 = su.bounding_boxes(seg10, offset=(3, 4, 5))
+    ids10 = sorted(sz10)
+    filt10, rem10 = su.filter_segs_by_size(seg10, 30, to_ignore=[1, 900])
+    filt_id10 = su.filter_segs_by_id(seg10, [2, 900, 5], copy=True)
+    map10 = {1: 77, 900: 5, 123456: 9, 2: 0}
+    rel10 = su.relabel_data(seg10, map10, copy=True)
+    ov10, r10, c10 = su.count_overlaps(seg10, base10)
+    ovo10, _, _ = su.count_overlaps(seg10, base10, orig_ids=True)
+    np.savez_compressed(os.path.join(HERE, "g10_seg_utils.npz"), seg=seg10, base=base10,
+                        ids=np.array(ids10, dtype=np.int64), sizes=np.array([sz10[i] for i in ids10], dtype=np.int64),
+                        coms=np.array([com10[i] for i in ids10], dtype=np.int64),
+                        bboxes=np.array([bb10[i].astuple() for i in ids10], dtype=np.int64),
+                        uniq=np.asarray(su.nonzero_unique_ids(seg10), dtype=np.int64),
+                        filt=filt10, filt_ids=np.array(sorted(rem10), dtype=np.int64),
+                        filt_sizes=np.array([rem10[i] for i in sorted(rem10)], dtype=np.int64), filt_by_id=filt_id10,
+                        map_keys=np.array(list(map10.keys()), dtype=np.int64),
+                        map_vals=np.array(list(map10.values()), dtype=np.int64), relabelled=rel10,
+                        ov_row=np.asarray(ov10.row, dtype=np.int64), ov_col=np.asarray(ov10.col, dtype=np.int64),
+                        ov_val=np.asarray(ov10.data, dtype=np.int64), ov_shape=np.array(ov10.shape),
+                        ov_row_ids=np.asarray(r10, dtype=np.int64), ov_col_ids=np.asarray(c10).astype(np.uint64),
+                        ovo_row=np.asarray(ovo10.row, dtype=np.int64), ovo_col=np.asarray(ovo10.col).astype(np.uint64),
+                        ovo_val=np.asarray(ovo10.data, dtype=np.int64), ovo_shape=np.array(ovo10.shape, dtype=np.uint64))
+    out["g10"] = (len(ids10), int(ov10.nnz), len(rem10))
     print("golden written:", out)
 
 

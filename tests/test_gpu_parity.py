@@ -167,6 +167,34 @@ def test_g9_hashed_merge_golden(syn):
     assert tasks.merge_seginfo_task(full.copy())[1] is None
 
 
+def test_g10_seg_utils_golden(syn):
+    """The standalone seg_utils calls of the path against outputs of the executed reference."""
+    g = gold("g10_seg_utils.npz")
+    seg, base = g["seg"], g["base"]
+    su = syn.seg_utils
+    ids = g["ids"].tolist()
+    szs = su.segment_sizes(seg)
+    assert szs == dict(zip(ids, g["sizes"].tolist())) and list(szs) == ids
+    assert su.centers_of_mass(seg, offset=(3, 4, 5)) == {i: tuple(c) for (i, c) in zip(ids, g["coms"].tolist())}
+    bb = su.bounding_boxes(seg, offset=(3, 4, 5))
+    assert {k: v.astuple() for (k, v) in bb.items()} == {i: tuple(b) for (i, b) in zip(ids, g["bboxes"].tolist())}
+    assert np.array_equal(su.nonzero_unique_ids(seg), g["uniq"])
+    filt, rem = su.filter_segs_by_size(seg, 30, to_ignore=[1, 900])
+    assert np.array_equal(filt, g["filt"]) and rem == dict(zip(g["filt_ids"].tolist(), g["filt_sizes"].tolist()))
+    assert filt is not seg and np.array_equal(su.filter_segs_by_id(seg, [2, 900, 5], copy=True), g["filt_by_id"])
+    mapping = dict(zip(g["map_keys"].tolist(), g["map_vals"].tolist()))
+    assert np.array_equal(su.relabel_data(seg, mapping, copy=True), g["relabelled"])
+    mat, r_ids, c_ids = su.count_overlaps(seg, base)
+    assert np.array_equal(r_ids, g["ov_row_ids"]) and np.array_equal(c_ids, g["ov_col_ids"])
+    assert mat.shape == tuple(g["ov_shape"].tolist())
+    assert np.array_equal(mat.row, g["ov_row"]) and np.array_equal(mat.col, g["ov_col"])
+    assert np.array_equal(mat.data, g["ov_val"])
+    mo, _, _ = su.count_overlaps(seg, base, orig_ids=True)
+    assert mo.shape == tuple(int(x) for x in g["ovo_shape"])
+    assert np.array_equal(mo.row, g["ovo_row"]) and np.array_equal(np.asarray(mo.col).astype(np.uint64), g["ovo_col"])
+    assert np.array_equal(mo.data, g["ovo_val"])
+
+
 def test_g5_centroids_golden(syn):
     g = gold("g5_centroids.npz")
     c = syn.centers_of_mass(g["seg"])

@@ -144,3 +144,27 @@ def test_g7_cc_task_overlap_seg():
     assert list(info.columns) == g["info_columns"].tolist()
     assert np.array_equal(np.asarray(info.index, dtype=np.int64), g["info_index"])
     assert np.array_equal(info.to_numpy().astype(np.int64), g["info_table"])
+
+
+def test_g10_seg_utils():
+    """describe / filtering / relabel / overlap restatements against the reference's standalone seg_utils calls."""
+    g = gold("g10_seg_utils.npz")
+    seg, base = g["seg"], g["base"]
+    ids = g["ids"].tolist()
+    assert orc.segment_sizes_np(seg) == dict(zip(ids, g["sizes"].tolist()))
+    want_com = {i: tuple(c) for (i, c) in zip(ids, g["coms"].tolist())}
+    assert orc.centers_of_mass_np(seg, offset=(3, 4, 5)) == want_com
+    sums_c = orc.centers_of_mass_c(seg)                       # the plain-C flavour (no offset)
+    assert {i: (c[0] + 3, c[1] + 4, c[2] + 5) for (i, c) in sums_c.items()} == want_com
+    assert orc.bounding_boxes_np(seg, offset=(3, 4, 5)) == {i: tuple(b) for (i, b) in zip(ids, g["bboxes"].tolist())}
+    filt, rem = orc.filter_segs_by_size_np(seg, 30, to_ignore=[1, 900])
+    assert np.array_equal(filt, g["filt"]) and rem == dict(zip(g["filt_ids"].tolist(), g["filt_sizes"].tolist()))
+    mapping = dict(zip(g["map_keys"].tolist(), g["map_vals"].tolist()))
+    assert np.array_equal(orc.relabel_data_np(seg, mapping), g["relabelled"])
+    for fn in (orc.count_overlaps_np, orc.count_overlaps_c):
+        r, c, v, shape = fn(seg, base)
+        assert np.array_equal(r, g["ovo_row"]) and np.array_equal(c.astype(np.uint64), g["ovo_col"])
+        assert np.array_equal(v, g["ovo_val"]) and tuple(shape) == tuple(int(x) for x in g["ovo_shape"])
+        # orig_ids=False: the same entries as indices into the sorted id arrays
+        assert np.array_equal(np.searchsorted(g["ov_row_ids"], r), g["ov_row"])
+        assert np.array_equal(np.searchsorted(g["ov_col_ids"], c.astype(np.uint64)), g["ov_col"])
