@@ -74,8 +74,10 @@ def read_all_chunk_seg_infos(proc_url):
     return _grid_array({bbox_from_fname(f).min(): read_dframe(os.path.join(d, f)) for f in fnames}), d
 
 
-def write_merged_seg_info(dframe, proc_url):
-    write_dframe(dframe, os.path.join(proc_url, fn.merged_seginfo_fname))
+def write_merged_seg_info(dframe, proc_url, hash_tag=None):
+    """One file for the whole merge, or one per dst-id hash bucket of the sharded merge (seginfo.py:183-194)."""
+    name = fn.merged_seginfo_fname if hash_tag is None else fn.merged_seginfo_fmtstr.format(tag=hash_tag)
+    write_dframe(dframe, os.path.join(proc_url, name))
 
 
 def read_merged_seg_info(proc_url):
@@ -152,4 +154,39 @@ def write_chunk_id_maps(chunk_id_maps, chunk_bounds, proc_url):
 
 def read_chunk_id_map(proc_url, chunk_bounds):
     df = read_dframe(cleft_map_fname(proc_url, chunk_bounds))
+    return dict(zip(df.index, df[cn.dst_id]))
+
+
+# ---- chunk id -> unique (global) id maps and the duplicate / size-threshold map of the merge sharded by hash
+#      (synaptor/proc/io/idmap.py:26-92, 208-262) ---------------------------------------------------
+def unique_ids_fname(storagestr, chunk_bounds):
+    return os.path.join(storagestr, fn.uniquemap_dirname, fn.uniquemap_fmtstr.format(tag=fname_chunk_tag(chunk_bounds)))
+
+
+def write_chunk_unique_ids(mapping, storagestr, chunk_bounds):
+    write_dframe(make_dframe_from_dict(mapping), unique_ids_fname(storagestr, chunk_bounds))
+
+
+def read_unique_ids(filename):
+    df = read_dframe(filename)
+    return dict(zip(df.index, df[cn.dst_id]))
+
+
+def read_chunk_unique_ids(proc_url, chunk_bounds):
+    return read_unique_ids(unique_ids_fname(proc_url, chunk_bounds))
+
+
+def write_dup_id_map(id_map, storagestr, hash_index=None):
+    name = fn.dup_map_fname if hash_index is None else fn.tagged_dup_fname.format(i=hash_index)
+    write_dframe(make_dframe_from_dict(id_map), os.path.join(storagestr, name))
+
+
+def read_dup_id_map(proc_url):
+    """{src id: dst id}; like the reference, a missing file gives an empty mapping (with a warning)."""
+    try:
+        df = read_dframe(os.path.join(proc_url, fn.dup_map_fname))
+    except Exception as e:
+        print(e)
+        print("WARNING: no dup id map found, passing empty dup mapping")
+        df = pd.DataFrame({cn.dst_id: []})
     return dict(zip(df.index, df[cn.dst_id]))

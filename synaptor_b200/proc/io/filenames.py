@@ -2,9 +2,16 @@
 seginfo_dirname = "seg_infos"
 seginfo_fmtstr = "seg_info_{tag}.df"
 merged_seginfo_fname = "merged_cleft_info.df"
+merged_seginfo_fmtstr = "merged_cleft_info_{tag}.df"
 
 idmap_dirname = "id_maps"
 idmap_fmtstr = "id_map_{tag}.df"
+
+uniquemap_dirname = "unique_ids"
+uniquemap_fmtstr = "unique_ids_{tag}.df"
+
+dup_map_fname = "dup_id_map.df"
+tagged_dup_fname = "dup_id_map_{i}.df"
 
 overlaps_dirname = "overlaps"
 overlaps_fmtstr = "chunk_overlap_{tag}.df"

@@ -363,6 +363,31 @@ def main():
                         ovo_row=np.asarray(ovo10.row, dtype=np.int64), ovo_col=np.asarray(ovo10.col).astype(np.uint64),
                         ovo_val=np.asarray(ovo10.data, dtype=np.int64), ovo_shape=np.array(ovo10.shape, dtype=np.uint64))
     out["g10"] = (len(ids10), int(ov10.nnz), len(rem10))
+    # ---- G11: files of the merge sharded by hash written by the reference's local writers (idmap.py, seginfo.py) ----
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "unique_ids"))
+        bb11 = boxes[3]
+        taskio.write_chunk_unique_ids({int(k): int(v) for (k, v) in maps9[(0, 1, 1)].items()}, tmp, bb11)
+        dup11 = {int(d): 0 for d in dropped}
+        taskio.write_dup_id_map(dup11, tmp)
+        taskio.write_dup_id_map(dup11, tmp, hash_index=3)
+        taskio.write_merged_seg_info(mg, tmp, hash_tag=4)
+        taskio.write_merged_seg_info(mg, tmp)
+        files11 = {}
+        for (root, _, names) in os.walk(tmp):
+            for n in names:
+                files11[os.path.relpath(os.path.join(root, n), tmp)] = open(os.path.join(root, n)).read()
+        back11 = taskio.read_chunk_unique_ids(tmp, bb11)
+    np.savez_compressed(os.path.join(HERE, "g11_formats_hashed.npz"), names=np.array(sorted(files11)),
+                        texts=np.array([files11[k] for k in sorted(files11)]), bbox=np.array(bb11.astuple()),
+                        unique_keys=np.array(list(maps9[(0, 1, 1)].keys()), dtype=np.int64),
+                        unique_vals=np.array(list(maps9[(0, 1, 1)].values()), dtype=np.int64),
+                        dup_keys=np.array(list(dup11.keys()), dtype=np.int64),
+                        merged_index=np.asarray(mg.index, dtype=np.float64), merged_table=mg.to_numpy(dtype=np.float64),
+                        merged_columns=np.array(list(mg.columns)), merged_index_name=str(mg.index.name),
+                        readback_keys=np.array(list(back11.keys()), dtype=np.int64),
+                        readback_vals=np.array(list(back11.values()), dtype=np.int64))
+    out["g11"] = sorted(files11)
     print("golden written:", out)
 
 

@@ -123,3 +123,34 @@ def test_g9_merge_seginfo_task_host():
     part = full.reset_index()
     m2, none = tasks.merge_seginfo_task(part)
     assert none is None and len(m2) == len(set(dst.values()))
+
+
+def test_g11_hashed_merge_files(tmp_path):
+    """unique-id maps, duplicate maps and per-bucket merged tables: byte-identical to the reference's local writers."""
+    from synaptor_b200.proc import io as taskio, colnames as cn
+    from synaptor_b200.types.bbox import BBox3d
+    g = gold("g11_formats_hashed.npz")
+    want = dict(zip(g["names"].tolist(), g["texts"].tolist()))
+    bb = BBox3d(tuple(g["bbox"][:3].tolist()), tuple(g["bbox"][3:].tolist()))
+    root = str(tmp_path)
+    uniq = dict(zip(g["unique_keys"].tolist(), g["unique_vals"].tolist()))
+    taskio.write_chunk_unique_ids(uniq, root, bb)
+    dup = {k: 0 for k in g["dup_keys"].tolist()}
+    taskio.write_dup_id_map(dup, root)
+    taskio.write_dup_id_map(dup, root, hash_index=3)
+    merged = pd.DataFrame(g["merged_table"].astype(np.int64), index=g["merged_index"].astype(np.int64),
+                          columns=g["merged_columns"].tolist())
+    merged.index.name = str(g["merged_index_name"])
+    taskio.write_merged_seg_info(merged, root, hash_tag=4)
+    taskio.write_merged_seg_info(merged, root)
+    got = {}
+    for (d, _, names) in os.walk(root):
+        for n in names:
+            got[os.path.relpath(os.path.join(d, n), root)] = open(os.path.join(d, n)).read()
+    assert got == want
+    back = taskio.read_chunk_unique_ids(root, bb)
+    assert back == dict(zip(g["readback_keys"].tolist(), g["readback_vals"].tolist())) == uniq
+    assert taskio.read_unique_ids(taskio.unique_ids_fname(root, bb)) == uniq
+    assert taskio.read_dup_id_map(root) == dup
+    assert taskio.read_dup_id_map(os.path.join(root, "nowhere")) == {}
+    assert taskio.read_merged_seg_info(root).equals(merged)
