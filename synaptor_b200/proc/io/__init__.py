@@ -190,3 +190,37 @@ def read_dup_id_map(proc_url):
         print("WARNING: no dup id map found, passing empty dup mapping")
         df = pd.DataFrame({cn.dst_id: []})
     return dict(zip(df.index, df[cn.dst_id]))
+
+
+# ---- continuation file names and the face-hash table (synaptor/proc/io/continuation.py:22-50, 207-216).  The
+#      HDF5 payload of these files is not written here (h5py is not part of this environment). ----------------
+FACE_REGEXP = re.compile("f[0-2]_(hi|lo)")
+CONTIN_TABLENAME = "continuations"
+
+
+def fname_face_tag(face):
+    return f"f{face.axis}_{'hi' if face.hi_index else 'lo'}"
+
+
+def face_from_tag(tag):
+    from ..seg.continuation import Face
+    return Face(int(tag[1]), tag[-2:] == "hi")
+
+
+def face_from_filename(fname):
+    m = FACE_REGEXP.search(fname)
+    assert m is not None, f"face not found in fname: {fname}"
+    return face_from_tag(m.group(0))
+
+
+def face_filename(proc_url, chunk_bounds, face, local=False):
+    basename = fn.contin_fmtstr.format(chunk_tag=fname_chunk_tag(chunk_bounds), face_tag=fname_face_tag(face))
+    return os.path.join(proc_url, basename) if local else os.path.join(proc_url, fn.contin_dirname, basename)
+
+
+def prep_face_hashes(face_hashes, chunk_bounds, proc_dir):
+    """(DataFrame of continuation file name and face hash per face, table name) -- what the merge sharded by hash
+    looks a face's files up by."""
+    faces, hashes = zip(*list(face_hashes.items()))
+    filenames = [face_filename(proc_dir, chunk_bounds, face) for face in faces]
+    return pd.DataFrame({cn.contin_filename: filenames, cn.facehash: hashes}), CONTIN_TABLENAME

@@ -4,6 +4,9 @@ seginfo_fmtstr = "seg_info_{tag}.df"
 merged_seginfo_fname = "merged_cleft_info.df"
 merged_seginfo_fmtstr = "merged_cleft_info_{tag}.df"
 
+contin_dirname = "continuations"
+contin_fmtstr = "continuations_{chunk_tag}_{face_tag}.h5"
+
 idmap_dirname = "id_maps"
 idmap_fmtstr = "id_map_{tag}.df"
 

@@ -6,7 +6,7 @@ from . import conncomps
 from .conncomps import connected_components, dilated_components
 
 from . import continuation
-from .continuation import Continuation, Face, extract_all_continuations
+from .continuation import Continuation, Face, ContinFile, extract_all_continuations
 from .continuation import hash_chunk_faces
 
 from . import merge

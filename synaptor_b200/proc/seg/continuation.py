@@ -5,6 +5,8 @@ face slices come from the device (syn_extract_faces); the per-id grouping is a
 vectorised numpy pass over the O(surface) face voxels instead of the reference's
 Python loop.
 """
+from collections import namedtuple
+
 import numpy as np
 
 from ... import _device as D
@@ -60,6 +62,10 @@ class Face(object):
         return f"<Face {self.axis},{'high' if self.hi_index else 'low'}>"
 
     __str__ = __repr__
+
+
+# a continuation file with the chunk bounds and the face it holds (continuation.py:79-80)
+ContinFile = namedtuple("ContinFile", ["filename", "bbox", "face"])
 
 
 def continuations_of_face(face_arr, face):

@@ -7,6 +7,7 @@ from .assign_ids import apply_id_map
 from . import merge_ccs
 from .merge_ccs import find_connected_continuations, merge_continuations
 from .merge_ccs import match_continuations, reconstruct_face
+from .merge_ccs import pair_continuation_files
 
 from . import merge_df
 from .merge_df import merge_seginfo_df, enforce_size_threshold, add_new_ids

@@ -12,6 +12,22 @@ from ... import colnames as cn
 from .... import _device as D
 
 
+def pair_continuation_files(contin_files):
+    """
+    Groups continuation files that describe the same chunk boundary (merge_ccs.py:11-32): the key of a hi face
+    is the chunk's end corner + axis, that of a lo face the end corner with the face axis replaced by the chunk's
+    begin -- the key seg.hash_chunk_faces hashes.  Returns a list of lists (duplicates removed); a complete
+    boundary has two entries, a face on the edge of the volume one.
+    """
+    pairs = dict()
+    for cf in contin_files:
+        corner = list(cf.bbox.max())
+        if not cf.face.hi_index:
+            corner[cf.face.axis] = cf.bbox.min()[cf.face.axis]
+        pairs.setdefault((*corner, cf.face.axis), []).append(cf)
+    return [list(set(v)) for v in pairs.values()]
+
+
 def reconstruct_face(continuations, shape=(1152, 1152)):
     face = np.zeros(shape, dtype=np.uint32)
     for c in continuations:

@@ -388,6 +388,20 @@ def main():
                         readback_keys=np.array(list(back11.keys()), dtype=np.int64),
                         readback_vals=np.array(list(back11.values()), dtype=np.int64))
     out["g11"] = sorted(files11)
+    # ---- G12: continuation file names, the face-hash table and the pairing of the files of a boundary -----------
+    from synaptor.proc.seg.continuation import ContinFile
+    df12, tn12 = taskio.prep_face_hashes(hash_chunk_faces(tuple(boxes[0].min()), tuple(boxes[0].max()), 64),
+                                          boxes[0], "procdir")
+    cfs12 = [ContinFile(taskio.continuation.face_filename("procdir", bb, f), bb, f)
+             for bb in boxes for f in Face.all_faces()]
+    groups12 = syn.proc.seg.merge.pair_continuation_files(cfs12 + cfs12[:5])
+    np.savez_compressed(os.path.join(HERE, "g12_contin_files.npz"), table_name=tn12,
+                        columns=np.array(list(df12.columns)), filenames=np.array(df12[rcn.contin_filename].tolist()),
+                        hashes=np.array(df12[rcn.facehash].tolist(), dtype=np.int64),
+                        boxes=np.array([bb.astuple() for bb in boxes]),
+                        groups=np.array(sorted("|".join(sorted(c.filename for c in grp)) for grp in groups12)),
+                        face_tags=np.array([taskio.continuation.fname_face_tag(f) for f in Face.all_faces()]))
+    out["g12"] = (len(df12), len(groups12))
     print("golden written:", out)
 
 

@@ -154,3 +154,29 @@ def test_g11_hashed_merge_files(tmp_path):
     assert taskio.read_dup_id_map(root) == dup
     assert taskio.read_dup_id_map(os.path.join(root, "nowhere")) == {}
     assert taskio.read_merged_seg_info(root).equals(merged)
+
+
+def test_g12_continuation_file_names_and_pairing():
+    """face tags, continuation file names, the face-hash table and pair_continuation_files against the reference."""
+    from synaptor_b200.proc import io as taskio, colnames as cn
+    from synaptor_b200.proc.seg import ContinFile, Face, hash_chunk_faces
+    from synaptor_b200.proc.seg.merge import pair_continuation_files
+    from synaptor_b200.types.bbox import BBox3d
+    g = gold("g12_contin_files.npz")
+    boxes = [BBox3d(tuple(b[:3]), tuple(b[3:])) for b in g["boxes"].tolist()]
+    assert [taskio.fname_face_tag(f) for f in Face.all_faces()] == g["face_tags"].tolist()
+    for f in Face.all_faces():
+        name = taskio.face_filename("procdir", boxes[2], f)
+        assert taskio.face_from_filename(name) == f and taskio.bbox_from_fname(name) == boxes[2]
+    assert taskio.face_filename("x", boxes[0], Face(1, False), local=True) == os.path.join(
+        "x", os.path.basename(taskio.face_filename("x", boxes[0], Face(1, False))))
+    df, table = taskio.prep_face_hashes(hash_chunk_faces(tuple(boxes[0].min()), tuple(boxes[0].max()), 64),
+                                        boxes[0], "procdir")
+    assert table == str(g["table_name"]) and list(df.columns) == g["columns"].tolist()
+    assert df[cn.contin_filename].tolist() == g["filenames"].tolist()
+    assert df[cn.facehash].tolist() == g["hashes"].tolist()
+    cfs = [ContinFile(taskio.face_filename("procdir", bb, f), bb, f) for bb in boxes for f in Face.all_faces()]
+    groups = pair_continuation_files(cfs + cfs[:5])
+    assert sorted("|".join(sorted(c.filename for c in grp)) for grp in groups) == g["groups"].tolist()
+    # the two files of an interior boundary land in one group, and in one hash bucket
+    assert sum(len(grp) == 2 for grp in groups) == 12 and sum(len(grp) == 1 for grp in groups) == 24
