@@ -157,8 +157,7 @@ struct Workspace {
     u32 *par, *rank, *runlabel, *complab;
     CompStat *stat;
     TileRec *recs;
-    PairKey *pkeys;
-    u64 *pcount, *pfirst;
+    PairSlot *pslots;
     u32 *bcount, *bfill, *sorted_slot;     // pair ordering: bucket counts (nb + 1), fill cursors (nb), bucket order
     u32 nbuckets;
     u32 paircap;
@@ -185,7 +184,7 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     w->tg = make_tiles(g);
     w->tileflag = (u32 *)take(((size_t)w->tg.ntiles + 8) * 4);
     w->paircap = 0;
-    w->pkeys = nullptr; w->pcount = w->pfirst = nullptr; w->bcount = w->bfill = w->sorted_slot = nullptr;
+    w->pslots = nullptr; w->bcount = w->bfill = w->sorted_slot = nullptr;
     w->nbuckets = nb;
     if (max_pairs > 0) {
         w->bcount = (u32 *)take(((size_t)nb + 1) * 4 + (size_t)nb * 4);   // bucket counts + fill cursors
@@ -210,9 +209,7 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     w->recs = (TileRec *)take((size_t)max_runs * sizeof(TileRec));
     if (max_pairs > 0) {
         w->paircap = pow2_at_least(2 * max_pairs);
-        w->pkeys = (PairKey *)take((size_t)w->paircap * sizeof(PairKey));
-        w->pcount = (u64 *)take((size_t)w->paircap * 8);
-        w->pfirst = (u64 *)take((size_t)w->paircap * 8);
+        w->pslots = (PairSlot *)take((size_t)w->paircap * sizeof(PairSlot));
         w->sorted_slot = (u32 *)take((size_t)max_pairs * 4);
     }
     w->total = off;
@@ -419,7 +416,7 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
     static const bool no_fuse = getenv("SYN_NO_FUSED_SCAN") != nullptr;
     const bool fused_scan = sector_out && !dilate && !no_fuse;
     const u64 *bs = (const u64 *)base_seg;
-    PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap ? W.paircap - 1 : 0, W.cnt};
+    PairTable T{W.pslots, W.paircap ? W.paircap - 1 : 0, W.cnt};
     if (sector_out) {
         const i64 ntiles = ((i64)g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
         static const int stream_ctas = getenv("SYN_STREAM_CTAS") ? atoi(getenv("SYN_STREAM_CTAS")) : 0;   // per SM; 0 = occupancy
@@ -615,7 +612,7 @@ int syn_count_overlaps(const uint32_t *seg1, const uint64_t *seg2, int64_t nx, i
                     (long long)workspace_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(workspace, 0, W.zero_bytes, st));
-    PairTable T{W.pkeys, W.pcount, W.pfirst, W.paircap - 1, W.cnt};
+    PairTable T{W.pslots, W.paircap - 1, W.cnt};
     k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
     CK_LAUNCH();
     k_overlap_scan<<<grid_for((i64)g.nwords * 32, 256, 8), 256, 0, st>>>(seg1, (const u64 *)seg2, g, T, W.cnt);
@@ -833,10 +830,8 @@ int syn_merge_overlaps(const uint32_t *rows, const uint64_t *cols, const int64_t
     if (n == 0) return SYN_OK;
     const u32 cap = pow2_at_least(2 * n);
     char *buf = nullptr;
-    CK(cudaMallocAsync(&buf, (size_t)cap * (sizeof(PairKey) + 16) + sizeof(Counts), st));
-    PairTable T{(PairKey *)buf, (u64 *)(buf + (size_t)cap * sizeof(PairKey)),
-                (u64 *)(buf + (size_t)cap * (sizeof(PairKey) + 8)), cap - 1,
-                (Counts *)(buf + (size_t)cap * (sizeof(PairKey) + 16))};
+    CK(cudaMallocAsync(&buf, (size_t)cap * sizeof(PairSlot) + sizeof(Counts), st));
+    PairTable T{(PairSlot *)buf, cap - 1, (Counts *)(buf + (size_t)cap * sizeof(PairSlot))};
     CK(cudaMemsetAsync(T.cnt, 0, sizeof(Counts), st));
     k_pair_table_init<<<grid_for(cap, 256, 8), 256, 0, st>>>(T);
     CK_LAUNCH();

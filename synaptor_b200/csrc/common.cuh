@@ -109,11 +109,18 @@ struct Counts {
 #define SYN_TIMER_MARK(cnt, slot) do { } while (0)
 #endif
 
-// open-addressing table of (label, base id) pairs in HBM (finalize.cuh)
+// open-addressing table of (label, base id) pairs in HBM (finalize.cuh).  One 32-byte slot = one L2 sector:
+// the 16-byte key (claimed with one 128-bit CAS), the count and the first position, so that a probe reads the
+// key AND the current first position with one request.
+struct __align__(32) PairSlot {
+    PairKey key;     // all-ones = empty
+    u64 count;
+    u64 first;       // smallest padded bit position (row * wz * 32 + z) of the pair
+};
+static_assert(sizeof(PairSlot) == 32, "PairSlot must be 32 bytes");
+
 struct PairTable {
-    PairKey *keys;   // [cap] 16-byte keys, all-ones = empty
-    u64 *count;      // [cap]
-    u64 *first;      // [cap] smallest padded bit position (row * wz * 32 + z) of the pair
+    PairSlot *slots; // [cap]
     u32 capmask;     // cap - 1 (cap is a power of two)
     Counts *cnt;
 };

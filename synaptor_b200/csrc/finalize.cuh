@@ -34,20 +34,26 @@ __device__ __forceinline__ void pair_insert(const PairTable &T, u32 label, u64 b
         // Keys are write-once (empty -> key).  A plain 16 B read can only be stale or torn
         // while the slot is being claimed, and then at least one half still reads all-ones:
         // in that case the 128-bit CAS is the authority.
-        PairKey cur = T.keys[h];
+        u64 cb, cl, cf;                                       // key and (stale) first position: one 32 B read
+        [[maybe_unused]] u64 cc;                              // (the count travels along)
+        asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(cb), "=l"(cl), "=l"(cc), "=l"(cf) : "l"(T.slots + h));
+        PairKey cur{cb, cl};
         bool hit = cur.base == want.base && cur.label == want.label;
         if (!hit && (cur.base == ~0ull || cur.label == ~0ull)) {
-            cur = cas128(T.keys + h, empty, want);
+            cur = cas128(&T.slots[h].key, empty, want);
             if (cur.base == empty.base && cur.label == empty.label) {  // claimed
                 atomicAdd((u64 *)&T.cnt->v[SYN_CNT_TABLE_SLOTS], 1ull);
                 hit = true;
             } else {
                 hit = cur.base == want.base && cur.label == want.label;
             }
+            cf = ~0ull;
         }
         if (hit) {
-            atomicAdd(T.count + h, (u64)n);
-            atomicMin(T.first + h, pos);
+            atomicAdd(&T.slots[h].count, (u64)n);
+            // the first position only ever decreases: a (possibly stale) value that is already smaller makes the
+            // atomic unnecessary
+            if (pos < cf) atomicMin(&T.slots[h].first, pos);
             return;
         }
         h = (h + 1) & T.capmask;
@@ -58,9 +64,7 @@ __device__ __forceinline__ void pair_insert(const PairTable &T, u32 label, u64 b
 __global__ void __launch_bounds__(256) k_pair_table_init(PairTable T)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.capmask; i += gridDim.x * blockDim.x) {
-        T.keys[i] = PairKey{~0ull, ~0ull};
-        T.count[i] = 0;
-        T.first[i] = ~0ull;
+        T.slots[i] = PairSlot{PairKey{~0ull, ~0ull}, 0ull, ~0ull};
     }
 }
 
@@ -423,7 +427,7 @@ constexpr int PB_SHIFT = 12;
 __global__ void __launch_bounds__(256) k_pair_count(PairTable T, u32 *__restrict__ bcount)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.capmask; i += gridDim.x * blockDim.x) {
-        const u64 f = T.first[i];
+        const u64 f = T.slots[i].first;
         if (f != ~0ull) atomicAdd(bcount + (f >> PB_SHIFT), 1u);
     }
 }
@@ -449,7 +453,7 @@ __global__ void __launch_bounds__(256) k_pair_scatter(PairTable T, const u32 *__
                                                       u32 *__restrict__ sorted_slot, i64 max_pairs)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.capmask; i += gridDim.x * blockDim.x) {
-        const u64 f = T.first[i];
+        const u64 f = T.slots[i].first;
         if (f == ~0ull) continue;
         const u32 b = (u32)(f >> PB_SHIFT);
         const u32 j = bbase[b] + atomicAdd(bfill + b, 1u);
@@ -466,15 +470,15 @@ __global__ void __launch_bounds__(256) k_pair_emit(PairTable T, const u32 *__res
     if ((i64)np > max_pairs) return;     // capacity error already flagged by the scatter
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < np; j += gridDim.x * blockDim.x) {
         const u32 slot = sorted_slot[j];
-        const u64 f = T.first[slot];
+        const u64 f = T.slots[slot].first;
         const u32 b = (u32)(f >> PB_SHIFT);
         const u32 lo = bbase[b], hi = (b + 1 < nb) ? bbase[b + 1] : np;
         u32 r = lo;
-        for (u32 t = lo; t < hi; ++t) r += (T.first[sorted_slot[t]] < f);
-        const PairKey k = T.keys[slot];
+        for (u32 t = lo; t < hi; ++t) r += (T.slots[sorted_slot[t]].first < f);
+        const PairKey k = T.slots[slot].key;
         rows[r] = (u32)k.label;
         cols[r] = k.base;
-        vals[r] = (i64)T.count[slot];
+        vals[r] = (i64)T.slots[slot].count;
     }
 }
 
@@ -506,9 +510,9 @@ __global__ void __launch_bounds__(256) k_mo_init(u64 *__restrict__ argcol, i64 *
 __global__ void __launch_bounds__(256) k_mo_rowmax(PairTable T, i64 *__restrict__ maxval, i64 n_ids)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.capmask; i += gridDim.x * blockDim.x) {
-        const PairKey k = T.keys[i];
+        const PairKey k = T.slots[i].key;
         if (k.label == ~0ull || (i64)k.label >= n_ids) continue;
-        atomicMax((u64 *)maxval + k.label, T.count[i]);
+        atomicMax((u64 *)maxval + k.label, T.slots[i].count);
     }
 }
 
@@ -516,9 +520,9 @@ __global__ void __launch_bounds__(256) k_mo_rowarg(PairTable T, const i64 *__res
                                                    u64 *__restrict__ argcol, i64 n_ids)
 {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= T.capmask; i += gridDim.x * blockDim.x) {
-        const PairKey k = T.keys[i];
+        const PairKey k = T.slots[i].key;
         if (k.label == ~0ull || (i64)k.label >= n_ids) continue;
-        if ((i64)T.count[i] == maxval[k.label]) atomicMin(argcol + k.label, k.base);
+        if ((i64)T.slots[i].count == maxval[k.label]) atomicMin(argcol + k.label, k.base);
     }
 }
 
