@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from util import flatten_conts, gold, sorted_triples, table_of
+from util import flatten_conts, gold, table_of
 
 
 @pytest.mark.parametrize("flavour", ["np", "c"])

@@ -10,7 +10,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from oracle import oracle as orc
-import synaptor_b200 as syn
 from synaptor_b200.proc import tasks as T
 
 shape = (512, 512, 512)

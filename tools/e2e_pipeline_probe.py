@@ -2,7 +2,6 @@
 """Probe of the pipelined multi-chunk path: per-chunk completion times and where host threads block."""
 import os
 import sys
-import threading
 import time
 from collections import defaultdict
 
