@@ -232,6 +232,55 @@ SYN_API int syn_merge_ccs_grid(const uint32_t *faces_all, const int64_t *tables_
                                int64_t *merged_out, uint32_t *fmap_out, int64_t *n_merged_dev, void *stream);
 
 /*
+ * The chunk pass in two halves with the cross-chunk merge in between -- the single-box form of the reference's
+ * chunk_ccs -> merge_ccs -> remap_ids -> chunk_overlaps workflow (proc/tasks.py:26-69, 72-122, 314-333, 290-297;
+ * kube/task_generation/chunk_overlaps.py:14 runs the overlap task on the REMAPPED volume).  The label volume is
+ * written once, already in merged global ids, and the overlaps are counted against those ids.
+ *
+ * A chunk's contribution to the merge is one PACKED SLOT of syn_packed_slot_bytes(cap_rows, cap_entries) bytes:
+ *   int64 hdr[16]  : [0] rows of the segment table, [1] face entries, [2..7] first entry of face 0..5
+ *                    (Face.all_faces() order, proc/seg/continuation.py:52-59), [8] flags (1 rows overflow,
+ *                    2 entries overflow, 4 a capacity error of the chunk pass)
+ *   int64 table[cap_rows][SYN_SEG_NCOLS]   as syn_chunk_ccs' seg_table
+ *   uint32 entry[cap_entries][2]           (position inside the face, table row + 1) of every face voxel that
+ *                                          belongs to a surviving segment, raster order inside a face -- the
+ *                                          content of the reference's Continuation objects (continuation.py:15-35)
+ *
+ * syn_chunk_ccs_begin  : syn_chunk_ccs up to the segment table; zero-fills the label sectors without foreground,
+ *                        fills the packed slot.  No host synchronisation.
+ * syn_merge_ccs_packed : merge_ccs_task (proc/tasks.py:72-122) over the gathered slots of ALL chunks:
+ *                        id_base_out[c] = ids before chunk c in np.ndindex order (assign_ids.py:8-42; chunk c's row r
+ *                        is global id id_base[c] + r + 1), edges between facing faces (merge_ccs.py:69-128),
+ *                        union-find to the smallest id (proc/utils.py:39-86), merged table + size threshold
+ *                        (merge_df.py:13-68).  plan_dev: device int32 [2 + nchunks + 4 npairs] =
+ *                        {nchunks, npairs, slot of chunk c ..., (chunk here, hi face, chunk there, lo face) ...}.
+ *                        merged_out int64 [nchunks cap_rows][SYN_SEG_NCOLS] (ascending id); fmap_out uint32
+ *                        [nchunks cap_rows + 1]: global id -> final id (0 = under the size threshold);
+ *                        info_out int64[8]: [0] total ids, [1] merged rows, [2] edges, [3] flags (1: a slot
+ *                        overflowed, 2: max_edges too small).  No host synchronisation.
+ * syn_chunk_ccs_finish : the rest of syn_chunk_ccs for a chunk started with syn_chunk_ccs_begin (same shape,
+ *                        workspace, capacities, pointers): label of table row r = final_lut[final_lut_base_dev[0]
+ *                        + r + 1] (final_lut NULL: r + 1), foreground label sectors, (label, base id) counts.
+ */
+SYN_API int64_t syn_packed_slot_bytes(int64_t cap_rows, int64_t cap_entries);
+SYN_API int syn_chunk_ccs_begin(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity,
+                                int dil_k, int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out,
+                                const uint64_t *base_seg, int64_t max_pairs, void *packed_slot, int64_t cap_rows,
+                                int64_t cap_entries, void *workspace, int64_t workspace_bytes, int64_t max_runs,
+                                void *stream);
+SYN_API int syn_chunk_ccs_finish(const float *pred, int64_t nx, int64_t ny, int64_t nz, int connectivity, int dil_k,
+                                 uint32_t *labels_out, const uint64_t *base_seg, uint32_t *pair_rows,
+                                 uint64_t *pair_cols, int64_t *pair_counts, int64_t max_pairs, int64_t cap_rows,
+                                 const uint32_t *final_lut, const int64_t *final_lut_base_dev, int64_t final_lut_len,
+                                 void *workspace, int64_t workspace_bytes, int64_t max_runs, int64_t *counts_host,
+                                 void *stream);
+SYN_API int64_t syn_merge_packed_workspace_bytes(int64_t nchunks, int64_t cap_rows, int64_t max_edges);
+SYN_API int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
+                                 const int32_t *plan_dev, int64_t nchunks, int64_t npairs, int64_t size_thr,
+                                 int64_t max_edges, void *workspace, int64_t workspace_bytes, int64_t *id_base_out,
+                                 int64_t *merged_out, uint32_t *fmap_out, int64_t *info_out, void *stream);
+
+/*
  * syn_merge_overlaps -- proc/tasks.py:300-311 (merge_overlaps_task: consolidate_overlaps,
  * overlap/merge/merge_overlaps.py:24-40, then find_max_overlaps, overlap/overlap.py:15-28).
  * rows / cols / counts: device arrays of n (label, base id, voxel count) triples of all chunks,

@@ -52,6 +52,14 @@ SIGNATURES = {
     "syn_merge_seg_tables": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "syn_merge_ccs_grid": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp]),
+    "syn_packed_slot_bytes": (_i64, [_i64, _i64]),
+    "syn_chunk_ccs_begin": (_i32, [_vp, _i64, _i64, _i64, _f32, _i32, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64,
+                                   _vp, _i64, _i64, _vp]),
+    "syn_chunk_ccs_finish": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp,
+                                    _i64, _vp, _i64, _i64, _vp, _vp]),
+    "syn_merge_packed_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "syn_merge_ccs_packed": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp,
+                                    _vp]),
     "syn_merge_overlaps": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "syn_launch_count": (ctypes.c_longlong, []),
     "syn_profile_enable": (_i32, [_i32]),

@@ -12,6 +12,7 @@
 #include "aux.cuh"
 #include "ccl.cuh"
 #include "finalize.cuh"
+#include "merge.cuh"
 
 using namespace syn;
 
@@ -148,9 +149,9 @@ struct Workspace {
     u32 *startw;                           // stored run-start words (multi-label variant only)
     u32 *actw;                             // compact list of non-empty mask words
     u32 *bndw;                             // non-empty words on a tile border
-    u64 *scanstate;                        // 4 look-back state arrays + tickets, zeroed per call
+    u64 *scanstate;                        // 5 look-back state arrays + tickets, zeroed per call
     u32 *scan_tickets;
-    size_t scan_off[4];
+    size_t scan_off[5];
     size_t zero_bytes;                     // head of the workspace that every call zeroes
     u32 *tileagg, *tilebase;               // run counts / run-id bases of the stream tiles (k_stream)
     size_t ts_cap;
@@ -172,14 +173,16 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     const size_t nw = (size_t)g.nwords + 8;
     // ---- everything that must be zero at the start of a call sits at the head of the workspace: one memset ----
     w->cnt = (Counts *)take(sizeof(Counts));
-    // look-back state of the four scan instances (slot 0: mask words, 16 items; 1: runs, 8; 2: components, 2;
-    // 3: pair buckets, 8) + their tickets
+    // look-back state of the five scan instances (slot 0: mask words, 16 items; 1: runs, 8; 2: components, 2;
+    // 3: pair buckets, 8; 4: face voxels, 8) + their tickets
     const u32 nb = max_pairs > 0 ? (u32)((((u64)g.nwords * 32) >> PB_SHIFT) + 1) : 0;
-    const size_t cap[4] = {nw / (SCAN_THREADS * 16) + 2, (size_t)max_runs / (SCAN_THREADS * 8) + 2,
-                           (size_t)max_runs / (SCAN_THREADS * 2) + 2, (size_t)nb / (SCAN_THREADS * 8) + 2};
+    const size_t nface = (size_t)(2 * (g.ny * g.nz + g.nx * g.nz + g.nx * g.ny));
+    const size_t cap[5] = {nw / (SCAN_THREADS * 16) + 2, (size_t)max_runs / (SCAN_THREADS * 8) + 2,
+                           (size_t)max_runs / (SCAN_THREADS * 2) + 2, (size_t)nb / (SCAN_THREADS * 8) + 2,
+                           nface / (SCAN_THREADS * 8) + 2};
     size_t so = 0;
-    for (int i = 0; i < 4; ++i) { w->scan_off[i] = so; so += cap[i]; }
-    w->scanstate = (u64 *)take((so + 8) * 8);
+    for (int i = 0; i < 5; ++i) { w->scan_off[i] = so; so += cap[i]; }
+    w->scanstate = (u64 *)take((so + 8) * 8);          // + 16 u32 tickets (two per slot)
     w->scan_tickets = w->scanstate ? (u32 *)(w->scanstate + so) : nullptr;
     w->tg = make_tiles(g);
     w->tileflag = (u32 *)take(((size_t)w->tg.ntiles + 8) * 4);
@@ -252,7 +255,7 @@ int grid_for(i64 items, int threads, int per_sm)
     return (int)(need < cap ? need : cap);
 }
 
-// single-pass scan #slot (0..3) with its own look-back state inside the workspace
+// single-pass scan #slot (0..4) with its own look-back state inside the workspace
 template <int ITEMS, class Src, class Dst>
 int launch_scan(const Workspace &W, int slot, Src src, Dst dst, i64 max_items, i64 *total_out, cudaStream_t st)
 {
@@ -369,54 +372,100 @@ int syn_read_counts(const void *workspace, int64_t *counts_host, void *stream)
 
 namespace {
 
-// `ml_base`: base segmentation of the multi-label variant (cc_task(overlap_seg=...), conncomps.py:24-28), else null
-int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity, int dil_k,
-                   int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out, int64_t *seg_table,
-                   int64_t max_segs, const uint64_t *base_seg, uint32_t *pair_rows, uint64_t *pair_cols,
-                   int64_t *pair_counts, int64_t max_pairs, void *workspace, int64_t workspace_bytes,
-                   int64_t max_runs, int64_t *counts_host, void *stream, const uint64_t *ml_base)
-{
+// One chunk_ccs call, split into the part that needs only the chunk itself (ccs_begin: everything up to the
+// segment table) and the part that writes the foreground labels and counts the overlaps (ccs_finish).  In between
+// a caller may run the cross-chunk merge and hand the final id map to ccs_finish, so that the label volume is
+// written ONCE, already in merged global ids (proc/tasks.py:314-333 remap_ids_task folded into the label write).
+struct CcsCall {
+    // arguments
+    const float *pred;
+    float thresh;
+    int connectivity, dil_k;
+    i64 dust;
+    i64 off[3];
+    u32 *labels;
+    i64 *seg_table;
+    i64 max_segs;
+    const u64 *base;
+    u32 *prow;
+    u64 *pcol;
+    i64 *pval;
+    i64 max_pairs;
+    void *workspace;
+    i64 ws_bytes, max_runs;
+    i64 *counts_host;
+    cudaStream_t st;
+    const u64 *ml_base;     // base segmentation of the multi-label variant (cc_task(overlap_seg=...)), else null
+    bool defer;             // table-relative labels (row + 1) instead of component numbers; run labels in finish
+    const u32 *lut;         // finish, deferred: final label = lut[lut_base[0] + row + 1] (null: row + 1)
+    const i64 *lut_base;
+    i64 lut_len;
+    // derived
     Geom g;
-    int rc = make_geom(nx, ny, nz, &g);
-    if (rc != SYN_OK) return rc;
-    if (!pred || !labels_out || !workspace) return fail(SYN_ERR_INVALID, "null pointer argument");
-    if (connectivity != 6 && connectivity != 18 && connectivity != 26)
-        return fail(SYN_ERR_INVALID, "connectivity must be 6, 18 or 26 (got %d)", connectivity);
-    if (dil_k < 0 || dil_k > 32) return fail(SYN_ERR_INVALID, "dil_k must be in [0, 32] (got %d)", dil_k);
-    if (max_runs < 1 || max_runs >= (1ll << 32) - 8192) return fail(SYN_ERR_INVALID, "bad max_runs");
-    if (max_segs < 0 || (max_segs > 0 && !seg_table)) return fail(SYN_ERR_INVALID, "bad seg table arguments");
-    const bool has_base = base_seg != nullptr;
-    if (has_base && (max_pairs < 1 || !pair_rows || !pair_cols || !pair_counts))
-        return fail(SYN_ERR_INVALID, "base_seg given without pair output arrays");
-    if (!has_base) max_pairs = 0;
-    const bool dilate = dil_k > 0;
-    const bool ml = ml_base != nullptr;
-    if (ml && (dilate || connectivity != 6 || has_base))
-        return fail(SYN_ERR_INVALID, "the multi-label variant is 6-connected, without dilation or pair counting");
     Workspace W;
-    carve((char *)workspace, g, max_runs, max_pairs, dilate, ml, &W);
-    if (ml) W.tg = TileGeom{0, 0, 0, 0, 0, 0, 0, 0};     // generic global path: no shared-memory tile pass
-    W.tg.diag = connectivity > 6;                        // rows with diagonal neighbours across a tile border
-    if ((i64)W.total > workspace_bytes)
-        return fail(SYN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %lld", W.total,
-                    (long long)workspace_bytes);
-    cudaStream_t st = (cudaStream_t)stream;
+    bool has_base, dilate, ml, vec_in, sector_out, fused_scan;
+    RunIdx R;
+    PairTable T;
+};
 
-    CK(cudaMemsetAsync(workspace, 0, W.zero_bytes, st));     // counters, scan state, tile flags, pair buckets
+int ccs_setup(CcsCall &c, int64_t nx, int64_t ny, int64_t nz, bool need_pairs_out)
+{
+    int rc = make_geom(nx, ny, nz, &c.g);
+    if (rc != SYN_OK) return rc;
+    if (!c.pred || !c.labels || !c.workspace) return fail(SYN_ERR_INVALID, "null pointer argument");
+    if (c.connectivity != 6 && c.connectivity != 18 && c.connectivity != 26)
+        return fail(SYN_ERR_INVALID, "connectivity must be 6, 18 or 26 (got %d)", c.connectivity);
+    if (c.dil_k < 0 || c.dil_k > 32) return fail(SYN_ERR_INVALID, "dil_k must be in [0, 32] (got %d)", c.dil_k);
+    if (c.max_runs < 1 || c.max_runs >= (1ll << 32) - 8192) return fail(SYN_ERR_INVALID, "bad max_runs");
+    if (c.max_segs < 0 || (c.max_segs > 0 && !c.seg_table)) return fail(SYN_ERR_INVALID, "bad seg table arguments");
+    c.has_base = c.base != nullptr;
+    if (c.has_base && (c.max_pairs < 1 || (need_pairs_out && (!c.prow || !c.pcol || !c.pval))))
+        return fail(SYN_ERR_INVALID, "base_seg given without pair output arrays");
+    if (!c.has_base) c.max_pairs = 0;
+    c.dilate = c.dil_k > 0;
+    c.ml = c.ml_base != nullptr;
+    if (c.ml && (c.dilate || c.connectivity != 6 || c.has_base))
+        return fail(SYN_ERR_INVALID, "the multi-label variant is 6-connected, without dilation or pair counting");
+    const Geom &g = c.g;
+    Workspace &W = c.W;
+    carve((char *)c.workspace, g, c.max_runs, c.max_pairs, c.dilate, c.ml, &W);
+    if (c.ml) W.tg = TileGeom{0, 0, 0, 0, 0, 0, 0, 0};   // generic global path: no shared-memory tile pass
+    W.tg.diag = c.connectivity > 6;                      // rows with diagonal neighbours across a tile border
+    if ((i64)W.total > c.ws_bytes)
+        return fail(SYN_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %lld", W.total, (long long)c.ws_bytes);
+    // Sector mode (nz % 8 == 0, aligned buffers): ONE streaming kernel reads the predictions and the base volume
+    // and zero-fills the label sectors without foreground (16 B/voxel, HBM bound); without dilation it also
+    // produces the tiled run-id prefix and the active / border word lists.  Otherwise: plain threshold kernel,
+    // and the generic output pass at the end.
+    c.vec_in = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(c.pred) & 15) == 0);
+    c.sector_out = !c.ml && (nz % 8 == 0) && c.vec_in && ((reinterpret_cast<uintptr_t>(c.labels) & 31) == 0) &&
+                   (!c.has_base || (reinterpret_cast<uintptr_t>(c.base) & 15) == 0);
+    static const bool no_fuse = getenv("SYN_NO_FUSED_SCAN") != nullptr;
+    c.fused_scan = c.sector_out && !c.dilate && !no_fuse;
+    c.R = RunIdx{W.runbase, c.fused_scan ? W.tilebase : nullptr, g.cpr, c.ml ? W.startw : nullptr, c.ml_base};
+    c.T = PairTable{W.pslots, W.paircap ? W.paircap - 1 : 0, W.cnt};
+    return SYN_OK;
+}
+
+int ccs_begin(CcsCall &c)
+{
+    const Geom &g = c.g;
+    Workspace &W = c.W;
+    cudaStream_t st = c.st;
+    const float *pred = c.pred;
+    u32 *labels_out = c.labels;
+    const float thresh = c.thresh;
+    const i64 max_runs = c.max_runs;
+    const bool has_base = c.has_base, dilate = c.dilate, ml = c.ml, vec_in = c.vec_in, sector_out = c.sector_out,
+               fused_scan = c.fused_scan;
+    const i64 nz = g.nz;
+    int rc;
+
+    CK(cudaMemsetAsync(c.workspace, 0, W.zero_bytes, st));     // counters, scan state, tile flags, pair buckets
     g_prof_n = 0;
     PROF("start");
 
-    // --- K1.  Sector mode (nz % 8 == 0, aligned buffers): ONE streaming kernel reads the predictions and the
-    // base volume and zero-fills the label sectors without foreground (16 B/voxel, HBM bound); without dilation
-    // it also produces the tiled run-id prefix and the active / border word lists.  Otherwise: plain threshold
-    // kernel, and the generic output pass at the end. ---------------------------------------------------------
-    const bool vec_in = (nz % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
-    const bool sector_out = !ml && (nz % 8 == 0) && vec_in && ((reinterpret_cast<uintptr_t>(labels_out) & 31) == 0) &&
-                            (!has_base || (reinterpret_cast<uintptr_t>(base_seg) & 15) == 0);
-    static const bool no_fuse = getenv("SYN_NO_FUSED_SCAN") != nullptr;
-    const bool fused_scan = sector_out && !dilate && !no_fuse;
-    const u64 *bs = (const u64 *)base_seg;
-    PairTable T{W.pslots, W.paircap ? W.paircap - 1 : 0, W.cnt};
+    const u64 *bs = c.base;
     if (sector_out) {
         const i64 ntiles = ((i64)g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
         static const int stream_ctas = getenv("SYN_STREAM_CTAS") ? atoi(getenv("SYN_STREAM_CTAS")) : 0;   // per SM; 0 = occupancy
@@ -449,7 +498,7 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
         PROF("stream");
     } else if (ml) {
         k_threshold_ml<<<wave_grid(k_threshold_ml, 256, div_up_u32(g.nwords, 8)), 256, 0, st>>>(
-            pred, (const u64 *)ml_base, W.omask, W.startw, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
+            pred, c.ml_base, W.omask, W.startw, g, thresh, (u64 *)&W.cnt->v[SYN_CNT_FG_VOXELS]);
         CK_LAUNCH();
         PROF("threshold_ml");
     } else {
@@ -466,18 +515,17 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
     if (dilate) {
         // k radius-1 passes, ping-pong between lmask and the (not yet used) run-prefix array; the last lands in lmask
         const u32 *src = W.omask;
-        for (int i = 1; i <= dil_k; ++i) {
-            u32 *dst = ((dil_k - i) & 1) ? W.runbase : W.lmask;
+        for (int i = 1; i <= c.dil_k; ++i) {
+            u32 *dst = ((c.dil_k - i) & 1) ? W.runbase : W.lmask;
             k_dilate_step<<<grid_for(g.nwords, 256, 8), 256, 0, st>>>(src, dst, g);
             CK_LAUNCH();
             src = dst;
         }
         PROF("dilate");
     }
-    const RunIdx R{W.runbase, fused_scan ? W.tilebase : nullptr, g.cpr, ml ? W.startw : nullptr,
-                   (const u64 *)ml_base};
+    const RunIdx &R = c.R;
     if (has_base) {      // (folding this into the streaming kernel cost it 10 % of its bandwidth: measured, reverted)
-        k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(T);
+        k_pair_table_init<<<grid_for(W.paircap, 256, 8), 256, 0, st>>>(c.T);
         CK_LAUNCH();
         PROF("pair_init");
     }
@@ -502,8 +550,8 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
 
     // --- unions ------------------------------------------------------------------------------
     const bool bnd_list = W.tg.tx != 0;   // both producers of the active-word list also list the border words
-    if (connectivity == 6) rc = launch_union<6>(W, g, R, bnd_list, max_runs, st);
-    else if (connectivity == 18) rc = launch_union<18>(W, g, R, bnd_list, max_runs, st);
+    if (c.connectivity == 6) rc = launch_union<6>(W, g, R, bnd_list, max_runs, st);
+    else if (c.connectivity == 18) rc = launch_union<18>(W, g, R, bnd_list, max_runs, st);
     else rc = launch_union<26>(W, g, R, bnd_list, max_runs, st);
     if (rc != SYN_OK) return rc;
 
@@ -523,46 +571,100 @@ int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float 
 
     // --- scan #3: dust decision + table ----------------------------------------------------------
     {
-        KeepSrc src{W.stat, W.cnt, dust_thresh, (u32)(nx - 1), (u32)(ny - 1), (u32)(nz - 1)};
-        i64 ox = offset_xyz ? offset_xyz[0] : 0, oy = offset_xyz ? offset_xyz[1] : 0, oz = offset_xyz ? offset_xyz[2] : 0;
-        rc = launch_scan<2>(W, 2, src, TableDst{W.stat, W.complab, (i64 *)seg_table, max_segs, ox, oy, oz}, max_runs,
-                            &W.cnt->v[SYN_CNT_KEPT], st);
+        KeepSrc src{W.stat, W.cnt, c.dust, (u32)(g.nx - 1), (u32)(g.ny - 1), (u32)(g.nz - 1)};
+        rc = launch_scan<2>(W, 2, src,
+                            TableDst{W.stat, W.complab, c.seg_table, c.max_segs, c.off[0], c.off[1], c.off[2], c.defer},
+                            max_runs, &W.cnt->v[SYN_CNT_KEPT], st);
         if (rc != SYN_OK) return rc;
         PROF("dust_table");
     }
-    k_run_labels<<<wave_grid(k_run_labels, 256, div_up_u32(max_runs, 256 * 4)), 256, 0, st>>>(W.par, W.rank, W.complab,
-                                                                                             W.runlabel, W.cnt, max_segs);
+    return SYN_OK;
+}
+
+int ccs_run_labels(CcsCall &c)
+{
+    Workspace &W = c.W;
+    cudaStream_t st = c.st;
+    k_run_labels<<<wave_grid(k_run_labels, 256, div_up_u32(c.max_runs, 256 * 4)), 256, 0, st>>>(
+        W.par, W.rank, W.complab, W.runlabel, W.cnt, c.max_segs, c.defer ? c.lut : nullptr, c.lut_base, c.lut_len);
     CK_LAUNCH();
     PROF("run_labels");
+    return SYN_OK;
+}
 
+int ccs_finish(CcsCall &c)
+{
+    const Geom &g = c.g;
+    Workspace &W = c.W;
+    cudaStream_t st = c.st;
+    const bool has_base = c.has_base;
+    const RunIdx &R = c.R;
+    const u64 *bs = c.base;
+    u32 *labels_out = c.labels;
+    int rc;
     // --- foreground sectors (+ overlaps) -------------------------------------------------------------
-    if (sector_out) {
+    if (c.sector_out) {
         const i64 needw = div_up_u32(g.nwords, SL_BATCH * SL_WARPS);   // one warp per batch of active words, at most
         if (has_base)
             k_sector_labels<true><<<wave_grid(k_sector_labels<true>, 256, needw), 256, 0, st>>>(
-                W.lmask, W.omask, R, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
+                W.lmask, W.omask, R, W.runlabel, labels_out, bs, g, c.T, W.actw, W.cnt);
         else
             k_sector_labels<false><<<wave_grid(k_sector_labels<false>, 256, needw), 256, 0, st>>>(
-                W.lmask, W.omask, R, W.runlabel, labels_out, bs, g, T, W.actw, W.cnt);
+                W.lmask, W.omask, R, W.runlabel, labels_out, bs, g, c.T, W.actw, W.cnt);
         CK_LAUNCH();
         PROF("sector_labels");
     } else {
         const int grid = grid_for((i64)g.nchunks * 32 / 2 + 1, 256, 8);
         if (has_base)
             k_write_labels<false, true, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, R, W.runlabel, labels_out,
-                                                                bs, g, T, W.cnt);
+                                                                bs, g, c.T, W.cnt);
         else
             k_write_labels<false, false, 2><<<grid, 256, 0, st>>>(W.lmask, W.omask, R, W.runlabel, labels_out,
-                                                                 bs, g, T, W.cnt);
+                                                                 bs, g, c.T, W.cnt);
         CK_LAUNCH();
         PROF("write_labels");
     }
     if (has_base) {
-        rc = order_and_emit_pairs(g, W, T, pair_rows, (u64 *)pair_cols, (i64 *)pair_counts, max_pairs, st);
+        rc = order_and_emit_pairs(g, W, c.T, c.prow, c.pcol, c.pval, c.max_pairs, st);
         if (rc != SYN_OK) return rc;
     }
     if (g_prof_on) g_prof_valid = true;
-    return finish_counts(W, (i64 *)counts_host, st);
+    return finish_counts(W, c.counts_host, st);
+}
+
+CcsCall make_call(const float *pred, float thresh, int connectivity, int dil_k, int64_t dust_thresh,
+                  const int64_t *offset_xyz, uint32_t *labels_out, int64_t *seg_table, int64_t max_segs,
+                  const uint64_t *base_seg, uint32_t *pair_rows, uint64_t *pair_cols, int64_t *pair_counts,
+                  int64_t max_pairs, void *workspace, int64_t workspace_bytes, int64_t max_runs, int64_t *counts_host,
+                  void *stream, const uint64_t *ml_base)
+{
+    CcsCall c{};
+    c.pred = pred; c.thresh = thresh; c.connectivity = connectivity; c.dil_k = dil_k; c.dust = dust_thresh;
+    for (int k = 0; k < 3; ++k) c.off[k] = offset_xyz ? offset_xyz[k] : 0;
+    c.labels = labels_out; c.seg_table = (i64 *)seg_table; c.max_segs = max_segs;
+    c.base = (const u64 *)base_seg; c.prow = pair_rows; c.pcol = (u64 *)pair_cols; c.pval = (i64 *)pair_counts;
+    c.max_pairs = max_pairs; c.workspace = workspace; c.ws_bytes = workspace_bytes; c.max_runs = max_runs;
+    c.counts_host = (i64 *)counts_host; c.st = (cudaStream_t)stream; c.ml_base = (const u64 *)ml_base;
+    c.defer = false; c.lut = nullptr; c.lut_base = nullptr; c.lut_len = 0;
+    return c;
+}
+
+int chunk_ccs_impl(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity, int dil_k,
+                   int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out, int64_t *seg_table,
+                   int64_t max_segs, const uint64_t *base_seg, uint32_t *pair_rows, uint64_t *pair_cols,
+                   int64_t *pair_counts, int64_t max_pairs, void *workspace, int64_t workspace_bytes,
+                   int64_t max_runs, int64_t *counts_host, void *stream, const uint64_t *ml_base)
+{
+    CcsCall c = make_call(pred, thresh, connectivity, dil_k, dust_thresh, offset_xyz, labels_out, seg_table, max_segs,
+                          base_seg, pair_rows, pair_cols, pair_counts, max_pairs, workspace, workspace_bytes, max_runs,
+                          counts_host, stream, ml_base);
+    int rc = ccs_setup(c, nx, ny, nz, true);
+    if (rc != SYN_OK) return rc;
+    rc = ccs_begin(c);
+    if (rc != SYN_OK) return rc;
+    rc = ccs_run_labels(c);
+    if (rc != SYN_OK) return rc;
+    return ccs_finish(c);
 }
 
 }  // namespace
@@ -589,6 +691,65 @@ int syn_chunk_ccs_multilabel(const float *pred, const uint64_t *overlap_seg, int
     return chunk_ccs_impl(pred, nx, ny, nz, thresh, 6, 0, dust_thresh, offset_xyz, labels_out, seg_table, max_segs,
                           nullptr, nullptr, nullptr, nullptr, 0, workspace, workspace_bytes, max_runs, counts_host,
                           stream, overlap_seg);
+}
+
+/* ---- the chunk pass in two halves, with the cross-chunk merge in between (see CcsCall) ---- */
+
+int64_t syn_packed_slot_bytes(int64_t cap_rows, int64_t cap_entries)
+{
+    if (cap_rows < 1 || cap_entries < 1) return SYN_ERR_INVALID;
+    return (int64_t)pk_slot_bytes(cap_rows, cap_entries);
+}
+
+int syn_chunk_ccs_begin(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity,
+                        int dil_k, int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out,
+                        const uint64_t *base_seg, int64_t max_pairs, void *packed_slot, int64_t cap_rows,
+                        int64_t cap_entries, void *workspace, int64_t workspace_bytes, int64_t max_runs, void *stream)
+{
+    if (!packed_slot || cap_rows < 1 || cap_entries < 1) return fail(SYN_ERR_INVALID, "bad packed slot arguments");
+    if ((reinterpret_cast<uintptr_t>(packed_slot) & 15) != 0) return fail(SYN_ERR_INVALID, "packed slot must be 16-byte aligned");
+    i64 *hdr = (i64 *)packed_slot;
+    CcsCall c = make_call(pred, thresh, connectivity, dil_k, dust_thresh, offset_xyz, labels_out, (int64_t *)(hdr + PK_HDR), cap_rows,
+                          base_seg, nullptr, nullptr, nullptr, max_pairs, workspace, workspace_bytes, max_runs, nullptr,
+                          stream, nullptr);
+    c.defer = true;
+    int rc = ccs_setup(c, nx, ny, nz, false);
+    if (rc != SYN_OK) return rc;
+    rc = ccs_begin(c);
+    if (rc != SYN_OK) return rc;
+    // the chunk's face voxels in table-relative ids, ordered (face, position): what merge_continuations needs
+    // of the label volume (proc/seg/continuation.py:87-133), without the label volume
+    cudaStream_t st = c.st;
+    const Geom &g = c.g;
+    CK(cudaMemsetAsync(hdr, 0, PK_HDR * 8, st));
+    FaceCtx F{c.W.lmask, c.W.omask, c.R, c.W.par, c.W.rank, c.W.complab, c.W.cnt, g, g.ny * g.nz, g.nx * g.nz, g.nx * g.ny};
+    uint2 *entries = reinterpret_cast<uint2 *>(hdr + PK_HDR + cap_rows * SYN_SEG_NCOLS);
+    const i64 nface = 2 * (F.a0 + F.a1 + F.a2);
+    rc = launch_scan<8>(c.W, 4, FaceSrc{F}, FaceDst{F, hdr, entries, cap_entries, cap_rows}, nface, &hdr[PK_NENT], st);
+    if (rc != SYN_OK) return rc;
+    PROF("face_entries");
+    return SYN_OK;
+}
+
+int syn_chunk_ccs_finish(const float *pred, int64_t nx, int64_t ny, int64_t nz, int connectivity, int dil_k,
+                         uint32_t *labels_out, const uint64_t *base_seg, uint32_t *pair_rows, uint64_t *pair_cols,
+                         int64_t *pair_counts, int64_t max_pairs, int64_t cap_rows, const uint32_t *final_lut,
+                         const int64_t *final_lut_base_dev, int64_t final_lut_len, void *workspace,
+                         int64_t workspace_bytes, int64_t max_runs, int64_t *counts_host, void *stream)
+{
+    if (final_lut && (!final_lut_base_dev || final_lut_len < 1)) return fail(SYN_ERR_INVALID, "bad final lut arguments");
+    CcsCall c = make_call(pred, 0.f, connectivity, dil_k, 0, nullptr, labels_out, nullptr, 0, base_seg, pair_rows,
+                          pair_cols, pair_counts, max_pairs, workspace, workspace_bytes, max_runs, counts_host, stream,
+                          nullptr);
+    c.defer = true;
+    c.max_segs = 0;
+    c.lut = final_lut; c.lut_base = (const i64 *)final_lut_base_dev; c.lut_len = final_lut_len;
+    int rc = ccs_setup(c, nx, ny, nz, true);
+    if (rc != SYN_OK) return rc;
+    c.max_segs = cap_rows;
+    rc = ccs_run_labels(c);
+    if (rc != SYN_OK) return rc;
+    return ccs_finish(c);
 }
 
 int64_t syn_overlap_workspace_bytes(int64_t nx, int64_t ny, int64_t nz, int64_t max_pairs)
@@ -816,6 +977,59 @@ int syn_merge_ccs_grid(const uint32_t *faces_all, const int64_t *tables_all, con
         base += kept[i];
     }
     return syn_merge_seg_tables(rows_scratch, total, gmap_out, size_thr, merged_out, fmap_out, n_merged_dev, stream);
+}
+
+int64_t syn_merge_packed_workspace_bytes(int64_t nchunks, int64_t cap_rows, int64_t max_edges)
+{
+    if (nchunks < 1 || nchunks > MG_MAXCHUNKS || cap_rows < 1 || max_edges < 1) return SYN_ERR_INVALID;
+    const size_t cap_total = (size_t)nchunks * (size_t)cap_rows;
+    if (cap_total >= (1ull << 31)) return SYN_ERR_INVALID;
+    return (int64_t)(al((size_t)max_edges * 8) + 2 * al((cap_total + 1) * 4) + al((cap_total + 1) * sizeof(MergeAcc2)) +
+                     al(cap_total * 4));
+}
+
+int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
+                         const int32_t *plan_dev, int64_t nchunks, int64_t npairs, int64_t size_thr, int64_t max_edges,
+                         void *workspace, int64_t workspace_bytes, int64_t *id_base_out, int64_t *merged_out,
+                         uint32_t *fmap_out, int64_t *info_out, void *stream)
+{
+    if (!slots_all || !plan_dev || !workspace || !id_base_out || !merged_out || !fmap_out || !info_out || npairs < 0)
+        return fail(SYN_ERR_INVALID, "bad arguments");
+    const int64_t need = syn_merge_packed_workspace_bytes(nchunks, cap_rows, max_edges);
+    if (need < 0) return fail(SYN_ERR_INVALID, "bad nchunks / cap_rows / max_edges");
+    if (need > workspace_bytes)
+        return fail(SYN_ERR_WORKSPACE, "merge workspace too small: need %lld bytes, got %lld", (long long)need,
+                    (long long)workspace_bytes);
+    if (slot_bytes != (int64_t)pk_slot_bytes(cap_rows, cap_entries)) return fail(SYN_ERR_INVALID, "slot_bytes mismatch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cap_total = (size_t)nchunks * (size_t)cap_rows;
+    char *p = (char *)workspace;
+    u32 *edges = (u32 *)p; p += al((size_t)max_edges * 8);
+    u32 *par = (u32 *)p; p += al((cap_total + 1) * 4);
+    u32 *gmap = (u32 *)p; p += al((cap_total + 1) * 4);
+    MergeAcc2 *acc = (MergeAcc2 *)p; p += al((cap_total + 1) * sizeof(MergeAcc2));
+    u32 *members = (u32 *)p;
+    const Packed P{(const unsigned char *)slots_all, slot_bytes, cap_rows, cap_entries};
+    const int *plan = (const int *)plan_dev;
+    i64 *base = (i64 *)id_base_out, *info = (i64 *)info_out;
+    const int wide = grid_for((i64)cap_total + 1, 256, 4);
+    k_mg_prefix_init<<<wide, 256, 0, st>>>(P, plan, base, info, par, acc);
+    CK_LAUNCH();
+    if (npairs > 0) {
+        k_mg_match<<<dim3(16, (unsigned)npairs), 256, 0, st>>>(P, plan, base, edges, max_edges, info);
+        CK_LAUNCH();
+        k_mg_union<<<grid_for(max_edges, 256, 2), 256, 0, st>>>(edges, max_edges, info, par);
+        CK_LAUNCH();
+    }
+    k_mg_flatacc<<<wide, 256, 0, st>>>(P, plan, base, info, par, gmap, acc);
+    CK_LAUNCH();
+    k_mg_scan<<<1, MGS_THREADS, 0, st>>>(acc, size_thr, info);
+    CK_LAUNCH();
+    k_mg_fill<<<wide, 256, 0, st>>>(info, gmap, acc, members, fmap_out);
+    CK_LAUNCH();
+    k_mg_emit<<<wide, 256, 0, st>>>(P, plan, base, info, acc, members, (i64 *)merged_out);
+    CK_LAUNCH();
+    return SYN_OK;
 }
 
 int syn_merge_overlaps(const uint32_t *rows, const uint64_t *cols, const int64_t *counts, int64_t n, int64_t n_ids,

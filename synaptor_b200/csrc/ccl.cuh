@@ -1673,20 +1673,22 @@ __device__ __forceinline__ i64 centroid_f32(u64 sum, u64 size)
     return (i64)roundf(q);
 }
 
-// complab[c] = final label of component c (c + 1 if kept, else 0); kept components get a table row
+// complab[c] = label of component c: c + 1 if kept, else 0 (`rel`: its table row + 1 instead -- the chunk-relative
+// id the cross-chunk merge works with); kept components get a table row
 struct TableDst {
     const CompStat *stat;
     u32 *complab;
     i64 *table;
     i64 max_segs;
     i64 ox, oy, oz;
+    bool rel;
     template <int N>
     __device__ __forceinline__ void store(u64 i0, u64 n, u32 ex, const u32 (&item)[N]) const
     {
 #pragma unroll
         for (int t = 0; t < N; ++t) {
             const u64 c = i0 + t;
-            if (c < n) complab[c] = item[t] ? (u32)c + 1u : 0u;
+            if (c < n) complab[c] = item[t] ? (rel ? ex + 1u : (u32)c + 1u) : 0u;
             if (item[t]) {
                 const u32 rowi = ex;
                 if ((i64)rowi < max_segs) {
@@ -1710,13 +1712,17 @@ struct TableDst {
     }
 };
 
-// final per-run label: canonical id if kept else 0; also tracks the largest kept id
+// final per-run label: the component's label if kept else 0; also tracks the largest label.  With `lut` (the
+// deferred pass: complab holds table rows + 1) the label goes through the cross-chunk id map first:
+// label = lut[lut_base[0] + row + 1] (remap_ids_task, proc/tasks.py:314-333, folded into the label write).
 __global__ void __launch_bounds__(256) k_run_labels(const u32 *__restrict__ par, const u32 *__restrict__ rank,
                                                     const u32 *__restrict__ complab, u32 *__restrict__ runlabel,
-                                                    Counts *cnt, i64 max_segs)
+                                                    Counts *cnt, i64 max_segs, const u32 *__restrict__ lut,
+                                                    const i64 *__restrict__ lut_base, i64 lut_len)
 {
     if (cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) return;
     const u64 nruns = (u64)cnt->v[SYN_CNT_RUNS];
+    const i64 lb = lut ? lut_base[0] : 0;
     u32 mx = 0;
     // 4 consecutive runs per thread: 16-byte loads of the (flattened) parents, 16-byte stores of the labels
     for (u64 g0 = (blockIdx.x * (u64)blockDim.x + threadIdx.x) * 4; g0 < nruns; g0 += (u64)gridDim.x * blockDim.x * 4) {
@@ -1731,10 +1737,13 @@ __global__ void __launch_bounds__(256) k_run_labels(const u32 *__restrict__ par,
 #pragma unroll
         for (int t = 0; t < 4; ++t) lab[t] = (g0 + t < nruns) ? __ldcg(rank + p[t]) : 0u;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            lab[t] = (g0 + t < nruns) ? __ldcg(complab + lab[t]) : 0u;
-            mx = max(mx, lab[t]);
+        for (int t = 0; t < 4; ++t) lab[t] = (g0 + t < nruns) ? __ldcg(complab + lab[t]) : 0u;
+        if (lut) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) lab[t] = (lab[t] && lb + (i64)lab[t] < lut_len) ? __ldg(lut + lb + lab[t]) : 0u;
         }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) mx = max(mx, lab[t]);
         if (g0 + 4 <= nruns) *reinterpret_cast<uint4 *>(runlabel + g0) = make_uint4(lab[0], lab[1], lab[2], lab[3]);
         else {
 #pragma unroll

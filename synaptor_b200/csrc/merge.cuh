@@ -1,0 +1,460 @@
+// merge.cuh -- the cross-chunk merge with the chunk results packed for ONE exchange.
+//
+// Replaces, on the device (reference: synaptor/proc/tasks.py:72-122 merge_ccs_task):
+//   assign_unique_ids_serial      proc/seg/merge/assign_ids.py:8-42   (global ids = prefix of the row counts)
+//   extract_all_continuations     proc/seg/continuation.py:87-133     (face voxels of the surviving segments)
+//   merge_continuations           proc/seg/merge/merge_ccs.py:69-139  (edges between facing faces)
+//   find_connected_components /   proc/utils.py:39-86                 (union-find to the smallest id)
+//     make_id_map
+//   merge_seginfo_df /            proc/seg/merge/merge_df.py:13-68    (size sum, bbox min/max, weighted centroid,
+//     enforce_size_threshold                                           size threshold)
+//
+// A chunk's contribution to the exchange is one fixed-size PACKED SLOT:
+//   int64 hdr[16]   : [0] kept rows, [1] face entries, [2..7] first entry of face 0..5, [8] flags
+//   int64 table[cap_rows][11]   the chunk's segment table (written in place by the chunk pipeline)
+//   uint2 entry[cap_entries]    (position in the face, chunk-relative id = table row + 1) of every labelled
+//                               face voxel, faces in Face.all_faces() order, raster order inside a face
+// Every rank gathers the slots of all chunks (one all_gather) and runs the same deterministic kernels on them.
+#pragma once
+#include "ccl.cuh"
+
+namespace syn {
+
+constexpr int PK_HDR = 16;              // int64 words
+constexpr int PK_KEPT = 0, PK_NENT = 1, PK_FOFF = 2, PK_FLAGS = 8;
+constexpr int PK_F_ROWS = 1, PK_F_ENTRIES = 2, PK_F_CCS = 4;
+
+__host__ __device__ __forceinline__ size_t pk_slot_bytes(i64 cap_rows, i64 cap_entries)
+{
+    return (size_t)PK_HDR * 8 + (size_t)cap_rows * SYN_SEG_NCOLS * 8 + (size_t)cap_entries * 8;
+}
+
+// ---------------------------------------------------------------------------
+// Face entries of one chunk, straight from the bitmask and the union-find arrays (the label volume need not
+// exist yet): an ordered compaction (single-pass scan, k_scan_1p) over the 2 (ny nz + nx nz + nx ny) face voxels.
+// ---------------------------------------------------------------------------
+struct FaceCtx {
+    const u32 *lmask, *omask;
+    RunIdx R;
+    const u32 *par, *rank, *complab;
+    const Counts *cnt;
+    Geom g;
+    i64 a0, a1, a2;     // areas of the faces normal to axis 0, 1, 2
+
+    // face voxel i (all six faces back to back) -> face number, position inside the face, label
+    __device__ __forceinline__ u32 label(i64 i, int *face, u32 *pos) const
+    {
+        i64 j = i, x, y, z;
+        const i64 nx = g.nx, ny = g.ny, nz = g.nz;
+        if (j < 2 * a0) {                   // axis 0: hi then lo; in-face coordinates (y, z)
+            const bool hi = j < a0;
+            if (!hi) j -= a0;
+            *face = hi ? 0 : 1;
+            x = hi ? nx - 1 : 0;
+            y = j / nz;
+            z = j - y * nz;
+        } else if (j < 2 * a0 + 2 * a1) {   // axis 1: (x, z)
+            j -= 2 * a0;
+            const bool hi = j < a1;
+            if (!hi) j -= a1;
+            *face = hi ? 2 : 3;
+            y = hi ? ny - 1 : 0;
+            x = j / nz;
+            z = j - x * nz;
+        } else {                            // axis 2: (x, y)
+            j -= 2 * a0 + 2 * a1;
+            const bool hi = j < a2;
+            if (!hi) j -= a2;
+            *face = hi ? 4 : 5;
+            z = hi ? nz - 1 : 0;
+            x = j / ny;
+            y = j - x * ny;
+        }
+        *pos = (u32)j;
+        const u32 row = (u32)(x * ny + y), k = (u32)(z >> 5), b = (u32)(z & 31);
+        const u32 w = row * g.wz + k;
+        if (!((omask[w] >> b) & 1u)) return 0u;
+        const u32 run = R.at(w, row, k) + __popc(R.starts(lmask, w, k) & mask_le(b)) - 1u;
+        return complab[rank[par[run]]];
+    }
+    __device__ __forceinline__ i64 face_start(int f) const
+    {
+        const i64 s[6] = {0, a0, 2 * a0, 2 * a0 + a1, 2 * a0 + 2 * a1, 2 * a0 + 2 * a1 + a2};
+        return s[f];
+    }
+};
+
+struct FaceSrc {
+    FaceCtx F;
+    __device__ __forceinline__ u64 n() const { return (u64)(2 * (F.a0 + F.a1 + F.a2)); }
+    template <int N>
+    __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
+    {
+        const bool bad = (F.cnt->v[SYN_CNT_ERRFLAGS] & SYN_EF_RUNS) != 0;
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            item[t] = 0;
+            if (!bad && i0 + t < n) {
+                int f;
+                u32 pos;
+                item[t] = F.label((i64)(i0 + t), &f, &pos) != 0;
+            }
+        }
+    }
+};
+
+struct FaceDst {
+    FaceCtx F;
+    i64 *hdr;           // packed-slot header
+    uint2 *entries;
+    i64 cap_entries, cap_rows;
+    template <int N>
+    __device__ __forceinline__ void store(u64 i0, u64 n, u32 ex, const u32 (&item)[N]) const
+    {
+        if (i0 == 0) {
+            const i64 kept = F.cnt->v[SYN_CNT_KEPT];
+            hdr[PK_KEPT] = kept;
+            i64 fl = 0;
+            if (F.cnt->v[SYN_CNT_ERRFLAGS] & (SYN_EF_RUNS | SYN_EF_SEGS)) fl |= PK_F_CCS;
+            if (kept > cap_rows) fl |= PK_F_ROWS;
+            if (fl) atomicOr((u64 *)&hdr[PK_FLAGS], (u64)fl);
+        }
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            const i64 i = (i64)(i0 + t);
+            if (i < (i64)n) {
+#pragma unroll
+                for (int f = 0; f < 6; ++f)
+                    if (i == F.face_start(f)) hdr[PK_FOFF + f] = (i64)ex;
+                if (item[t]) {
+                    int f;
+                    u32 pos;
+                    const u32 lab = F.label(i, &f, &pos);
+                    if ((i64)ex < cap_entries) entries[ex] = make_uint2(pos, lab);
+                    else atomicOr((u64 *)&hdr[PK_FLAGS], (u64)PK_F_ENTRIES);
+                }
+            }
+            ex += item[t];
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// The merge proper.  `plan` (device int32): [0] nchunks, [1] npairs, slot_of_chunk[nchunks],
+// pairs[npairs][4] = (chunk here, face here (hi), chunk there, face there (lo)).
+// ---------------------------------------------------------------------------
+constexpr int MG_MAXCHUNKS = 1024;
+constexpr u32 MG_NONE = 0xFFFFFFFFu;
+
+struct Packed {
+    const unsigned char *all;
+    i64 slot_bytes, cap_rows, cap_entries;
+    __device__ __forceinline__ const i64 *hdr(int slot) const
+    {
+        return reinterpret_cast<const i64 *>(all + (size_t)slot * slot_bytes);
+    }
+    __device__ __forceinline__ const i64 *table(int slot) const { return hdr(slot) + PK_HDR; }
+    __device__ __forceinline__ const uint2 *entries(int slot) const
+    {
+        return reinterpret_cast<const uint2 *>(hdr(slot) + PK_HDR + cap_rows * SYN_SEG_NCOLS);
+    }
+};
+
+struct MergeAcc2 {
+    u64 size;
+    i64 lo[3], hi[3];
+    u32 count;   // fragments
+    u32 off;     // start of the member list
+    u32 cursor;  // fill position
+    u32 outrow;  // row in the compacted output (kept destinations only)
+};
+
+// info[]: 0 total ids, 1 merged rows, 2 edges, 3 flags (bit 0: a slot reported an overflow, bit 1: edge capacity)
+constexpr int MG_TOTAL = 0, MG_NMERGED = 1, MG_NEDGES = 2, MG_FLAGS = 3;
+
+// global id bases (exclusive prefix of the row counts in chunk order: assign_ids.py:8-25) + initialisation of
+// the union-find parents and the accumulators of ids 0..total.  Every CTA recomputes the (tiny) prefix.
+__global__ void __launch_bounds__(256) k_mg_prefix_init(Packed P, const int *__restrict__ plan, i64 *__restrict__ base,
+                                                        i64 *__restrict__ info, u32 *__restrict__ par,
+                                                        MergeAcc2 *__restrict__ acc)
+{
+    __shared__ u32 sm[33];
+    const int nchunks = plan[0];
+    u32 k[4], v = 0;
+    u32 bad = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = (int)threadIdx.x * 4 + q;
+        k[q] = 0;
+        if (c < nchunks) {
+            const i64 *h = P.hdr(plan[2 + c]);
+            i64 kept = h[PK_KEPT];
+            if (h[PK_FLAGS] || kept < 0 || kept > P.cap_rows || h[PK_NENT] > P.cap_entries) { bad = 1; kept = 0; }
+            k[q] = (u32)kept;
+        }
+        v += k[q];
+    }
+    u32 total;
+    u32 ex = block_excl_scan(v, sm, &total);
+    if (blockIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = (int)threadIdx.x * 4 + q;
+            if (c < nchunks) base[c] = (i64)ex;
+            ex += k[q];
+        }
+        if (threadIdx.x == 0) {
+            base[nchunks] = (i64)total;
+            info[MG_TOTAL] = (i64)total;
+            info[MG_NMERGED] = 0;
+            info[MG_NEDGES] = 0;
+            info[MG_FLAGS] = 0;
+        }
+    }
+    if (__syncthreads_or((int)bad) && blockIdx.x == 0 && threadIdx.x == 0) info[MG_FLAGS] = 1;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= total; i += gridDim.x * blockDim.x) {
+        par[i] = i;
+        MergeAcc2 a;
+        a.size = 0;
+        a.lo[0] = a.lo[1] = a.lo[2] = 0x7FFFFFFFFFFFFFFFll;
+        a.hi[0] = a.hi[1] = a.hi[2] = -0x7FFFFFFFFFFFFFFFll - 1;
+        a.count = a.off = a.cursor = 0;
+        a.outrow = MG_NONE;
+        acc[i] = a;
+    }
+}
+
+// edges between facing faces (merge_ccs.py:117-128): a hi-face entry of the chunk here matches the lo-face entry
+// of the chunk there at the same position (binary search in the ordered list).  blockIdx.y = face pair.
+__global__ void __launch_bounds__(256) k_mg_match(Packed P, const int *__restrict__ plan, const i64 *__restrict__ base,
+                                                  u32 *__restrict__ edges, i64 max_edges, i64 *__restrict__ info)
+{
+    if (info[MG_FLAGS] & 1) return;
+    const int nchunks = plan[0];
+    const int *pr = plan + 2 + nchunks + 4 * blockIdx.y;
+    const int cA = pr[0], fA = pr[1], cB = pr[2], fB = pr[3];
+    const int sA = plan[2 + cA], sB = plan[2 + cB];
+    const i64 *hA = P.hdr(sA), *hB = P.hdr(sB);
+    const i64 oA = hA[PK_FOFF + fA], eA = fA < 5 ? hA[PK_FOFF + fA + 1] : hA[PK_NENT];
+    const i64 oB = hB[PK_FOFF + fB], eB = fB < 5 ? hB[PK_FOFF + fB + 1] : hB[PK_NENT];
+    const uint2 *A = P.entries(sA) + oA, *B = P.entries(sB) + oB;
+    const i64 nA = eA - oA, nB = eB - oB;
+    const u32 bA = (u32)base[cA], bB = (u32)base[cB];
+    const int lane = threadIdx.x & 31;
+    for (i64 i0 = (i64)blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < nA; i0 += (i64)gridDim.x * blockDim.x) {
+        const i64 i = i0 + lane;
+        u32 a = 0, b = 0;
+        if (i < nA) {
+            const uint2 e = A[i];
+            i64 lo = 0, hi = nB;        // first entry of B with pos >= e.x
+            while (lo < hi) {
+                const i64 mid = (lo + hi) >> 1;
+                if (B[mid].x < e.x) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo < nB) {
+                const uint2 f = B[lo];
+                if (f.x == e.x) { a = bA + e.y; b = bB + f.y; }
+            }
+        }
+        bool act = a != 0;
+        const u32 pa = __shfl_up_sync(SYN_FULL, a, 1), pb = __shfl_up_sync(SYN_FULL, b, 1);
+        if (lane > 0 && pa == a && pb == b) act = false;     // raster-ordered faces: long runs of one pair
+        const u32 m = __ballot_sync(SYN_FULL, act);
+        if (!m) continue;
+        u64 basei = 0;
+        if (lane == 0) basei = atomicAdd((u64 *)&info[MG_NEDGES], (u64)__popc(m));
+        basei = __shfl_sync(SYN_FULL, (unsigned long long)basei, 0);
+        if (act) {
+            const u64 e = basei + __popc(m & mask_lt((u32)lane));
+            if ((i64)e < max_edges) { edges[2 * e] = a; edges[2 * e + 1] = b; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mg_union(const u32 *__restrict__ edges, i64 max_edges, i64 *__restrict__ info,
+                                                  u32 *par)
+{
+    if (info[MG_FLAGS] & 1) return;
+    i64 n = info[MG_NEDGES];
+    if (n > max_edges) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr((u64 *)&info[MG_FLAGS], 2ull);
+        n = max_edges;
+    }
+    const i64 total = info[MG_TOTAL];
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const u32 a = edges[2 * i], b = edges[2 * i + 1];
+        if ((i64)a <= total && (i64)b <= total) uf_union(par, a, b);
+    }
+}
+
+// chunk of global id gid (1-based): the last c with base[c] < gid
+__device__ __forceinline__ int mg_chunk_of(const i64 *s_base, int nchunks, i64 gid)
+{
+    int lo = 0, hi = nchunks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_base[mid] < gid) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ const i64 *mg_row(const Packed &P, const int *plan, const i64 *s_base, int nchunks, i64 gid)
+{
+    const int c = mg_chunk_of(s_base, nchunks, gid);
+    return P.table(plan[2 + c]) + (gid - 1 - s_base[c]) * SYN_SEG_NCOLS;
+}
+
+// gmap[id] = smallest id of its component; size / bbox / fragment count per destination
+__global__ void __launch_bounds__(256) k_mg_flatacc(Packed P, const int *__restrict__ plan, const i64 *__restrict__ base,
+                                                    const i64 *__restrict__ info, const u32 *par, u32 *__restrict__ gmap,
+                                                    MergeAcc2 *acc)
+{
+    __shared__ i64 s_base[MG_MAXCHUNKS + 1];
+    const int nchunks = plan[0];
+    for (int c = threadIdx.x; c <= nchunks; c += blockDim.x) s_base[c] = base[c];
+    __syncthreads();
+    if (info[MG_FLAGS] & 1) return;
+    const i64 total = info[MG_TOTAL];
+    for (i64 gid = blockIdx.x * (i64)blockDim.x + threadIdx.x; gid <= total; gid += (i64)gridDim.x * blockDim.x) {
+        if (gid == 0) { gmap[0] = 0; continue; }
+        const u32 d = uf_find_ro(par, (u32)gid);
+        gmap[gid] = d;
+        const i64 *r = mg_row(P, plan, s_base, nchunks, gid);
+        MergeAcc2 *a = acc + d;
+        atomicAdd(&a->size, (u64)r[SYN_SEG_SIZE]);
+        atomicAdd(&a->count, 1u);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&a->lo[k], r[SYN_SEG_BX + k]);
+            atomicMax(&a->hi[k], r[SYN_SEG_EX + k]);
+        }
+    }
+}
+
+// one block: exclusive scans of the fragment counts (member list offsets) and of the kept flags (output rows)
+constexpr int MGS_THREADS = 1024, MGS_ITEMS = 8;
+__global__ void __launch_bounds__(MGS_THREADS) k_mg_scan(MergeAcc2 *acc, i64 size_thr, i64 *__restrict__ info)
+{
+    __shared__ u32 sm[33];
+    if (info[MG_FLAGS] & 1) return;
+    const i64 total = info[MG_TOTAL];
+    u32 carry_c = 0, carry_k = 0;
+    for (i64 b0 = 1; b0 <= total; b0 += MGS_THREADS * MGS_ITEMS) {
+        const i64 i0 = b0 + (i64)threadIdx.x * MGS_ITEMS;
+        u32 c[MGS_ITEMS], k[MGS_ITEMS], vc = 0, vk = 0;
+#pragma unroll
+        for (int t = 0; t < MGS_ITEMS; ++t) {
+            c[t] = k[t] = 0;
+            if (i0 + t <= total) {
+                c[t] = acc[i0 + t].count;
+                k[t] = (c[t] > 0) && ((i64)acc[i0 + t].size >= size_thr);
+            }
+            vc += c[t];
+            vk += k[t];
+        }
+        u32 tc, tk;
+        u32 ec = block_excl_scan(vc, sm, &tc) + carry_c;
+        u32 ek = block_excl_scan(vk, sm, &tk) + carry_k;
+#pragma unroll
+        for (int t = 0; t < MGS_ITEMS; ++t) {
+            if (i0 + t <= total && c[t]) {
+                acc[i0 + t].off = ec;
+                acc[i0 + t].outrow = k[t] ? ek : MG_NONE;
+            }
+            ec += c[t];
+            ek += k[t];
+        }
+        carry_c += tc;
+        carry_k += tk;
+    }
+    if (threadIdx.x == 0) info[MG_NMERGED] = (i64)carry_k;
+}
+
+__global__ void __launch_bounds__(256) k_mg_fill(const i64 *__restrict__ info, const u32 *__restrict__ gmap,
+                                                 MergeAcc2 *acc, u32 *__restrict__ members, u32 *__restrict__ fmap)
+{
+    if (info[MG_FLAGS] & 1) return;
+    const i64 total = info[MG_TOTAL];
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= total; i += (i64)gridDim.x * blockDim.x) {
+        if (i == 0) { fmap[0] = 0; continue; }
+        MergeAcc2 *a = acc + gmap[i];
+        members[a->off + atomicAdd(&a->cursor, 1u)] = (u32)i;
+        fmap[i] = a->outrow != MG_NONE ? gmap[i] : 0u;       // merged segments under the size threshold map to 0
+    }
+}
+
+__device__ __forceinline__ void mg_sort_u32(u32 *m, u32 n)
+{
+    if (n <= 16) {
+        for (u32 i = 1; i < n; ++i) {
+            const u32 v = m[i];
+            int j = (int)i - 1;
+            while (j >= 0 && m[j] > v) { m[j + 1] = m[j]; --j; }
+            m[j + 1] = v;
+        }
+        return;
+    }
+    // heap sort: a component with many fragments must not cost O(n^2) in one thread
+    auto sift = [&](u32 start, u32 end) {
+        u32 root = start;
+        while (2 * root + 1 < end) {
+            u32 ch = 2 * root + 1;
+            if (ch + 1 < end && m[ch] < m[ch + 1]) ++ch;
+            if (m[root] >= m[ch]) return;
+            const u32 t = m[root]; m[root] = m[ch]; m[ch] = t;
+            root = ch;
+        }
+    };
+    for (int s = (int)(n / 2) - 1; s >= 0; --s) sift((u32)s, n);
+    for (u32 e = n - 1; e > 0; --e) {
+        const u32 t = m[0]; m[0] = m[e]; m[e] = t;
+        sift(0, e);
+    }
+}
+
+// merged rows (merge_df.py:13-61): centroid = int(sum_i c_i * (s_i / S)) in float64, members in ascending id
+// order, Kahan-compensated like pandas' groupby().sum()
+__global__ void __launch_bounds__(256) k_mg_emit(Packed P, const int *__restrict__ plan, const i64 *__restrict__ base,
+                                                 const i64 *__restrict__ info, const MergeAcc2 *__restrict__ acc,
+                                                 u32 *members, i64 *__restrict__ out)
+{
+    __shared__ i64 s_base[MG_MAXCHUNKS + 1];
+    const int nchunks = plan[0];
+    for (int c = threadIdx.x; c <= nchunks; c += blockDim.x) s_base[c] = base[c];
+    __syncthreads();
+    if (info[MG_FLAGS] & 1) return;
+    const i64 total = info[MG_TOTAL];
+    for (i64 d = blockIdx.x * (i64)blockDim.x + threadIdx.x + 1; d <= total; d += (i64)gridDim.x * blockDim.x) {
+        const MergeAcc2 a = acc[d];
+        if (a.count == 0 || a.outrow == MG_NONE) continue;
+        u32 *m = members + a.off;
+        mg_sort_u32(m, a.count);
+        double sum[3] = {0.0, 0.0, 0.0}, comp[3] = {0.0, 0.0, 0.0};
+        const double S = (double)a.size;
+        for (u32 i = 0; i < a.count; ++i) {
+            const i64 *r = mg_row(P, plan, s_base, nchunks, (i64)m[i]);
+            const double w = __ddiv_rn((double)r[SYN_SEG_SIZE], S);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double val = __dmul_rn((double)r[SYN_SEG_CX + k], w);
+                const double y = val - comp[k];           // Kahan, as pandas' group_sum
+                const double t = sum[k] + y;
+                comp[k] = (t - sum[k]) - y;
+                sum[k] = t;
+            }
+        }
+        i64 *o = out + (i64)a.outrow * SYN_SEG_NCOLS;
+        o[SYN_SEG_ID] = d;
+        o[SYN_SEG_SIZE] = (i64)a.size;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            o[SYN_SEG_CX + k] = (i64)sum[k];              // astype(int): truncation
+            o[SYN_SEG_BX + k] = a.lo[k];
+            o[SYN_SEG_EX + k] = a.hi[k];
+        }
+    }
+}
+
+}  // namespace syn

@@ -16,6 +16,7 @@ after which every rank runs the same tiny deterministic device computation (face
 edges, union-find to the minimum id, merged table) and relabels its own chunks through a
 LUT.  Nothing here computes on the host except shape bookkeeping.
 """
+import ctypes
 import itertools
 from dataclasses import dataclass
 
@@ -321,3 +322,367 @@ def merge_overlaps_device(results, merge, rank=None, world=None, group=None, ops
     mv = maxval.cpu().numpy()[:n_ids]
     ids = np.nonzero(mv > 0)[0]
     return ids.astype(np.int64), argcol.cpu().numpy().view(np.uint64)[ids], mv[ids]
+
+
+# ==================================================================================================
+# The whole-volume job: chunk_ccs -> merge_ccs -> remap_ids -> chunk_overlaps with ONE exchange and
+# ONE write of the label volume.
+# ==================================================================================================
+def grid_chunks(vol_shape, chunk_shape):
+    """(grid, [(begin xyz, shape xyz)]) of the chunk grid in np.ndindex order (types/bbox/chunking.py:13-69:
+    the last chunk along an axis is the remainder)."""
+    from .types.bbox import chunk_bboxes
+    boxes = chunk_bboxes(tuple(int(v) for v in vol_shape), tuple(int(c) for c in chunk_shape))
+    grid = tuple(-(-int(v) // int(c)) for (v, c) in zip(vol_shape, chunk_shape))
+    return grid, [(tuple(int(x) for x in b.min()), tuple(int(x) for x in b.shape())) for b in boxes]
+
+
+def merge_plan(grid, world):
+    """int32 plan of syn_merge_ccs_packed: {nchunks, npairs, slot of chunk c ..., (chunk here, hi face, chunk there,
+    lo face) ...}.  Chunk i lives on rank i % world, in that rank's local slot i // world."""
+    nchunks = int(np.prod(grid))
+    per_rank = -(-nchunks // world)
+    slots = [(i % world) * per_rank + i // world for i in range(nchunks)]
+    pairs = interior_face_pairs(grid)
+    plan = [nchunks, len(pairs)] + slots + [v for p in pairs for v in p]
+    return np.asarray(plan, dtype=np.int32), per_rank, len(pairs)
+
+
+class VolumeJob:
+    """
+    Device-resident segmentation of a chunked volume, chunks spread round robin over the ranks of `group`
+    (one process per GPU).  One step =
+
+      per own chunk : syn_chunk_ccs_begin   threshold, labelling, dust filter, segment table, face entries
+      exchange      : ONE all_gather of the packed slots (tables + face entries, ~1-2 MB per chunk)
+      every rank    : syn_merge_ccs_packed  global ids, face matching, union-find, merged table, size threshold
+      per own chunk : syn_chunk_ccs_finish  foreground labels written ONCE, in final global ids; overlap counts
+
+    (reference: proc/tasks.py:26-69 cc_task, :72-122 merge_ccs_task, :314-333 remap_ids_task, :290-297
+    overlap_task on the remapped volume -- four task waves with files in between).  No host synchronisation
+    inside a step; with graph=True the kernels of a step are replayed from two CUDA graphs around the all_gather.
+    """
+
+    def __init__(self, vol_shape, chunk_shape, thresh, dust_thresh, size_thr, connectivity=6, with_base=True,
+                 rank=None, world=None, group=None, device=None, vol_offset=(0, 0, 0), graph=True):
+        from . import _device as D
+        from . import _cabi as C
+        import torch.distributed as dist
+        self.D, self.C = D, C
+        self.torch = torch = D._torch()
+        self.dist = dist
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if world > 1 else 0
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.grid, chunks = grid_chunks(vol_shape, chunk_shape)
+        self.vol_shape = tuple(int(v) for v in vol_shape)
+        self.chunk_begin = [tuple(b + o for (b, o) in zip(beg, vol_offset)) for (beg, _) in chunks]
+        self.chunk_rel_begin = [beg for (beg, _) in chunks]
+        self.chunk_shape = [shp for (_, shp) in chunks]
+        self.nchunks = len(chunks)
+        self.owners = chunk_owners(self.grid, self.world)
+        self.mine = [i for i in range(self.nchunks) if self.owners[i] == self.rank]
+        self.thresh, self.dust, self.size_thr = np.float32(thresh), int(dust_thresh), int(size_thr)
+        self.conn, self.with_base, self.use_graph = int(connectivity), bool(with_base), bool(graph)
+        plan, self.per_rank, self.npairs = merge_plan(self.grid, self.world)
+        self.plan = torch.from_numpy(plan).to(self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.pred = [None] * len(self.mine)
+        self.base = [None] * len(self.mine)
+        self.labels = [torch.empty(self.chunk_shape[i], dtype=torch.int32, device=self.device) for i in self.mine]
+        self.caps_runs = [D.default_capacities(self.chunk_shape[i])[0] for i in self.mine]
+        self.max_pairs = [D.default_capacities(self.chunk_shape[i])[2] if with_base else 0 for i in self.mine]
+        self.ws = [None] * len(self.mine)
+        self.pairs = [None] * len(self.mine)
+        self.cap_rows = self.cap_entries = None
+        self.graphs = None
+        self.launches_per_step = 0
+        self.offsets = [(ctypes_i64x3(self.chunk_begin[i])) for i in self.mine]
+
+    # ---- buffers -----------------------------------------------------------------------------------
+    def set_inputs(self, local_index, pred, base=None):
+        """Resident inputs of own chunk #local_index (chunk self.mine[local_index]): float32 cuda tensor and,
+        with_base, the int64-typed uint64 base ids.  The tensors must stay alive (and in place) while the job runs."""
+        torch = self.torch
+        shp = self.chunk_shape[self.mine[local_index]]
+        if not (pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous() and tuple(pred.shape) == shp):
+            raise ValueError(f"pred of chunk {self.mine[local_index]} must be a contiguous float32 cuda tensor {shp}")
+        if self.with_base:
+            if base is None or not (base.is_cuda and base.dtype == torch.int64 and base.is_contiguous()
+                                    and tuple(base.shape) == shp):
+                raise ValueError("base must be a contiguous int64-typed cuda tensor of the chunk's shape")
+        self.pred[local_index], self.base[local_index] = pred, (base if self.with_base else None)
+        self.graphs = None
+
+    def _alloc(self, cap_rows, cap_entries):
+        torch, L = self.torch, self.C.lib()
+        # even capacities: every slot of the gathered buffer stays 16-byte aligned
+        self.cap_rows, self.cap_entries = (int(cap_rows) + 1) & ~1, (int(cap_entries) + 1) & ~1
+        self.slot_bytes = int(L.syn_packed_slot_bytes(self.cap_rows, self.cap_entries))
+        nslots = self.per_rank * self.world
+        self.my_slots = torch.zeros((self.per_rank, self.slot_bytes), dtype=torch.uint8, device=self.device)
+        self.all_slots = self.my_slots if self.world == 1 else torch.zeros(
+            (nslots, self.slot_bytes), dtype=torch.uint8, device=self.device)
+        cap_total = self.nchunks * self.cap_rows
+        self.max_edges = max(1024, self.nchunks * self.cap_entries // 2)
+        nb = int(L.syn_merge_packed_workspace_bytes(self.nchunks, self.cap_rows, self.max_edges))
+        if nb < 0:
+            raise ValueError("chunk grid / capacities out of range for the packed merge")
+        self.merge_ws = torch.empty(nb, dtype=torch.uint8, device=self.device)
+        self.id_base = torch.zeros(self.nchunks + 1, dtype=torch.int64, device=self.device)
+        self.merged = torch.empty((cap_total, self.C.SEG_NCOLS), dtype=torch.int64, device=self.device)
+        self.fmap = torch.zeros(cap_total + 1, dtype=torch.int32, device=self.device)
+        self.info = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self.graphs = None
+
+    def _alloc_chunk(self, li):
+        torch, L = self.torch, self.C.lib()
+        nx, ny, nz = self.chunk_shape[self.mine[li]]
+        nb = L.syn_ccs_workspace_bytes(nx, ny, nz, self.caps_runs[li], self.max_pairs[li])
+        if nb < 0:
+            self.C.check(int(nb))
+        self.ws[li] = torch.empty(int(nb), dtype=torch.uint8, device=self.device)
+        if self.with_base:
+            mp = self.max_pairs[li]
+            self.pairs[li] = (torch.empty(mp, dtype=torch.int32, device=self.device),
+                              torch.empty(mp, dtype=torch.int64, device=self.device),
+                              torch.empty(mp, dtype=torch.int64, device=self.device))
+        self.graphs = None
+
+    # ---- the three stages of a step (all asynchronous on the current stream) --------------------------
+    def _begin(self, li, slot_ptr=None, cap_rows=None, cap_entries=None):
+        L, C = self.C.lib(), self.C
+        nx, ny, nz = self.chunk_shape[self.mine[li]]
+        base = self.base[li]
+        C.check(L.syn_chunk_ccs_begin(
+            self.pred[li].data_ptr(), nx, ny, nz, ctypes_f32(self.thresh), self.conn, 0, self.dust,
+            ctypes.cast(self.offsets[li], ctypes.c_void_p), self.labels[li].data_ptr(),
+            base.data_ptr() if base is not None else None,
+            self.max_pairs[li], slot_ptr if slot_ptr is not None else self.my_slots[li].data_ptr(),
+            cap_rows or self.cap_rows, cap_entries or self.cap_entries, self.ws[li].data_ptr(), self.ws[li].numel(),
+            self.caps_runs[li], self.D._stream_ptr(self.torch)))
+
+    def _merge(self):
+        L, C = self.C.lib(), self.C
+        C.check(L.syn_merge_ccs_packed(
+            self.all_slots.data_ptr(), self.slot_bytes, self.cap_rows, self.cap_entries, self.plan.data_ptr(),
+            self.nchunks, self.npairs, self.size_thr, self.max_edges, self.merge_ws.data_ptr(), self.merge_ws.numel(),
+            self.id_base.data_ptr(), self.merged.data_ptr(), self.fmap.data_ptr(), self.info.data_ptr(),
+            self.D._stream_ptr(self.torch)))
+
+    def _finish(self, li):
+        L, C = self.C.lib(), self.C
+        ci = self.mine[li]
+        nx, ny, nz = self.chunk_shape[ci]
+        base = self.base[li]
+        pr = self.pairs[li] or (None, None, None)
+        lut_base = self.id_base[ci:ci + 1]
+        C.check(L.syn_chunk_ccs_finish(
+            self.pred[li].data_ptr(), nx, ny, nz, self.conn, 0, self.labels[li].data_ptr(),
+            base.data_ptr() if base is not None else None,
+            pr[0].data_ptr() if pr[0] is not None else None, pr[1].data_ptr() if pr[1] is not None else None,
+            pr[2].data_ptr() if pr[2] is not None else None, self.max_pairs[li], self.cap_rows,
+            self.fmap.data_ptr(), lut_base.data_ptr(), self.fmap.numel(), self.ws[li].data_ptr(), self.ws[li].numel(),
+            self.caps_runs[li], None, self.D._stream_ptr(self.torch)))
+
+    def _gather(self):
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.all_slots.view(-1), self.my_slots.view(-1), group=self.group)
+
+    # ---- sizing --------------------------------------------------------------------------------------
+    def prepare(self):
+        """Sizes every buffer from one un-timed pass over the own chunks (collective: all ranks agree on the slot
+        capacities), then captures the graphs.  Called by the first run()."""
+        torch, D = self.torch, self.D
+        for li in range(len(self.mine)):
+            if self.pred[li] is None:
+                raise RuntimeError(f"inputs of own chunk #{li} not set")
+        need_rows, need_ent = 1, 1
+        with torch.cuda.stream(self.stream):
+            for li, ci in enumerate(self.mine):
+                nx, ny, nz = self.chunk_shape[ci]
+                for _attempt in range(6):
+                    if self.ws[li] is None:
+                        self._alloc_chunk(li)
+                    big_rows = D.default_capacities((nx, ny, nz))[1]
+                    big_ent = 2 * (ny * nz + nx * nz + nx * ny)
+                    nb = int(self.C.lib().syn_packed_slot_bytes(big_rows, big_ent))
+                    tmp = torch.zeros(nb, dtype=torch.uint8, device=self.device)
+                    self._begin(li, tmp.data_ptr(), big_rows, big_ent)
+                    cnt = self._read_counts(li)
+                    hdr = tmp[:128].view(torch.int64).cpu().numpy()
+                    del tmp
+                    if cnt["errflags"] & self.C.EF_RUNS:
+                        self.caps_runs[li] = max(cnt["runs"], self.caps_runs[li] + 1)
+                        self.ws[li] = None
+                        continue
+                    break
+                else:
+                    raise self.C.CapacityError(self.C.SYN_ERR_CAPACITY, "run capacity still too small", None)
+                need_rows = max(need_rows, int(hdr[0]))
+                need_ent = max(need_ent, int(hdr[1]))
+                # keep the per-chunk workspaces tight: the run-indexed arrays dominate them
+                tight = max(1 << 16, int(cnt["runs"] * 1.25) + 1024)
+                if tight < self.caps_runs[li]:
+                    self.caps_runs[li] = tight
+                    self.ws[li] = None
+                    self._alloc_chunk(li)
+        need = torch.tensor([need_rows, need_ent], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(need, op=self.dist.ReduceOp.MAX, group=self.group)
+        need_rows, need_ent = (int(v) for v in need.cpu())
+        if self.cap_rows is None or need_rows > self.cap_rows or need_ent > self.cap_entries:
+            self._alloc(max(self.cap_rows or 0, int(need_rows * 1.25) + 64), max(self.cap_entries or 0,
+                                                                                  int(need_ent * 1.25) + 256))
+        self._capture()
+
+    def _read_counts(self, li):
+        counts = np.zeros(self.C.NCOUNTS, dtype=np.int64)
+        import ctypes
+        self.C.check(self.C.lib().syn_read_counts(self.ws[li].data_ptr(), counts.ctypes.data_as(ctypes.c_void_p),
+                                                  self.D._stream_ptr(self.torch)))
+        return self.D._counts_dict(counts)
+
+    def _stage_a(self):
+        for li in range(len(self.mine)):
+            self._begin(li)
+
+    def _stage_b(self):
+        self._merge()
+        for li in range(len(self.mine)):
+            self._finish(li)
+
+    def _capture(self):
+        torch, L = self.torch, self.C.lib()
+        self.graphs = None
+        with torch.cuda.stream(self.stream):
+            n0 = L.syn_launch_count()
+            self._stage_a()                      # warm: function attributes, occupancy queries
+            self._gather()
+            self._stage_b()
+            self.launches_per_step = int(L.syn_launch_count() - n0)
+            self.stream.synchronize()
+            if not self.use_graph:
+                return
+            if self.world == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._stage_a()
+                    self._stage_b()
+                self.graphs = (g,)
+            else:
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga, stream=self.stream):
+                    self._stage_a()
+                with torch.cuda.graph(gb, stream=self.stream):
+                    self._stage_b()
+                self.graphs = (ga, gb)
+
+    # ---- running -------------------------------------------------------------------------------------
+    def run(self):
+        """Queues one step on the job's stream (ordered after the caller's current stream).  Asynchronous."""
+        torch = self.torch
+        if self.cap_rows is None or (self.use_graph and self.graphs is None):
+            self.prepare()
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            if self.graphs is None:
+                self._stage_a()
+                self._gather()
+                self._stage_b()
+            elif len(self.graphs) == 1:
+                self.graphs[0].replay()
+            else:
+                self.graphs[0].replay()
+                self._gather()
+                self.graphs[1].replay()
+        cur.wait_stream(self.stream)
+
+    def check(self):
+        """Synchronises; True when the last step fitted every capacity.  Otherwise grows what overflowed
+        (collective) and returns False: run() again."""
+        torch = self.torch
+        self.stream.synchronize()
+        info = self.info.cpu().numpy()
+        ok = int(info[3]) == 0
+        grow_pairs = False
+        for li in range(len(self.mine)):
+            cnt = self._read_counts(li)
+            ef = cnt["errflags"]
+            if ef & self.C.EF_RUNS:
+                self.caps_runs[li] = max(cnt["runs"], self.caps_runs[li] + 1)
+            if ef & self.C.EF_TABLE:
+                self.max_pairs[li] *= 4
+            if ef & self.C.EF_PAIRS:
+                self.max_pairs[li] = max(cnt["pairs"], self.max_pairs[li] + 1)
+            if ef & (self.C.EF_RUNS | self.C.EF_TABLE | self.C.EF_PAIRS):
+                ok, grow_pairs = False, True
+                self.ws[li] = None
+        flag = torch.tensor([0 if ok else 1], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX, group=self.group)
+        if int(flag.cpu()[0]) == 0:
+            return True
+        # rows / entries / edges: resize from the headers (prepare() re-measures them)
+        if int(info[3]) & 2:
+            self.cap_entries = None if self.cap_entries is None else self.cap_entries * 2
+        self.cap_rows = None
+        self.prepare()
+        return False
+
+    # ---- results (each synchronises) -------------------------------------------------------------------
+    def counts(self, local_index):
+        self.stream.synchronize()
+        return self._read_counts(local_index)
+
+    def merged_table(self):
+        """[n_merged, 11] int64 numpy: id, size, centroid xyz, bbox begin xyz, bbox end xyz (ascending id)."""
+        self.stream.synchronize()
+        n = int(self.info.cpu()[1])
+        return self.merged[:n].cpu().numpy()
+
+    def info_dict(self):
+        self.stream.synchronize()
+        i = self.info.cpu().numpy()
+        return {"total_ids": int(i[0]), "n_merged": int(i[1]), "n_edges": int(i[2]), "flags": int(i[3])}
+
+    def chunk_table(self, chunk_index):
+        """Segment table of ANY chunk of the grid (every rank holds all of them after the exchange)."""
+        self.stream.synchronize()
+        slot = int(self.plan[2 + chunk_index].cpu())
+        raw = self.all_slots[slot]
+        kept = int(raw[:8].view(self.torch.int64).cpu()[0])
+        t = raw[128:128 + self.cap_rows * 88].view(self.torch.int64).view(self.cap_rows, 11)
+        return t[:kept].cpu().numpy()
+
+    def chunk_id_map(self, chunk_index):
+        """{chunk-local id: final global id} of a chunk (the reference's chunk_id_maps entry, tasks.py:72-122)."""
+        t = self.chunk_table(chunk_index)
+        base = int(self.id_base.cpu()[chunk_index])
+        fm = self.fmap[base + 1: base + 1 + len(t)].cpu().numpy().view(np.uint32)
+        return dict(zip(t[:, 0].tolist(), fm.tolist()))
+
+    def overlaps(self, local_index):
+        """(rows, cols, vals, shape) of own chunk #local_index: overlap_task on the remapped chunk."""
+        cnt = self.counts(local_index)
+        n = cnt["pairs"]
+        pr = self.pairs[local_index]
+        rows = pr[0][:n].cpu().numpy().view(np.uint32).astype(np.int64)
+        cols = pr[1][:n].cpu().numpy().view(np.uint64)
+        vals = pr[2][:n].cpu().numpy()
+        shape = (0, 0) if cnt["max_label"] == 0 or cnt["max_base"] == 0 else (cnt["max_label"] + 1, cnt["max_base"] + 1)
+        return rows, cols, vals, shape
+
+
+def ctypes_i64x3(v):
+    import ctypes
+    return (ctypes.c_int64 * 3)(int(v[0]), int(v[1]), int(v[2]))
+
+
+def ctypes_f32(v):
+    import ctypes
+    return ctypes.c_float(float(v))

@@ -1,0 +1,119 @@
+"""
+The whole-volume job (synaptor_b200.multi.VolumeJob: chunk_ccs -> merge_ccs -> remap_ids -> chunk_overlaps with the
+label volume written once in final ids) against the oracle's restatement of the reference workflow
+(proc/tasks.py:26-69, 72-122, 314-333, 290-297).  Bit-exact, merged centroids included.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from util import oracle_volume_job
+
+pytestmark = pytest.mark.gpu
+
+
+def run_job(vol, base_vol, cshape, thresh, dust, size_thr, graph, vol_offset=(0, 0, 0), world=1, rank=0):
+    import torch
+    from synaptor_b200 import multi
+    dev = torch.device("cuda", torch.cuda.current_device())
+    job = multi.VolumeJob(vol.shape, cshape, thresh, dust, size_thr, with_base=base_vol is not None, rank=rank,
+                          world=world, device=dev, vol_offset=vol_offset, graph=graph)
+    keep = []
+    for li, ci in enumerate(job.mine):
+        beg, shp = job.chunk_rel_begin[ci], job.chunk_shape[ci]
+        sl = tuple(slice(b, b + s) for (b, s) in zip(beg, shp))
+        p = torch.from_numpy(np.ascontiguousarray(vol[sl])).to(dev)
+        b = torch.from_numpy(np.ascontiguousarray(base_vol[sl]).view(np.int64)).to(dev) if base_vol is not None else None
+        keep.append((p, b))
+        job.set_inputs(li, p, b)
+    for _ in range(4):
+        job.run()
+        if job.check():
+            break
+    else:
+        raise AssertionError("capacities never settled")
+    return job
+
+
+def compare(job, want, vol_shape, base_vol):
+    final = np.zeros(vol_shape, dtype=np.uint32)
+    for li, ci in enumerate(job.mine):
+        gi, sl, beg = want["chunks"][ci]
+        final[sl] = job.labels[li].cpu().numpy().view(np.uint32)
+    assert np.array_equal(final, want["final"]), f"{np.count_nonzero(final != want['final'])} voxels differ"
+    got = {int(r[0]): r[1:].tolist() for r in job.merged_table()}
+    assert got == {int(k): [int(x) for x in v] for (k, v) in want["merged"].items()}
+    for ci in range(job.nchunks):
+        gi = want["chunks"][ci][0]
+        assert job.chunk_id_map(ci) == {int(k): int(v) for (k, v) in want["id_maps"][gi].items()}
+        info = want["infos"][gi]
+        t = job.chunk_table(ci)
+        assert np.array_equal(t[:, 0], np.asarray(info.index, dtype=np.int64))
+        assert np.array_equal(t[:, 1:], info.to_numpy(dtype=np.int64).reshape(len(info), 10))
+    if base_vol is not None:
+        for li, ci in enumerate(job.mine):
+            r, c, v, shape = job.overlaps(li)
+            wr, wc, wv, wshape = want["overlaps"][ci]
+            assert shape == wshape
+            assert np.array_equal(r, wr) and np.array_equal(c, wc) and np.array_equal(v, wv)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("vshape,cshape", [
+    ((40, 36, 32), (20, 18, 16)),        # 2x2x2, generic (non-sector) path
+    ((48, 24, 64), (16, 24, 32)),        # 3x1x2, sector path (nz % 8 == 0)
+    ((32, 32, 256), (16, 16, 128)),      # 2x2x2, TMA stream path (nz % 128 == 0)
+    ((50, 40, 72), (24, 16, 32)),        # 3x3x3 ragged: remainder chunks (chunking.py:47-69)
+    ((24, 24, 24), (24, 24, 24)),        # a single chunk: no face pairs at all
+])
+def test_volume_job_vs_oracle(vshape, cshape, graph):
+    vol = orc.synth_pred(vshape, seed=11, sigma=2.0, fg=0.10)
+    base_vol = orc.synth_base(vshape, seed=12, block=5, bg=0.1)
+    want = oracle_volume_job(vol, base_vol, cshape, 0.5, 10, 15, vol_offset=(100, 200, 300))
+    job = run_job(vol, base_vol, cshape, 0.5, 10, 15, graph, vol_offset=(100, 200, 300))
+    compare(job, want, vshape, base_vol)
+    info = job.info_dict()
+    assert info["flags"] == 0 and info["n_merged"] == len(want["merged"])
+    # the merged volume is a 1:1 relabelling of whole-volume CCL restricted to the surviving segments
+    final = want["final"]
+    whole = orc.label_c(vol > 0.5, 6)[0]
+    pairs = np.unique(np.stack([final[final != 0], whole[final != 0]], 1), axis=0)
+    assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1]))
+
+
+def test_volume_job_no_base_dense_noise():
+    rng = np.random.default_rng(3)
+    vol = rng.random((36, 40, 64), dtype=np.float32)
+    want = oracle_volume_job(vol, None, (12, 20, 32), 0.6, 3, 5)
+    job = run_job(vol, None, (12, 20, 32), 0.6, 3, 5, graph=True)
+    compare(job, want, vol.shape, None)
+
+
+def test_volume_job_empty_and_full():
+    for fill in (0.0, 1.0):
+        vol = np.full((16, 16, 32), fill, dtype=np.float32)
+        want = oracle_volume_job(vol, None, (8, 16, 16), 0.5, 10, 10)
+        job = run_job(vol, None, (8, 16, 16), 0.5, 10, 10, graph=False)
+        compare(job, want, vol.shape, None)
+
+
+def test_volume_job_rerun_new_data_grows_capacities():
+    """The same job object on denser data: check() reports the overflow, grows, and the re-run is exact."""
+    import torch
+    vshape, cshape = (32, 32, 64), (16, 16, 32)
+    sparse = orc.synth_pred(vshape, seed=5, sigma=2.0, fg=0.02)
+    job = run_job(sparse, None, cshape, 0.5, 10, 15, graph=True)
+    dense = np.random.default_rng(9).random(vshape, dtype=np.float32)
+    for li, ci in enumerate(job.mine):
+        beg, shp = job.chunk_rel_begin[ci], job.chunk_shape[ci]
+        sl = tuple(slice(b, b + s) for (b, s) in zip(beg, shp))
+        job.pred[li].copy_(torch.from_numpy(np.ascontiguousarray(dense[sl])))
+    ok = False
+    for _ in range(5):
+        job.run()
+        if job.check():
+            ok = True
+            break
+    assert ok
+    want = oracle_volume_job(dense, None, cshape, 0.5, 10, 15)
+    compare(job, want, vshape, None)
