@@ -3,24 +3,26 @@
 bench.py -- throughput of the chunk_ccs + chunk_overlaps hot path (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
-  python bench.py --impl reference ...                     (the CPU path on this box's host cores)
+  python bench.py --impl reference ...                     (the reference's CPU path on this box's host cores)
+  python bench.py --config c2|c3 ...                       (single-chunk configs, one GPU, device-resident only)
 
-A "step" is one pass of the fused chunk_ccs + chunk_overlaps pipeline over one
-512^3 chunk per GPU (BASELINE.json configs[1]: float32 cleft prediction, threshold
-0.5, 6-connectivity, dust 100, uint64 base segmentation).  With N GPUs every rank
-owns one chunk of an (N*512) x 512 x 512 volume (weak scaling; chunks shard
-naturally, no data-path collective in the timed step).  The cross-chunk merge_ccs
-exchange (NCCL all_gather of segment counts, boundary faces and tables, device
-union-find, LUT remap) is run and timed separately (config.merge_ccs_ms_separate).
+Default workload (every N) -- the north-star job, BASELINE.json configs[3]: a 2048 x 2048 x 256 volume as
+2 x 2 x 2 chunks of 1024 x 1024 x 128 (types/bbox/chunking.py:13-44), chunk i on rank i % N (strong scaling:
+N = 1 runs all eight).  One step = chunk_ccs on every owned chunk + merge_ccs (ONE NCCL all_gather of the packed
+segment tables and face entries, device union-find) + remap_ids (folded into the single label write) +
+chunk_overlaps against the uint64 base segmentation -- synaptor/proc/tasks.py:26-69, 72-122, 314-333, 290-297.
+The result of the measured configuration is checked, once, outside the timed region, against the CPU oracle
+(bit-exact: final volume, merged table, id maps, overlap triples; 1:1 with whole-volume labelling).
 
 value   : Gvoxel/s, whole job, inputs resident in HBM, outputs left in HBM (CUDA events, max over ranks)
-e2e     : the same through the public API synaptor_b200.proc.tasks.cc_overlap_task with pinned HOST
-          buffers, H2D + D2H + host-side table/continuation materialisation inside the timed region
-roofline: the dominant kernel (dense label write + pair histogram, 12 B/voxel algorithmic) timed with
-          CUDA events on the launching stream in a second, event-instrumented pass of K steps
+e2e     : the same job through synaptor_b200.proc.tasks.volume_tasks with HOST chunk arrays (H2D of every chunk,
+          D2H of the final label volume + tables + overlaps, host materialisation) inside the timed region
+roofline: the dominant kernel k_stream (16 B/voxel algorithmic: 4 pred + 8 base read, 4 label write) timed with
+          CUDA events on the launching stream in an event-instrumented pass
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -33,16 +35,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CHUNK = (512, 512, 512)
 THRESH, DUST, CONN = 0.5, 100, 6
+SIZE_THR = 100
 METRIC = "Gvoxels/s chunk_ccs+overlaps"
-BYTES_PER_VOXEL_PIPELINE = 16   # 4 B pred read + 4 B label write + 8 B base read
-BYTES_PER_VOXEL_STREAM_KERNEL = 16  # k_stream: 4 B pred read + 8 B base read + 4 B label (zero-fill) write
-CPU_SAMPLE = (256, 256, 256)
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_stream launch on the 512^3 workload (ncu --set full,
-# profiles/r01m_top_summary.txt: 1.610673 GB read + 491.01 MB written in 331.9 us (under ncu); the algorithmic 16 B/voxel are
-# 2.147 GB -- the foreground sectors are not zero-filled by this kernel)
-STREAM_TRAFFIC_512 = 2101686120
+BYTES_PER_VOXEL = 16            # 4 B pred read + 4 B label write + 8 B base read
+VOLUME = (2048, 2048, 256)
+CHUNK = (1024, 1024, 128)
+CONFIGS = {
+    # name: (shape, sigma, fg, workload text)
+    "c2": ((512, 512, 512), 2.0, 0.03, "configs[1]: chunk_ccs+chunk_overlaps 512x512x512, float32 pred (sigma 2, fg 3%), "
+           "thr 0.5, 6-conn, dust 100, uint64 base (32^3 blocks)"),
+    "c3": ((1024, 1024, 128), 1.0, 0.10, "configs[2]: chunk_ccs+chunk_overlaps 1024x1024x128 dense small clefts "
+           "(sigma 1, fg 10%), thr 0.5, 6-conn, dust 100, uint64 base (32^3 blocks)"),
+}
+WORKLOAD_C4 = ("configs[3]: 2048x2048x256 volume (sigma 2, fg 3%, uint64 base of 32^3 blocks) as 8 chunks of "
+               "1024x1024x128, chunk i on GPU i % N: chunk_ccs + merge_ccs (one NCCL all_gather) + remap_ids "
+               "(folded into the label write) + chunk_overlaps; thr 0.5, 6-conn, dust 100, merge size_thr 100")
 
 
 def peaks():
@@ -51,6 +59,19 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def stream_traffic(shape):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE k_stream launch from the committed ncu summaries
+    (profiles/ncu_traffic.json, keyed by kernel and chunk shape); None when that shape was never captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            tab = json.load(f)
+        e = tab["k_stream"].get("x".join(str(s) for s in shape))
+        return (int(e["bytes"]), e["source"]) if e else (None, None)
+    except (OSError, KeyError, ValueError):
+        return None, None
 
 
 class ClockSampler:
@@ -71,7 +92,7 @@ class ClockSampler:
 
     def wait_first_sample(self, timeout=5.0):
         """nvidia-smi needs a moment to start (longer on an 8-GPU box): do not enter the timed region before the
-        first sample has been written, or a 7 ms region is over before the sampler runs."""
+        first sample has been written, or a short region is over before the sampler runs."""
         t0 = time.time()
         while self.proc is not None and time.time() - t0 < timeout:
             try:
@@ -114,78 +135,198 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's numpy port (reference cost profile: np.unique, find_objects, Counter ...)
+# Synthetic inputs of the big volume, generated ON THE GPU from a position hash: any rank can produce any chunk
+# (same values whatever the partition), continuous across chunk borders, no 4 GiB host filter.  Same recipe as
+# oracle.synth_pred / synth_base: white noise -> separable Gaussian (sigma, truncated at 4 sigma, wrap)
+# -> logistic squashing around the (1 - fg) quantile; base ids constant on 32^3 blocks, 40 bits, 5 % zeros.
 # --------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    seed, shape = args
+def _mix64(torch, x):
+    # splitmix64 finaliser in wrapping int64 arithmetic (logical shifts emulated with masks)
+    x = x * (-7046029254386353131)
+    x = x ^ ((x >> 30) & ((1 << 34) - 1))
+    x = x * (-4658895280553007687)
+    x = x ^ ((x >> 27) & ((1 << 37) - 1))
+    x = x * (-7723592293110705685)
+    x = x ^ ((x >> 31) & ((1 << 33) - 1))
+    return x
+
+
+def gen_pred_chunk(torch, dev, vol_shape, beg, shp, seed=0, sigma=2.0, fg=0.03):
+    from scipy.stats import norm
+    r = int(4.0 * sigma + 0.5)
+    k = torch.arange(-r, r + 1, device=dev, dtype=torch.float32)
+    w = torch.exp(-0.5 * (k / sigma) ** 2)
+    w = w / w.sum()
+    std_f = float((w * w).sum().sqrt()) ** 3                 # std of unit white noise after the 3 passes
+    coords = [((torch.arange(beg[a] - r, beg[a] + shp[a] + r, device=dev, dtype=torch.int64)) % vol_shape[a])
+              for a in range(3)]
+    lin = (coords[0][:, None, None] * vol_shape[1] + coords[1][None, :, None]) * vol_shape[2] + coords[2][None, None, :]
+    h = _mix64(torch, lin + seed * 1000003)
+    del lin
+    u1 = ((h & 0xFFFFFF).to(torch.float32) + 0.5) / 16777216.0
+    u2 = (((h >> 24) & 0xFFFFFF).to(torch.float32) + 0.5) / 16777216.0
+    del h
+    x = torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(6.283185307179586 * u2)
+    del u1, u2
+    for axis in range(3):                                    # valid correlation = sum of shifted slices
+        n = x.shape[axis] - 2 * r
+        acc = None
+        for i in range(2 * r + 1):
+            term = x.narrow(axis, i, n) * w[i]
+            acc = term if acc is None else acc.add_(term)
+        x = acc
+    t = float(norm.ppf(1.0 - fg)) * std_f
+    return torch.sigmoid((x - t) / std_f * 4.0).contiguous()
+
+
+def gen_base_chunk(torch, dev, vol_shape, beg, shp, seed=1, block=32, bg=0.05):
+    g = [-(-vol_shape[a] // block) for a in range(3)]
+    b = [torch.div(torch.arange(beg[a], beg[a] + shp[a], device=dev, dtype=torch.int64), block, rounding_mode="floor")
+         for a in range(3)]
+    ub = [torch.unique_consecutive(v) for v in b]
+    lin = (ub[0][:, None, None] * g[1] + ub[1][None, :, None]) * g[2] + ub[2][None, None, :]
+    h = _mix64(torch, lin + seed * 7919 + 12345)
+    ids = (h & ((1 << 40) - 1)) + 1
+    zero = ((h >> 40) & 0xFFFF).to(torch.float32) / 65536.0 < bg
+    ids = torch.where(zero, torch.zeros_like(ids), ids)
+    idx = [v - v[0] for v in b]
+    return ids.index_select(0, idx[0]).index_select(1, idx[1]).index_select(2, idx[2]).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own code (baseline/_ref through oracle/refshim.py) on the same job, one task per chunk
+# and process as the reference deploys it; falls back to the oracle's port when no reference copy is present.
+# --------------------------------------------------------------------------------------------------
+def _ref_worker(conn, pred, base, use_ref):
+    import io
+    from contextlib import redirect_stdout
     os.environ["OMP_NUM_THREADS"] = "1"
     from oracle import oracle as orc
-    pred = orc.synth_pred(shape, seed=seed, sigma=2.0, fg=0.03)
-    base = orc.synth_base(shape, seed=seed + 1)
-    t0 = time.perf_counter()
-    ccs, _, info = orc.cc_task_np(pred, THRESH, DUST)
-    orc.count_overlaps_np(ccs, base)
-    return time.perf_counter() - t0, len(info)
+    if use_ref:
+        from oracle import refshim
+        syn, _ = refshim.load()
+    sink = io.StringIO()
+    ccs = {}
+    while True:
+        msg = conn.recv()
+        if msg[0] == "cc":
+            _, ci, beg = msg
+            if use_ref:
+                with redirect_stdout(sink):
+                    ccs[ci], conts, info = syn.proc.tasks.cc_task(pred, THRESH, DUST, offset=beg)
+            else:
+                ccs[ci], conts, info = orc.cc_task_np(pred, THRESH, DUST, offset=beg)
+            conn.send((conts, info))
+        elif msg[0] == "remap_overlap":
+            _, ci, id_map = msg
+            if use_ref:
+                with redirect_stdout(sink):
+                    fin = syn.proc.tasks.remap_ids_task(ccs.pop(ci), id_map, copy=False)
+                    nnz = syn.proc.tasks.overlap_task(fin, base).nnz
+            else:
+                fin = orc.remap_ids(ccs.pop(ci), id_map)
+                nnz = len(orc.count_overlaps_np(fin, base)[0])
+            conn.send(nnz)
+        else:
+            return
 
 
-def cpu_baseline(nproc=None, shape=CPU_SAMPLE, reps=1):
-    """One reference-style task (cc_task + overlap_task) per process, one chunk each, like the reference's
-    one-task-per-chunk deployment.  Returns (Gvoxel/s aggregate, cores, wall seconds)."""
+def cpu_job(steps=1, warmup=0, budget_s=None, chunk=CHUNK, grid=(2, 2, 2)):
+    """The C4 job on the host cores: one process per chunk (cc_task, later remap_ids_task + overlap_task), the
+    parent runs merge_ccs_task in between.  Inputs resident in the workers before the clock starts.  The eight
+    chunks are copies of ONE seamless tile (oracle.synth_pred uses mode="wrap", so the copies are continuous across
+    the chunk borders and the merge has real work).  Returns a dict."""
+    import io
     import multiprocessing as mp
+    from contextlib import redirect_stdout
     from oracle import oracle as orc
+    from oracle import refshim
+    use_ref = refshim.available() is not None
     cores = len(os.sched_getaffinity(0))
-    nproc = nproc or max(1, cores)          # every host core the process may use: one reference-style task per core
+    nchunks = int(np.prod(grid))
+    nproc = min(cores, nchunks)
+    pred = orc.synth_pred(chunk, seed=0, sigma=2.0, fg=0.03)
+    base = orc.synth_base(chunk, seed=1)
+    if use_ref:
+        syn, where = refshim.load()
     ctx = mp.get_context("fork")
-    jobs = [(100 + i, shape) for i in range(nproc * reps)]
-    with ctx.Pool(nproc) as pool:
-        pool.map(_cpu_worker, [(1, (32, 32, 32))] * nproc)     # import + page-in outside the timing
+    gidx = list(np.ndindex(grid))
+    begs = [tuple(int(i) * int(c) for (i, c) in zip(gi, chunk)) for gi in gidx]
+    procs, conns = [], []
+    for i in range(nproc):          # fewer cores than chunks: a worker takes several chunks, one after the other
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_ref_worker, args=(b, pred, base, use_ref), daemon=True)
+        p.start()
+        procs.append(p); conns.append(a)
+    rounds = [[ci for ci in range(r * nproc, min((r + 1) * nproc, nchunks))] for r in range(-(-nchunks // nproc))]
+    walls, info_last, done = [], {}, 0
+    t_start = time.perf_counter()
+    for it in range(warmup + steps):
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, jobs, chunksize=1)
-        wall = time.perf_counter() - t0
-    # synthetic-input generation happens inside the workers but outside their timed span; use the sum of the
-    # per-task compute spans spread over nproc workers as the wall time of the compute
-    compute_wall = sum(r[0] for r in res) / nproc
-    vox = float(np.prod(shape)) * len(jobs)
-    kind = "port"
-    ref_so = orc.ref_ext("_describe") is not None
-    sample = (f"{len(jobs)} chunks of {shape[0]}x{shape[1]}x{shape[2]} (same generator/params as the GPU workload), "
-              f"one oracle cc_task_np + count_overlaps_np per process on {nproc} processes; numpy/scipy port of the "
-              f"reference's Python steps with scipy.ndimage.label for the absent cc3d"
-              + (" and the reference's own compiled _describe/_relabel from oracle/_ref" if ref_so else ""))
-    return vox / compute_wall / 1e9, nproc, compute_wall, kind, sample, wall
-
-
-def workload_name(shape):
-    return (f"configs[1]: chunk_ccs+chunk_overlaps {shape[0]}x{shape[1]}x{shape[2]} per GPU, "
-            "float32 pred (sigma 2, fg 3%), thr 0.5, 6-conn, dust 100, uint64 base (32^3 blocks)")
+        cont_arr = np.empty(grid, dtype=object)
+        info_arr = np.empty(grid, dtype=object)
+        for rd in rounds:
+            for (j, ci) in enumerate(rd):
+                conns[j].send(("cc", ci, begs[ci]))
+            for (j, ci) in enumerate(rd):
+                cont_arr[gidx[ci]], info_arr[gidx[ci]] = conns[j].recv()
+        t1 = time.perf_counter()
+        if use_ref:     # maxfaceshape = sorted(chunkshape)[1:]  (cloud/kube/parser.py:85-86)
+            with redirect_stdout(io.StringIO()):
+                merged, id_maps = syn.proc.tasks.merge_ccs_task(cont_arr, info_arr, SIZE_THR, tuple(sorted(chunk)[1:]))
+        else:
+            merged, id_maps = orc.merge_ccs_task(cont_arr, info_arr, SIZE_THR, (max(chunk), max(chunk)))
+        t2 = time.perf_counter()
+        nnz = 0
+        for rd in rounds:
+            for (j, ci) in enumerate(rd):
+                conns[j].send(("remap_overlap", ci, id_maps[gidx[ci]]))
+            for (j, ci) in enumerate(rd):
+                nnz += conns[j].recv()
+        t3 = time.perf_counter()
+        if it >= warmup:
+            walls.append(t3 - t0)
+            done += 1
+        info_last = {"cc_s": t1 - t0, "merge_s": t2 - t1, "remap_overlap_s": t3 - t2, "merged_segments": len(merged),
+                     "overlap_nnz": int(nnz)}
+        if budget_s is not None and done >= 1 and time.perf_counter() - t_start > budget_s:
+            break
+    for c in conns:
+        c.send(("quit",))
+    for p in procs:
+        p.join(timeout=10)
+    vox = float(np.prod(chunk)) * nchunks
+    wall = float(np.mean(walls))
+    kind = "reference" if use_ref else "port"
+    sample = (f"the whole job per step: {nchunks} chunks of {chunk[0]}x{chunk[1]}x{chunk[2]} (copies of one seamless "
+              f"oracle.synth_pred tile, same sigma/fg/base recipe as the GPU workload), one process per chunk on "
+              f"{nproc} processes: cc_task -> merge_ccs_task (parent) -> remap_ids_task + overlap_task; "
+              + ("the reference's own code from baseline/_ref (scipy.ndimage.label standing in for the absent cc3d, "
+                 "scipy csgraph for igraph)" if use_ref else
+                 "numpy/scipy port of the reference's Python steps (oracle.cc_task_np / merge_ccs_task / "
+                 "count_overlaps_np) with the reference's compiled _describe/_relabel from oracle/_ref"))
+    return {"value": vox / wall / 1e9, "cores": nproc, "kind": kind, "sample": sample, "seconds": wall,
+            "steps": done, **info_last}
 
 
 def run_reference(args, out_fd):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    # each step = one bounded sample of the workload (one 256^3 chunk per host core, all cores busy); a single
-    # warm-up sample whatever W is, so that the whole run stays within a few minutes
-    vals, walls = [], []
-    info = None
     n_warm = 1 if args.warmup >= 1 else 0
-    for _ in range(n_warm):
-        cpu_baseline(reps=1)
-    for _ in range(max(1, args.steps)):
-        info = cpu_baseline(reps=1)
-        vals.append(info[0])
-        walls.append(info[2])
-    v = float(np.mean(vals))
-    gv, cores, wall, kind, sample, _ = info
+    r = cpu_job(steps=max(1, args.steps), warmup=n_warm, budget_s=150.0, chunk=CHUNK, grid=job_grid())
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "Gvoxel/s", "n_gpus": args.gpus,
-        "steps": max(1, args.steps), "warmup": n_warm, "ms_per_step": float(np.mean(walls)) * 1e3,
-        "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32->u32/u64", "data": "synthetic",
-        "config": {"workload": workload_name(tuple(args.chunk)), "sample_shape": list(CPU_SAMPLE),
-                   "sample": "each step is a bounded CPU sample of the workload: " + sample},
-        "cpu_baseline": {"value": v, "unit": "Gvoxel/s", "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": v, "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Gvoxel/s", "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": n_warm, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32->u32/u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_C4, "volume": list(VOLUME), "chunk": list(CHUNK), "grid": list(job_grid()),
+                   "merge_ccs_in_step": True,
+                   "sample": "each step is " + r["sample"] + "; steps are cut off after a 150 s wall budget",
+                   "stage_s": {k: r[k] for k in ("cc_s", "merge_s", "remap_overlap_s")},
+                   "merged_segments": r["merged_segments"]},
+        "cpu_baseline": {"value": r["value"], "unit": "Gvoxel/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "Gvoxel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line, out_fd)
@@ -195,6 +336,94 @@ def run_reference(args, out_fd):
 # --------------------------------------------------------------------------------------------------
 def emit(line, fd):
     os.write(fd, (json.dumps(line) + "\n").encode())
+
+
+def numa_bind(torch, local):
+    """Pins this process to the CPUs of the GPU's NUMA node, so that the pinned host buffers of the e2e leg are
+    first-touched next to the GPU's PCIe root.  Returns a short description."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"node {node}: no allowed cpus"
+        os.sched_setaffinity(0, allowed)
+        return f"node {node}, {len(allowed)} cpus"
+    except Exception as e:      # noqa: BLE001 -- optional tuning, never fatal
+        return f"not bound ({type(e).__name__})"
+
+
+def bench_chunk_config(torch, dev, name, args, check):
+    """Single-chunk configs (c2, c3): device-resident fused chunk_ccs + chunk_overlaps, CUDA-graph replay, K steps;
+    per-kernel CUDA-event times; full-size parity against the oracle outside the timed region."""
+    from oracle import oracle as orc
+    from synaptor_b200 import _cabi as C
+    from synaptor_b200 import _device as D
+    shape, sigma, fg, text = CONFIGS[name]
+    pred_np = orc.synth_pred(shape, seed=0, sigma=sigma, fg=fg)
+    base_np = orc.synth_base(shape, seed=1000)
+    pred = torch.from_numpy(pred_np).to(dev)
+    base = torch.from_numpy(base_np.view(np.int64)).to(dev)
+    nvox = int(np.prod(shape))
+    L = C.lib()
+    pipe = D.ChunkPipeline(shape, DUST, thresh=THRESH, connectivity=CONN, device=dev, pred=pred, base=base)
+    pipe.run()
+    counts = dict(pipe.counts())
+    with torch.cuda.stream(pipe.stream):
+        for _ in range(max(3, args.warmup)):
+            pipe.graph.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            pipe.graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    C.check(L.syn_profile_enable(1))
+    acc = {}
+    res = pipe.result
+    for _ in range(args.steps):
+        D.chunk_ccs_device(pred, np.float32(THRESH), DUST, connectivity=CONN, base=base, sync=False, out=res,
+                           max_runs=res.caps[0], max_segs=res.caps[1], max_pairs=res.caps[2])
+        for (k, v) in C.profile_read().items():
+            acc[k] = acc.get(k, 0.0) + v / args.steps
+    C.check(L.syn_profile_enable(0))
+    peak, _ = peaks()
+    out = {"workload": text, "ms_per_step": ms, "gvoxel_s": nvox / (ms * 1e-3) / 1e9,
+           "pipeline_gb_s": BYTES_PER_VOXEL * nvox / (ms * 1e-3) / 1e9,
+           "pipeline_frac_of_measured_peak": BYTES_PER_VOXEL * nvox / (ms * 1e-3) / 1e9 / peak,
+           "pipeline_frac_of_8TBs_nominal": BYTES_PER_VOXEL * nvox / (ms * 1e-3) / 1e9 / 8000.0,
+           "components": counts["components"], "kept": counts["kept"], "pairs": counts["pairs"],
+           "runs": counts["runs"], "stage_ms": {k: round(float(v), 5) for (k, v) in acc.items()},
+           "launches_per_step": pipe.launches_per_run}
+    if check:
+        t0 = time.time()
+        want_ccs, _, want_info = orc.cc_task_c(pred_np, THRESH, DUST, with_continuations=False)
+        got = res.labels.cpu().numpy().view(np.uint32)
+        ok = bool(np.array_equal(got, want_ccs))
+        tab = res.seg_table[:counts["kept"]].cpu().numpy()
+        ok = ok and np.array_equal(tab[:, 0], np.asarray(want_info.index, dtype=np.int64)) and \
+            np.array_equal(tab[:, 1:], want_info.to_numpy(dtype=np.int64).reshape(-1, 10))
+        r, c, v, shp = orc.count_overlaps_c(want_ccs, base_np)
+        n = counts["pairs"]
+        ok = ok and n == len(r) and np.array_equal(res.pair_rows[:n].cpu().numpy().view(np.uint32), r.astype(np.uint32)) \
+            and np.array_equal(res.pair_cols[:n].cpu().numpy().view(np.uint64), c.astype(np.uint64)) \
+            and np.array_equal(res.pair_vals[:n].cpu().numpy(), v) \
+            and shp == (counts["max_label"] + 1, counts["max_base"] + 1)
+        out["parity"] = {"bit_exact_vs_oracle": bool(ok), "what": "labels, table, overlap triples + order, matrix shape "
+                         "at full size vs oracle.cc_task_c / count_overlaps_c", "seconds": round(time.time() - t0, 1)}
+    del pipe, pred, base
+    D.release_workspaces()
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -208,21 +437,32 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c4", choices=["c4", "c2", "c3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="time the plain syn_chunk_ccs call, not its CUDA graph")
-    ap.add_argument("--chunk", type=int, nargs=3, default=list(CHUNK))
+    ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle parity check of the measured job")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the c2 / c3 single-chunk measurements")
+    ap.add_argument("--no-numa", action="store_true")
+    ap.add_argument("--volume", type=int, nargs=3, default=None, help="debug: another volume shape for the job")
+    ap.add_argument("--chunk", type=int, nargs=3, default=None, help="debug: another chunk shape for the job")
     args = ap.parse_args()
+    global VOLUME, CHUNK
+    if args.volume:
+        VOLUME = tuple(args.volume)
+    if args.chunk:
+        CHUNK = tuple(args.chunk)
     if args.impl == "reference":
         return run_reference(args, real_stdout)
     args.warmup = max(args.warmup, 3)
 
     import torch
     import torch.distributed as dist
-    from oracle import oracle as orc          # synthetic-input generator + cpu_baseline leg only
+    from oracle import oracle as orc          # checker + cpu_baseline leg only
     import synaptor_b200 as syn
     from synaptor_b200 import _cabi as C
     from synaptor_b200 import _device as D
+    from synaptor_b200 import multi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -231,193 +471,357 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = "off" if args.no_numa else numa_bind(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    shape = tuple(args.chunk)
-    nvox = int(np.prod(shape))
-    # ---- synthetic inputs (pinned host copies for the e2e leg, device copies for the resident leg) ----
-    pred_np = orc.synth_pred(shape, seed=rank, sigma=2.0, fg=0.03)
-    base_np = orc.synth_base(shape, seed=1000 + rank)
-    pred_pin = torch.from_numpy(pred_np).pin_memory()
-    base_pin = torch.from_numpy(base_np.view(np.int64)).pin_memory()
-    del pred_np, base_np
-    pred = pred_pin.to(dev)
-    base = base_pin.to(dev)
-    t32 = np.float32(THRESH)
     L = C.lib()
-    grid = (world, 1, 1)
-    offset = (rank * shape[0], 0, 0)
-
-    merge_out = [None]
-    if world > 1:
-        from synaptor_b200 import multi
-
-    def step(out=None):
-        res = D.chunk_ccs_device(pred, t32, DUST, connectivity=CONN, base=base, offset=offset, sync=False, out=out)
-        return res
+    peak, peak_src = peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The timed steps replay ONE captured CUDA graph of the syn_chunk_ccs call (D.ChunkPipeline: stream capture of
-    # the same C-ABI call on the resident input tensors; 13 kernels + 1 memset per replay) -- what a production loop
-    # over equally shaped chunks does.  --no-graph times the plain call instead.
-    pipe = None if args.no_graph else D.ChunkPipeline(shape, DUST, thresh=THRESH, connectivity=CONN, offset=offset,
-                                                      device=dev, pred=pred, base=base)
-    # first call sizes the buffers (sync=True grows capacities if needed)
-    res = D.chunk_ccs_device(pred, t32, DUST, connectivity=CONN, base=base, offset=offset, sync=True)
-    counts = dict(res.counts)
-    run_stream = pipe.stream if pipe is not None else torch.cuda.current_stream()
-    if pipe is not None:
-        pipe.run()
-        assert pipe.counts()["kept"] == counts["kept"]
+    if args.config != "c4":
+        if world > 1:
+            raise SystemExit("--config c2 / c3 are single-GPU measurements")
+        sampler = ClockSampler(local)
+        sampler.start()
+        sampler.wait_first_sample()
+        r = bench_chunk_config(torch, dev, args.config, args, not args.no_check)
+        clocks = sampler.stop()
+        shape = CONFIGS[args.config][0]
+        nvox = int(np.prod(shape))
+        sk = float(r["stage_ms"]["stream"])
+        ach = BYTES_PER_VOXEL * nvox / (sk * 1e-3) / 1e9
+        traffic, tsrc = stream_traffic(shape)
+        line = {"metric": METRIC, "value": r["gvoxel_s"], "unit": "Gvoxel/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32->u32/u64", "data": "synthetic",
+                "config": {"workload": r["workload"], "cuda_graph": True,
+                           "l2": "inputs (1.6 GB/step) exceed the 126 MB L2; no flush needed", **{
+                               k: r[k] for k in ("components", "kept", "pairs", "runs")},
+                           "parity": r.get("parity")},
+                "roofline": {"bound": "hbm", "kernel": "k_stream<base,scan,tma>", "achieved": ach, "peak": peak,
+                             "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": tsrc,
+                             "peak_source": peak_src, "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL, "kernel_ms": sk,
+                             "pipeline": {"bytes_per_voxel": BYTES_PER_VOXEL, "achieved": r["pipeline_gb_s"],
+                                          "frac": r["pipeline_frac_of_measured_peak"],
+                                          "frac_of_8TBs_nominal": r["pipeline_frac_of_8TBs_nominal"]},
+                             "stage_ms": r["stage_ms"]},
+                "clocks": clocks, "gpu_launches": r["launches_per_step"] * args.steps}
+        emit(line, real_stdout)
+        return 0
 
-    def timed_step():
-        if pipe is not None:
-            pipe.graph.replay()
-        else:
-            step(res)
+    # ---------------------------------------------------------------------------------------------
+    # the north-star job
+    # ---------------------------------------------------------------------------------------------
+    job = multi.VolumeJob(VOLUME, CHUNK, THRESH, DUST, SIZE_THR, connectivity=CONN, with_base=True, rank=rank,
+                          world=world, device=dev, graph=not args.no_graph)
+    nvox_total = int(np.prod(VOLUME))
+    inputs = []
+    t_gen = time.time()
+    for li, ci in enumerate(job.mine):
+        beg, shp = job.chunk_rel_begin[ci], job.chunk_shape[ci]
+        p = gen_pred_chunk(torch, dev, VOLUME, beg, shp, seed=0, sigma=2.0, fg=0.03)
+        b = gen_base_chunk(torch, dev, VOLUME, beg, shp, seed=1)
+        inputs.append((p, b))
+        job.set_inputs(li, p, b)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    for _ in range(4):
+        job.run()
+        if job.check():
+            break
+    else:
+        raise SystemExit("capacities never settled")
+    info0 = job.info_dict()
+    counts0 = [job.counts(li) for li in range(len(job.mine))]
 
     sampler = ClockSampler(local)
     sampler.start()
     sampler.wait_first_sample()
-    with torch.cuda.stream(run_stream):
+    with torch.cuda.stream(job.stream):
         for _ in range(2 * args.warmup):        # load already running when the timed steps start (clock samples)
-            timed_step()
-        launches0 = L.syn_launch_count()
+            job.run()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for _ in range(args.steps):
-            timed_step()
+            job.run()
         e1.record()
         barrier()
-    launches = (args.steps * pipe.launches_per_run) if pipe is not None else (L.syn_launch_count() - launches0)
     ms_total = e0.elapsed_time(e1)
-    after = pipe.counts() if pipe is not None else D.read_counts(res)
-    assert after["errflags"] == 0 and after["kept"] == counts["kept"] and after["pairs"] == counts["pairs"], after
-    # ---- cross-chunk merge_ccs exchange (config 4), timed on its own: NCCL all_gathers of counts, faces and
-    # tables + device union-find + LUT remap of every rank's label volume.  Not part of the headline metric
-    # (chunk_ccs + chunk_overlaps shard with no data-path collective).
-    n_merged, merge_ms = None, None
-    if world > 1:
-        times = []
-        for _ in range(max(3, min(args.steps, 5))):
-            res = step(res)
-            res.counts = {}
-            barrier()
-            t0 = time.perf_counter()
-            merge_out[0] = multi.merge_ccs_device(res, grid, rank=rank, world=world, size_thr=DUST)
-            barrier()
-            times.append((time.perf_counter() - t0) * 1e3)
-        n_merged = merge_out[0].n_merged
-        merge_ms = float(np.median(times))
+    if not job.check():
+        raise SystemExit("a capacity overflowed inside the timed steps")
+    launches = job.launches_per_step * args.steps
 
-    # ---- event-instrumented passes: one CUDA event after every kernel of syn_chunk_ccs ----------------
-    def profiled(mode):
-        C.check(L.syn_profile_enable(mode))
-        acc = {}
+    # ---- merge breakdown: events around the exchange and the merge kernels (plain launches, K steps) ----
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    brk = {"chunk_begin": 0.0, "gather": 0.0, "merge": 0.0, "chunk_finish": 0.0}
+    with torch.cuda.stream(job.stream):
         for _ in range(args.steps):
-            D.chunk_ccs_device(pred, t32, DUST, connectivity=CONN, base=base, offset=offset, sync=False, out=res)
+            a, b, c, d, e = ev(), ev(), ev(), ev(), ev()
+            barrier()
+            a.record(); job._stage_a(); b.record(); job._gather(); c.record(); job._merge(); d.record()
+            for li in range(len(job.mine)):
+                job._finish(li)
+            e.record()
+            torch.cuda.synchronize()
+            for (k, (x, y)) in zip(brk, ((a, b), (b, c), (c, d), (d, e))):
+                brk[k] += x.elapsed_time(y) / args.steps
+    # ---- per-kernel times of ONE chunk (own chunk 0): begin + finish with an event after every kernel ----
+    C.check(L.syn_profile_enable(1))
+    stage_ms = {}
+    with torch.cuda.stream(job.stream):
+        for _ in range(args.steps):
+            job._begin(0)
+            job._finish(0)
             for (k, v) in C.profile_read().items():
-                acc[k] = acc.get(k, 0.0) + v / args.steps
-        C.check(L.syn_profile_enable(0))
-        return acc
-    stage_ms = profiled(1)
-    for _ in range(50):                     # ~35 ms more of the same step under the sampler (20 ms sampling period)
-        res = step(res)
+                stage_ms[k] = stage_ms.get(k, 0.0) + v / args.steps
+    C.check(L.syn_profile_enable(0))
+    with torch.cuda.stream(job.stream):
+        for _ in range(30):                     # more of the same under the sampler (20 ms sampling period)
+            job.run()
     torch.cuda.synchronize()
     clocks = sampler.stop()
 
-    # ---- e2e through the public API with pinned host buffers ---------------------------------------
+    # ---- parity of the measured job against the oracle (once, outside the timed region) ----------------
+    parity = None
+    if not args.no_check:
+        parity = check_job(torch, dist, orc, job, inputs, rank, world, dev)
+
+    # ---- e2e through the public API with host chunk arrays -----------------------------------------
     e2e = None
     if not args.no_e2e:
-        pn, bn = pred_pin.numpy(), base_pin.numpy().view(np.uint64)
-        # one public call per chunk: pinned host arrays in (H2D inside), numpy / DataFrame / COO out (D2H + host
-        # materialisation inside).  Warm-up in the steady-state pattern of the timed loop (the previous result is
-        # still referenced while the next one is produced, so two pinned output blocks circulate).
-        n_e2e = max(3, min(args.steps, 6))
-        for _ in range(3):
-            ccs, conts, info, mat = syn.proc.tasks.cc_overlap_task(pn, bn, THRESH, DUST, offset=offset)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            ccs, conts, info, mat = syn.proc.tasks.cc_overlap_task(pn, bn, THRESH, DUST, offset=offset)
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / n_e2e
-        assert len(info) == counts["kept"] and mat.nnz == counts["pairs"]
-        # the same chunks through the generator form of the call (cc_overlap_tasks: the next chunk's input copies
-        # are queued before the previous chunk is finished, so the PCIe link carries inputs back to back);
-        # reported next to the per-call figure, which stays the headline e2e value
-        for out in syn.proc.tasks.cc_overlap_tasks(((pn, bn, offset) for _ in range(3)), THRESH, DUST):
-            ccs, conts, info, mat = out
-        barrier()
-        t0 = time.perf_counter()
-        for out in syn.proc.tasks.cc_overlap_tasks(((pn, bn, offset) for _ in range(n_e2e)), THRESH, DUST):
-            ccs, conts, info, mat = out
-        torch.cuda.synchronize()
-        e2e_piped_s = (time.perf_counter() - t0) / n_e2e
-        assert len(info) == counts["kept"] and mat.nnz == counts["pairs"]
-        h2d = pred_pin.numel() * 4 + base_pin.numel() * 8
-        d2h = ccs.nbytes + len(info) * 11 * 8 + mat.nnz * 20 + sum(
-            2 * (shape[(a + 1) % 3] * shape[(a + 2) % 3]) * 4 for a in range(3))
-        e2e = {"seconds": e2e_s, "h2d": h2d, "d2h": d2h, "n": n_e2e, "piped_seconds": e2e_piped_s}
+        e2e = e2e_leg(torch, dist, syn, job, inputs, rank, world, dev, args, barrier, info0)
 
     # ---- reduce over ranks --------------------------------------------------------------------------
-    ms_max = ms_total
-    e2e_s_max = e2e["seconds"] if e2e else 0.0
+    vals = [ms_total, e2e["seconds"] if e2e else 0.0, e2e["floor_s"] if e2e else 0.0,
+            brk["chunk_begin"], brk["gather"], brk["merge"], brk["chunk_finish"]]
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s_max], dtype=torch.float64, device=dev)
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max, e2e_s_max = float(t[0]), float(t[1])
+        vals = [float(x) for x in t]
+    ms_max, e2e_s_max, floor_s_max = vals[0], vals[1], vals[2]
+    brk_max = dict(zip(brk, vals[3:]))
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        del inputs
+        job = None
+        torch.cuda.empty_cache()
+        for name in ("c2", "c3"):
+            extra[name] = bench_chunk_config(torch, dev, name, args, not args.no_check)
 
     if rank == 0:
-        peak, peak_src = peaks()
         ms_step = ms_max / args.steps
-        value = world * nvox / (ms_step * 1e-3) / 1e9
-        wl_ms = float(stage_ms['stream'])
-        achieved = BYTES_PER_VOXEL_STREAM_KERNEL * nvox / (wl_ms * 1e-3) / 1e9
-        pipe_gbs = BYTES_PER_VOXEL_PIPELINE * nvox / (ms_step * 1e-3) / 1e9
+        value = nvox_total / (ms_step * 1e-3) / 1e9
+        chunk_vox = int(np.prod(CHUNK))
+        sk = float(stage_ms["stream"])
+        ach = BYTES_PER_VOXEL * chunk_vox / (sk * 1e-3) / 1e9
+        traffic, tsrc = stream_traffic(CHUNK)
+        per_gpu_gbs = BYTES_PER_VOXEL * nvox_total / world / (ms_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32->u32/u64", "data": "synthetic",
-            "config": {"workload": workload_name(shape),
-                       "chunks_per_gpu": 1, "grid": list(grid), "merge_ccs_in_step": False,
-                       "cuda_graph": pipe is not None,
-                       "merge_ccs_ms_separate": merge_ms,
-                       "l2": "inputs (1.6 GB/step) exceed the 126 MB L2; no flush needed",
-                       "components": counts["components"], "kept": counts["kept"], "pairs": counts["pairs"],
-                       "runs": counts["runs"], "fg_voxels": counts["fg_voxels"], "merged_segments": n_merged},
-            "roofline": {"bound": "hbm", "kernel": "k_stream<base,scan,tma> (pred + base read [base by TMA bulk copies], threshold, label zero-fill, run prefix)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": STREAM_TRAFFIC_512 if shape == (512, 512, 512) else None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL_STREAM_KERNEL, "kernel_ms": wl_ms,
-                         "pipeline": {"bytes_per_voxel": BYTES_PER_VOXEL_PIPELINE, "achieved": pipe_gbs,
-                                      "frac": pipe_gbs / peak, "frac_of_8TBs_nominal": pipe_gbs / 8000.0},
+            "config": {"workload": WORKLOAD_C4, "volume": list(VOLUME), "chunk": list(CHUNK), "grid": list(job_grid()),
+                       "chunks_per_gpu": -(-int(np.prod(job_grid())) // world),
+                       "merge_ccs_in_step": True, "remap_in_step": True, "cuda_graph": not args.no_graph,
+                       "generator": "position-hash white noise -> separable Gaussian (sigma 2, wrap) -> logistic "
+                                    "around the 97 % quantile, on the GPU (bench.gen_pred_chunk); base: hashed 40-bit "
+                                    "ids on 32^3 blocks, 5 % zeros",
+                       "input_generation_s": round(t_gen, 2), "numa": numa,
+                       "l2": "every chunk's inputs (1.6 GB) exceed the 126 MB L2; no flush needed",
+                       "merge_breakdown_ms": {k: round(v, 4) for (k, v) in brk_max.items()},
+                       "merge_breakdown_note": "plain launches with CUDA events around the stages, max over ranks: "
+                                               "chunk_begin (all owned chunks) / gather (all_gather of the packed "
+                                               "slots) / merge (7 kernels) / chunk_finish (all owned chunks)",
+                       "total_ids": info0["total_ids"], "merged_segments": info0["n_merged"],
+                       "face_edges": info0["n_edges"],
+                       "slot_bytes": job_slot_bytes[0], "rank0_chunk_counts": {
+                           k: counts0[0][k] for k in ("runs", "components", "kept", "pairs", "fg_voxels")},
+                       "parity": parity},
+            "roofline": {"bound": "hbm", "kernel": "k_stream<base,scan,tma> (pred + base read [base by TMA bulk copies], "
+                                                   "threshold, label zero-fill, run prefix); one launch per chunk",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                         "traffic_source": tsrc, "peak_source": peak_src,
+                         "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL, "kernel_ms": sk,
+                         "pipeline": {"bytes_per_voxel": BYTES_PER_VOXEL, "achieved_per_gpu": per_gpu_gbs,
+                                      "frac": per_gpu_gbs / peak, "frac_of_8TBs_nominal": per_gpu_gbs / 8000.0,
+                                      "note": "whole step incl. merge, per GPU"},
                          "stage_ms": {n: round(float(v), 5) for (n, v) in stage_ms.items()}},
             "clocks": clocks,
             "gpu_launches": int(launches),
         }
+        if extra:
+            line["config"]["other_configs"] = extra
         if e2e:
-            line["e2e"] = {"value": world * nvox / e2e_s_max / 1e9, "unit": "Gvoxel/s",
+            line["e2e"] = {"value": nvox_total / e2e_s_max / 1e9, "unit": "Gvoxel/s",
                            "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
-                           "ms_per_step": e2e_s_max * 1e3, "chunks": int(e2e["n"]),
-                           "ms_per_step_generator_call_rank0": e2e["piped_seconds"] * 1e3,
-                           "api": "synaptor_b200.proc.tasks.cc_overlap_task (one call per chunk; pinned host arrays in, "
-                                  "numpy / DataFrame / COO out)"}
+                           "ms_per_step": e2e_s_max * 1e3, "steps": int(e2e["n"]),
+                           "h2d_floor_ms": floor_s_max * 1e3,
+                           "frac_of_h2d_floor": floor_s_max / e2e_s_max if e2e_s_max else None,
+                           "h2d_floor_note": "bare pinned->device copy of this rank's input bytes, all ranks at once, "
+                                             "max over ranks",
+                           "pageable_ms_per_step": e2e.get("pageable_ms"),
+                           "bytes_note": "per rank (every rank copies its own chunks)",
+                           "api": "synaptor_b200.proc.tasks.volume_tasks (host chunk arrays in; final uint32 label "
+                                  "chunks, merged DataFrame, chunk id maps, overlap COO matrices out)"}
         if not args.no_cpu_baseline and world == 1:
-            gv, cores, wall, kind, sample, _ = cpu_baseline()
-            line["cpu_baseline"] = {"value": gv, "unit": "Gvoxel/s", "cores": cores, "kind": kind, "sample": sample,
-                                    "seconds": wall}
+            r = cpu_job(steps=1, warmup=0, chunk=CHUNK, grid=job_grid())
+            line["cpu_baseline"] = {"value": r["value"], "unit": "Gvoxel/s", "cores": r["cores"], "kind": r["kind"],
+                                    "sample": r["sample"], "seconds": r["seconds"]}
         emit(line, real_stdout)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+job_slot_bytes = [None]
+
+
+def job_grid():
+    return tuple(-(-v // c) for (v, c) in zip(VOLUME, CHUNK))
+
+
+def check_job(torch, dist, orc, job, inputs, rank, world, dev):
+    """Gathers inputs and results of all ranks on rank 0 and compares with the oracle workflow (bit-exact) and with
+    whole-volume labelling (1:1 on the survivors)."""
+    job_slot_bytes[0] = job.slot_bytes
+    t0 = time.time()
+    merged_local = job.merged_table()
+    mine = {}
+    for li, ci in enumerate(job.mine):
+        r, c, v, shp = job.overlaps(li)
+        mine[ci] = (inputs[li][0], inputs[li][1], job.labels[li], (r, c, v, shp))
+    vol = base = final = None
+    overlaps = {}
+    if rank == 0:
+        vol = np.empty(VOLUME, dtype=np.float32)
+        base = np.empty(VOLUME, dtype=np.uint64)
+        final = np.empty(VOLUME, dtype=np.uint32)
+    for ci in range(job.nchunks):
+        owner = job.owners[ci]
+        beg, shp = job.chunk_rel_begin[ci], job.chunk_shape[ci]
+        sl = tuple(slice(b, b + s) for (b, s) in zip(beg, shp))
+        if owner == 0:
+            if rank == 0:
+                p, b, lab, ov = mine[ci]
+        elif rank == owner:
+            p, b, lab, ov = mine[ci]
+            dist.send(p, 0); dist.send(b, 0); dist.send(lab, 0)
+            meta = torch.tensor([len(ov[0]), ov[3][0], ov[3][1]], dtype=torch.int64, device=dev)
+            dist.send(meta, 0)
+            if len(ov[0]):
+                dist.send(torch.from_numpy(np.stack([ov[0].astype(np.int64), ov[1].view(np.int64), ov[2]])).to(dev), 0)
+        elif rank == 0:
+            p = torch.empty(shp, dtype=torch.float32, device=dev)
+            b = torch.empty(shp, dtype=torch.int64, device=dev)
+            lab = torch.empty(shp, dtype=torch.int32, device=dev)
+            dist.recv(p, owner); dist.recv(b, owner); dist.recv(lab, owner)
+            meta = torch.empty(3, dtype=torch.int64, device=dev)
+            dist.recv(meta, owner)
+            n, s0, s1 = (int(x) for x in meta.cpu())
+            if n:
+                t = torch.empty((3, n), dtype=torch.int64, device=dev)
+                dist.recv(t, owner)
+                t = t.cpu().numpy()
+                ov = (t[0], t[1].view(np.uint64), t[2], (s0, s1))
+            else:
+                ov = (np.zeros(0, np.int64), np.zeros(0, np.uint64), np.zeros(0, np.int64), (s0, s1))
+        if rank == 0:
+            vol[sl] = p.cpu().numpy()
+            base[sl] = b.cpu().numpy().view(np.uint64)
+            final[sl] = lab.cpu().numpy().view(np.uint32)
+            overlaps[ci] = ov
+    if rank != 0:
+        return None
+    t_gather = time.time() - t0
+    t0 = time.time()
+    want = orc.volume_job(vol, base, CHUNK, THRESH, DUST, SIZE_THR)
+    ok_final = bool(np.array_equal(final, want["final"]))
+    got_m = {int(r[0]): r[1:].tolist() for r in merged_local}
+    ok_merged = got_m == {int(k): [int(x) for x in v] for (k, v) in want["merged"].items()}
+    ok_maps = all(job.chunk_id_map(ci) == {int(k): int(v) for (k, v) in want["id_maps"][want["chunks"][ci][0]].items()}
+                  for ci in range(job.nchunks))
+    ok_ov = True
+    for ci in range(job.nchunks):
+        r, c, v, shp = overlaps[ci]
+        wr, wc, wv, wshp = want["overlaps"][ci]
+        ok_ov = ok_ov and tuple(shp) == tuple(wshp) and np.array_equal(r, wr) and np.array_equal(c, wc) and \
+            np.array_equal(v, wv)
+    t_oracle = time.time() - t0
+    t0 = time.time()
+    whole = orc.label_c(vol > np.float32(THRESH), 6)[0]
+    fg = final != 0
+    a, b = final[fg].astype(np.int64), whole[fg].astype(np.int64)
+    pairs = np.unique(a * (int(whole.max()) + 1) + b)
+    one_to_one = len(np.unique(pairs // (int(whole.max()) + 1))) == len(pairs) == len(np.unique(pairs % (int(whole.max()) + 1)))
+    sizes = np.bincount(whole.ravel())
+    survivors = np.nonzero(sizes >= SIZE_THR)[0]
+    survivors = survivors[survivors != 0]
+    all_kept = bool(np.array_equal(np.unique(b), survivors))
+    return {"bit_exact_vs_oracle": bool(ok_final and ok_merged and ok_maps and ok_ov),
+            "final_volume": ok_final, "merged_table_incl_centroids": bool(ok_merged), "chunk_id_maps": bool(ok_maps),
+            "overlap_triples_order_shape": bool(ok_ov),
+            "one_to_one_with_whole_volume_labelling": bool(one_to_one),
+            "survivors_are_exactly_components_of_size_ge_thr": all_kept,
+            "what": "oracle.volume_job (cc_task_c per chunk -> merge_ccs_task -> remap_ids -> count_overlaps_c) and "
+                    "oracle.label_c on the whole 2048x2048x256 volume, same inputs, n_gpus as measured",
+            "merged_segments": len(want["merged"]),
+            "seconds": {"gather": round(t_gather, 1), "oracle": round(t_oracle, 1), "whole_volume": round(time.time() - t0, 1)}}
+
+
+def e2e_leg(torch, dist, syn, job, inputs, rank, world, dev, args, barrier, info0):
+    """The job through the public host-array API; plus the bare copy floor of the same input bytes."""
+    preds = [p.cpu().pin_memory().numpy() for (p, _) in inputs]
+    bases = [b.cpu().pin_memory().numpy().view(np.uint64) for (_, b) in inputs]
+    begs = [job.chunk_rel_begin[ci] for ci in job.mine]
+    kw = dict(vol_shape=VOLUME, chunk_shape=CHUNK, cc_thresh=THRESH, sz_thresh=DUST, size_thr=SIZE_THR,
+              rank=rank, world=world)
+    n = max(2, min(args.steps, 4))
+    out = None
+    for _ in range(2):
+        out = syn.proc.tasks.volume_tasks(preds, bases, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        out = syn.proc.tasks.volume_tasks(preds, bases, **kw)
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / n
+    assert len(out.merged_info) == info0["n_merged"], (len(out.merged_info), info0["n_merged"])
+    h2d = sum(p.nbytes for p in preds) + sum(b.nbytes for b in bases)
+    d2h = sum(c.nbytes for c in out.ccs) + out.d2h_small_bytes
+    # pageable (non-pinned) inputs, as a caller without pinned memory delivers them
+    pageable_ms = None
+    if rank == 0 or world > 1:
+        pp = [np.array(p, copy=True) for p in preds]
+        bb = [np.array(b, copy=True) for b in bases]
+        syn.proc.tasks.volume_tasks(pp, bb, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        syn.proc.tasks.volume_tasks(pp, bb, **kw)
+        torch.cuda.synchronize()
+        pageable_ms = (time.perf_counter() - t0) * 1e3
+        del pp, bb
+    # floor: the same input bytes, pinned -> device, nothing else, all ranks at once
+    tp = [torch.from_numpy(p) for p in preds]
+    tb = [torch.from_numpy(b.view(np.int64)) for b in bases]
+    dp = [torch.empty_like(t, device=dev) for t in tp]
+    db = [torch.empty_like(t, device=dev) for t in tb]
+    floor = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for (s, d) in zip(tp + tb, dp + db):
+            d.copy_(s, non_blocking=True)
+        torch.cuda.synchronize()
+        floor.append(time.perf_counter() - t0)
+    return {"seconds": sec, "h2d": h2d, "d2h": d2h, "n": n, "floor_s": min(floor), "pageable_ms": pageable_ms}
 
 
 if __name__ == "__main__":

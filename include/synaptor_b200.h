@@ -137,6 +137,14 @@ SYN_API int syn_extract_faces(const uint32_t *labels, int64_t nx, int64_t ny, in
                       uint32_t *faces_out, void *stream);
 
 /*
+ * syn_transpose_zyx -- the np.ascontiguousarray of proc/seg/conncomps.py:21 for the F-ordered [x,y,z] chunk that
+ * CloudVolume hands the tasks (io/backends/cloudvolume.py:6-20), on the device: src_zyx holds the array's bytes as
+ * they are (= C-contiguous [nz][ny][nx]), dst_xyz receives C-contiguous [nx][ny][nz].  elem_bytes 4 or 8.
+ */
+SYN_API int syn_transpose_zyx(const void *src_zyx, void *dst_xyz, int64_t nx, int64_t ny, int64_t nz, int elem_bytes,
+                              void *stream);
+
+/*
  * syn_relabel_lut -- seg_utils.relabel_data (seg_utils/relabel.py:7-27 ->
  * _relabel.cpp:19-38) with the dict given as a dense table: values v < lut_len
  * become lut[v] (identity entries for non-keys), others stay.  In place.

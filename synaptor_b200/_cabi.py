@@ -41,6 +41,7 @@ SIGNATURES = {
     "syn_overlap_workspace_bytes": (_i64, [_i64] * 4),
     "syn_count_overlaps": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "syn_extract_faces": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "syn_transpose_zyx": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "syn_relabel_lut": (_i32, [_vp, _i64, _vp, _i64, _vp]),
     "syn_segment_stats": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "syn_max_u32": (_i32, [_vp, _i64, _vp, _vp]),

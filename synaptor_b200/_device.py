@@ -148,9 +148,10 @@ def to_device_f32(torch, d, device):
         raise ValueError(f"expected a 3-D volume, got shape {d.shape}")
     if d.dtype != np.float32:
         float32_threshold(d.dtype, 0)  # raises for inexact dtypes
-        d = d.astype(np.float32)
-    d = np.ascontiguousarray(d)  # conncomps.py:21 (F-order chunks from CloudVolume)
-    return torch.from_numpy(d).to(device, non_blocking=True)
+    # conncomps.py:21 makes the (F-ordered, CloudVolume) chunk C-contiguous on the host; here the bytes go to the
+    # device as they are and the transpose runs there
+    out = torch.empty(tuple(int(s) for s in d.shape), dtype=torch.float32, device=device)
+    return upload_f32(torch, out, d)
 
 
 def to_device_u64(torch, a, device):
@@ -161,8 +162,11 @@ def to_device_u64(torch, a, device):
     a = np.asarray(a)
     if a.dtype.kind not in "iu":
         raise TypeError(f"base segmentation must be an integer array, got {a.dtype}")
-    a = np.ascontiguousarray(a, dtype=np.uint64)
-    return torch.from_numpy(a.view(np.int64)).to(device, non_blocking=True)
+    if a.ndim != 3:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        return torch.from_numpy(a.view(np.int64)).to(device, non_blocking=True)
+    out = torch.empty(tuple(int(s) for s in a.shape), dtype=torch.int64, device=device)
+    return upload_u64(torch, out, a)
 
 
 def to_device_u32(torch, a, device):
@@ -177,6 +181,72 @@ def to_device_u32(torch, a, device):
         a = a.astype(np.uint32)  # pybind forcecast semantics of the reference's uint32 overloads
     a = np.ascontiguousarray(a)
     return torch.from_numpy(a.view(np.int32)).to(device, non_blocking=True)
+
+
+def _host_tensor(torch, a, np_dtype, torch_view=None):
+    """numpy array -> (CPU tensor sharing its memory, f_order flag).  C-contiguous arrays are used as they are;
+    F-contiguous ones (what CloudVolume hands the reference's tasks, io/backends/cloudvolume.py:6-20) are taken
+    as their transposed C-contiguous view [Z, Y, X] -- the bytes are copied unchanged and the transpose happens
+    on the device; anything else is made C-contiguous on the host (conncomps.py:21)."""
+    a = np.asarray(a)
+    if a.dtype != np_dtype:
+        a = a.astype(np_dtype)
+    f_order = False
+    if not a.flags.c_contiguous:
+        if a.ndim == 3 and a.flags.f_contiguous:
+            a, f_order = a.T, True
+        else:
+            a = np.ascontiguousarray(a)
+    if torch_view is not None:
+        a = a.view(torch_view)
+    return torch.from_numpy(a), f_order
+
+
+def _transpose_into(torch, dst, src_zyx):
+    """dst [X,Y,Z] <- src [Z,Y,X] on the device (syn_transpose_zyx: tiled through shared memory)."""
+    nx, ny, nz = (int(s) for s in dst.shape)
+    with torch.cuda.device(dst.device):
+        C.check(C.lib().syn_transpose_zyx(src_zyx.data_ptr(), dst.data_ptr(), nx, ny, nz, int(dst.element_size()),
+                                          _stream_ptr(torch)))
+    return dst
+
+
+def upload_f32(torch, dst, src):
+    """Copies a host prediction chunk (numpy, any order / pinned or pageable; or a tensor) into the resident
+    float32 cuda tensor `dst` on the current stream."""
+    if isinstance(src, torch.Tensor):
+        dst.copy_(src, non_blocking=True)
+        return dst
+    if np.asarray(src).dtype != np.float32:
+        float32_threshold(np.asarray(src).dtype, 0)          # raises for inexact dtypes
+    t, f_order = _host_tensor(torch, src, np.float32)
+    if tuple(t.shape) != (tuple(dst.shape)[::-1] if f_order else tuple(dst.shape)):
+        raise ValueError(f"chunk shape {tuple(np.asarray(src).shape)} != {tuple(dst.shape)}")
+    if not f_order:
+        dst.copy_(t, non_blocking=True)
+        return dst
+    stage = torch.empty(t.shape, dtype=dst.dtype, device=dst.device)
+    stage.copy_(t, non_blocking=True)
+    return _transpose_into(torch, dst, stage)
+
+
+def upload_u64(torch, dst, src):
+    """As upload_f32 for uint64 ids into an int64-typed cuda tensor."""
+    if isinstance(src, torch.Tensor):
+        dst.copy_(src.view(torch.int64), non_blocking=True)
+        return dst
+    a = np.asarray(src)
+    if a.dtype.kind not in "iu":
+        raise TypeError(f"base segmentation must be an integer array, got {a.dtype}")
+    t, f_order = _host_tensor(torch, a, np.uint64, np.int64)
+    if tuple(t.shape) != (tuple(dst.shape)[::-1] if f_order else tuple(dst.shape)):
+        raise ValueError(f"chunk shape {tuple(a.shape)} != {tuple(dst.shape)}")
+    if not f_order:
+        dst.copy_(t, non_blocking=True)
+        return dst
+    stage = torch.empty(t.shape, dtype=dst.dtype, device=dst.device)
+    stage.copy_(t, non_blocking=True)
+    return _transpose_into(torch, dst, stage)
 
 
 @dataclass

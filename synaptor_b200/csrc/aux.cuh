@@ -42,6 +42,32 @@ __global__ void __launch_bounds__(256) k_extract_faces(const u32 *__restrict__ l
 }
 
 // ---------------------------------------------------------------------------
+// [Z][Y][X] -> [X][Y][Z]: what np.ascontiguousarray does to the F-ordered chunk CloudVolume hands the reference's
+// tasks (proc/seg/conncomps.py:21, io/backends/cloudvolume.py:6-20), done on the device after the bytes were
+// copied as they are.  32 x 32 tiles of one y-plane through (padded) shared memory: reads coalesced along x,
+// writes coalesced along z.  grid = (ceil(nx/32), ceil(nz/32), ny), block = (32, 8).
+// ---------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) k_transpose_zyx(const T *__restrict__ src, T *__restrict__ dst, i64 nx, i64 ny,
+                                                       i64 nz)
+{
+    __shared__ T tile[32][33];
+    const i64 y = blockIdx.z;
+    const i64 x0 = (i64)blockIdx.x * 32, z0 = (i64)blockIdx.y * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const i64 z = z0 + threadIdx.y + j, x = x0 + threadIdx.x;
+        if (z < nz && x < nx) tile[threadIdx.y + j][threadIdx.x] = src[(z * ny + y) * nx + x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const i64 x = x0 + threadIdx.y + j, z = z0 + threadIdx.x;
+        if (x < nx && z < nz) dst[(x * ny + y) * nz + z] = tile[threadIdx.x][threadIdx.y + j];
+    }
+}
+
+// ---------------------------------------------------------------------------
 // relabel through a dense table (_relabel.cpp:19-38 with the dict as a LUT)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_relabel_lut(u32 *__restrict__ d, i64 n, const u32 *__restrict__ lut,

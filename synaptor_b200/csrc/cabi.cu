@@ -792,6 +792,21 @@ int syn_extract_faces(const uint32_t *labels, int64_t nx, int64_t ny, int64_t nz
     return SYN_OK;
 }
 
+int syn_transpose_zyx(const void *src_zyx, void *dst_xyz, int64_t nx, int64_t ny, int64_t nz, int elem_bytes,
+                      void *stream)
+{
+    if (!src_zyx || !dst_xyz || nx <= 0 || ny <= 0 || nz <= 0) return fail(SYN_ERR_INVALID, "bad arguments");
+    if (elem_bytes != 4 && elem_bytes != 8) return fail(SYN_ERR_INVALID, "element size must be 4 or 8 bytes");
+    if (ny > 65535 || (nz + 31) / 32 > 65535) return fail(SYN_ERR_INVALID, "shape too large for the transpose grid");
+    const dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((nz + 31) / 32), (unsigned)ny), block(32, 8);
+    if (elem_bytes == 4)
+        k_transpose_zyx<u32><<<grid, block, 0, (cudaStream_t)stream>>>((const u32 *)src_zyx, (u32 *)dst_xyz, nx, ny, nz);
+    else
+        k_transpose_zyx<u64><<<grid, block, 0, (cudaStream_t)stream>>>((const u64 *)src_zyx, (u64 *)dst_xyz, nx, ny, nz);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
 int syn_relabel_lut(uint32_t *labels, int64_t n, const uint32_t *lut, int64_t lut_len, void *stream)
 {
     if (!labels || n < 0 || (lut_len > 0 && !lut)) return fail(SYN_ERR_INVALID, "bad arguments");

@@ -634,6 +634,93 @@ class VolumeJob:
         self.prepare()
         return False
 
+    # ---- host arrays in, host results out ------------------------------------------------------------------
+    def run_host(self, preds, bases=None):
+        """
+        One step with HOST inputs (numpy arrays of the own chunks, C- or F-ordered, pinned or pageable): the input
+        copies of the chunks run on a copy-in stream ahead of the chunk passes, the final label chunks come back on
+        a copy-out stream while the remaining chunks are still being written.  Returns (list of uint32 label chunks
+        in final ids (views of pooled pinned blocks), merged table numpy [n, 11], list of own chunk tables, list of
+        {chunk-local id: final id}, list of (rows, cols, vals, shape) overlap triples).
+        """
+        torch, D = self.torch, self.D
+        n_own = len(self.mine)
+        if len(preds) != n_own or (self.with_base and (bases is None or len(bases) != n_own)):
+            raise ValueError(f"rank {self.rank} owns {n_own} chunks")
+        if any(p is None for p in self.pred) or not getattr(self, "_own_inputs", False):
+            for li, ci in enumerate(self.mine):
+                shp = self.chunk_shape[ci]
+                self.pred[li] = torch.empty(shp, dtype=torch.float32, device=self.device)
+                self.base[li] = torch.empty(shp, dtype=torch.int64, device=self.device) if self.with_base else None
+            self._own_inputs = True
+            self.graphs = None
+        s_in = D.side_stream(torch, self.device, "in")
+        s_out = D.side_stream(torch, self.device, "out")
+        if self.cap_rows is None:            # first call: blocking upload + sizing pass
+            for li in range(n_own):
+                D.upload_f32(torch, self.pred[li], preds[li])
+                if self.with_base:
+                    D.upload_u64(torch, self.base[li], bases[li])
+            torch.cuda.synchronize(self.device)
+            g = self.use_graph
+            self.use_graph = False           # the host path launches per chunk as its inputs arrive
+            self.prepare()
+            self.use_graph = g
+        for _attempt in range(4):
+            cur = torch.cuda.current_stream(self.device)
+            s_in.wait_stream(cur)
+            ev_in = []
+            with torch.cuda.stream(s_in):
+                for li in range(n_own):
+                    D.upload_f32(torch, self.pred[li], preds[li])
+                    if self.with_base:
+                        D.upload_u64(torch, self.base[li], bases[li])
+                    e = torch.cuda.Event()
+                    e.record(s_in)
+                    ev_in.append(e)
+            hosts, ev_out = [], []
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                for li in range(n_own):
+                    self.stream.wait_event(ev_in[li])
+                    self._begin(li)
+                self._gather()
+                self._merge()
+                for li in range(n_own):
+                    self._finish(li)
+                    e = torch.cuda.Event()
+                    e.record(self.stream)
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(e)
+                        h = D.pinned_acquire(torch, self.labels[li].shape, self.labels[li].dtype)
+                        h.copy_(self.labels[li], non_blocking=True)
+                        e2 = torch.cuda.Event()
+                        e2.record(s_out)
+                    hosts.append(h)
+                    ev_out.append(e2)
+            if self.check():
+                break
+            for h in hosts:
+                D.pinned_release(h)
+        else:
+            raise self.C.CapacityError(self.C.SYN_ERR_CAPACITY, "capacities never settled", None)
+        merged = self.merged_table()
+        base_ids = self.id_base.cpu().numpy()
+        tables, maps, ovs = [], [], []
+        for li, ci in enumerate(self.mine):
+            t = self.my_slots[li, 128:128 + self.cap_rows * 88].view(torch.int64).view(self.cap_rows, 11)
+            kept = int(base_ids[ci + 1] - base_ids[ci])
+            t = t[:kept].cpu().numpy()
+            fm = self.fmap[int(base_ids[ci]) + 1: int(base_ids[ci]) + 1 + kept].cpu().numpy().view(np.uint32)
+            tables.append(t)
+            maps.append(dict(zip(t[:, 0].tolist(), fm.tolist())))
+            ovs.append(self.overlaps(li) if self.with_base else None)
+        labels = []
+        for (h, e) in zip(hosts, ev_out):
+            e.synchronize()
+            labels.append(D.pinned_numpy(h, np.uint32))
+        return labels, merged, tables, maps, ovs
+
     # ---- results (each synchronises) -------------------------------------------------------------------
     def counts(self, local_index):
         self.stream.synchronize()

@@ -307,3 +307,65 @@ def remap_ids_task(clefts, *id_maps, copy=False):
         id_map = timed("Updating id map: round {i}".format(i=i + 1), merge_misc.update_id_map, id_map, next_map,
                        reused_ids=True)
     return timed("Relabeling data by id map", seg_utils.relabel_data, clefts, id_map, copy=copy)
+
+
+# --------------------------------------------------------------------------------------------------
+# The four task waves of a chunked volume in one call (single box, one process per GPU)
+# --------------------------------------------------------------------------------------------------
+class VolumeResult:
+    """Outputs of volume_tasks for the chunks of THIS rank (np.ndindex order) plus the global merge results."""
+    __slots__ = ("ccs", "merged_info", "chunk_id_maps", "chunk_infos", "overlaps", "chunk_indices", "d2h_small_bytes")
+
+
+_volume_jobs = {}
+
+
+def volume_tasks(desc_chunks, base_chunks, vol_shape, chunk_shape, cc_thresh, sz_thresh, size_thr,
+                 offset=(0, 0, 0), connectivity=6, rank=None, world=None, group=None):
+    """
+    chunk_ccs -> merge_ccs -> remap_ids -> chunk_overlaps of a chunked volume (tasks.py:26-69, 72-122, 314-333,
+    290-297; the reference runs them as four waves of tasks with files in between).  `desc_chunks` / `base_chunks`:
+    the float32 prediction and uint64 base-segmentation arrays of the chunks THIS rank owns (chunk i of the
+    np.ndindex chunk grid lives on rank i % world), host arrays in any memory order (or None for base_chunks).
+    Collective over `group` when world > 1 (torch.distributed, NCCL).
+
+    Returns a VolumeResult:
+      ccs            [uint32 ndarray per own chunk]  final (merged, size-thresholded) global ids, as remap_ids_task
+      merged_info    DataFrame of the merged segments (merge_ccs_task's first output; int64 index, ascending id)
+      chunk_id_maps  [{chunk-local id: final id} per own chunk]   (merge_ccs_task's second output, own entries)
+      chunk_infos    [seg-info DataFrame per own chunk]           (cc_task's third output)
+      overlaps       [scipy COO per own chunk]                    overlap_task on the remapped chunk
+    """
+    from .. import multi
+    torch = D._torch()
+    if world is None:
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+    with_base = base_chunks is not None
+    key = (tuple(vol_shape), tuple(chunk_shape), float(cc_thresh), int(sz_thresh), int(size_thr), tuple(offset),
+           int(connectivity), int(rank), int(world), with_base, torch.cuda.current_device(), id(group))
+    job = _volume_jobs.get(key)
+    if job is None:
+        _volume_jobs.clear()                      # one resident job at a time: its buffers are volume sized
+        t32 = D.float32_threshold(np.float32, cc_thresh)
+        job = multi.VolumeJob(vol_shape, chunk_shape, t32, sz_thresh, size_thr, connectivity=connectivity,
+                              with_base=with_base, rank=rank, world=world, group=group, vol_offset=offset, graph=False)
+        _volume_jobs[key] = job
+    labels, merged, tables, maps, ovs = job.run_host(desc_chunks, base_chunks)
+    out = VolumeResult()
+    out.ccs = labels
+    out.merged_info = seg.misc.seg_info_from_table(merged[:, 0], merged[:, 1:])
+    out.chunk_id_maps = maps
+    out.chunk_infos = [seg.misc.seg_info_from_table(t[:, 0], t[:, 1:]) for t in tables]
+    out.overlaps = None
+    small = merged.nbytes + sum(t.nbytes for t in tables)
+    if with_base:
+        out.overlaps = []
+        for (r, c, v, shp) in ovs:
+            out.overlaps.append(seg_utils.overlap.make_coo(r, c, v, shp[0], shp[1]) if shp != (0, 0)
+                                else seg_utils.overlap.make_coo([], [], [], 0, 0))
+            small += len(r) * 20
+    out.chunk_indices = list(job.mine)
+    out.d2h_small_bytes = int(small)
+    return out

@@ -117,3 +117,44 @@ def test_volume_job_rerun_new_data_grows_capacities():
     assert ok
     want = oracle_volume_job(dense, None, cshape, 0.5, 10, 15)
     compare(job, want, vshape, None)
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_volume_tasks_host_arrays(order):
+    """The public host-array call (proc.tasks.volume_tasks): C- and F-ordered chunk arrays (the F-ordered ones are
+    transposed on the device, conncomps.py:21), results as the reference's task outputs."""
+    import synaptor_b200 as syn
+    vshape, cshape = (48, 40, 64), (24, 20, 32)
+    vol = orc.synth_pred(vshape, seed=17, sigma=2.0, fg=0.10)
+    base_vol = orc.synth_base(vshape, seed=18, block=6, bg=0.1)
+    want = oracle_volume_job(vol, base_vol, cshape, 0.5, 10, 15, vol_offset=(5, 6, 7))
+    conv = np.asfortranarray if order == "F" else np.ascontiguousarray
+    preds = [conv(vol[sl]) for (_, sl, _) in want["chunks"]]
+    bases = [conv(base_vol[sl]) for (_, sl, _) in want["chunks"]]
+    for _ in range(2):          # second call: the cached job, steady state
+        out = syn.proc.tasks.volume_tasks(preds, bases, vshape, cshape, 0.5, 10, 15, offset=(5, 6, 7), rank=0, world=1)
+    for (ci, (gi, sl, beg)) in enumerate(want["chunks"]):
+        assert out.ccs[ci].dtype == np.uint32 and np.array_equal(out.ccs[ci], want["final"][sl])
+        assert out.chunk_id_maps[ci] == {int(k): int(v) for (k, v) in want["id_maps"][gi].items()}
+        info = want["infos"][gi]
+        assert list(out.chunk_infos[ci].columns) == list(info.columns)
+        assert np.array_equal(out.chunk_infos[ci].to_numpy(), info.to_numpy())
+        assert list(out.chunk_infos[ci].index) == list(info.index)
+        wr, wc, wv, wshape = want["overlaps"][ci]
+        m = out.overlaps[ci]
+        assert m.shape == wshape and np.array_equal(m.row, wr) and np.array_equal(m.col, wc) and np.array_equal(m.data, wv)
+    got = {int(i): [int(x) for x in row] for (i, row) in zip(out.merged_info.index, out.merged_info.to_numpy())}
+    assert got == {int(k): [int(x) for x in v] for (k, v) in want["merged"].items()}
+    assert out.merged_info.index.name == "cleft_segid"
+
+
+def test_f_order_single_chunk_tasks():
+    """cc_task / cc_overlap_task with an F-ordered chunk (what CloudVolume delivers) == the C-ordered result."""
+    import synaptor_b200 as syn
+    pred = orc.synth_pred((40, 24, 72), seed=4, sigma=1.5, fg=0.1)
+    base = orc.synth_base(pred.shape, seed=5, block=8)
+    want = orc.cc_task_c(pred, 0.5, 10)
+    got = syn.proc.tasks.cc_overlap_task(np.asfortranarray(pred), np.asfortranarray(base), 0.5, 10)
+    assert np.array_equal(got[0], want[0])
+    r, c, v, shp = orc.count_overlaps_c(want[0], base)
+    assert got[3].shape == shp and np.array_equal(got[3].row, r) and np.array_equal(got[3].col, c)

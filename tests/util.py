@@ -47,33 +47,5 @@ def sorted_triples(r, c, v):
 
 
 def oracle_volume_job(vol, base_vol, cshape, thresh, dust, size_thr, vol_offset=(0, 0, 0)):
-    """
-    The reference workflow on a chunked volume, all on the CPU oracle: cc_task per chunk (ragged last chunks),
-    merge_ccs_task, remap_ids_task, overlap_task on the remapped chunks.
-    Returns dict(grid, chunks=[(grid index, slices, begin)], final (whole remapped volume), merged {id: row},
-    id_maps (object array), chunk_infos, overlaps=[(rows, cols, vals, shape)]).
-    """
     from oracle import oracle as orc
-    grid = tuple(-(-v // c) for (v, c) in zip(vol.shape, cshape))
-    cont_arr = np.empty(grid, dtype=object)
-    info_arr = np.empty(grid, dtype=object)
-    chunks, ccs_all = [], []
-    for gi in np.ndindex(grid):
-        beg = tuple(a * b for (a, b) in zip(gi, cshape))
-        sl = tuple(slice(b, min(b + c, v)) for (b, c, v) in zip(beg, cshape, vol.shape))
-        off = tuple(b + o for (b, o) in zip(beg, vol_offset))
-        ccs, conts, info = orc.cc_task_c(np.ascontiguousarray(vol[sl]), thresh, dust, offset=off)
-        cont_arr[gi], info_arr[gi] = conts, info
-        chunks.append((gi, sl, beg))
-        ccs_all.append(ccs)
-    face = (max(cshape), max(cshape))
-    merged, id_maps = orc.merge_ccs_task(cont_arr, info_arr, size_thr, face)
-    final = np.zeros(vol.shape, dtype=np.uint32)
-    overlaps = []
-    for ((gi, sl, beg), ccs) in zip(chunks, ccs_all):
-        fin = orc.remap_ids(ccs.copy(), id_maps[gi])
-        final[sl] = fin
-        if base_vol is not None:
-            overlaps.append(orc.count_overlaps_c(fin, np.ascontiguousarray(base_vol[sl])))
-    return dict(grid=grid, chunks=chunks, final=final, merged=merged, id_maps=id_maps, infos=info_arr,
-                overlaps=overlaps, chunk_ccs=ccs_all)
+    return orc.volume_job(vol, base_vol, cshape, thresh, dust, size_thr, vol_offset=vol_offset)
