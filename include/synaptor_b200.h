@@ -248,14 +248,16 @@ SYN_API int syn_merge_ccs_grid(const uint32_t *faces_all, const int64_t *tables_
  * A chunk's contribution to the merge is one PACKED SLOT of syn_packed_slot_bytes(cap_rows, cap_entries) bytes:
  *   int64 hdr[16]  : [0] rows of the segment table, [1] face entries, [2..7] first entry of face 0..5
  *                    (Face.all_faces() order, proc/seg/continuation.py:52-59), [8] flags (1 rows overflow,
- *                    2 entries overflow, 4 a capacity error of the chunk pass)
+ *                    2 entries overflow, 4 a capacity error of the chunk pass), [9..14] end of the entries of
+ *                    face 0..5
  *   int64 table[cap_rows][SYN_SEG_NCOLS]   as syn_chunk_ccs' seg_table
  *   uint32 entry[cap_entries][2]           (position inside the face, table row + 1) of every face voxel that
  *                                          belongs to a surviving segment, raster order inside a face -- the
  *                                          content of the reference's Continuation objects (continuation.py:15-35)
  *
  * syn_chunk_ccs_begin  : syn_chunk_ccs up to the segment table; zero-fills the label sectors without foreground,
- *                        fills the packed slot.  No host synchronisation.
+ *                        fills the packed slot.  face_mask: bit f set = face f has a neighbour chunk and its
+ *                        entries are wanted (the others stay empty).  No host synchronisation.
  * syn_merge_ccs_packed : merge_ccs_task (proc/tasks.py:72-122) over the gathered slots of ALL chunks:
  *                        id_base_out[c] = ids before chunk c in np.ndindex order (assign_ids.py:8-42; chunk c's row r
  *                        is global id id_base[c] + r + 1), edges between facing faces (merge_ccs.py:69-128),
@@ -274,8 +276,8 @@ SYN_API int64_t syn_packed_slot_bytes(int64_t cap_rows, int64_t cap_entries);
 SYN_API int syn_chunk_ccs_begin(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity,
                                 int dil_k, int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out,
                                 const uint64_t *base_seg, int64_t max_pairs, void *packed_slot, int64_t cap_rows,
-                                int64_t cap_entries, void *workspace, int64_t workspace_bytes, int64_t max_runs,
-                                void *stream);
+                                int64_t cap_entries, int face_mask, void *workspace, int64_t workspace_bytes,
+                                int64_t max_runs, void *stream);
 SYN_API int syn_chunk_ccs_finish(const float *pred, int64_t nx, int64_t ny, int64_t nz, int connectivity, int dil_k,
                                  uint32_t *labels_out, const uint64_t *base_seg, uint32_t *pair_rows,
                                  uint64_t *pair_cols, int64_t *pair_counts, int64_t max_pairs, int64_t cap_rows,

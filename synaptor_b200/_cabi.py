@@ -55,7 +55,7 @@ SIGNATURES = {
                                   _vp]),
     "syn_packed_slot_bytes": (_i64, [_i64, _i64]),
     "syn_chunk_ccs_begin": (_i32, [_vp, _i64, _i64, _i64, _f32, _i32, _i32, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64,
-                                   _vp, _i64, _i64, _vp]),
+                                   _i32, _vp, _i64, _i64, _vp]),
     "syn_chunk_ccs_finish": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp,
                                     _i64, _vp, _i64, _i64, _vp, _vp]),
     "syn_merge_packed_workspace_bytes": (_i64, [_i64, _i64, _i64]),

@@ -704,7 +704,8 @@ int64_t syn_packed_slot_bytes(int64_t cap_rows, int64_t cap_entries)
 int syn_chunk_ccs_begin(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity,
                         int dil_k, int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out,
                         const uint64_t *base_seg, int64_t max_pairs, void *packed_slot, int64_t cap_rows,
-                        int64_t cap_entries, void *workspace, int64_t workspace_bytes, int64_t max_runs, void *stream)
+                        int64_t cap_entries, int face_mask, void *workspace, int64_t workspace_bytes, int64_t max_runs,
+                        void *stream)
 {
     if (!packed_slot || cap_rows < 1 || cap_entries < 1) return fail(SYN_ERR_INVALID, "bad packed slot arguments");
     if ((reinterpret_cast<uintptr_t>(packed_slot) & 15) != 0) return fail(SYN_ERR_INVALID, "packed slot must be 16-byte aligned");
@@ -722,9 +723,23 @@ int syn_chunk_ccs_begin(const float *pred, int64_t nx, int64_t ny, int64_t nz, f
     cudaStream_t st = c.st;
     const Geom &g = c.g;
     CK(cudaMemsetAsync(hdr, 0, PK_HDR * 8, st));
-    FaceCtx F{c.W.lmask, c.W.omask, c.R, c.W.par, c.W.rank, c.W.complab, c.W.cnt, g, g.ny * g.nz, g.nx * g.nz, g.nx * g.ny};
+    FaceCtx F{c.W.lmask, c.W.omask, c.R, c.W.par, c.W.rank, c.W.complab, c.W.cnt, g, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
+    const i64 area3[3] = {g.ny * g.nz, g.nx * g.nz, g.nx * g.ny};
+    i64 nface = 0;
+    for (int f = 0; f < 6; ++f) {
+        if (area3[f / 2] >= (1ll << 31)) return fail(SYN_ERR_INVALID, "chunk face too large");
+        F.start[f] = (u32)nface;
+        F.area[f] = ((face_mask >> f) & 1) ? (u32)area3[f / 2] : 0u;
+        nface += F.area[f];
+    }
+    if (nface >= (1ll << 32)) return fail(SYN_ERR_INVALID, "chunk faces too large");
+    F.start[6] = (u32)nface;
     uint2 *entries = reinterpret_cast<uint2 *>(hdr + PK_HDR + cap_rows * SYN_SEG_NCOLS);
-    const i64 nface = 2 * (F.a0 + F.a1 + F.a2);
+    if (nface == 0) {       // no wanted face (a single-chunk grid): only the row count travels
+        k_pack_header_only<<<1, 32, 0, st>>>(hdr, c.W.cnt, cap_rows);
+        CK_LAUNCH();
+        return SYN_OK;
+    }
     rc = launch_scan<8>(c.W, 4, FaceSrc{F}, FaceDst{F, hdr, entries, cap_entries, cap_rows}, nface, &hdr[PK_NENT], st);
     if (rc != SYN_OK) return rc;
     PROF("face_entries");
@@ -1000,7 +1015,7 @@ int64_t syn_merge_packed_workspace_bytes(int64_t nchunks, int64_t cap_rows, int6
     const size_t cap_total = (size_t)nchunks * (size_t)cap_rows;
     if (cap_total >= (1ull << 31)) return SYN_ERR_INVALID;
     return (int64_t)(al((size_t)max_edges * 8) + 2 * al((cap_total + 1) * 4) + al((cap_total + 1) * sizeof(MergeAcc2)) +
-                     al(cap_total * 4));
+                     al(cap_total * 4) + al(((cap_total + 1) / (SCAN_THREADS * 8) + 8) * 8));
 }
 
 int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
@@ -1023,23 +1038,36 @@ int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_
     u32 *par = (u32 *)p; p += al((cap_total + 1) * 4);
     u32 *gmap = (u32 *)p; p += al((cap_total + 1) * 4);
     MergeAcc2 *acc = (MergeAcc2 *)p; p += al((cap_total + 1) * sizeof(MergeAcc2));
-    u32 *members = (u32 *)p;
+    u32 *members = (u32 *)p; p += al(cap_total * 4);
+    // look-back state of the kept-flag scan: [tiles] + ticket (2 u32) + member cursor (u32), zeroed by k_mg_prefix_init
+    const size_t scan_tiles = (cap_total + 1) / (SCAN_THREADS * 8) + 2;
+    u64 *scan_state = (u64 *)p;
+    u32 *scan_ticket = (u32 *)(scan_state + scan_tiles);
+    u32 *member_cursor = scan_ticket + 2;
     const Packed P{(const unsigned char *)slots_all, slot_bytes, cap_rows, cap_entries};
     const int *plan = (const int *)plan_dev;
     i64 *base = (i64 *)id_base_out, *info = (i64 *)info_out;
     const int wide = grid_for((i64)cap_total + 1, 256, 4);
-    k_mg_prefix_init<<<wide, 256, 0, st>>>(P, plan, base, info, par, acc);
+    k_mg_prefix_init<<<wide, 256, 0, st>>>(P, plan, base, info, par, acc, scan_state, (u32)scan_tiles + 2);
     CK_LAUNCH();
     if (npairs > 0) {
-        k_mg_match<<<dim3(16, (unsigned)npairs), 256, 0, st>>>(P, plan, base, edges, max_edges, info);
+        // enough CTAs for about one entry per thread on the largest face (binary searches are dependent loads)
+        const unsigned mx = (unsigned)std::max<i64>(1, std::min<i64>(64, (cap_entries / 3 + 255) / 256));
+        k_mg_match<<<dim3(mx, (unsigned)npairs), 256, 0, st>>>(P, plan, base, edges, max_edges, info);
         CK_LAUNCH();
         k_mg_union<<<grid_for(max_edges, 256, 2), 256, 0, st>>>(edges, max_edges, info, par);
         CK_LAUNCH();
     }
     k_mg_flatacc<<<wide, 256, 0, st>>>(P, plan, base, info, par, gmap, acc);
     CK_LAUNCH();
-    k_mg_scan<<<1, MGS_THREADS, 0, st>>>(acc, size_thr, info);
-    CK_LAUNCH();
+    {
+        const i64 ntiles = ((i64)cap_total + 1 + SCAN_THREADS * 8 - 1) / (SCAN_THREADS * 8);
+        k_scan_1p<MgKeepSrc, MgKeepDst, 8><<<wave_grid(k_scan_1p<MgKeepSrc, MgKeepDst, 8>, SCAN_THREADS, ntiles),
+                                             SCAN_THREADS, 0, st>>>(MgKeepSrc{acc, info, size_thr},
+                                                                    MgKeepDst{acc, member_cursor}, scan_state,
+                                                                    scan_ticket, &info[MG_NMERGED]);
+        CK_LAUNCH();
+    }
     k_mg_fill<<<wide, 256, 0, st>>>(info, gmap, acc, members, fmap_out);
     CK_LAUNCH();
     k_mg_emit<<<wide, 256, 0, st>>>(P, plan, base, info, acc, members, (i64 *)merged_out);

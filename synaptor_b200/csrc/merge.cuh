@@ -10,7 +10,8 @@
 //     enforce_size_threshold                                           size threshold)
 //
 // A chunk's contribution to the exchange is one fixed-size PACKED SLOT:
-//   int64 hdr[16]   : [0] kept rows, [1] face entries, [2..7] first entry of face 0..5, [8] flags
+//   int64 hdr[16]   : [0] kept rows, [1] face entries, [2..7] first entry of face 0..5, [8] flags,
+//                     [9..14] end of the entries of face 0..5
 //   int64 table[cap_rows][11]   the chunk's segment table (written in place by the chunk pipeline)
 //   uint2 entry[cap_entries]    (position in the face, chunk-relative id = table row + 1) of every labelled
 //                               face voxel, faces in Face.all_faces() order, raster order inside a face
@@ -21,7 +22,7 @@
 namespace syn {
 
 constexpr int PK_HDR = 16;              // int64 words
-constexpr int PK_KEPT = 0, PK_NENT = 1, PK_FOFF = 2, PK_FLAGS = 8;
+constexpr int PK_KEPT = 0, PK_NENT = 1, PK_FOFF = 2, PK_FLAGS = 8, PK_FEND = 9;
 constexpr int PK_F_ROWS = 1, PK_F_ENTRIES = 2, PK_F_CCS = 4;
 
 __host__ __device__ __forceinline__ size_t pk_slot_bytes(i64 cap_rows, i64 cap_entries)
@@ -39,54 +40,44 @@ struct FaceCtx {
     const u32 *par, *rank, *complab;
     const Counts *cnt;
     Geom g;
-    i64 a0, a1, a2;     // areas of the faces normal to axis 0, 1, 2
+    u32 area[6];        // voxels of face f (0 when the face is not wanted: it has no neighbour chunk)
+    u32 start[7];       // first item of face f in the scan; start[6] = total
 
-    // face voxel i (all six faces back to back) -> face number, position inside the face, label
-    __device__ __forceinline__ u32 label(i64 i, int *face, u32 *pos) const
+    // item i of the scan -> face number, position inside the face, label (32-bit arithmetic throughout)
+    __device__ __forceinline__ u32 label(u32 i, int *face, u32 *pos) const
     {
-        i64 j = i, x, y, z;
-        const i64 nx = g.nx, ny = g.ny, nz = g.nz;
-        if (j < 2 * a0) {                   // axis 0: hi then lo; in-face coordinates (y, z)
-            const bool hi = j < a0;
-            if (!hi) j -= a0;
-            *face = hi ? 0 : 1;
-            x = hi ? nx - 1 : 0;
+        int f = 0;
+#pragma unroll
+        for (int q = 1; q < 6; ++q) f += (i >= start[q]);
+        const u32 j = i - start[f];
+        const u32 nx = (u32)g.nx, ny = (u32)g.ny, nz = (u32)g.nz;
+        u32 x, y, z;
+        if (f < 2) {                        // axis 0: hi then lo; in-face coordinates (y, z)
+            x = f == 0 ? nx - 1 : 0;
             y = j / nz;
             z = j - y * nz;
-        } else if (j < 2 * a0 + 2 * a1) {   // axis 1: (x, z)
-            j -= 2 * a0;
-            const bool hi = j < a1;
-            if (!hi) j -= a1;
-            *face = hi ? 2 : 3;
-            y = hi ? ny - 1 : 0;
+        } else if (f < 4) {                 // axis 1: (x, z)
+            y = f == 2 ? ny - 1 : 0;
             x = j / nz;
             z = j - x * nz;
         } else {                            // axis 2: (x, y)
-            j -= 2 * a0 + 2 * a1;
-            const bool hi = j < a2;
-            if (!hi) j -= a2;
-            *face = hi ? 4 : 5;
-            z = hi ? nz - 1 : 0;
-            x = j / ny;
-            y = j - x * ny;
+            z = f == 4 ? nz - 1 : 0;
+            if (g.nys < 32) { x = j >> g.nys; y = j & (ny - 1u); }
+            else { x = j / ny; y = j - x * ny; }
         }
-        *pos = (u32)j;
-        const u32 row = (u32)(x * ny + y), k = (u32)(z >> 5), b = (u32)(z & 31);
+        *face = f;
+        *pos = j;
+        const u32 row = x * ny + y, k = z >> 5, b = z & 31u;
         const u32 w = row * g.wz + k;
         if (!((omask[w] >> b) & 1u)) return 0u;
         const u32 run = R.at(w, row, k) + __popc(R.starts(lmask, w, k) & mask_le(b)) - 1u;
         return complab[rank[par[run]]];
     }
-    __device__ __forceinline__ i64 face_start(int f) const
-    {
-        const i64 s[6] = {0, a0, 2 * a0, 2 * a0 + a1, 2 * a0 + 2 * a1, 2 * a0 + 2 * a1 + a2};
-        return s[f];
-    }
 };
 
 struct FaceSrc {
     FaceCtx F;
-    __device__ __forceinline__ u64 n() const { return (u64)(2 * (F.a0 + F.a1 + F.a2)); }
+    __device__ __forceinline__ u64 n() const { return (u64)F.start[6]; }
     template <int N>
     __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
     {
@@ -97,7 +88,7 @@ struct FaceSrc {
             if (!bad && i0 + t < n) {
                 int f;
                 u32 pos;
-                item[t] = F.label((i64)(i0 + t), &f, &pos) != 0;
+                item[t] = F.label((u32)(i0 + t), &f, &pos) != 0;
             }
         }
     }
@@ -121,11 +112,14 @@ struct FaceDst {
         }
 #pragma unroll
         for (int t = 0; t < N; ++t) {
-            const i64 i = (i64)(i0 + t);
-            if (i < (i64)n) {
+            const u32 i = (u32)(i0 + t);
+            if (i0 + t < n) {
+                // entry range of every wanted face that starts / ends here (an unwanted face keeps 0 .. 0)
 #pragma unroll
-                for (int f = 0; f < 6; ++f)
-                    if (i == F.face_start(f)) hdr[PK_FOFF + f] = (i64)ex;
+                for (int f = 0; f < 6; ++f) {
+                    if (F.area[f] && i == F.start[f]) hdr[PK_FOFF + f] = (i64)ex;
+                    if (F.area[f] && i == F.start[f] + F.area[f] - 1u) hdr[PK_FEND + f] = (i64)(ex + item[t]);
+                }
                 if (item[t]) {
                     int f;
                     u32 pos;
@@ -138,6 +132,18 @@ struct FaceDst {
         }
     }
 };
+
+__global__ void k_pack_header_only(i64 *hdr, const Counts *cnt, i64 cap_rows)
+{
+    if (threadIdx.x == 0) {
+        const i64 kept = cnt->v[SYN_CNT_KEPT];
+        hdr[PK_KEPT] = kept;
+        i64 fl = 0;
+        if (cnt->v[SYN_CNT_ERRFLAGS] & (SYN_EF_RUNS | SYN_EF_SEGS)) fl |= PK_F_CCS;
+        if (kept > cap_rows) fl |= PK_F_ROWS;
+        hdr[PK_FLAGS] = fl;
+    }
+}
 
 // ---------------------------------------------------------------------------
 // The merge proper.  `plan` (device int32): [0] nchunks, [1] npairs, slot_of_chunk[nchunks],
@@ -176,8 +182,10 @@ constexpr int MG_TOTAL = 0, MG_NMERGED = 1, MG_NEDGES = 2, MG_FLAGS = 3;
 // the union-find parents and the accumulators of ids 0..total.  Every CTA recomputes the (tiny) prefix.
 __global__ void __launch_bounds__(256) k_mg_prefix_init(Packed P, const int *__restrict__ plan, i64 *__restrict__ base,
                                                         i64 *__restrict__ info, u32 *__restrict__ par,
-                                                        MergeAcc2 *__restrict__ acc)
+                                                        MergeAcc2 *__restrict__ acc, u64 *__restrict__ scan_zero,
+                                                        u32 n_scan_zero)
 {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_scan_zero; i += gridDim.x * blockDim.x) scan_zero[i] = 0;
     __shared__ u32 sm[33];
     const int nchunks = plan[0];
     u32 k[4], v = 0;
@@ -235,8 +243,8 @@ __global__ void __launch_bounds__(256) k_mg_match(Packed P, const int *__restric
     const int cA = pr[0], fA = pr[1], cB = pr[2], fB = pr[3];
     const int sA = plan[2 + cA], sB = plan[2 + cB];
     const i64 *hA = P.hdr(sA), *hB = P.hdr(sB);
-    const i64 oA = hA[PK_FOFF + fA], eA = fA < 5 ? hA[PK_FOFF + fA + 1] : hA[PK_NENT];
-    const i64 oB = hB[PK_FOFF + fB], eB = fB < 5 ? hB[PK_FOFF + fB + 1] : hB[PK_NENT];
+    const i64 oA = hA[PK_FOFF + fA], eA = hA[PK_FEND + fA];
+    const i64 oB = hB[PK_FOFF + fB], eB = hB[PK_FEND + fB];
     const uint2 *A = P.entries(sA) + oA, *B = P.entries(sB) + oB;
     const i64 nA = eA - oA, nB = eB - oB;
     const u32 bA = (u32)base[cA], bB = (u32)base[cB];
@@ -333,44 +341,45 @@ __global__ void __launch_bounds__(256) k_mg_flatacc(Packed P, const int *__restr
     }
 }
 
-// one block: exclusive scans of the fragment counts (member list offsets) and of the kept flags (output rows)
-constexpr int MGS_THREADS = 1024, MGS_ITEMS = 8;
-__global__ void __launch_bounds__(MGS_THREADS) k_mg_scan(MergeAcc2 *acc, i64 size_thr, i64 *__restrict__ info)
-{
-    __shared__ u32 sm[33];
-    if (info[MG_FLAGS] & 1) return;
-    const i64 total = info[MG_TOTAL];
-    u32 carry_c = 0, carry_k = 0;
-    for (i64 b0 = 1; b0 <= total; b0 += MGS_THREADS * MGS_ITEMS) {
-        const i64 i0 = b0 + (i64)threadIdx.x * MGS_ITEMS;
-        u32 c[MGS_ITEMS], k[MGS_ITEMS], vc = 0, vk = 0;
+// output rows: exclusive scan of the kept flags (count > 0 and size >= size_thr) in id order, through the
+// single-pass look-back scan (k_scan_1p); a destination with more than one fragment also claims its stretch of
+// the member array here (a bump allocator: the stretches need not be in id order)
+struct MgKeepSrc {
+    const MergeAcc2 *acc;
+    const i64 *info;
+    i64 size_thr;
+    __device__ __forceinline__ u64 n() const { return (info[MG_FLAGS] & 1) ? 0 : (u64)info[MG_TOTAL] + 1; }
+    template <int N>
+    __device__ __forceinline__ void load(u64 i0, u64 n, u32 (&item)[N]) const
+    {
 #pragma unroll
-        for (int t = 0; t < MGS_ITEMS; ++t) {
-            c[t] = k[t] = 0;
-            if (i0 + t <= total) {
-                c[t] = acc[i0 + t].count;
-                k[t] = (c[t] > 0) && ((i64)acc[i0 + t].size >= size_thr);
+        for (int t = 0; t < N; ++t) {
+            item[t] = 0;
+            if (i0 + t < n && i0 + t > 0) {
+                const MergeAcc2 *a = acc + i0 + t;
+                item[t] = (a->count > 0) && ((i64)a->size >= size_thr);
             }
-            vc += c[t];
-            vk += k[t];
         }
-        u32 tc, tk;
-        u32 ec = block_excl_scan(vc, sm, &tc) + carry_c;
-        u32 ek = block_excl_scan(vk, sm, &tk) + carry_k;
-#pragma unroll
-        for (int t = 0; t < MGS_ITEMS; ++t) {
-            if (i0 + t <= total && c[t]) {
-                acc[i0 + t].off = ec;
-                acc[i0 + t].outrow = k[t] ? ek : MG_NONE;
-            }
-            ec += c[t];
-            ek += k[t];
-        }
-        carry_c += tc;
-        carry_k += tk;
     }
-    if (threadIdx.x == 0) info[MG_NMERGED] = (i64)carry_k;
-}
+};
+struct MgKeepDst {
+    MergeAcc2 *acc;
+    u32 *cursor;        // bump allocator of the member array
+    template <int N>
+    __device__ __forceinline__ void store(u64 i0, u64 n, u32 ex, const u32 (&item)[N]) const
+    {
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            if (i0 + t < n && i0 + t > 0) {
+                MergeAcc2 *a = acc + i0 + t;
+                if (item[t]) a->outrow = ex;
+                const u32 c = a->count;
+                if (c > 1) a->off = atomicAdd(cursor, c);
+            }
+            ex += item[t];
+        }
+    }
+};
 
 __global__ void __launch_bounds__(256) k_mg_fill(const i64 *__restrict__ info, const u32 *__restrict__ gmap,
                                                  MergeAcc2 *acc, u32 *__restrict__ members, u32 *__restrict__ fmap)
@@ -380,7 +389,7 @@ __global__ void __launch_bounds__(256) k_mg_fill(const i64 *__restrict__ info, c
     for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= total; i += (i64)gridDim.x * blockDim.x) {
         if (i == 0) { fmap[0] = 0; continue; }
         MergeAcc2 *a = acc + gmap[i];
-        members[a->off + atomicAdd(&a->cursor, 1u)] = (u32)i;
+        if (a->count > 1) members[a->off + atomicAdd(&a->cursor, 1u)] = (u32)i;
         fmap[i] = a->outrow != MG_NONE ? gmap[i] : 0u;       // merged segments under the size threshold map to 0
     }
 }
@@ -429,8 +438,12 @@ __global__ void __launch_bounds__(256) k_mg_emit(Packed P, const int *__restrict
     for (i64 d = blockIdx.x * (i64)blockDim.x + threadIdx.x + 1; d <= total; d += (i64)gridDim.x * blockDim.x) {
         const MergeAcc2 a = acc[d];
         if (a.count == 0 || a.outrow == MG_NONE) continue;
-        u32 *m = members + a.off;
-        mg_sort_u32(m, a.count);
+        u32 self = (u32)d;                 // a destination is its own smallest member
+        u32 *m = &self;
+        if (a.count > 1) {
+            m = members + a.off;
+            mg_sort_u32(m, a.count);
+        }
         double sum[3] = {0.0, 0.0, 0.0}, comp[3] = {0.0, 0.0, 0.0};
         const double S = (double)a.size;
         for (u32 i = 0; i < a.count; ++i) {

@@ -401,6 +401,12 @@ class VolumeJob:
         self.graphs = None
         self.launches_per_step = 0
         self.offsets = [(ctypes_i64x3(self.chunk_begin[i])) for i in self.mine]
+        # faces with a neighbour chunk: only their voxels take part in the merge (merge_ccs.py:69-114)
+        masks = [0] * self.nchunks
+        for (ca, fa, cb, fb) in interior_face_pairs(self.grid):
+            masks[ca] |= 1 << fa
+            masks[cb] |= 1 << fb
+        self.face_masks = [masks[i] for i in self.mine]
 
     # ---- buffers -----------------------------------------------------------------------------------
     def set_inputs(self, local_index, pred, base=None):
@@ -462,7 +468,8 @@ class VolumeJob:
             ctypes.cast(self.offsets[li], ctypes.c_void_p), self.labels[li].data_ptr(),
             base.data_ptr() if base is not None else None,
             self.max_pairs[li], slot_ptr if slot_ptr is not None else self.my_slots[li].data_ptr(),
-            cap_rows or self.cap_rows, cap_entries or self.cap_entries, self.ws[li].data_ptr(), self.ws[li].numel(),
+            cap_rows or self.cap_rows, cap_entries or self.cap_entries, self.face_masks[li], self.ws[li].data_ptr(),
+            self.ws[li].numel(),
             self.caps_runs[li], self.D._stream_ptr(self.torch)))
 
     def _merge(self):

@@ -158,3 +158,72 @@ def test_f_order_single_chunk_tasks():
     assert np.array_equal(got[0], want[0])
     r, c, v, shp = orc.count_overlaps_c(want[0], base)
     assert got[3].shape == shp and np.array_equal(got[3].row, r) and np.array_equal(got[3].col, c)
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        vshape, cshape = (64, 48, 96), (24, 24, 32)          # 3 x 2 x 3 = 18 chunks, ragged, uneven over 4 ranks
+        vol = orc.synth_pred(vshape, seed=31, sigma=2.0, fg=0.10)
+        base_vol = orc.synth_base(vshape, seed=32, block=6, bg=0.1)
+        out = {"rank": rank}
+        for graph in (False, True):
+            job = run_job(vol, base_vol, cshape, 0.5, 10, 15, graph, world=world, rank=rank)
+            out[graph] = {"labels": {ci: job.labels[li].cpu().numpy().view(np.uint32) for li, ci in enumerate(job.mine)},
+                          "merged": job.merged_table(), "maps": [job.chunk_id_map(ci) for ci in range(job.nchunks)],
+                          "ov": {ci: job.overlaps(li) for li, ci in enumerate(job.mine)}, "info": job.info_dict()}
+        q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_volume_job_nccl_ranks():
+    """The job over 2+ real GPUs (NCCL all_gather of the packed slots): every rank's chunks and the replicated merge
+    results equal the oracle workflow.  Skipped on a single-GPU box."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    vshape, cshape = (64, 48, 96), (24, 24, 32)
+    vol = orc.synth_pred(vshape, seed=31, sigma=2.0, fg=0.10)
+    base_vol = orc.synth_base(vshape, seed=32, block=6, bg=0.1)
+    want = oracle_volume_job(vol, base_vol, cshape, 0.5, 10, 15)
+    wm = {int(k): [int(x) for x in v] for (k, v) in want["merged"].items()}
+    for graph in (False, True):
+        seen = set()
+        for o in outs:
+            r = o[graph]
+            assert {int(x[0]): x[1:].tolist() for x in r["merged"]} == wm
+            assert r["info"]["flags"] == 0
+            for ci in range(len(want["chunks"])):
+                gi = want["chunks"][ci][0]
+                assert r["maps"][ci] == {int(k): int(v) for (k, v) in want["id_maps"][gi].items()}
+            for (ci, lab) in r["labels"].items():
+                assert np.array_equal(lab, want["final"][want["chunks"][ci][1]])
+                rr, cc, vv, shp = r["ov"][ci]
+                wr, wc, wv, wshp = want["overlaps"][ci]
+                assert shp == wshp and np.array_equal(rr, wr) and np.array_equal(cc, wc) and np.array_equal(vv, wv)
+                seen.add(ci)
+        assert seen == set(range(len(want["chunks"])))
