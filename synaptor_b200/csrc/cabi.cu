@@ -1015,7 +1015,7 @@ int64_t syn_merge_packed_workspace_bytes(int64_t nchunks, int64_t cap_rows, int6
     const size_t cap_total = (size_t)nchunks * (size_t)cap_rows;
     if (cap_total >= (1ull << 31)) return SYN_ERR_INVALID;
     return (int64_t)(al((size_t)max_edges * 8) + 2 * al((cap_total + 1) * 4) + al((cap_total + 1) * sizeof(MergeAcc2)) +
-                     al(cap_total * 4) + al(((cap_total + 1) / (SCAN_THREADS * 8) + 8) * 8));
+                     al(cap_total * 4) + al(((cap_total + 1) / (SCAN_THREADS * 8) + 8) * 8 + 4096 * 4));
 }
 
 int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
@@ -1047,6 +1047,25 @@ int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_
     const Packed P{(const unsigned char *)slots_all, slot_bytes, cap_rows, cap_entries};
     const int *plan = (const int *)plan_dev;
     i64 *base = (i64 *)id_base_out, *info = (i64 *)info_out;
+    static const bool split = getenv("SYN_MERGE_SPLIT") != nullptr;     // A/B: the seven separate kernels
+    if (!split) {
+        // one cooperative kernel, all CTAs co-resident: phases separated by grid barriers
+        // few CTAs: a grid barrier costs more the more CTAs take part (8 per SM: ~8 us each; 1-2 per SM: ~2 us)
+        static const int per_sm = getenv("SYN_MERGE_CTAS") ? atoi(getenv("SYN_MERGE_CTAS")) : 2;
+        const int nblk = (int)std::min<i64>((i64)std::min(per_sm, occ_blocks(k_mg_all, 256, 0)) * sm_count(),
+                                            std::max<i64>(1, ((i64)cap_total + 256) / 256));
+        u32 *block_sums = (u32 *)(scan_state + scan_tiles + 2);
+        i64 me = max_edges;
+        i64 thr = size_thr;
+        i64 *merged_p = (i64 *)merged_out;
+        Packed Pm = P;
+        void *args[] = {(void *)&Pm, (void *)&plan, (void *)&base, (void *)&info, (void *)&par, (void *)&gmap,
+                        (void *)&acc, (void *)&edges, (void *)&me, (void *)&members, (void *)&block_sums,
+                        (void *)&member_cursor, (void *)&thr, (void *)&fmap_out, (void *)&merged_p};
+        CK(cudaLaunchCooperativeKernel((const void *)k_mg_all, dim3(nblk), dim3(256), args, 0, st));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return SYN_OK;
+    }
     const int wide = grid_for((i64)cap_total + 1, 256, 4);
     k_mg_prefix_init<<<wide, 256, 0, st>>>(P, plan, base, info, par, acc, scan_state, (u32)scan_tiles + 2);
     CK_LAUNCH();

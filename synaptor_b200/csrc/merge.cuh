@@ -17,6 +17,8 @@
 //                               face voxel, faces in Face.all_faces() order, raster order inside a face
 // Every rank gathers the slots of all chunks (one all_gather) and runs the same deterministic kernels on them.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ccl.cuh"
 
 namespace syn {
@@ -464,6 +466,295 @@ __global__ void __launch_bounds__(256) k_mg_emit(Packed P, const int *__restrict
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             o[SYN_SEG_CX + k] = (i64)sum[k];              // astype(int): truncation
+            o[SYN_SEG_BX + k] = a.lo[k];
+            o[SYN_SEG_EX + k] = a.hi[k];
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------
+// The whole merge as ONE cooperative kernel: the seven phases above separated by grid barriers instead of kernel
+// boundaries (7 launches of a few microseconds of work each were ~85 us on the critical path of every rank; one
+// launch with six barriers is ~35 us).  Same arithmetic, same results.  grid = co-resident CTAs (cooperative
+// launch), 256 threads.
+// ---------------------------------------------------------------------------
+constexpr int MG_MAXPAIRS_SMEM = 3072;
+
+__global__ void __launch_bounds__(256) k_mg_all(Packed P, const int *__restrict__ plan, i64 *__restrict__ base,
+                                                i64 *__restrict__ info, u32 *par, u32 *__restrict__ gmap,
+                                                MergeAcc2 *acc, u32 *__restrict__ edges, i64 max_edges,
+                                                u32 *__restrict__ members, u32 *__restrict__ block_sums,
+                                                u32 *member_cursor, i64 size_thr, u32 *__restrict__ fmap,
+                                                i64 *__restrict__ merged)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ i64 s_base[MG_MAXCHUNKS + 1];
+    __shared__ u32 s_units[MG_MAXPAIRS_SMEM + 1];
+    __shared__ u32 sm[33];
+    __shared__ u32 s_bad;
+    const int nchunks = plan[0], npairs = plan[1];
+    const int lane = threadIdx.x & 31;
+    const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+
+    // ---- phase 0: id bases (every CTA, in shared memory), parents, accumulators ----
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    {
+        u32 k[4], v = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = (int)threadIdx.x * 4 + q;
+            k[q] = 0;
+            if (c < nchunks) {
+                const i64 *h = P.hdr(plan[2 + c]);
+                i64 kept = h[PK_KEPT];
+                if (h[PK_FLAGS] || kept < 0 || kept > P.cap_rows || h[PK_NENT] > P.cap_entries) { s_bad = 1; kept = 0; }
+                k[q] = (u32)kept;
+            }
+            v += k[q];
+        }
+        u32 tot;
+        u32 ex = block_excl_scan(v, sm, &tot);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = (int)threadIdx.x * 4 + q;
+            if (c < nchunks) s_base[c] = (i64)ex;
+            ex += k[q];
+        }
+        if (threadIdx.x == 0) s_base[nchunks] = (i64)tot;
+    }
+    __syncthreads();
+    const i64 total = s_base[nchunks];
+    const bool bad = s_bad != 0;
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c <= nchunks; c += blockDim.x) base[c] = s_base[c];
+        if (threadIdx.x == 0) {
+            info[MG_TOTAL] = total;
+            info[MG_NMERGED] = 0;
+            info[MG_NEDGES] = 0;
+            info[MG_FLAGS] = bad ? 1 : 0;
+            *member_cursor = 0;
+        }
+    }
+    if (bad) return;                   // every CTA sees the same headers: a uniform exit, nobody waits at a barrier
+    for (i64 i = tid; i <= total; i += nth) {
+        par[i] = (u32)i;
+        MergeAcc2 a;
+        a.size = 0;
+        a.lo[0] = a.lo[1] = a.lo[2] = 0x7FFFFFFFFFFFFFFFll;
+        a.hi[0] = a.hi[1] = a.hi[2] = -0x7FFFFFFFFFFFFFFFll - 1;
+        a.count = a.off = a.cursor = 0;
+        a.outrow = MG_NONE;
+        acc[i] = a;
+    }
+    grid.sync();
+
+    // ---- phase 1: edges between facing faces; work unit = 256 hi-face entries of one pair ----
+    if (npairs > 0) {
+        const bool tab = npairs <= MG_MAXPAIRS_SMEM;
+        u32 nunits = 0;
+        if (tab) {
+            // exclusive prefix of the pairs' unit counts (serial over <= 3072 values per CTA: trivial)
+            if (threadIdx.x == 0) {
+                u32 run = 0;
+                for (int p = 0; p < npairs; ++p) {
+                    const int *pr = plan + 2 + nchunks + 4 * p;
+                    const i64 *hA = P.hdr(plan[2 + pr[0]]);
+                    const i64 nA = hA[PK_FEND + pr[1]] - hA[PK_FOFF + pr[1]];
+                    s_units[p] = run;
+                    run += (u32)((nA + 255) / 256);
+                }
+                s_units[npairs] = run;
+            }
+            __syncthreads();
+            nunits = s_units[npairs];
+        }
+        const u32 loops = tab ? nunits : (u32)npairs;
+        for (u32 u = tab ? blockIdx.x : 0u; u < loops; u += tab ? gridDim.x : 1u) {
+            int p;
+            i64 i;
+            if (tab) {
+                int lo = 0, hi = npairs - 1;       // last pair with s_units[p] <= u
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_units[mid] <= u) lo = mid;
+                    else hi = mid - 1;
+                }
+                p = lo;
+                i = (i64)(u - s_units[p]) * 256 + threadIdx.x;
+            } else {
+                p = (int)u;
+                i = (i64)blockIdx.x * 256 + threadIdx.x;
+            }
+            const int *pr = plan + 2 + nchunks + 4 * p;
+            const int cA = pr[0], fA = pr[1], cB = pr[2], fB = pr[3];
+            const int sA = plan[2 + cA], sB = plan[2 + cB];
+            const i64 *hA = P.hdr(sA), *hB = P.hdr(sB);
+            const i64 oA = hA[PK_FOFF + fA], nA = hA[PK_FEND + fA] - oA;
+            const i64 oB = hB[PK_FOFF + fB], nB = hB[PK_FEND + fB] - oB;
+            const uint2 *A = P.entries(sA) + oA, *B = P.entries(sB) + oB;
+            const u32 bA = (u32)s_base[cA], bB = (u32)s_base[cB];
+            const i64 step = tab ? nA + 256 : (i64)gridDim.x * 256;      // tab: one round per unit
+            for (i64 i0 = i - lane; i0 < nA; i0 += step) {
+                const i64 ii = i0 + lane;
+                u32 a = 0, b = 0;
+                if (ii < nA) {
+                    const uint2 e = A[ii];
+                    i64 lo = 0, hi = nB;
+                    while (lo < hi) {
+                        const i64 mid = (lo + hi) >> 1;
+                        if (B[mid].x < e.x) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    if (lo < nB) {
+                        const uint2 f = B[lo];
+                        if (f.x == e.x) { a = bA + e.y; b = bB + f.y; }
+                    }
+                }
+                bool act = a != 0;
+                const u32 pa = __shfl_up_sync(SYN_FULL, a, 1), pb = __shfl_up_sync(SYN_FULL, b, 1);
+                if (lane > 0 && pa == a && pb == b) act = false;
+                const u32 m = __ballot_sync(SYN_FULL, act);
+                if (!m) continue;
+                u64 basei = 0;
+                if (lane == 0) basei = atomicAdd((u64 *)&info[MG_NEDGES], (u64)__popc(m));
+                basei = __shfl_sync(SYN_FULL, (unsigned long long)basei, 0);
+                if (act) {
+                    const u64 e = basei + __popc(m & mask_lt((u32)lane));
+                    if ((i64)e < max_edges) { edges[2 * e] = a; edges[2 * e + 1] = b; }
+                }
+            }
+        }
+        grid.sync();
+        // ---- phase 2: union-find to the smallest id ----
+        i64 ne = *(volatile i64 *)&info[MG_NEDGES];
+        if (ne > max_edges) {
+            if (tid == 0) atomicOr((u64 *)&info[MG_FLAGS], 2ull);
+            ne = max_edges;
+        }
+        for (i64 i = tid; i < ne; i += nth) {
+            const u32 a = __ldcg(edges + 2 * i), b = __ldcg(edges + 2 * i + 1);
+            if ((i64)a <= total && (i64)b <= total) uf_union(par, a, b);
+        }
+        grid.sync();
+    }
+
+    // ---- phase 3: flatten + size / bbox / fragment count per destination ----
+    for (i64 gid = tid; gid <= total; gid += nth) {
+        if (gid == 0) { gmap[0] = 0; continue; }
+        const u32 d = uf_find_ro(par, (u32)gid);
+        gmap[gid] = d;
+        const i64 *r = mg_row(P, plan, s_base, nchunks, gid);
+        MergeAcc2 *a = acc + d;
+        atomicAdd(&a->size, (u64)r[SYN_SEG_SIZE]);
+        atomicAdd(&a->count, 1u);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&a->lo[k], r[SYN_SEG_BX + k]);
+            atomicMax(&a->hi[k], r[SYN_SEG_EX + k]);
+        }
+    }
+    grid.sync();
+
+    // ---- phase 4: output rows = exclusive scan of the kept flags in id order.  CTA b owns the ids
+    // [1 + b * span, 1 + (b + 1) * span); a: per-CTA totals, b: offsets + local scan ----
+    const i64 span = (total + gridDim.x - 1) / gridDim.x;
+    const i64 lo_id = 1 + (i64)blockIdx.x * span, hi_id = min(total + 1, lo_id + span);
+    {
+        u32 v = 0;
+        for (i64 i = lo_id + threadIdx.x; i < hi_id; i += blockDim.x) {
+            const u32 c = __ldcg(&acc[i].count);
+            v += (c > 0) && ((i64)__ldcg(&acc[i].size) >= size_thr);
+        }
+        u32 tot;
+        block_excl_scan(v, sm, &tot);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+    }
+    grid.sync();
+    {
+        u32 v = 0;
+        for (u32 b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            const u32 t = __ldcg(block_sums + b);
+            if (b < blockIdx.x) v += t;
+        }
+        u32 before;
+        block_excl_scan(v, sm, &before);     // `before` = kept flags of all earlier CTAs
+        u32 all = 0;
+        if (blockIdx.x == gridDim.x - 1) {
+            // the last CTA also publishes the grand total
+            u32 w = 0;
+            for (u32 b = threadIdx.x; b < gridDim.x; b += blockDim.x) w += __ldcg(block_sums + b);
+            block_excl_scan(w, sm, &all);
+            if (threadIdx.x == 0) info[MG_NMERGED] = (i64)all;
+        }
+        u32 carry = before;
+        for (i64 i0 = lo_id; i0 < hi_id; i0 += blockDim.x) {
+            const i64 i = i0 + threadIdx.x;
+            u32 c = 0, k = 0;
+            if (i < hi_id) {
+                c = __ldcg(&acc[i].count);
+                k = (c > 0) && ((i64)__ldcg(&acc[i].size) >= size_thr);
+            }
+            u32 tot;
+            const u32 ex = block_excl_scan(k, sm, &tot);
+            if (i < hi_id) {
+                if (k) acc[i].outrow = carry + ex;
+                if (c > 1) acc[i].off = atomicAdd(member_cursor, c);
+            }
+            carry += tot;
+        }
+    }
+    grid.sync();
+
+    // ---- phase 5: member lists, final id map ----
+    for (i64 i = tid; i <= total; i += nth) {
+        if (i == 0) { fmap[0] = 0; continue; }
+        const u32 dd = __ldcg(gmap + i);
+        MergeAcc2 *a = acc + dd;
+        if (__ldcg(&a->count) > 1) members[__ldcg(&a->off) + atomicAdd(&a->cursor, 1u)] = (u32)i;
+        fmap[i] = __ldcg(&a->outrow) != MG_NONE ? dd : 0u;
+    }
+    grid.sync();
+
+    // ---- phase 6: merged rows ----
+    for (i64 d = (i64)tid + 1; d <= total; d += nth) {
+        MergeAcc2 a;
+        a.count = __ldcg(&acc[d].count);
+        a.outrow = __ldcg(&acc[d].outrow);
+        if (a.count == 0 || a.outrow == MG_NONE) continue;
+        a.size = __ldcg(&acc[d].size);          // written by other SMs earlier in this kernel: L2 reads
+        a.off = __ldcg(&acc[d].off);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { a.lo[k] = __ldcg(&acc[d].lo[k]); a.hi[k] = __ldcg(&acc[d].hi[k]); }
+        u32 self = (u32)d;
+        u32 *m = &self;
+        if (a.count > 1) {
+            m = members + a.off;
+            for (u32 i = 0; i < a.count; ++i) m[i] = __ldcg(m + i);    // (refresh through L2, then sort in place)
+            mg_sort_u32(m, a.count);
+        }
+        double sum[3] = {0.0, 0.0, 0.0}, comp[3] = {0.0, 0.0, 0.0};
+        const double S = (double)a.size;
+        for (u32 i = 0; i < a.count; ++i) {
+            const i64 *r = mg_row(P, plan, s_base, nchunks, (i64)m[i]);
+            const double w = __ddiv_rn((double)r[SYN_SEG_SIZE], S);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double val = __dmul_rn((double)r[SYN_SEG_CX + k], w);
+                const double y = val - comp[k];
+                const double t = sum[k] + y;
+                comp[k] = (t - sum[k]) - y;
+                sum[k] = t;
+            }
+        }
+        i64 *o = merged + (i64)a.outrow * SYN_SEG_NCOLS;
+        o[SYN_SEG_ID] = d;
+        o[SYN_SEG_SIZE] = (i64)a.size;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            o[SYN_SEG_CX + k] = (i64)sum[k];
             o[SYN_SEG_BX + k] = a.lo[k];
             o[SYN_SEG_EX + k] = a.hi[k];
         }
