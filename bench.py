@@ -564,9 +564,7 @@ def main():
         for _ in range(args.steps):
             a, b, c, d, e = ev(), ev(), ev(), ev(), ev()
             barrier()
-            a.record(); job._stage_a(); b.record(); job._gather(); c.record(); job._merge(); d.record()
-            for li in range(len(job.mine)):
-                job._finish(li)
+            a.record(); job._stage_a(); b.record(); job._gather(); c.record(); job._stage_b(after_ids=d.record)
             e.record()
             torch.cuda.synchronize()
             for (k, (x, y)) in zip(brk, ((a, b), (b, c), (c, d), (d, e))):
@@ -638,7 +636,8 @@ def main():
                        "merge_breakdown_ms": {k: round(v, 4) for (k, v) in brk_max.items()},
                        "merge_breakdown_note": "plain launches with CUDA events around the stages, max over ranks: "
                                                "chunk_begin (all owned chunks) / gather (all_gather of the packed "
-                                               "slots) / merge (7 kernels) / chunk_finish (all owned chunks)",
+                                               "slots) / merge (the id map: one cooperative kernel) / chunk_finish "
+                                               "(all owned chunks, with the merged table on a second stream)",
                        "total_ids": info0["total_ids"], "merged_segments": info0["n_merged"],
                        "face_edges": info0["n_edges"],
                        "slot_bytes": job_slot_bytes[0], "rank0_chunk_counts": {

@@ -55,9 +55,13 @@ int g_prof_n = 0;
 bool g_prof_created = false;
 bool g_prof_valid = false;
 
+std::mutex g_prof_mu;     // the profiling hooks are for one measuring thread; the lock only keeps the state sane
+
 int prof_mark(const char *name, cudaStream_t st)
 {
-    if (!g_prof_on || g_prof_n >= PROF_MAX) return SYN_OK;
+    if (!g_prof_on) return SYN_OK;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof_n >= PROF_MAX) return SYN_OK;
     g_prof_name[g_prof_n] = name;
     CK(cudaEventRecord(g_prof_ev[g_prof_n], st));
     ++g_prof_n;
@@ -218,24 +222,29 @@ void carve(char *base, const Geom &g, i64 max_runs, i64 max_pairs, bool dilate, 
     w->total = off;
 }
 
-// grid = (resident CTAs per SM for this kernel) x (SM count): one full wave, no tail
+// grid = (resident CTAs per SM for this kernel) x (SM count): one full wave, no tail.
+// Function attributes and occupancy are per DEVICE: the cache is keyed by (device, kernel, threads, smem), so a
+// process that drives several GPUs sets the opt-in shared-memory size on each of them.
 std::mutex g_occ_mu;
-struct OccEntry { const void *fn; int threads; size_t smem; int blocks; };
-OccEntry g_occ[128];
+struct OccEntry { int dev; const void *fn; int threads; size_t smem; int blocks; };
+OccEntry g_occ[512];
 int g_nocc = 0;
 
 template <class K>
 int occ_blocks(K kernel, int threads, size_t dyn_smem)
 {
     const void *fn = (const void *)kernel;
+    int dev = 0;
+    cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_occ_mu);
     for (int i = 0; i < g_nocc; ++i)
-        if (g_occ[i].fn == fn && g_occ[i].threads == threads && g_occ[i].smem == dyn_smem) return g_occ[i].blocks;
+        if (g_occ[i].dev == dev && g_occ[i].fn == fn && g_occ[i].threads == threads && g_occ[i].smem == dyn_smem)
+            return g_occ[i].blocks;
     if (dyn_smem > 48 * 1024)
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, dyn_smem) != cudaSuccess || nb < 1) nb = 1;
-    if (g_nocc < 128) g_occ[g_nocc++] = OccEntry{fn, threads, dyn_smem, nb};
+    if (g_nocc < 512) g_occ[g_nocc++] = OccEntry{dev, fn, threads, dyn_smem, nb};
     return nb;
 }
 
@@ -309,11 +318,7 @@ template <int CONN>
 int launch_union(const Workspace &W, const Geom &g, RunIdx R, bool bnd_list, i64 max_runs, cudaStream_t st)
 {
     if (W.tg.tx) {
-        static bool attr_set = false;   // one flag per template instantiation
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_tile_ccl<CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM);
-            attr_set = true;
-        }
+        (void)occ_blocks(k_tile_ccl<CONN>, TILE_THREADS, TILE_SMEM);     // opt-in shared memory, once per device
         k_tile_ccl<CONN><<<W.tg.ntiles, TILE_THREADS, TILE_SMEM, st>>>(W.lmask, W.omask, R, W.par, W.tileflag, W.recs, g,
                                                             W.tg, W.cnt, (u32)max_runs);
         CK_LAUNCH();
@@ -1009,13 +1014,91 @@ int syn_merge_ccs_grid(const uint32_t *faces_all, const int64_t *tables_all, con
     return syn_merge_seg_tables(rows_scratch, total, gmap_out, size_thr, merged_out, fmap_out, n_merged_dev, stream);
 }
 
+namespace {
+struct MergeWs {
+    u32 *edges, *par, *gmap, *members;
+    MergeAcc2 *acc;
+    u64 *scan_state, *msize;
+    u32 *scan_ticket, *member_cursor, *block_sums;
+    size_t scan_tiles, cap_total;
+};
+size_t merge_ws_carve(char *p0, int64_t nchunks, int64_t cap_rows, int64_t max_edges, MergeWs *w)
+{
+    char *p = p0;
+    const size_t cap_total = (size_t)nchunks * (size_t)cap_rows;
+    w->cap_total = cap_total;
+    w->edges = (u32 *)p; p += al((size_t)max_edges * 8);
+    w->par = (u32 *)p; p += al((cap_total + 1) * 4);
+    w->gmap = (u32 *)p; p += al((cap_total + 1) * 4);
+    w->acc = (MergeAcc2 *)p; p += al((cap_total + 1) * sizeof(MergeAcc2));
+    w->members = (u32 *)p; p += al(cap_total * 4);
+    w->msize = (u64 *)p; p += al((cap_total + 1) * 8);
+    // look-back state of the kept-flag scan: [tiles] + ticket (2 u32) + member cursor (u32), then per-CTA sums
+    w->scan_tiles = (cap_total + 1) / (SCAN_THREADS * 8) + 2;
+    w->scan_state = (u64 *)p;
+    w->scan_ticket = (u32 *)(w->scan_state + w->scan_tiles);
+    w->member_cursor = w->scan_ticket + 2;
+    w->block_sums = (u32 *)(w->scan_state + w->scan_tiles + 2);
+    p += al((w->scan_tiles + 2) * 8 + 4096 * 4);
+    return (size_t)(p - p0);
+}
+int merge_args_ok(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
+                  const int32_t *plan_dev, int64_t nchunks, int64_t npairs, int64_t max_edges, void *workspace,
+                  int64_t workspace_bytes)
+{
+    if (!slots_all || !plan_dev || !workspace || npairs < 0) return fail(SYN_ERR_INVALID, "bad arguments");
+    const int64_t need = syn_merge_packed_workspace_bytes(nchunks, cap_rows, max_edges);
+    if (need < 0) return fail(SYN_ERR_INVALID, "bad nchunks / cap_rows / max_edges");
+    if (need > workspace_bytes)
+        return fail(SYN_ERR_WORKSPACE, "merge workspace too small: need %lld bytes, got %lld", (long long)need,
+                    (long long)workspace_bytes);
+    if (slot_bytes != (int64_t)pk_slot_bytes(cap_rows, cap_entries)) return fail(SYN_ERR_INVALID, "slot_bytes mismatch");
+    return SYN_OK;
+}
+}  // namespace
+
 int64_t syn_merge_packed_workspace_bytes(int64_t nchunks, int64_t cap_rows, int64_t max_edges)
 {
     if (nchunks < 1 || nchunks > MG_MAXCHUNKS || cap_rows < 1 || max_edges < 1) return SYN_ERR_INVALID;
-    const size_t cap_total = (size_t)nchunks * (size_t)cap_rows;
-    if (cap_total >= (1ull << 31)) return SYN_ERR_INVALID;
-    return (int64_t)(al((size_t)max_edges * 8) + 2 * al((cap_total + 1) * 4) + al((cap_total + 1) * sizeof(MergeAcc2)) +
-                     al(cap_total * 4) + al(((cap_total + 1) / (SCAN_THREADS * 8) + 8) * 8 + 4096 * 4));
+    if ((size_t)nchunks * (size_t)cap_rows >= (1ull << 31)) return SYN_ERR_INVALID;
+    MergeWs w;
+    return (int64_t)merge_ws_carve(nullptr, nchunks, cap_rows, max_edges, &w);
+}
+
+int syn_merge_ccs_table(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
+                        const int32_t *plan_dev, int64_t nchunks, int64_t size_thr, int64_t max_edges,
+                        void *workspace, int64_t workspace_bytes, const int64_t *id_base, int64_t *merged_out,
+                        int64_t *info, void *stream)
+{
+    int rc = merge_args_ok(slots_all, slot_bytes, cap_rows, cap_entries, plan_dev, nchunks, 0, max_edges, workspace,
+                           workspace_bytes);
+    if (rc != SYN_OK) return rc;
+    if (!id_base || !merged_out || !info) return fail(SYN_ERR_INVALID, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    MergeWs w;
+    merge_ws_carve((char *)workspace, nchunks, cap_rows, max_edges, &w);
+    const Packed P{(const unsigned char *)slots_all, slot_bytes, cap_rows, cap_entries};
+    const int *plan = (const int *)plan_dev;
+    const i64 *base = (const i64 *)id_base;
+    i64 *inf = (i64 *)info;
+    const int wide = grid_for((i64)w.cap_total + 1, 256, 4);
+    k_mg_tab_init<<<wide, 256, 0, st>>>(inf, w.acc, w.scan_state, (u32)w.scan_tiles + 2);
+    CK_LAUNCH();
+    k_mg_tab_acc<<<wide, 256, 0, st>>>(P, plan, base, inf, w.gmap, w.acc);
+    CK_LAUNCH();
+    {
+        const i64 ntiles = ((i64)w.cap_total + 1 + SCAN_THREADS * 8 - 1) / (SCAN_THREADS * 8);
+        k_scan_1p<MgKeepSrc, MgKeepDst, 8><<<wave_grid(k_scan_1p<MgKeepSrc, MgKeepDst, 8>, SCAN_THREADS, ntiles),
+                                             SCAN_THREADS, 0, st>>>(MgKeepSrc{w.acc, inf, size_thr},
+                                                                    MgKeepDst{w.acc, w.member_cursor}, w.scan_state,
+                                                                    w.scan_ticket, &inf[MG_NMERGED]);
+        CK_LAUNCH();
+    }
+    k_mg_tab_fill<<<wide, 256, 0, st>>>(inf, w.gmap, w.acc, w.members);
+    CK_LAUNCH();
+    k_mg_emit<<<wide, 256, 0, st>>>(P, plan, base, inf, w.acc, w.members, (i64 *)merged_out);
+    CK_LAUNCH();
+    return SYN_OK;
 }
 
 int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
@@ -1023,75 +1106,29 @@ int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_
                          void *workspace, int64_t workspace_bytes, int64_t *id_base_out, int64_t *merged_out,
                          uint32_t *fmap_out, int64_t *info_out, void *stream)
 {
-    if (!slots_all || !plan_dev || !workspace || !id_base_out || !merged_out || !fmap_out || !info_out || npairs < 0)
-        return fail(SYN_ERR_INVALID, "bad arguments");
-    const int64_t need = syn_merge_packed_workspace_bytes(nchunks, cap_rows, max_edges);
-    if (need < 0) return fail(SYN_ERR_INVALID, "bad nchunks / cap_rows / max_edges");
-    if (need > workspace_bytes)
-        return fail(SYN_ERR_WORKSPACE, "merge workspace too small: need %lld bytes, got %lld", (long long)need,
-                    (long long)workspace_bytes);
-    if (slot_bytes != (int64_t)pk_slot_bytes(cap_rows, cap_entries)) return fail(SYN_ERR_INVALID, "slot_bytes mismatch");
+    int rc = merge_args_ok(slots_all, slot_bytes, cap_rows, cap_entries, plan_dev, nchunks, npairs, max_edges,
+                           workspace, workspace_bytes);
+    if (rc != SYN_OK) return rc;
+    if (!id_base_out || !fmap_out || !info_out) return fail(SYN_ERR_INVALID, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t cap_total = (size_t)nchunks * (size_t)cap_rows;
-    char *p = (char *)workspace;
-    u32 *edges = (u32 *)p; p += al((size_t)max_edges * 8);
-    u32 *par = (u32 *)p; p += al((cap_total + 1) * 4);
-    u32 *gmap = (u32 *)p; p += al((cap_total + 1) * 4);
-    MergeAcc2 *acc = (MergeAcc2 *)p; p += al((cap_total + 1) * sizeof(MergeAcc2));
-    u32 *members = (u32 *)p; p += al(cap_total * 4);
-    // look-back state of the kept-flag scan: [tiles] + ticket (2 u32) + member cursor (u32), zeroed by k_mg_prefix_init
-    const size_t scan_tiles = (cap_total + 1) / (SCAN_THREADS * 8) + 2;
-    u64 *scan_state = (u64 *)p;
-    u32 *scan_ticket = (u32 *)(scan_state + scan_tiles);
-    u32 *member_cursor = scan_ticket + 2;
-    const Packed P{(const unsigned char *)slots_all, slot_bytes, cap_rows, cap_entries};
+    MergeWs w;
+    merge_ws_carve((char *)workspace, nchunks, cap_rows, max_edges, &w);
+    Packed P{(const unsigned char *)slots_all, slot_bytes, cap_rows, cap_entries};
     const int *plan = (const int *)plan_dev;
     i64 *base = (i64 *)id_base_out, *info = (i64 *)info_out;
-    static const bool split = getenv("SYN_MERGE_SPLIT") != nullptr;     // A/B: the seven separate kernels
-    if (!split) {
-        // one cooperative kernel, all CTAs co-resident: phases separated by grid barriers
-        // few CTAs: a grid barrier costs more the more CTAs take part (8 per SM: ~8 us each; 1-2 per SM: ~2 us)
-        static const int per_sm = getenv("SYN_MERGE_CTAS") ? atoi(getenv("SYN_MERGE_CTAS")) : 2;
-        const int nblk = (int)std::min<i64>((i64)std::min(per_sm, occ_blocks(k_mg_all, 256, 0)) * sm_count(),
-                                            std::max<i64>(1, ((i64)cap_total + 256) / 256));
-        u32 *block_sums = (u32 *)(scan_state + scan_tiles + 2);
-        i64 me = max_edges;
-        i64 thr = size_thr;
-        i64 *merged_p = (i64 *)merged_out;
-        Packed Pm = P;
-        void *args[] = {(void *)&Pm, (void *)&plan, (void *)&base, (void *)&info, (void *)&par, (void *)&gmap,
-                        (void *)&acc, (void *)&edges, (void *)&me, (void *)&members, (void *)&block_sums,
-                        (void *)&member_cursor, (void *)&thr, (void *)&fmap_out, (void *)&merged_p};
-        CK(cudaLaunchCooperativeKernel((const void *)k_mg_all, dim3(nblk), dim3(256), args, 0, st));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        return SYN_OK;
-    }
-    const int wide = grid_for((i64)cap_total + 1, 256, 4);
-    k_mg_prefix_init<<<wide, 256, 0, st>>>(P, plan, base, info, par, acc, scan_state, (u32)scan_tiles + 2);
-    CK_LAUNCH();
-    if (npairs > 0) {
-        // enough CTAs for about one entry per thread on the largest face (binary searches are dependent loads)
-        const unsigned mx = (unsigned)std::max<i64>(1, std::min<i64>(64, (cap_entries / 3 + 255) / 256));
-        k_mg_match<<<dim3(mx, (unsigned)npairs), 256, 0, st>>>(P, plan, base, edges, max_edges, info);
-        CK_LAUNCH();
-        k_mg_union<<<grid_for(max_edges, 256, 2), 256, 0, st>>>(edges, max_edges, info, par);
-        CK_LAUNCH();
-    }
-    k_mg_flatacc<<<wide, 256, 0, st>>>(P, plan, base, info, par, gmap, acc);
-    CK_LAUNCH();
-    {
-        const i64 ntiles = ((i64)cap_total + 1 + SCAN_THREADS * 8 - 1) / (SCAN_THREADS * 8);
-        k_scan_1p<MgKeepSrc, MgKeepDst, 8><<<wave_grid(k_scan_1p<MgKeepSrc, MgKeepDst, 8>, SCAN_THREADS, ntiles),
-                                             SCAN_THREADS, 0, st>>>(MgKeepSrc{acc, info, size_thr},
-                                                                    MgKeepDst{acc, member_cursor}, scan_state,
-                                                                    scan_ticket, &info[MG_NMERGED]);
-        CK_LAUNCH();
-    }
-    k_mg_fill<<<wide, 256, 0, st>>>(info, gmap, acc, members, fmap_out);
-    CK_LAUNCH();
-    k_mg_emit<<<wide, 256, 0, st>>>(P, plan, base, info, acc, members, (i64 *)merged_out);
-    CK_LAUNCH();
-    return SYN_OK;
+    // the id map: ONE cooperative kernel, its phases separated by grid barriers (few CTAs: a barrier costs more the
+    // more CTAs take part)
+    static const int per_sm = getenv("SYN_MERGE_CTAS") ? atoi(getenv("SYN_MERGE_CTAS")) : 2;
+    const int nblk = (int)std::min<i64>((i64)std::min(per_sm, occ_blocks(k_mg_ids, 256, 0)) * sm_count(),
+                                        std::max<i64>(1, ((i64)w.cap_total + 256) / 256));
+    i64 me = max_edges, thr = size_thr;
+    void *args[] = {(void *)&P, (void *)&plan, (void *)&base, (void *)&info, (void *)&w.par, (void *)&w.gmap,
+                    (void *)&w.msize, (void *)&w.edges, (void *)&me, (void *)&thr, (void *)&fmap_out};
+    CK(cudaLaunchCooperativeKernel((const void *)k_mg_ids, dim3(nblk), dim3(256), args, 0, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!merged_out) return SYN_OK;            // the caller runs syn_merge_ccs_table itself (another stream)
+    return syn_merge_ccs_table(slots_all, slot_bytes, cap_rows, cap_entries, plan_dev, nchunks, size_thr, max_edges,
+                               workspace, workspace_bytes, id_base_out, merged_out, info_out, stream);
 }
 
 int syn_merge_overlaps(const uint32_t *rows, const uint64_t *cols, const int64_t *counts, int64_t n, int64_t n_ids,

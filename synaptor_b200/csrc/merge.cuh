@@ -180,124 +180,6 @@ struct MergeAcc2 {
 // info[]: 0 total ids, 1 merged rows, 2 edges, 3 flags (bit 0: a slot reported an overflow, bit 1: edge capacity)
 constexpr int MG_TOTAL = 0, MG_NMERGED = 1, MG_NEDGES = 2, MG_FLAGS = 3;
 
-// global id bases (exclusive prefix of the row counts in chunk order: assign_ids.py:8-25) + initialisation of
-// the union-find parents and the accumulators of ids 0..total.  Every CTA recomputes the (tiny) prefix.
-__global__ void __launch_bounds__(256) k_mg_prefix_init(Packed P, const int *__restrict__ plan, i64 *__restrict__ base,
-                                                        i64 *__restrict__ info, u32 *__restrict__ par,
-                                                        MergeAcc2 *__restrict__ acc, u64 *__restrict__ scan_zero,
-                                                        u32 n_scan_zero)
-{
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_scan_zero; i += gridDim.x * blockDim.x) scan_zero[i] = 0;
-    __shared__ u32 sm[33];
-    const int nchunks = plan[0];
-    u32 k[4], v = 0;
-    u32 bad = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int c = (int)threadIdx.x * 4 + q;
-        k[q] = 0;
-        if (c < nchunks) {
-            const i64 *h = P.hdr(plan[2 + c]);
-            i64 kept = h[PK_KEPT];
-            if (h[PK_FLAGS] || kept < 0 || kept > P.cap_rows || h[PK_NENT] > P.cap_entries) { bad = 1; kept = 0; }
-            k[q] = (u32)kept;
-        }
-        v += k[q];
-    }
-    u32 total;
-    u32 ex = block_excl_scan(v, sm, &total);
-    if (blockIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int c = (int)threadIdx.x * 4 + q;
-            if (c < nchunks) base[c] = (i64)ex;
-            ex += k[q];
-        }
-        if (threadIdx.x == 0) {
-            base[nchunks] = (i64)total;
-            info[MG_TOTAL] = (i64)total;
-            info[MG_NMERGED] = 0;
-            info[MG_NEDGES] = 0;
-            info[MG_FLAGS] = 0;
-        }
-    }
-    if (__syncthreads_or((int)bad) && blockIdx.x == 0 && threadIdx.x == 0) info[MG_FLAGS] = 1;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i <= total; i += gridDim.x * blockDim.x) {
-        par[i] = i;
-        MergeAcc2 a;
-        a.size = 0;
-        a.lo[0] = a.lo[1] = a.lo[2] = 0x7FFFFFFFFFFFFFFFll;
-        a.hi[0] = a.hi[1] = a.hi[2] = -0x7FFFFFFFFFFFFFFFll - 1;
-        a.count = a.off = a.cursor = 0;
-        a.outrow = MG_NONE;
-        acc[i] = a;
-    }
-}
-
-// edges between facing faces (merge_ccs.py:117-128): a hi-face entry of the chunk here matches the lo-face entry
-// of the chunk there at the same position (binary search in the ordered list).  blockIdx.y = face pair.
-__global__ void __launch_bounds__(256) k_mg_match(Packed P, const int *__restrict__ plan, const i64 *__restrict__ base,
-                                                  u32 *__restrict__ edges, i64 max_edges, i64 *__restrict__ info)
-{
-    if (info[MG_FLAGS] & 1) return;
-    const int nchunks = plan[0];
-    const int *pr = plan + 2 + nchunks + 4 * blockIdx.y;
-    const int cA = pr[0], fA = pr[1], cB = pr[2], fB = pr[3];
-    const int sA = plan[2 + cA], sB = plan[2 + cB];
-    const i64 *hA = P.hdr(sA), *hB = P.hdr(sB);
-    const i64 oA = hA[PK_FOFF + fA], eA = hA[PK_FEND + fA];
-    const i64 oB = hB[PK_FOFF + fB], eB = hB[PK_FEND + fB];
-    const uint2 *A = P.entries(sA) + oA, *B = P.entries(sB) + oB;
-    const i64 nA = eA - oA, nB = eB - oB;
-    const u32 bA = (u32)base[cA], bB = (u32)base[cB];
-    const int lane = threadIdx.x & 31;
-    for (i64 i0 = (i64)blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < nA; i0 += (i64)gridDim.x * blockDim.x) {
-        const i64 i = i0 + lane;
-        u32 a = 0, b = 0;
-        if (i < nA) {
-            const uint2 e = A[i];
-            i64 lo = 0, hi = nB;        // first entry of B with pos >= e.x
-            while (lo < hi) {
-                const i64 mid = (lo + hi) >> 1;
-                if (B[mid].x < e.x) lo = mid + 1;
-                else hi = mid;
-            }
-            if (lo < nB) {
-                const uint2 f = B[lo];
-                if (f.x == e.x) { a = bA + e.y; b = bB + f.y; }
-            }
-        }
-        bool act = a != 0;
-        const u32 pa = __shfl_up_sync(SYN_FULL, a, 1), pb = __shfl_up_sync(SYN_FULL, b, 1);
-        if (lane > 0 && pa == a && pb == b) act = false;     // raster-ordered faces: long runs of one pair
-        const u32 m = __ballot_sync(SYN_FULL, act);
-        if (!m) continue;
-        u64 basei = 0;
-        if (lane == 0) basei = atomicAdd((u64 *)&info[MG_NEDGES], (u64)__popc(m));
-        basei = __shfl_sync(SYN_FULL, (unsigned long long)basei, 0);
-        if (act) {
-            const u64 e = basei + __popc(m & mask_lt((u32)lane));
-            if ((i64)e < max_edges) { edges[2 * e] = a; edges[2 * e + 1] = b; }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256) k_mg_union(const u32 *__restrict__ edges, i64 max_edges, i64 *__restrict__ info,
-                                                  u32 *par)
-{
-    if (info[MG_FLAGS] & 1) return;
-    i64 n = info[MG_NEDGES];
-    if (n > max_edges) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr((u64 *)&info[MG_FLAGS], 2ull);
-        n = max_edges;
-    }
-    const i64 total = info[MG_TOTAL];
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
-        const u32 a = edges[2 * i], b = edges[2 * i + 1];
-        if ((i64)a <= total && (i64)b <= total) uf_union(par, a, b);
-    }
-}
-
 // chunk of global id gid (1-based): the last c with base[c] < gid
 __device__ __forceinline__ int mg_chunk_of(const i64 *s_base, int nchunks, i64 gid)
 {
@@ -314,33 +196,6 @@ __device__ __forceinline__ const i64 *mg_row(const Packed &P, const int *plan, c
 {
     const int c = mg_chunk_of(s_base, nchunks, gid);
     return P.table(plan[2 + c]) + (gid - 1 - s_base[c]) * SYN_SEG_NCOLS;
-}
-
-// gmap[id] = smallest id of its component; size / bbox / fragment count per destination
-__global__ void __launch_bounds__(256) k_mg_flatacc(Packed P, const int *__restrict__ plan, const i64 *__restrict__ base,
-                                                    const i64 *__restrict__ info, const u32 *par, u32 *__restrict__ gmap,
-                                                    MergeAcc2 *acc)
-{
-    __shared__ i64 s_base[MG_MAXCHUNKS + 1];
-    const int nchunks = plan[0];
-    for (int c = threadIdx.x; c <= nchunks; c += blockDim.x) s_base[c] = base[c];
-    __syncthreads();
-    if (info[MG_FLAGS] & 1) return;
-    const i64 total = info[MG_TOTAL];
-    for (i64 gid = blockIdx.x * (i64)blockDim.x + threadIdx.x; gid <= total; gid += (i64)gridDim.x * blockDim.x) {
-        if (gid == 0) { gmap[0] = 0; continue; }
-        const u32 d = uf_find_ro(par, (u32)gid);
-        gmap[gid] = d;
-        const i64 *r = mg_row(P, plan, s_base, nchunks, gid);
-        MergeAcc2 *a = acc + d;
-        atomicAdd(&a->size, (u64)r[SYN_SEG_SIZE]);
-        atomicAdd(&a->count, 1u);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            atomicMin(&a->lo[k], r[SYN_SEG_BX + k]);
-            atomicMax(&a->hi[k], r[SYN_SEG_EX + k]);
-        }
-    }
 }
 
 // output rows: exclusive scan of the kept flags (count > 0 and size >= size_thr) in id order, through the
@@ -382,19 +237,6 @@ struct MgKeepDst {
         }
     }
 };
-
-__global__ void __launch_bounds__(256) k_mg_fill(const i64 *__restrict__ info, const u32 *__restrict__ gmap,
-                                                 MergeAcc2 *acc, u32 *__restrict__ members, u32 *__restrict__ fmap)
-{
-    if (info[MG_FLAGS] & 1) return;
-    const i64 total = info[MG_TOTAL];
-    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= total; i += (i64)gridDim.x * blockDim.x) {
-        if (i == 0) { fmap[0] = 0; continue; }
-        MergeAcc2 *a = acc + gmap[i];
-        if (a->count > 1) members[a->off + atomicAdd(&a->cursor, 1u)] = (u32)i;
-        fmap[i] = a->outrow != MG_NONE ? gmap[i] : 0u;       // merged segments under the size threshold map to 0
-    }
-}
 
 __device__ __forceinline__ void mg_sort_u32(u32 *m, u32 n)
 {
@@ -473,20 +315,17 @@ __global__ void __launch_bounds__(256) k_mg_emit(Packed P, const int *__restrict
 }
 
 
-// ---------------------------------------------------------------------------
-// The whole merge as ONE cooperative kernel: the seven phases above separated by grid barriers instead of kernel
-// boundaries (7 launches of a few microseconds of work each were ~85 us on the critical path of every rank; one
-// launch with six barriers is ~35 us).  Same arithmetic, same results.  grid = co-resident CTAs (cooperative
-// launch), 256 threads.
-// ---------------------------------------------------------------------------
 constexpr int MG_MAXPAIRS_SMEM = 3072;
 
-__global__ void __launch_bounds__(256) k_mg_all(Packed P, const int *__restrict__ plan, i64 *__restrict__ base,
+// ---------------------------------------------------------------------------
+// The part of the merge a chunk's label write waits for -- id bases, edges, union-find, merged sizes, final id
+// map -- as one cooperative kernel (k_mg_ids); the merged TABLE (bbox, centroid, output rows) is produced by the
+// split kernels (k_mg_tab_*, k_mg_emit) on a second stream, next to the label kernels.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mg_ids(Packed P, const int *__restrict__ plan, i64 *__restrict__ base,
                                                 i64 *__restrict__ info, u32 *par, u32 *__restrict__ gmap,
-                                                MergeAcc2 *acc, u32 *__restrict__ edges, i64 max_edges,
-                                                u32 *__restrict__ members, u32 *__restrict__ block_sums,
-                                                u32 *member_cursor, i64 size_thr, u32 *__restrict__ fmap,
-                                                i64 *__restrict__ merged)
+                                                u64 *msize, u32 *__restrict__ edges, i64 max_edges, i64 size_thr,
+                                                u32 *__restrict__ fmap)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -497,8 +336,6 @@ __global__ void __launch_bounds__(256) k_mg_all(Packed P, const int *__restrict_
     const int nchunks = plan[0], npairs = plan[1];
     const int lane = threadIdx.x & 31;
     const u32 tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-
-    // ---- phase 0: id bases (every CTA, in shared memory), parents, accumulators ----
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
     {
@@ -535,28 +372,19 @@ __global__ void __launch_bounds__(256) k_mg_all(Packed P, const int *__restrict_
             info[MG_NMERGED] = 0;
             info[MG_NEDGES] = 0;
             info[MG_FLAGS] = bad ? 1 : 0;
-            *member_cursor = 0;
         }
     }
     if (bad) return;                   // every CTA sees the same headers: a uniform exit, nobody waits at a barrier
     for (i64 i = tid; i <= total; i += nth) {
         par[i] = (u32)i;
-        MergeAcc2 a;
-        a.size = 0;
-        a.lo[0] = a.lo[1] = a.lo[2] = 0x7FFFFFFFFFFFFFFFll;
-        a.hi[0] = a.hi[1] = a.hi[2] = -0x7FFFFFFFFFFFFFFFll - 1;
-        a.count = a.off = a.cursor = 0;
-        a.outrow = MG_NONE;
-        acc[i] = a;
+        msize[i] = 0;
     }
     grid.sync();
-
-    // ---- phase 1: edges between facing faces; work unit = 256 hi-face entries of one pair ----
     if (npairs > 0) {
+        // ---- edges between facing faces; work unit = 256 hi-face entries of one pair ----
         const bool tab = npairs <= MG_MAXPAIRS_SMEM;
         u32 nunits = 0;
         if (tab) {
-            // exclusive prefix of the pairs' unit counts (serial over <= 3072 values per CTA: trivial)
             if (threadIdx.x == 0) {
                 u32 run = 0;
                 for (int p = 0; p < npairs; ++p) {
@@ -628,7 +456,6 @@ __global__ void __launch_bounds__(256) k_mg_all(Packed P, const int *__restrict_
             }
         }
         grid.sync();
-        // ---- phase 2: union-find to the smallest id ----
         i64 ne = *(volatile i64 *)&info[MG_NEDGES];
         if (ne > max_edges) {
             if (tid == 0) atomicOr((u64 *)&info[MG_FLAGS], 2ull);
@@ -640,14 +467,51 @@ __global__ void __launch_bounds__(256) k_mg_all(Packed P, const int *__restrict_
         }
         grid.sync();
     }
-
-    // ---- phase 3: flatten + size / bbox / fragment count per destination ----
+    // ---- destination of every id, merged sizes ----
     for (i64 gid = tid; gid <= total; gid += nth) {
         if (gid == 0) { gmap[0] = 0; continue; }
         const u32 d = uf_find_ro(par, (u32)gid);
         gmap[gid] = d;
+        atomicAdd(msize + d, (u64)mg_row(P, plan, s_base, nchunks, gid)[SYN_SEG_SIZE]);
+    }
+    grid.sync();
+    // ---- final id map: merged segments under the size threshold map to 0 (merge_df.py:64-68) ----
+    for (i64 gid = tid; gid <= total; gid += nth) {
+        const u32 d = gid ? __ldcg(gmap + gid) : 0u;
+        fmap[gid] = (gid && (i64)__ldcg(msize + d) >= size_thr) ? d : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mg_tab_init(const i64 *__restrict__ info, MergeAcc2 *__restrict__ acc,
+                                                     u64 *__restrict__ scan_zero, u32 n_scan_zero)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_scan_zero; i += gridDim.x * blockDim.x) scan_zero[i] = 0;
+    if (info[MG_FLAGS] & 1) return;
+    const i64 total = info[MG_TOTAL];
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x; i <= total; i += (i64)gridDim.x * blockDim.x) {
+        MergeAcc2 a;
+        a.size = 0;
+        a.lo[0] = a.lo[1] = a.lo[2] = 0x7FFFFFFFFFFFFFFFll;
+        a.hi[0] = a.hi[1] = a.hi[2] = -0x7FFFFFFFFFFFFFFFll - 1;
+        a.count = a.off = a.cursor = 0;
+        a.outrow = MG_NONE;
+        acc[i] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mg_tab_acc(Packed P, const int *__restrict__ plan, const i64 *__restrict__ base,
+                                                    const i64 *__restrict__ info, const u32 *__restrict__ gmap,
+                                                    MergeAcc2 *acc)
+{
+    __shared__ i64 s_base[MG_MAXCHUNKS + 1];
+    const int nchunks = plan[0];
+    for (int c = threadIdx.x; c <= nchunks; c += blockDim.x) s_base[c] = base[c];
+    __syncthreads();
+    if (info[MG_FLAGS] & 1) return;
+    const i64 total = info[MG_TOTAL];
+    for (i64 gid = blockIdx.x * (i64)blockDim.x + threadIdx.x + 1; gid <= total; gid += (i64)gridDim.x * blockDim.x) {
         const i64 *r = mg_row(P, plan, s_base, nchunks, gid);
-        MergeAcc2 *a = acc + d;
+        MergeAcc2 *a = acc + gmap[gid];
         atomicAdd(&a->size, (u64)r[SYN_SEG_SIZE]);
         atomicAdd(&a->count, 1u);
 #pragma unroll
@@ -656,108 +520,16 @@ __global__ void __launch_bounds__(256) k_mg_all(Packed P, const int *__restrict_
             atomicMax(&a->hi[k], r[SYN_SEG_EX + k]);
         }
     }
-    grid.sync();
+}
 
-    // ---- phase 4: output rows = exclusive scan of the kept flags in id order.  CTA b owns the ids
-    // [1 + b * span, 1 + (b + 1) * span); a: per-CTA totals, b: offsets + local scan ----
-    const i64 span = (total + gridDim.x - 1) / gridDim.x;
-    const i64 lo_id = 1 + (i64)blockIdx.x * span, hi_id = min(total + 1, lo_id + span);
-    {
-        u32 v = 0;
-        for (i64 i = lo_id + threadIdx.x; i < hi_id; i += blockDim.x) {
-            const u32 c = __ldcg(&acc[i].count);
-            v += (c > 0) && ((i64)__ldcg(&acc[i].size) >= size_thr);
-        }
-        u32 tot;
-        block_excl_scan(v, sm, &tot);
-        if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
-    }
-    grid.sync();
-    {
-        u32 v = 0;
-        for (u32 b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-            const u32 t = __ldcg(block_sums + b);
-            if (b < blockIdx.x) v += t;
-        }
-        u32 before;
-        block_excl_scan(v, sm, &before);     // `before` = kept flags of all earlier CTAs
-        u32 all = 0;
-        if (blockIdx.x == gridDim.x - 1) {
-            // the last CTA also publishes the grand total
-            u32 w = 0;
-            for (u32 b = threadIdx.x; b < gridDim.x; b += blockDim.x) w += __ldcg(block_sums + b);
-            block_excl_scan(w, sm, &all);
-            if (threadIdx.x == 0) info[MG_NMERGED] = (i64)all;
-        }
-        u32 carry = before;
-        for (i64 i0 = lo_id; i0 < hi_id; i0 += blockDim.x) {
-            const i64 i = i0 + threadIdx.x;
-            u32 c = 0, k = 0;
-            if (i < hi_id) {
-                c = __ldcg(&acc[i].count);
-                k = (c > 0) && ((i64)__ldcg(&acc[i].size) >= size_thr);
-            }
-            u32 tot;
-            const u32 ex = block_excl_scan(k, sm, &tot);
-            if (i < hi_id) {
-                if (k) acc[i].outrow = carry + ex;
-                if (c > 1) acc[i].off = atomicAdd(member_cursor, c);
-            }
-            carry += tot;
-        }
-    }
-    grid.sync();
-
-    // ---- phase 5: member lists, final id map ----
-    for (i64 i = tid; i <= total; i += nth) {
-        if (i == 0) { fmap[0] = 0; continue; }
-        const u32 dd = __ldcg(gmap + i);
-        MergeAcc2 *a = acc + dd;
-        if (__ldcg(&a->count) > 1) members[__ldcg(&a->off) + atomicAdd(&a->cursor, 1u)] = (u32)i;
-        fmap[i] = __ldcg(&a->outrow) != MG_NONE ? dd : 0u;
-    }
-    grid.sync();
-
-    // ---- phase 6: merged rows ----
-    for (i64 d = (i64)tid + 1; d <= total; d += nth) {
-        MergeAcc2 a;
-        a.count = __ldcg(&acc[d].count);
-        a.outrow = __ldcg(&acc[d].outrow);
-        if (a.count == 0 || a.outrow == MG_NONE) continue;
-        a.size = __ldcg(&acc[d].size);          // written by other SMs earlier in this kernel: L2 reads
-        a.off = __ldcg(&acc[d].off);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { a.lo[k] = __ldcg(&acc[d].lo[k]); a.hi[k] = __ldcg(&acc[d].hi[k]); }
-        u32 self = (u32)d;
-        u32 *m = &self;
-        if (a.count > 1) {
-            m = members + a.off;
-            for (u32 i = 0; i < a.count; ++i) m[i] = __ldcg(m + i);    // (refresh through L2, then sort in place)
-            mg_sort_u32(m, a.count);
-        }
-        double sum[3] = {0.0, 0.0, 0.0}, comp[3] = {0.0, 0.0, 0.0};
-        const double S = (double)a.size;
-        for (u32 i = 0; i < a.count; ++i) {
-            const i64 *r = mg_row(P, plan, s_base, nchunks, (i64)m[i]);
-            const double w = __ddiv_rn((double)r[SYN_SEG_SIZE], S);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double val = __dmul_rn((double)r[SYN_SEG_CX + k], w);
-                const double y = val - comp[k];
-                const double t = sum[k] + y;
-                comp[k] = (t - sum[k]) - y;
-                sum[k] = t;
-            }
-        }
-        i64 *o = merged + (i64)a.outrow * SYN_SEG_NCOLS;
-        o[SYN_SEG_ID] = d;
-        o[SYN_SEG_SIZE] = (i64)a.size;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            o[SYN_SEG_CX + k] = (i64)sum[k];
-            o[SYN_SEG_BX + k] = a.lo[k];
-            o[SYN_SEG_EX + k] = a.hi[k];
-        }
+__global__ void __launch_bounds__(256) k_mg_tab_fill(const i64 *__restrict__ info, const u32 *__restrict__ gmap,
+                                                     MergeAcc2 *acc, u32 *__restrict__ members)
+{
+    if (info[MG_FLAGS] & 1) return;
+    const i64 total = info[MG_TOTAL];
+    for (i64 i = blockIdx.x * (i64)blockDim.x + threadIdx.x + 1; i <= total; i += (i64)gridDim.x * blockDim.x) {
+        MergeAcc2 *a = acc + gmap[i];
+        if (a->count > 1) members[a->off + atomicAdd(&a->cursor, 1u)] = (u32)i;
     }
 }
 

@@ -390,6 +390,7 @@ class VolumeJob:
         plan, self.per_rank, self.npairs = merge_plan(self.grid, self.world)
         self.plan = torch.from_numpy(plan).to(self.device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.side = torch.cuda.Stream(device=self.device)      # merged table, next to the label kernels
         self.pred = [None] * len(self.mine)
         self.base = [None] * len(self.mine)
         self.labels = [torch.empty(self.chunk_shape[i], dtype=torch.int32, device=self.device) for i in self.mine]
@@ -472,13 +473,26 @@ class VolumeJob:
             self.ws[li].numel(),
             self.caps_runs[li], self.D._stream_ptr(self.torch)))
 
-    def _merge(self):
+    def _merge_ids(self):
+        """The part of the merge the label writes wait for: id bases, edges, union-find, final id map."""
         L, C = self.C.lib(), self.C
         C.check(L.syn_merge_ccs_packed(
             self.all_slots.data_ptr(), self.slot_bytes, self.cap_rows, self.cap_entries, self.plan.data_ptr(),
             self.nchunks, self.npairs, self.size_thr, self.max_edges, self.merge_ws.data_ptr(), self.merge_ws.numel(),
-            self.id_base.data_ptr(), self.merged.data_ptr(), self.fmap.data_ptr(), self.info.data_ptr(),
+            self.id_base.data_ptr(), None, self.fmap.data_ptr(), self.info.data_ptr(),
             self.D._stream_ptr(self.torch)))
+
+    def _merge_table(self):
+        """The merged segment table (on whatever stream is current: a side stream next to the label kernels)."""
+        L, C = self.C.lib(), self.C
+        C.check(L.syn_merge_ccs_table(
+            self.all_slots.data_ptr(), self.slot_bytes, self.cap_rows, self.cap_entries, self.plan.data_ptr(),
+            self.nchunks, self.size_thr, self.max_edges, self.merge_ws.data_ptr(), self.merge_ws.numel(),
+            self.id_base.data_ptr(), self.merged.data_ptr(), self.info.data_ptr(), self.D._stream_ptr(self.torch)))
+
+    def _merge(self):
+        self._merge_ids()
+        self._merge_table()
 
     def _finish(self, li):
         L, C = self.C.lib(), self.C
@@ -557,10 +571,18 @@ class VolumeJob:
         for li in range(len(self.mine)):
             self._begin(li)
 
-    def _stage_b(self):
-        self._merge()
+    def _stage_b(self, after_ids=None):
+        torch = self.torch
+        self._merge_ids()
+        if after_ids is not None:
+            after_ids()
+        cur = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(cur)                 # fork: the table needs nothing but the id map
+        with torch.cuda.stream(self.side):
+            self._merge_table()
         for li in range(len(self.mine)):
             self._finish(li)
+        cur.wait_stream(self.side)                 # join
 
     def _capture(self):
         torch, L = self.torch, self.C.lib()
@@ -692,7 +714,10 @@ class VolumeJob:
                     self.stream.wait_event(ev_in[li])
                     self._begin(li)
                 self._gather()
-                self._merge()
+                self._merge_ids()
+                self.side.wait_stream(self.stream)
+                with torch.cuda.stream(self.side):
+                    self._merge_table()
                 for li in range(n_own):
                     self._finish(li)
                     e = torch.cuda.Event()
@@ -705,6 +730,7 @@ class VolumeJob:
                         e2.record(s_out)
                     hosts.append(h)
                     ev_out.append(e2)
+                self.stream.wait_stream(self.side)
             if self.check():
                 break
             for h in hosts:

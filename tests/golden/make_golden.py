@@ -402,6 +402,49 @@ def main():
                         groups=np.array(sorted("|".join(sorted(c.filename for c in grp)) for grp in groups12)),
                         face_tags=np.array([taskio.continuation.fname_face_tag(f) for f in Face.all_faces()]))
     out["g12"] = (len(df12), len(groups12))
+    # ---- G13: merge_overlaps_task (tasks.py:300-311) over the overlap matrices of the REMAPPED g4 chunks (what the
+    #          kube workflow feeds it), ties included; merge_seginfo_df with an extra (max_overlap) column ----------
+    from scipy.sparse import coo_matrix as coo_matrix13
+    base13 = (orc.synth_base(vol.shape, seed=12, block=5, bg=0.1) % np.uint64(7)) * np.uint64(1 << 33)   # few ids: ties
+    ovs13 = np.empty(grid, dtype=object)
+    tri13 = {}
+    for (i, (gi, bb)) in enumerate(zip(np.ndindex(grid), boxes)):
+        ovs13[gi] = quiet(tasks.overlap_task, np.ascontiguousarray(final[bb.index()]),
+                          np.ascontiguousarray(base13[bb.index()]))
+        tri13[f"ov_{i}"] = np.stack([np.asarray(ovs13[gi].row, dtype=np.int64), np.asarray(ovs13[gi].col, dtype=np.int64),
+                                     np.asarray(ovs13[gi].data, dtype=np.int64)], 1)
+        tri13[f"ov_shape_{i}"] = np.array(ovs13[gi].shape, dtype=np.int64)
+    mo13 = quiet(tasks.merge_overlaps_task, ovs13)
+    cons13 = syn.proc.overlap.merge.consolidate_overlaps(ovs13)
+    vals13 = np.asarray(cons13.data, dtype=np.int64)
+    nties13 = 0
+    for r in np.unique(cons13.row):
+        v = vals13[cons13.row == r]
+        nties13 += int((v == v.max()).sum() > 1)
+    # merge_seginfo_df with an extra column: the dst ids of g9's full table, plus a per-fragment marker column
+    df13 = full9.copy()
+    df13["max_overlap"] = np.arange(len(df13), dtype=np.int64) * 3 + 1000
+    merged13 = syn.proc.seg.merge.merge_seginfo_df(df13, new_id_colname=rcn.dst_id)
+    # hand-made chunk matrices with exact ties after the duplicates are summed (rows 5 and 9), entry order scrambled
+    tA = coo_matrix13(([3, 2, 4, 1, 7], ([5, 5, 9, 9, 2], [20, 10, 40, 30, 8])), shape=(12, 50))
+    tB = coo_matrix13(([1, 3, 6, 7], ([5, 9, 2, 11], [10, 30, 8, 3])), shape=(12, 50))
+    tarr = np.empty((2, 1, 1), dtype=object)
+    tarr[0, 0, 0], tarr[1, 0, 0] = tA, tB
+    tmo = quiet(tasks.merge_overlaps_task, tarr)
+    tri13["tie_in_a"] = np.stack([tA.row, tA.col, tA.data], 1).astype(np.int64)
+    tri13["tie_in_b"] = np.stack([tB.row, tB.col, tB.data], 1).astype(np.int64)
+    tri13["tie_out"] = np.stack([tmo.row, tmo.col, tmo.data], 1).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "g13_merge_overlaps.npz"), base=base13, **tri13,
+                        max_row=np.asarray(mo13.row, dtype=np.int64), max_col=np.asarray(mo13.col, dtype=np.int64),
+                        max_val=np.asarray(mo13.data, dtype=np.int64), n_rows_with_ties=nties13,
+                        cons_row=np.asarray(cons13.row, dtype=np.int64), cons_col=np.asarray(cons13.col, dtype=np.int64),
+                        cons_val=vals13,
+                        df_index=np.asarray(df13.index, dtype=np.int64), df_table=df13[[rcn.size] + rcn.centroid_cols + rcn.bbox_cols].to_numpy(dtype=np.int64),
+                        df_dst=df13[rcn.dst_id].to_numpy(dtype=np.float64), df_extra=df13["max_overlap"].to_numpy(dtype=np.int64),
+                        merged_index=np.asarray(merged13.index, dtype=np.float64),
+                        merged_columns=np.array(list(merged13.columns)),
+                        merged_table=merged13.to_numpy(dtype=np.float64))
+    out["g13"] = (int(mo13.nnz), nties13, len(merged13), list(merged13.columns))
     print("golden written:", out)
 
 

@@ -638,3 +638,34 @@ def test_chunk_pipeline_graph_replay(syn):
         gr, gc, gv = res.pairs_numpy()
         assert np.array_equal(gr, r) and np.array_equal(gc, cc.astype(np.uint64)) and np.array_equal(gv, v)
     assert pipe.launches_per_run >= 10
+
+
+def test_g13_merge_overlaps_device_golden(syn):
+    """multi.merge_overlaps_device (syn_merge_overlaps) == the executed reference's merge_overlaps_task
+    (tasks.py:300-311) on the remapped g4 chunks and on matrices with exact ties."""
+    import torch
+    from types import SimpleNamespace
+    from synaptor_b200 import multi
+    g = gold("g13_merge_overlaps.npz")
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def run(tris, n_ids):
+        results, luts = [], []
+        for t in tris:
+            r = SimpleNamespace(labels=torch.zeros(1, device=dev),
+                                pair_rows=torch.from_numpy(t[:, 0].astype(np.uint32).view(np.int32).copy()).to(dev),
+                                pair_cols=torch.from_numpy(t[:, 1].astype(np.int64).copy()).to(dev),
+                                pair_vals=torch.from_numpy(t[:, 2].astype(np.int64).copy()).to(dev),
+                                counts={"pairs": len(t)})
+            results.append(r)
+            luts.append(torch.arange(n_ids, dtype=torch.int32, device=dev))        # rows are final ids already
+        merge = SimpleNamespace(chunk_luts=luts, fmap=torch.zeros(n_ids, dtype=torch.int32, device=dev))
+        ids, cols, vals = multi.merge_overlaps_device(results, merge, rank=0, world=1)
+        return {int(i): (int(c), int(v)) for (i, c, v) in zip(ids, cols, vals)}
+
+    tris = [g[f"ov_{i}"] for i in range(8)]
+    n_ids = int(max(int(t[:, 0].max()) for t in tris if len(t))) + 1
+    want = {int(r): (int(c), int(v)) for (r, c, v) in zip(g["max_row"], g["max_col"], g["max_val"])}
+    assert run(tris, n_ids) == want
+    want_t = {int(r): (int(c), int(v)) for (r, c, v) in g["tie_out"]}
+    assert run([g["tie_in_a"], g["tie_in_b"]], 12) == want_t

@@ -168,3 +168,81 @@ def test_g10_seg_utils():
         # orig_ids=False: the same entries as indices into the sorted id arrays
         assert np.array_equal(np.searchsorted(g["ov_row_ids"], r), g["ov_row"])
         assert np.array_equal(np.searchsorted(g["ov_col_ids"], c.astype(np.uint64)), g["ov_col"])
+
+
+# ---- G13: merge_overlaps_task + merge_seginfo_df with extra columns, pinned to the executed reference ----------
+def _g13_chunk_mats(g):
+    import scipy.sparse as sp
+    mats = []
+    for i in range(8):
+        t, shp = g[f"ov_{i}"], tuple(int(x) for x in g[f"ov_shape_{i}"])
+        mats.append(sp.coo_matrix((t[:, 2], (t[:, 0], t[:, 1])), shape=shp) if shp != (0, 0)
+                    else sp.coo_matrix((0, 0), dtype=np.int64))
+    arr = np.empty((2, 2, 2), dtype=object)
+    for (i, gi) in enumerate(np.ndindex(2, 2, 2)):
+        arr[gi] = mats[i]
+    return arr
+
+
+def test_g13_merge_overlaps_task_host():
+    """proc.tasks.merge_overlaps_task (host objects in, as the reference: tasks.py:300-311) == executed reference,
+    on the remapped g4 chunks and on hand-made matrices with exact ties (the smallest base id wins a tie)."""
+    import io
+    from contextlib import redirect_stdout
+    import scipy.sparse as sp
+    from synaptor_b200.proc import tasks
+    g = gold("g13_merge_overlaps.npz")
+    with redirect_stdout(io.StringIO()):
+        mo = tasks.merge_overlaps_task(_g13_chunk_mats(g))
+    assert np.array_equal(np.asarray(mo.row, dtype=np.int64), g["max_row"])
+    assert np.array_equal(np.asarray(mo.col, dtype=np.int64), g["max_col"])
+    assert np.array_equal(np.asarray(mo.data, dtype=np.int64), g["max_val"])
+    ta, tb = g["tie_in_a"], g["tie_in_b"]
+    arr = np.empty((2, 1, 1), dtype=object)
+    arr[0, 0, 0] = sp.coo_matrix((ta[:, 2], (ta[:, 0], ta[:, 1])), shape=(12, 50))
+    arr[1, 0, 0] = sp.coo_matrix((tb[:, 2], (tb[:, 0], tb[:, 1])), shape=(12, 50))
+    with redirect_stdout(io.StringIO()):
+        tmo = tasks.merge_overlaps_task(arr)
+    got = np.stack([tmo.row, tmo.col, tmo.data], 1).astype(np.int64)
+    assert np.array_equal(got, g["tie_out"])
+    # the oracle's restatement agrees too
+    want = {int(r): (int(c), int(v)) for (r, c, v) in g["tie_out"]}
+    rows = np.concatenate([ta[:, 0], tb[:, 0]]); cols = np.concatenate([ta[:, 1], tb[:, 1]]); vals = np.concatenate([ta[:, 2], tb[:, 2]])
+    tot = {}
+    for (a, b, n) in zip(rows.tolist(), cols.tolist(), vals.tolist()):
+        tot[(a, b)] = tot.get((a, b), 0) + n
+    best = {}
+    for ((a, b), n) in sorted(tot.items()):
+        if a not in best or n > best[a][1]:
+            best[a] = (b, n)
+    assert best == want
+
+
+def test_g13_merge_seginfo_df_extra_columns():
+    """merge_seginfo_df keeps columns beyond the ten seg-info ones, from the smallest fragment of each merged id
+    (merge_df.py:30-31), and sums like pandas: identical to the executed reference's frame, compared by id."""
+    import pandas as pd
+    from synaptor_b200.proc import colnames as cn
+    from synaptor_b200.proc.seg.merge import merge_seginfo_df
+    g = gold("g13_merge_overlaps.npz")
+    df = pd.DataFrame(g["df_table"], index=g["df_index"], columns=cn.seg_info_cols)
+    df.index.name = cn.seg_id
+    df[cn.dst_id] = g["df_dst"]
+    df["max_overlap"] = g["df_extra"]
+    got = merge_seginfo_df(df, new_id_colname=cn.dst_id)
+    assert list(got.columns) == list(g["merged_columns"])
+    want = {int(i): row for (i, row) in zip(g["merged_index"], g["merged_table"])}
+    assert set(int(i) for i in got.index) == set(want)
+    for (i, row) in zip(got.index, got.to_numpy(dtype=np.float64)):
+        assert np.array_equal(row, want[int(i)]), (i, row, want[int(i)])
+
+
+def test_kahan_sum_is_pandas_group_sum():
+    """The oracle's (and the device's) ordered Kahan sum is what pandas' groupby().sum() computes."""
+    import pandas as pd
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 40, size=4000)
+    vals = rng.random(4000) * 10.0 ** rng.integers(-3, 9, size=4000)
+    want = pd.DataFrame({"k": keys, "v": vals}).groupby("k")["v"].sum()
+    for k in want.index:
+        assert orc.kahan_sum(vals[keys == k]) == want[k]
