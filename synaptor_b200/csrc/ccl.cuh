@@ -1223,12 +1223,15 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
             atomicAdd(sl + 1, n * xl);
             atomicAdd(sl + 2, n * yl);
             atomicAdd(sl + 3, n * z0 + bitpos_sum(bits));
+            // the box only ever grows: a (possibly stale) value that already covers this piece makes the atomic
+            // unnecessary -- and neighbouring lanes mostly hit the SAME slot, where atomics serialise
+            const u32 zlo = z0 + (u32)__ffs(bits) - 1u, zhi = z0 + 31u - (u32)__clz(bits);
             atomicMin(sl + 4, xl);
             atomicMin(sl + 5, yl);
-            atomicMin(sl + 6, z0 + (u32)__ffs(bits) - 1u);
+            atomicMin(sl + 6, zlo);
             atomicMax(sl + 7, xl);
             atomicMax(sl + 8, yl);
-            atomicMax(sl + 9, z0 + 31u - (u32)__clz(bits));
+            atomicMax(sl + 9, zhi);
         }
     }
     __syncthreads();
@@ -1243,7 +1246,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_ccl(const u32 *__restrict
         rec.sz = sl[3];
         rec.minx = sl[4] + x0; rec.miny = sl[5] + y0; rec.minz = sl[6];
         rec.maxx = sl[7] + x0; rec.maxy = sl[8] + y0; rec.maxz = sl[9];
-        rec.pad[0] = rec.pad[1] = 0;
+        // pad[0] = 1: the component cannot reach another tile (it touches no tile border that has a neighbour
+        // tile), so this record IS the component: k_stats_merge stores it without atomics.  Not with dilation:
+        // the box covers original voxels only, the connectivity runs through the dilated ones.
+        const bool reach = (sl[4] == 0 && x0 > 0) || (sl[7] + 1 == vx && x0 + vx < (u32)g.nx) ||
+                           (sl[5] == 0 && y0 > 0) || (sl[8] + 1 == vy && y0 + vy < (u32)g.ny);
+        rec.pad[0] = (same_mask && sl[0] && !reach) ? 1u : 0u;
+        rec.pad[1] = 0;
         recs[s_recbase + idx] = rec;           // a local root with no ORIGINAL voxel (dilation) has size 0: harmless
     }
     SYN_TIMER_MARK(cnt, 7);   // records
@@ -1600,6 +1609,17 @@ __global__ void __launch_bounds__(256) k_stats_merge(const TileRec *__restrict__
             first = false;
         }
         if (r.size == 0) continue;
+        if (r.pad[0]) {
+            // a component that lives in one tile: its single record is stored as it is (no atomics; the look-back
+            // scan initialised the same slot before this kernel started)
+            CompStat s;
+            s.size = r.size; s.sx = r.sx; s.sy = r.sy; s.sz = r.sz;
+            s.minx = r.minx; s.miny = r.miny; s.minz = r.minz;
+            s.maxx = r.maxx; s.maxy = r.maxy; s.maxz = r.maxz;
+            s.keep = 0; s.row = 0;
+            stat[c] = s;
+            continue;
+        }
         if (c == cand) {
             atomicAdd(&s_acc[0], (unsigned long long)r.size);
             atomicAdd(&s_acc[1], (unsigned long long)r.sx);
