@@ -664,14 +664,7 @@ class VolumeJob:
         return False
 
     # ---- host arrays in, host results out ------------------------------------------------------------------
-    def run_host(self, preds, bases=None):
-        """
-        One step with HOST inputs (numpy arrays of the own chunks, C- or F-ordered, pinned or pageable): the input
-        copies of the chunks run on a copy-in stream ahead of the chunk passes, the final label chunks come back on
-        a copy-out stream while the remaining chunks are still being written.  Returns (list of uint32 label chunks
-        in final ids (views of pooled pinned blocks), merged table numpy [n, 11], list of own chunk tables, list of
-        {chunk-local id: final id}, list of (rows, cols, vals, shape) overlap triples).
-        """
+    def _host_setup(self, preds, bases):
         torch, D = self.torch, self.D
         n_own = len(self.mine)
         if len(preds) != n_own or (self.with_base and (bases is None or len(bases) != n_own)):
@@ -683,8 +676,6 @@ class VolumeJob:
                 self.base[li] = torch.empty(shp, dtype=torch.int64, device=self.device) if self.with_base else None
             self._own_inputs = True
             self.graphs = None
-        s_in = D.side_stream(torch, self.device, "in")
-        s_out = D.side_stream(torch, self.device, "out")
         if self.cap_rows is None:            # first call: blocking upload + sizing pass
             for li in range(n_own):
                 D.upload_f32(torch, self.pred[li], preds[li])
@@ -695,64 +686,182 @@ class VolumeJob:
             self.use_graph = False           # the host path launches per chunk as its inputs arrive
             self.prepare()
             self.use_graph = g
-        for _attempt in range(4):
-            cur = torch.cuda.current_stream(self.device)
-            s_in.wait_stream(cur)
-            ev_in = []
-            with torch.cuda.stream(s_in):
-                for li in range(n_own):
-                    D.upload_f32(torch, self.pred[li], preds[li])
-                    if self.with_base:
-                        D.upload_u64(torch, self.base[li], bases[li])
-                    e = torch.cuda.Event()
-                    e.record(s_in)
-                    ev_in.append(e)
-            hosts, ev_out = [], []
-            self.stream.wait_stream(cur)
-            with torch.cuda.stream(self.stream):
-                for li in range(n_own):
-                    self.stream.wait_event(ev_in[li])
-                    self._begin(li)
-                self._gather()
-                self._merge_ids()
-                self.side.wait_stream(self.stream)
-                with torch.cuda.stream(self.side):
-                    self._merge_table()
-                for li in range(n_own):
-                    self._finish(li)
-                    e = torch.cuda.Event()
-                    e.record(self.stream)
-                    with torch.cuda.stream(s_out):
-                        s_out.wait_event(e)
-                        h = D.pinned_acquire(torch, self.labels[li].shape, self.labels[li].dtype)
-                        h.copy_(self.labels[li], non_blocking=True)
-                        e2 = torch.cuda.Event()
-                        e2.record(s_out)
-                    hosts.append(h)
-                    ev_out.append(e2)
-                self.stream.wait_stream(self.side)
-            if self.check():
-                break
-            for h in hosts:
+            self._tickets = [None, None]
+
+    def _staging(self, slot):
+        """Pinned host copies of the small outputs of one in-flight volume (two volumes can be in flight)."""
+        torch = self.torch
+        st = getattr(self, "_stage", None)
+        if st is None or st.get("caps") != (self.cap_rows, self.cap_entries, tuple(self.max_pairs)):
+            st = self._stage = {"caps": (self.cap_rows, self.cap_entries, tuple(self.max_pairs)), "slots": {}}
+        if slot not in st["slots"]:
+            def pin(t):
+                return torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            d = {"info": pin(self.info), "id_base": pin(self.id_base), "merged": pin(self.merged), "fmap": pin(self.fmap),
+                 "tables": pin(self.my_slots), "counts": [pin(w[:self.C.NCOUNTS * 8]) for w in self.ws],
+                 "pairs": [tuple(pin(t) for t in pr) if pr is not None else None for pr in self.pairs]}
+            st["slots"][slot] = d
+        return st["slots"][slot]
+
+    def _host_enqueue(self, preds, bases, prev=None):
+        """Queues one volume: input copies (copy-in stream), chunk passes + exchange + merge + label writes (job
+        stream), label volumes and the small outputs back to pinned host memory (copy-out stream).  Nothing here
+        waits for the GPU.  `prev`: the ticket of the volume queued before this one, still in flight."""
+        torch, D = self.torch, self.D
+        n_own = len(self.mine)
+        s_in = D.side_stream(torch, self.device, "in")
+        s_out = D.side_stream(torch, self.device, "out")
+        slot = 0 if prev is None else 1 - prev["slot"]
+        stg = self._staging(slot)
+        cur = torch.cuda.current_stream(self.device)
+        s_in.wait_stream(cur)
+        ev_in = []
+        with torch.cuda.stream(s_in):
+            for li in range(n_own):
+                if prev is not None:
+                    s_in.wait_event(prev["ev_fin"][li])      # the previous volume still reads this chunk's inputs
+                D.upload_f32(torch, self.pred[li], preds[li])
+                if self.with_base:
+                    D.upload_u64(torch, self.base[li], bases[li])
+                e = torch.cuda.Event()
+                e.record(s_in)
+                ev_in.append(e)
+        hosts, ev_out, ev_fin = [], [], []
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            if prev is not None:
+                self.stream.wait_event(prev["ev_small"])      # its tables / counters / pairs are on the host now
+            for li in range(n_own):
+                self.stream.wait_event(ev_in[li])
+                if prev is not None:
+                    self.stream.wait_event(prev["ev_out"][li])   # its label chunk has left the device buffer
+                self._begin(li)
+            self._gather()
+            self._merge_ids()
+            self.side.wait_stream(self.stream)
+            with torch.cuda.stream(self.side):
+                self._merge_table()
+            for li in range(n_own):
+                self._finish(li)
+                e = torch.cuda.Event()
+                e.record(self.stream)
+                ev_fin.append(e)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(e)
+                    h = D.pinned_acquire(torch, self.labels[li].shape, self.labels[li].dtype)
+                    h.copy_(self.labels[li], non_blocking=True)
+                    e2 = torch.cuda.Event()
+                    e2.record(s_out)
+                hosts.append(h)
+                ev_out.append(e2)
+            self.stream.wait_stream(self.side)
+            e_all = torch.cuda.Event()
+            e_all.record(self.stream)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(e_all)
+            stg["info"].copy_(self.info, non_blocking=True)
+            stg["id_base"].copy_(self.id_base, non_blocking=True)
+            stg["fmap"].copy_(self.fmap, non_blocking=True)
+            stg["merged"].copy_(self.merged, non_blocking=True)
+            stg["tables"].copy_(self.my_slots, non_blocking=True)
+            for li in range(n_own):
+                stg["counts"][li].copy_(self.ws[li][:self.C.NCOUNTS * 8], non_blocking=True)
+                if self.pairs[li] is not None:
+                    for (h, d) in zip(stg["pairs"][li], self.pairs[li]):
+                        h.copy_(d, non_blocking=True)
+            ev_small = torch.cuda.Event()
+            ev_small.record(s_out)
+        return {"slot": slot, "hosts": hosts, "ev_out": ev_out, "ev_fin": ev_fin, "ev_small": ev_small, "stg": stg}
+
+    def _host_collect(self, t):
+        """Waits for a queued volume and builds its host results; None when a capacity overflowed."""
+        D, C = self.D, self.C
+        t["ev_small"].synchronize()
+        stg = t["stg"]
+        info = stg["info"].numpy()
+        bad = int(info[3]) != 0
+        counts = []
+        for li in range(len(self.mine)):
+            cd = D._counts_dict(stg["counts"][li].numpy().view(np.int64).copy())
+            counts.append(cd)
+            bad = bad or (cd["errflags"] & (C.EF_RUNS | C.EF_TABLE | C.EF_PAIRS | C.EF_SEGS)) != 0
+        if bad:
+            for e in t["ev_out"]:
+                e.synchronize()
+            for h in t["hosts"]:
                 D.pinned_release(h)
-        else:
-            raise self.C.CapacityError(self.C.SYN_ERR_CAPACITY, "capacities never settled", None)
-        merged = self.merged_table()
-        base_ids = self.id_base.cpu().numpy()
+            return None
+        n_merged = int(info[1])
+        merged = stg["merged"].numpy()[:n_merged].copy()
+        base_ids = stg["id_base"].numpy()
+        fmap = stg["fmap"].numpy().view(np.uint32)
+        slots = stg["tables"].numpy()
         tables, maps, ovs = [], [], []
         for li, ci in enumerate(self.mine):
-            t = self.my_slots[li, 128:128 + self.cap_rows * 88].view(torch.int64).view(self.cap_rows, 11)
             kept = int(base_ids[ci + 1] - base_ids[ci])
-            t = t[:kept].cpu().numpy()
-            fm = self.fmap[int(base_ids[ci]) + 1: int(base_ids[ci]) + 1 + kept].cpu().numpy().view(np.uint32)
-            tables.append(t)
-            maps.append(dict(zip(t[:, 0].tolist(), fm.tolist())))
-            ovs.append(self.overlaps(li) if self.with_base else None)
+            tab = slots[li, 128:128 + self.cap_rows * 88].view(np.int64).reshape(self.cap_rows, 11)[:kept].copy()
+            fm = fmap[int(base_ids[ci]) + 1: int(base_ids[ci]) + 1 + kept]
+            tables.append(tab)
+            maps.append(dict(zip(tab[:, 0].tolist(), fm.tolist())))
+            if self.with_base:
+                cd = counts[li]
+                n = cd["pairs"]
+                pr = stg["pairs"][li]
+                shape = (0, 0) if cd["max_label"] == 0 or cd["max_base"] == 0 else (cd["max_label"] + 1, cd["max_base"] + 1)
+                ovs.append((pr[0].numpy()[:n].view(np.uint32).astype(np.int64), pr[1].numpy()[:n].view(np.uint64).copy(),
+                            pr[2].numpy()[:n].copy(), shape))
+            else:
+                ovs.append(None)
         labels = []
-        for (h, e) in zip(hosts, ev_out):
+        for (h, e) in zip(t["hosts"], t["ev_out"]):
             e.synchronize()
             labels.append(D.pinned_numpy(h, np.uint32))
         return labels, merged, tables, maps, ovs
+
+    def run_host(self, preds, bases=None):
+        """
+        One volume with HOST inputs (numpy arrays of the own chunks, C- or F-ordered, pinned or pageable): the input
+        copies of the chunks run on a copy-in stream ahead of the chunk passes, the final label chunks come back on
+        a copy-out stream while the remaining chunks are still being written.  Returns (list of uint32 label chunks
+        in final ids (views of pooled pinned blocks), merged table numpy [n, 11], list of own chunk tables, list of
+        {chunk-local id: final id}, list of (rows, cols, vals, shape) overlap triples).
+        """
+        self._host_setup(preds, bases)
+        for _attempt in range(4):
+            out = self._host_collect(self._host_enqueue(preds, bases))
+            if out is not None:
+                return out
+            self.check()                     # grows what overflowed (collective)
+        raise self.C.CapacityError(self.C.SYN_ERR_CAPACITY, "capacities never settled", None)
+
+    def run_host_stream(self, volumes):
+        """
+        run_host over a sequence of volumes, software-pipelined: `volumes` yields (preds, bases) of the own chunks;
+        the results come back in order.  The input copies of volume k + 1 are queued BEFORE volume k is collected,
+        so the label volumes going back to the host, and the host-side construction of the result objects, run
+        under the next volume's input copies (PCIe is full duplex): the link carries input copies back to back.
+        Collective when world > 1: every rank must iterate the same number of volumes.
+        """
+        prev = prev_args = None
+        for (preds, bases) in volumes:
+            self._host_setup(preds, bases)
+            cur = self._host_enqueue(preds, bases, prev=prev)
+            if prev is not None:
+                out = self._host_collect(prev)
+                if out is None:                              # overflow: drain, grow, redo that volume on its own
+                    self._host_collect(cur)
+                    self.check()
+                    yield self.run_host(*prev_args)
+                    cur = self._host_enqueue(preds, bases)
+                else:
+                    yield out
+            prev, prev_args = cur, (preds, bases)
+        if prev is not None:
+            out = self._host_collect(prev)
+            if out is None:
+                self.check()
+                out = self.run_host(*prev_args)
+            yield out
 
     # ---- results (each synchronises) -------------------------------------------------------------------
     def counts(self, local_index):

@@ -320,29 +320,14 @@ class VolumeResult:
 _volume_jobs = {}
 
 
-def volume_tasks(desc_chunks, base_chunks, vol_shape, chunk_shape, cc_thresh, sz_thresh, size_thr,
-                 offset=(0, 0, 0), connectivity=6, rank=None, world=None, group=None):
-    """
-    chunk_ccs -> merge_ccs -> remap_ids -> chunk_overlaps of a chunked volume (tasks.py:26-69, 72-122, 314-333,
-    290-297; the reference runs them as four waves of tasks with files in between).  `desc_chunks` / `base_chunks`:
-    the float32 prediction and uint64 base-segmentation arrays of the chunks THIS rank owns (chunk i of the
-    np.ndindex chunk grid lives on rank i % world), host arrays in any memory order (or None for base_chunks).
-    Collective over `group` when world > 1 (torch.distributed, NCCL).
-
-    Returns a VolumeResult:
-      ccs            [uint32 ndarray per own chunk]  final (merged, size-thresholded) global ids, as remap_ids_task
-      merged_info    DataFrame of the merged segments (merge_ccs_task's first output; int64 index, ascending id)
-      chunk_id_maps  [{chunk-local id: final id} per own chunk]   (merge_ccs_task's second output, own entries)
-      chunk_infos    [seg-info DataFrame per own chunk]           (cc_task's third output)
-      overlaps       [scipy COO per own chunk]                    overlap_task on the remapped chunk
-    """
+def _volume_job(vol_shape, chunk_shape, cc_thresh, sz_thresh, size_thr, offset, connectivity, rank, world, group,
+                with_base):
     from .. import multi
     torch = D._torch()
     if world is None:
         import torch.distributed as dist
         world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank(group) if world > 1 else 0
-    with_base = base_chunks is not None
     key = (tuple(vol_shape), tuple(chunk_shape), float(cc_thresh), int(sz_thresh), int(size_thr), tuple(offset),
            int(connectivity), int(rank), int(world), with_base, torch.cuda.current_device(), id(group))
     job = _volume_jobs.get(key)
@@ -352,7 +337,10 @@ def volume_tasks(desc_chunks, base_chunks, vol_shape, chunk_shape, cc_thresh, sz
         job = multi.VolumeJob(vol_shape, chunk_shape, t32, sz_thresh, size_thr, connectivity=connectivity,
                               with_base=with_base, rank=rank, world=world, group=group, vol_offset=offset, graph=False)
         _volume_jobs[key] = job
-    labels, merged, tables, maps, ovs = job.run_host(desc_chunks, base_chunks)
+    return job
+
+
+def _volume_result(job, with_base, labels, merged, tables, maps, ovs):
     out = VolumeResult()
     out.ccs = labels
     out.merged_info = seg.misc.seg_info_from_table(merged[:, 0], merged[:, 1:])
@@ -369,3 +357,39 @@ def volume_tasks(desc_chunks, base_chunks, vol_shape, chunk_shape, cc_thresh, sz
     out.chunk_indices = list(job.mine)
     out.d2h_small_bytes = int(small)
     return out
+
+
+def volume_tasks(desc_chunks, base_chunks, vol_shape, chunk_shape, cc_thresh, sz_thresh, size_thr,
+                 offset=(0, 0, 0), connectivity=6, rank=None, world=None, group=None):
+    """
+    chunk_ccs -> merge_ccs -> remap_ids -> chunk_overlaps of a chunked volume (tasks.py:26-69, 72-122, 314-333,
+    290-297; the reference runs them as four waves of tasks with files in between).  `desc_chunks` / `base_chunks`:
+    the float32 prediction and uint64 base-segmentation arrays of the chunks THIS rank owns (chunk i of the
+    np.ndindex chunk grid lives on rank i % world), host arrays in any memory order (or None for base_chunks).
+    Collective over `group` when world > 1 (torch.distributed, NCCL).
+
+    Returns a VolumeResult:
+      ccs            [uint32 ndarray per own chunk]  final (merged, size-thresholded) global ids, as remap_ids_task
+      merged_info    DataFrame of the merged segments (merge_ccs_task's first output; int64 index, ascending id)
+      chunk_id_maps  [{chunk-local id: final id} per own chunk]   (merge_ccs_task's second output, own entries)
+      chunk_infos    [seg-info DataFrame per own chunk]           (cc_task's third output)
+      overlaps       [scipy COO per own chunk]                    overlap_task on the remapped chunk
+    """
+    with_base = base_chunks is not None
+    job = _volume_job(vol_shape, chunk_shape, cc_thresh, sz_thresh, size_thr, offset, connectivity, rank, world, group,
+                      with_base)
+    return _volume_result(job, with_base, *job.run_host(desc_chunks, base_chunks))
+
+
+def volume_tasks_stream(volumes, vol_shape, chunk_shape, cc_thresh, sz_thresh, size_thr, offset=(0, 0, 0),
+                        connectivity=6, rank=None, world=None, group=None, with_base=True):
+    """
+    volume_tasks over a sequence of equally shaped volumes, software-pipelined: `volumes` yields
+    (desc_chunks, base_chunks); VolumeResults come back in order, each identical to volume_tasks'.  The input copies
+    of volume k + 1 are queued before volume k is collected, so its label volumes going back and the host-side
+    construction of its DataFrames / id maps / COO matrices run under the next volume's input copies.
+    """
+    job = _volume_job(vol_shape, chunk_shape, cc_thresh, sz_thresh, size_thr, offset, connectivity, rank, world, group,
+                      with_base)
+    for res in job.run_host_stream(volumes):
+        yield _volume_result(job, with_base, *res)

@@ -227,3 +227,44 @@ def test_volume_job_nccl_ranks():
                 assert shp == wshp and np.array_equal(rr, wr) and np.array_equal(cc, wc) and np.array_equal(vv, wv)
                 seen.add(ci)
         assert seen == set(range(len(want["chunks"])))
+
+
+def test_volume_tasks_stream_pipelined():
+    """The generator form: several volumes (different data, same shape) in flight; each result == volume_tasks'."""
+    import synaptor_b200 as syn
+    vshape, cshape = (40, 40, 64), (20, 40, 32)
+    vols = []
+    for k in range(4):
+        vol = orc.synth_pred(vshape, seed=40 + k, sigma=2.0, fg=0.05 + 0.04 * k)
+        base_vol = orc.synth_base(vshape, seed=50 + k, block=6, bg=0.1)
+        want = oracle_volume_job(vol, base_vol, cshape, 0.5, 10, 15)
+        preds = [np.ascontiguousarray(vol[sl]) for (_, sl, _) in want["chunks"]]
+        bases = [np.ascontiguousarray(base_vol[sl]) for (_, sl, _) in want["chunks"]]
+        vols.append((preds, bases, want))
+    outs = list(syn.proc.tasks.volume_tasks_stream(((p, b) for (p, b, _) in vols), vshape, cshape, 0.5, 10, 15,
+                                                   rank=0, world=1))
+    assert len(outs) == len(vols)
+    for (out, (_, _, want)) in zip(outs, vols):
+        for (ci, (gi, sl, beg)) in enumerate(want["chunks"]):
+            assert np.array_equal(out.ccs[ci], want["final"][sl])
+            assert out.chunk_id_maps[ci] == {int(k): int(v) for (k, v) in want["id_maps"][gi].items()}
+            wr, wc, wv, wshape = want["overlaps"][ci]
+            m = out.overlaps[ci]
+            assert m.shape == wshape and np.array_equal(m.row, wr) and np.array_equal(m.col, wc) and np.array_equal(m.data, wv)
+        got = {int(i): [int(x) for x in row] for (i, row) in zip(out.merged_info.index, out.merged_info.to_numpy())}
+        assert got == {int(k): [int(x) for x in v] for (k, v) in want["merged"].items()}
+
+
+def test_pageable_large_input_staged():
+    """A pageable prediction / base chunk above the staging threshold (8 MB) goes through the threaded pinned staging
+    path (C- and F-ordered): same result as the oracle."""
+    import synaptor_b200 as syn
+    pred = orc.synth_pred((96, 128, 224), seed=8, sigma=2.0, fg=0.05)          # 11 MB float32, 22 MB uint64
+    base = orc.synth_base(pred.shape, seed=9, block=16)
+    want = orc.cc_task_c(pred, 0.5, 30, with_continuations=False)
+    r, c, v, shp = orc.count_overlaps_c(want[0], base)
+    for conv in (np.ascontiguousarray, np.asfortranarray):
+        got = syn.proc.tasks.cc_overlap_task(conv(pred), conv(base), 0.5, 30)
+        assert np.array_equal(got[0], want[0])
+        assert got[3].shape == shp and np.array_equal(got[3].row, r) and np.array_equal(got[3].col, c) \
+            and np.array_equal(got[3].data, v)
