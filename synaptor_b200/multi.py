@@ -369,7 +369,13 @@ class VolumeJob:
         from . import _cabi as C
         import torch.distributed as dist
         self.D, self.C = D, C
-        self.torch = torch = D._torch()
+        # (a CPU device is accepted for the tests of the host-side plumbing: they replace the CUDA entry points)
+        self.cuda = device is None or getattr(device, "type", "cuda") == "cuda"
+        if self.cuda:
+            self.torch = torch = D._torch()
+        else:
+            import torch
+            self.torch = torch
         self.dist = dist
         if world is None:
             world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -389,8 +395,8 @@ class VolumeJob:
         self.conn, self.with_base, self.use_graph = int(connectivity), bool(with_base), bool(graph)
         plan, self.per_rank, self.npairs = merge_plan(self.grid, self.world)
         self.plan = torch.from_numpy(plan).to(self.device)
-        self.stream = torch.cuda.Stream(device=self.device)
-        self.side = torch.cuda.Stream(device=self.device)      # merged table, next to the label kernels
+        self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.side = torch.cuda.Stream(device=self.device) if self.cuda else None   # merged table, next to the labels
         self.pred = [None] * len(self.mine)
         self.base = [None] * len(self.mine)
         self.labels = [torch.empty(self.chunk_shape[i], dtype=torch.int32, device=self.device) for i in self.mine]
@@ -460,7 +466,8 @@ class VolumeJob:
         self.graphs = None
 
     # ---- the three stages of a step (all asynchronous on the current stream) --------------------------
-    def _begin(self, li, slot_ptr=None, cap_rows=None, cap_entries=None):
+    def _begin(self, li, slot=None, cap_rows=None, cap_entries=None):
+        """slot: uint8 tensor receiving the packed slot (default: this chunk's slot of the exchange buffer)."""
         L, C = self.C.lib(), self.C
         nx, ny, nz = self.chunk_shape[self.mine[li]]
         base = self.base[li]
@@ -468,7 +475,7 @@ class VolumeJob:
             self.pred[li].data_ptr(), nx, ny, nz, ctypes_f32(self.thresh), self.conn, 0, self.dust,
             ctypes.cast(self.offsets[li], ctypes.c_void_p), self.labels[li].data_ptr(),
             base.data_ptr() if base is not None else None,
-            self.max_pairs[li], slot_ptr if slot_ptr is not None else self.my_slots[li].data_ptr(),
+            self.max_pairs[li], (slot if slot is not None else self.my_slots[li]).data_ptr(),
             cap_rows or self.cap_rows, cap_entries or self.cap_entries, self.face_masks[li], self.ws[li].data_ptr(),
             self.ws[li].numel(),
             self.caps_runs[li], self.D._stream_ptr(self.torch)))
@@ -522,7 +529,7 @@ class VolumeJob:
             if self.pred[li] is None:
                 raise RuntimeError(f"inputs of own chunk #{li} not set")
         need_rows, need_ent = 1, 1
-        with torch.cuda.stream(self.stream):
+        with self._on_stream():
             for li, ci in enumerate(self.mine):
                 nx, ny, nz = self.chunk_shape[ci]
                 for _attempt in range(6):
@@ -532,7 +539,7 @@ class VolumeJob:
                     big_ent = 2 * (ny * nz + nx * nz + nx * ny)
                     nb = int(self.C.lib().syn_packed_slot_bytes(big_rows, big_ent))
                     tmp = torch.zeros(nb, dtype=torch.uint8, device=self.device)
-                    self._begin(li, tmp.data_ptr(), big_rows, big_ent)
+                    self._begin(li, tmp, big_rows, big_ent)
                     cnt = self._read_counts(li)
                     hdr = tmp[:128].view(torch.int64).cpu().numpy()
                     del tmp
@@ -571,11 +578,24 @@ class VolumeJob:
         for li in range(len(self.mine)):
             self._begin(li)
 
+    def _on_stream(self):
+        import contextlib
+        return self.torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()
+
+    def _sync(self):
+        if self.cuda:
+            self.stream.synchronize()
+
     def _stage_b(self, after_ids=None):
         torch = self.torch
         self._merge_ids()
         if after_ids is not None:
             after_ids()
+        if not self.cuda:
+            self._merge_table()
+            for li in range(len(self.mine)):
+                self._finish(li)
+            return
         cur = torch.cuda.current_stream(self.device)
         self.side.wait_stream(cur)                 # fork: the table needs nothing but the id map
         with torch.cuda.stream(self.side):
@@ -587,14 +607,14 @@ class VolumeJob:
     def _capture(self):
         torch, L = self.torch, self.C.lib()
         self.graphs = None
-        with torch.cuda.stream(self.stream):
+        with self._on_stream():
             n0 = L.syn_launch_count()
             self._stage_a()                      # warm: function attributes, occupancy queries
             self._gather()
             self._stage_b()
             self.launches_per_step = int(L.syn_launch_count() - n0)
-            self.stream.synchronize()
-            if not self.use_graph:
+            self._sync()
+            if not self.use_graph or not self.cuda:
                 return
             if self.world == 1:
                 g = torch.cuda.CUDAGraph()
@@ -614,8 +634,13 @@ class VolumeJob:
     def run(self):
         """Queues one step on the job's stream (ordered after the caller's current stream).  Asynchronous."""
         torch = self.torch
-        if self.cap_rows is None or (self.use_graph and self.graphs is None):
+        if self.cap_rows is None or (self.use_graph and self.cuda and self.graphs is None):
             self.prepare()
+        if not self.cuda:
+            self._stage_a()
+            self._gather()
+            self._stage_b()
+            return
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
@@ -635,7 +660,7 @@ class VolumeJob:
         """Synchronises; True when the last step fitted every capacity.  Otherwise grows what overflowed
         (collective) and returns False: run() again."""
         torch = self.torch
-        self.stream.synchronize()
+        self._sync()
         info = self.info.cpu().numpy()
         ok = int(info[3]) == 0
         grow_pairs = False
@@ -865,23 +890,23 @@ class VolumeJob:
 
     # ---- results (each synchronises) -------------------------------------------------------------------
     def counts(self, local_index):
-        self.stream.synchronize()
+        self._sync()
         return self._read_counts(local_index)
 
     def merged_table(self):
         """[n_merged, 11] int64 numpy: id, size, centroid xyz, bbox begin xyz, bbox end xyz (ascending id)."""
-        self.stream.synchronize()
+        self._sync()
         n = int(self.info.cpu()[1])
         return self.merged[:n].cpu().numpy()
 
     def info_dict(self):
-        self.stream.synchronize()
+        self._sync()
         i = self.info.cpu().numpy()
         return {"total_ids": int(i[0]), "n_merged": int(i[1]), "n_edges": int(i[2]), "flags": int(i[3])}
 
     def chunk_table(self, chunk_index):
         """Segment table of ANY chunk of the grid (every rank holds all of them after the exchange)."""
-        self.stream.synchronize()
+        self._sync()
         slot = int(self.plan[2 + chunk_index].cpu())
         raw = self.all_slots[slot]
         kept = int(raw[:8].view(self.torch.int64).cpu()[0])
