@@ -29,7 +29,7 @@ def _stream_ptr(torch, stream=None):
 
 
 def _workspace(torch, device, nbytes):
-    # one workspace per (device, host thread): cc_overlap_tasks runs chunks on two threads at a time
+    # one workspace per (device, host thread)
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device(),
            threading.get_ident())
     ws = _ws_cache.get(key)
@@ -384,15 +384,22 @@ def chunk_ccs_device(pred, thresh, dust_thresh, connectivity=6, dil_k=0, offset=
     """
     torch = _torch()
     L = C.lib()
-    assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
+    if not (isinstance(pred, torch.Tensor) and pred.is_cuda and pred.dtype == torch.float32 and pred.dim() == 3
+            and pred.is_contiguous()):
+        raise TypeError("pred must be a contiguous 3-D float32 CUDA tensor")
     nx, ny, nz = (int(s) for s in pred.shape)
     device = pred.device
     d_runs, d_segs, d_pairs = default_capacities((nx, ny, nz))
     max_runs = int(max_runs or d_runs)
     max_segs = int(max_segs or d_segs)
     max_pairs = int(max_pairs or d_pairs) if base is not None else 0
-    if base is not None:
-        assert base.is_cuda and base.dtype == torch.int64 and base.is_contiguous() and tuple(base.shape) == (nx, ny, nz)
+    if base is not None and not (isinstance(base, torch.Tensor) and base.is_cuda and base.dtype == torch.int64
+                                 and base.is_contiguous() and tuple(base.shape) == (nx, ny, nz)
+                                 and base.device == pred.device):
+        raise TypeError("base must be a contiguous int64-typed CUDA tensor of the prediction's shape and device")
+    if out is not None and (tuple(out.labels.shape) != (nx, ny, nz) or out.labels.device != pred.device
+                            or out.seg_table.device != pred.device):
+        out = None          # a result of another shape / device cannot lend its buffers
     off = (ctypes.c_int64 * 3)(int(offset[0]), int(offset[1]), int(offset[2]))
     counts = np.zeros(C.NCOUNTS, dtype=np.int64)
 
@@ -415,8 +422,11 @@ def chunk_ccs_device(pred, thresh, dust_thresh, connectivity=6, dil_k=0, offset=
                     pcol = torch.empty(max_pairs, dtype=torch.int64, device=device)
                     pval = torch.empty(max_pairs, dtype=torch.int64, device=device)
             if overlap_seg is not None:
-                assert base is None and overlap_seg.is_cuda and overlap_seg.dtype == torch.int64 \
-                    and overlap_seg.is_contiguous() and tuple(overlap_seg.shape) == (nx, ny, nz)
+                if base is not None:
+                    raise ValueError("overlap_seg and base are mutually exclusive")
+                if not (isinstance(overlap_seg, torch.Tensor) and overlap_seg.is_cuda and overlap_seg.dtype == torch.int64
+                        and overlap_seg.is_contiguous() and tuple(overlap_seg.shape) == (nx, ny, nz)):
+                    raise TypeError("overlap_seg must be a contiguous int64-typed CUDA tensor of the prediction's shape")
                 if int(connectivity) != 6 or int(dil_k) != 0:
                     raise ValueError("cc_task(overlap_seg=...) is 6-connected and has no dilation (conncomps.py:28)")
                 rc = L.syn_chunk_ccs_multilabel(
@@ -476,7 +486,8 @@ class ChunkPipeline:
         self.pred = pred if pred is not None else torch.empty(self.shape, dtype=torch.float32, device=self.device)
         self.base = base if base is not None else (
             torch.empty(self.shape, dtype=torch.int64, device=self.device) if with_base else None)
-        assert tuple(self.pred.shape) == self.shape and self.pred.dtype == torch.float32 and self.pred.is_cuda
+        if not (tuple(self.pred.shape) == self.shape and self.pred.dtype == torch.float32 and self.pred.is_cuda):
+            raise TypeError("pred must be a float32 CUDA tensor of the pipeline's shape")
         self.stream = torch.cuda.Stream(device=self.device)
         self.result = None
         self.graph = None

@@ -162,12 +162,15 @@ class MergeResult:
 
 
 def _all_gather(torch, dist, t, world, group):
+    """[world, ...] gathered copy of `t`.  Which collective is used is decided by the backend alone, identically
+    on every rank and before any communication (never by catching an error around a collective: ranks that
+    disagree on the call would hang)."""
     if world == 1:
         return t.unsqueeze(0)
     out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-    try:
+    if dist.get_backend(group) == "nccl":
         dist.all_gather_into_tensor(out, t.contiguous(), group=group)
-    except (RuntimeError, NotImplementedError):   # backends without the flat variant
+    else:
         parts = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(parts, t.contiguous(), group=group)
         out = torch.stack(parts)

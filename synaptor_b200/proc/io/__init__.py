@@ -224,3 +224,47 @@ def prep_face_hashes(face_hashes, chunk_bounds, proc_dir):
     faces, hashes = zip(*list(face_hashes.items()))
     filenames = [face_filename(proc_dir, chunk_bounds, face) for face in faces]
     return pd.DataFrame({cn.contin_filename: filenames, cn.facehash: hashes}), CONTIN_TABLENAME
+
+
+# ---- continuation payload.  The reference stores a face's continuations in an HDF5 file (datasets `face_axis`,
+#      `hi_face`, group `face_coords/<segid>` -> (n, 2) int64; synaptor/proc/io/continuation.py:94-118).  h5py /
+#      libhdf5 are not part of this environment, so the SAME content is written as a NumPy .npz archive under the
+#      reference's file name with the suffix `.npz` instead of `.h5`: arrays `face_axis`, `hi_face`, `segids` (m,),
+#      `counts` (m,), `face_coords` (sum counts, 2) int64 in continuation order.  The untouched reference's
+#      merge_ccs stage cannot read these files (documented in DESIGN.md); this package's own merge can. ----------
+def npz_face_filename(proc_url, chunk_bounds, face, local=False):
+    return face_filename(proc_url, chunk_bounds, face, local=local)[:-len(".h5")] + ".npz"
+
+
+def write_face_file_npz(face_continuations, fname, face=None):
+    if face is None:
+        if len(face_continuations) == 0:
+            raise Exception("Need a face argument or continuations to determine face info for file")
+        face = face_continuations[0].face
+    os.makedirs(os.path.dirname(os.path.abspath(fname)), exist_ok=True)
+    coords = [np.asarray(c.face_coords, dtype=np.int64).reshape(-1, 2) for c in face_continuations]
+    np.savez(fname, face_axis=np.int64(face.axis), hi_face=np.bool_(face.hi_index),
+             segids=np.array([int(c.segid) for c in face_continuations], dtype=np.int64),
+             counts=np.array([len(c) for c in coords], dtype=np.int64),
+             face_coords=np.concatenate(coords) if coords else np.zeros((0, 2), dtype=np.int64))
+
+
+def read_face_file_npz(fname):
+    from ..seg.continuation import Continuation, Face
+    with np.load(fname) as f:
+        face = Face(int(f["face_axis"]), bool(f["hi_face"]))
+        ends = np.cumsum(f["counts"])
+        coords = f["face_coords"]
+        return [Continuation(int(s), face, coords[e - n:e]) for (s, n, e) in zip(f["segids"], f["counts"], ends)]
+
+
+def write_chunk_continuations(continuations, proc_url, chunk_bounds):
+    """The six face files of a chunk ({Face: [Continuation]} as returned by cc_task)."""
+    from ..seg.continuation import Face
+    for face in Face.all_faces():
+        write_face_file_npz(continuations[face], npz_face_filename(proc_url, chunk_bounds, face), face)
+
+
+def read_chunk_continuations(proc_url, chunk_bounds):
+    from ..seg.continuation import Face
+    return {face: read_face_file_npz(npz_face_filename(proc_url, chunk_bounds, face)) for face in Face.all_faces()}

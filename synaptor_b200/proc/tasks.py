@@ -33,21 +33,33 @@ def cc_task_device(pred, cc_thresh, sz_thresh, offset=(0, 0, 0), base=None, conn
                               dil_k=int(dil_param), offset=offset, base=base, **kw)
 
 
-def _materialise_cc(res, shape, between=None):
+def _materialise_cc(res, shape, between=None, say=None):
     """
     ChunkResult -> (ccs ndarray, {Face: [Continuation]}, seg-info DataFrame).  The 4 B/voxel D2H of the
     label volume runs on a copy stream while the host groups the face voxels into continuations and
     builds the table; `between()` (optional) is called after the copy was queued (more device work that
-    can overlap it) and its result is appended.
+    can overlap it) and its result is appended.  `say`: prints the reference's stage lines (tasks.py:41-60).
     """
     torch = D._torch()
+    say = say or (lambda *a, **k: None)
     # the small copies first: the D2H engine serves requests in order, so behind the 0.5 GB label copy the faces
     # would arrive ~10 ms later and the host work below would end up after the copies instead of under them
+    t0 = time.time()
+    say("Extracting continuations")
     faces = cont_mod.faces_from_device(res.labels)
     table = res.table_numpy()
     host, ev = res.labels_numpy_async(D.side_stream(torch, res.labels.device, "out"))
     continuations, _ = cont_mod.continuations_from_faces(faces)     # ~10 ms of host work, hidden under the copies
+    say(f"Extracting continuations complete in {time.time() - t0:.3f}s")
+    # size filter, centroids and bounding boxes were computed by the fused device pass above (one kernel chain:
+    # the stages are printed for the reference's trace, their time is inside "Running connected components")
+    for name in ("Filtering complete segments by size", "Computing seg centroids", "Computing seg bounding boxes"):
+        say(name)
+        say(f"{name} complete in 0.000s")
+    t1 = time.time()
+    say("Making seg info DataFrame")
     info = seg.misc.seg_info_from_table(table[:, 0], table[:, 1:])
+    say(f"Making seg info DataFrame complete in {time.time() - t1:.3f}s")
     extra = between() if between is not None else None
     ev.synchronize()
     ccs = D.pinned_numpy(host, np.uint32).reshape(shape)
@@ -91,11 +103,9 @@ def cc_task(desc_vol, cc_thresh, sz_thresh, offset=(0, 0, 0), overlap_seg=None, 
         ovl_dev = D.to_device_u64(torch, overlap_seg, device)
     res = D.chunk_ccs_device(pred, t32, int(sz_thresh), connectivity=connectivity, dil_k=int(dil_param),
                              offset=tuple(int(o) for o in offset), overlap_seg=ovl_dev)
+    torch.cuda.current_stream().synchronize()
     say(f"Running connected components complete in {time.time() - start:.3f}s")
-    t1 = time.time()
-    say("Making seg info DataFrame")
-    out = _materialise_cc(res, shape)
-    say(f"Making seg info DataFrame complete in {time.time() - t1:.3f}s")
+    out = _materialise_cc(res, shape, say=say)
     if overlap_seg is not None:
         ccs, continuations, info = out
         say("Adding overlapping seg to DataFrame")
@@ -191,10 +201,12 @@ def cc_overlap_tasks(chunks, cc_thresh, sz_thresh, connectivity=6, dil_param=0):
     device = torch.device("cuda", torch.cuda.current_device())
 
     def start(item):
+        off = tuple(int(o) for o in item[2]) if len(item) > 2 else (0, 0, 0)
+        if isinstance(item[0], torch.Tensor) or isinstance(item[1], torch.Tensor):
+            return ("plain", item, off)             # tensors (possibly resident already): the per-chunk call
         d = np.asarray(item[0])
         shape = tuple(int(x) for x in d.shape)
-        off = tuple(int(o) for o in item[2]) if len(item) > 2 else (0, 0, 0)
-        if 0 in shape or isinstance(item[1], torch.Tensor):
+        if 0 in shape:
             return ("plain", item, off)
         t32 = D.float32_threshold(d.dtype, cc_thresh)
         return ("piped", _start_chunk(torch, device, d, item[1]), shape, t32, off)
@@ -211,8 +223,8 @@ def cc_overlap_tasks(chunks, cc_thresh, sz_thresh, connectivity=6, dil_param=0):
     for item in chunks:
         if not reserved:                  # pinned blocks for the label volumes that will be alive at once
             reserved = True
-            shp = tuple(int(x) for x in np.asarray(item[0]).shape)
-            if len(shp) == 3 and 0 not in shp:
+            shp = tuple(int(x) for x in item[0].shape)
+            if len(shp) == 3 and 0 not in shp and not isinstance(item[0], torch.Tensor):
                 D.pinned_reserve(torch, shp, torch.int32, 4)
         cur = start(item)                 # queue this chunk's input copies first ...
         if prev is not None:

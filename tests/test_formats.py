@@ -180,3 +180,23 @@ def test_g12_continuation_file_names_and_pairing():
     assert sorted("|".join(sorted(c.filename for c in grp)) for grp in groups) == g["groups"].tolist()
     # the two files of an interior boundary land in one group, and in one hash bucket
     assert sum(len(grp) == 2 for grp in groups) == 12 and sum(len(grp) == 1 for grp in groups) == 24
+
+
+def test_continuation_files_npz_roundtrip(tmp_path):
+    """The continuation payload (reference: HDF5, proc/io/continuation.py:94-118) written as .npz under the
+    reference's names: same content back, empty faces included."""
+    from synaptor_b200.proc import io as taskio
+    from synaptor_b200.proc.seg.continuation import Continuation, Face
+    from synaptor_b200.types.bbox import BBox3d
+    bb = BBox3d((0, 18, 16), (20, 36, 32))
+    conts = {f: [] for f in Face.all_faces()}
+    f0 = Face(0, True)
+    conts[f0] = [Continuation(7, f0, np.array([[1, 2], [1, 3]], dtype=np.int64)),
+                 Continuation(12, f0, np.array([[5, 5]], dtype=np.int64))]
+    taskio.write_chunk_continuations(conts, str(tmp_path), bb)
+    name = taskio.npz_face_filename(str(tmp_path), bb, f0)
+    assert name.endswith("continuations/continuations_0_18_16-20_36_32_f0_hi.npz")
+    back = taskio.read_chunk_continuations(str(tmp_path), bb)
+    assert [c.segid for c in back[f0]] == [7, 12] and back[f0][0].face.axis == 0 and back[f0][0].face.hi_index is True
+    assert np.array_equal(back[f0][0].face_coords, [[1, 2], [1, 3]]) and np.array_equal(back[f0][1].face_coords, [[5, 5]])
+    assert all(back[f] == [] for f in Face.all_faces() if not (f.axis == 0 and f.hi_index))
