@@ -8,8 +8,9 @@ bench.py -- throughput of the chunk_ccs + chunk_overlaps hot path (BASELINE.json
 
 Default workload (every N) -- the north-star job, BASELINE.json configs[3]: a 2048 x 2048 x 256 volume as
 2 x 2 x 2 chunks of 1024 x 1024 x 128 (types/bbox/chunking.py:13-44), chunk i on rank i % N (strong scaling:
-N = 1 runs all eight).  One step = chunk_ccs on every owned chunk + merge_ccs (ONE NCCL all_gather of the packed
-segment tables and face entries, device union-find) + remap_ids (folded into the single label write) +
+N = 1 runs all eight).  One step = chunk_ccs on every owned chunk + merge_ccs (ONE exchange of the packed segment
+tables and face entries -- an own kernel storing them into the peers' memory over NVLink, or an NCCL all_gather
+with SYN_EXCHANGE=nccl -- then a device union-find) + remap_ids (folded into the single label write) +
 chunk_overlaps against the uint64 base segmentation -- synaptor/proc/tasks.py:26-69, 72-122, 314-333, 290-297.
 The result of the measured configuration is checked, once, outside the timed region, against the CPU oracle
 (bit-exact: final volume, merged table, id maps, overlap triples; 1:1 with whole-volume labelling).
@@ -49,8 +50,9 @@ CONFIGS = {
            "(sigma 1, fg 10%), thr 0.5, 6-conn, dust 100, uint64 base (32^3 blocks)"),
 }
 WORKLOAD_C4 = ("configs[3]: 2048x2048x256 volume (sigma 2, fg 3%, uint64 base of 32^3 blocks) as 8 chunks of "
-               "1024x1024x128, chunk i on GPU i % N: chunk_ccs + merge_ccs (one NCCL all_gather) + remap_ids "
-               "(folded into the label write) + chunk_overlaps; thr 0.5, 6-conn, dust 100, merge size_thr 100")
+               "1024x1024x128, chunk i on GPU i % N: chunk_ccs + merge_ccs (one exchange of packed tables + faces over "
+               "NVLink) + remap_ids (folded into the label write) + chunk_overlaps; thr 0.5, 6-conn, dust 100, merge "
+               "size_thr 100")
 
 
 def peaks():
@@ -537,6 +539,8 @@ def main():
         raise SystemExit("capacities never settled")
     info0 = job.info_dict()
     counts0 = [job.counts(li) for li in range(len(job.mine))]
+    exchange_info[0] = job.exchange_info()
+    job_slot_bytes[0] = job.slot_bytes
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -629,6 +633,7 @@ def main():
             "config": {"workload": WORKLOAD_C4, "volume": list(VOLUME), "chunk": list(CHUNK), "grid": list(job_grid()),
                        "chunks_per_gpu": -(-int(np.prod(job_grid())) // world),
                        "merge_ccs_in_step": True, "remap_in_step": True, "cuda_graph": not args.no_graph,
+                       "exchange": exchange_info[0],
                        "generator": "position-hash white noise -> separable Gaussian (sigma 2, wrap) -> logistic "
                                     "around the 97 % quantile, on the GPU (bench.gen_pred_chunk); base: hashed 40-bit "
                                     "ids on 32^3 blocks, 5 % zeros",
@@ -686,6 +691,7 @@ def main():
 
 
 job_slot_bytes = [None]
+exchange_info = [None]
 
 
 def job_grid():

@@ -287,6 +287,16 @@ SYN_API int syn_chunk_ccs_finish(const float *pred, int64_t nx, int64_t ny, int6
                                  const uint32_t *final_lut, const int64_t *final_lut_base_dev, int64_t final_lut_len,
                                  void *workspace, int64_t workspace_bytes, int64_t max_runs, int64_t *counts_host,
                                  void *stream);
+/*
+ * syn_push_slots -- the exchange of the packed slots over NVLink peer memory instead of an NCCL all_gather:
+ * stores the valid part (header, kept rows, face entries) of this rank's n_slots slots at the SAME offsets into
+ * the exchange buffers of the peers.  peer_dst: host array of n_peers device pointers (each peer's buffer,
+ * already offset to this rank's first slot; the own buffer included); multicast_dst: the NVSwitch multicast
+ * address of the same location (one store reaches every GPU), or NULL to store peer by peer.  The caller follows
+ * up with a cross-rank barrier on the stream (e.g. the symmetric-memory barrier of torch.distributed).
+ */
+SYN_API int syn_push_slots(const void *my_slots, int64_t n_slots, int64_t slot_bytes, int64_t cap_rows,
+                           int64_t cap_entries, void *const *peer_dst, int n_peers, void *multicast_dst, void *stream);
 SYN_API int64_t syn_merge_packed_workspace_bytes(int64_t nchunks, int64_t cap_rows, int64_t max_edges);
 SYN_API int syn_merge_ccs_table(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
                                 const int32_t *plan_dev, int64_t nchunks, int64_t size_thr, int64_t max_edges,

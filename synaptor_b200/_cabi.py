@@ -58,6 +58,7 @@ SIGNATURES = {
                                    _i32, _vp, _i64, _i64, _vp]),
     "syn_chunk_ccs_finish": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp,
                                     _i64, _vp, _i64, _i64, _vp, _vp]),
+    "syn_push_slots": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
     "syn_merge_packed_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "syn_merge_ccs_table": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "syn_merge_ccs_packed": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp,

@@ -1131,6 +1131,22 @@ int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_
                                workspace, workspace_bytes, id_base_out, merged_out, info_out, stream);
 }
 
+int syn_push_slots(const void *my_slots, int64_t n_slots, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
+                   void *const *peer_dst, int n_peers, void *multicast_dst, void *stream)
+{
+    if (!my_slots || n_slots < 1 || n_peers < 0 || n_peers > 16 || (!multicast_dst && (!peer_dst || n_peers < 1)))
+        return fail(SYN_ERR_INVALID, "bad arguments");
+    if (slot_bytes != (int64_t)pk_slot_bytes(cap_rows, cap_entries) || (slot_bytes & 15))
+        return fail(SYN_ERR_INVALID, "slot_bytes mismatch");
+    PeerPtrs P{};
+    for (int q = 0; q < n_peers; ++q) P.p[q] = peer_dst ? (unsigned char *)peer_dst[q] : nullptr;
+    const unsigned gx = (unsigned)std::max<i64>(8, std::min<i64>(128, 592 / n_slots));
+    k_push_slots<<<dim3(gx, (unsigned)n_slots), 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned char *)my_slots, slot_bytes, cap_rows, cap_entries, P, n_peers, (unsigned char *)multicast_dst);
+    CK_LAUNCH();
+    return SYN_OK;
+}
+
 int syn_merge_overlaps(const uint32_t *rows, const uint64_t *cols, const int64_t *counts, int64_t n, int64_t n_ids,
                        uint64_t *argcol_out, int64_t *maxval_out, void *stream)
 {

@@ -46,6 +46,7 @@ struct FaceCtx {
     u32 start[7];       // first item of face f in the scan; start[6] = total
 
     // item i of the scan -> face number, position inside the face, label (32-bit arithmetic throughout)
+    template <bool WITH_LABEL>
     __device__ __forceinline__ u32 label(u32 i, int *face, u32 *pos) const
     {
         int f = 0;
@@ -72,6 +73,9 @@ struct FaceCtx {
         const u32 row = x * ny + y, k = z >> 5, b = z & 31u;
         const u32 w = row * g.wz + k;
         if (!((omask[w] >> b) & 1u)) return 0u;
+        // a foreground voxel ON a chunk face belongs to a component that touches the face, and those are never
+        // dust (proc/tasks.py:45-51): its label is non-zero -- the counting pass needs nothing beyond the mask bit
+        if (!WITH_LABEL) return 1u;
         const u32 run = R.at(w, row, k) + __popc(R.starts(lmask, w, k) & mask_le(b)) - 1u;
         return complab[rank[par[run]]];
     }
@@ -90,7 +94,7 @@ struct FaceSrc {
             if (!bad && i0 + t < n) {
                 int f;
                 u32 pos;
-                item[t] = F.label((u32)(i0 + t), &f, &pos) != 0;
+                item[t] = F.label<false>((u32)(i0 + t), &f, &pos);
             }
         }
     }
@@ -125,7 +129,7 @@ struct FaceDst {
                 if (item[t]) {
                     int f;
                     u32 pos;
-                    const u32 lab = F.label(i, &f, &pos);
+                    const u32 lab = F.label<true>(i, &f, &pos);      // (0 only after a capacity error upstream)
                     if ((i64)ex < cap_entries) entries[ex] = make_uint2(pos, lab);
                     else atomicOr((u64 *)&hdr[PK_FLAGS], (u64)PK_F_ENTRIES);
                 }
@@ -315,6 +319,64 @@ __global__ void __launch_bounds__(256) k_mg_emit(Packed P, const int *__restrict
 }
 
 
+// ---------------------------------------------------------------------------
+// The exchange over NVLink peer memory: every rank stores the VALID part of its packed slots (header, kept rows,
+// face entries) straight into the exchange buffer of every peer -- one multimem.st per 16 bytes to the NVSwitch
+// multicast address of the symmetric buffer when there is one (the switch replicates the store to all GPUs, so a
+// rank sends its slot once, not world times), else one store per peer through the peers' mapped pointers.
+// A cross-rank barrier (signal pads of the symmetric memory) follows on the stream.
+// grid = (CTAs, slots of this rank).
+// ---------------------------------------------------------------------------
+struct PeerPtrs {
+    unsigned char *p[16];
+};
+
+__device__ __forceinline__ void multimem_st_16(void *mc, uint4 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_push_slots(const unsigned char *__restrict__ src, i64 slot_bytes, i64 cap_rows,
+                                                    i64 cap_entries, PeerPtrs peers, int n_peers, unsigned char *mc)
+{
+    const unsigned char *slot = src + (size_t)blockIdx.y * slot_bytes;
+    const i64 *hdr = reinterpret_cast<const i64 *>(slot);
+    i64 kept = hdr[PK_KEPT], nent = hdr[PK_NENT];
+    kept = kept < 0 ? 0 : (kept > cap_rows ? cap_rows : kept);
+    nent = nent < 0 ? 0 : (nent > cap_entries ? cap_entries : nent);
+    // two ranges of 16-byte units: [header + rows) and [entries)
+    const i64 r0 = (PK_HDR * 8 + kept * SYN_SEG_NCOLS * 8 + 15) / 16;
+    const i64 e0 = (PK_HDR * 8 + cap_rows * SYN_SEG_NCOLS * 8) / 16, e1 = e0 + (nent * 8 + 15) / 16;
+    const i64 n = r0 + (e1 - e0);
+    const size_t off = (size_t)blockIdx.y * slot_bytes;
+    // four independent 16-byte load -> store chains per thread and round: the stores cross NVLink, the more bytes
+    // in flight the better
+    const i64 nth = (i64)gridDim.x * blockDim.x;
+    for (i64 i0 = blockIdx.x * (i64)blockDim.x + threadIdx.x; i0 < n; i0 += 4 * nth) {
+        uint4 v[4];
+        i64 u[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const i64 i = i0 + t * nth;
+            u[t] = i < r0 ? i : e0 + (i - r0);
+            if (i < n) v[t] = *reinterpret_cast<const uint4 *>(slot + u[t] * 16);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (i0 + t * nth >= n) continue;
+            if (mc) multimem_st_16(mc + off + u[t] * 16, v[t]);
+            else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if (q < n_peers) *reinterpret_cast<uint4 *>(peers.p[q] + off + u[t] * 16) = v[t];
+            }
+        }
+    }
+    __threadfence_system();
+}
+
 constexpr int MG_MAXPAIRS_SMEM = 3072;
 
 // ---------------------------------------------------------------------------
@@ -438,7 +500,7 @@ __global__ void __launch_bounds__(256) k_mg_ids(Packed P, const int *__restrict_
                     }
                     if (lo < nB) {
                         const uint2 f = B[lo];
-                        if (f.x == e.x) { a = bA + e.y; b = bB + f.y; }
+                        if (f.x == e.x && e.y && f.y) { a = bA + e.y; b = bB + f.y; }
                     }
                 }
                 bool act = a != 0;

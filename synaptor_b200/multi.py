@@ -18,6 +18,7 @@ LUT.  Nothing here computes on the host except shape bookkeeping.
 """
 import ctypes
 import itertools
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -396,6 +397,13 @@ class VolumeJob:
         self.mine = [i for i in range(self.nchunks) if self.owners[i] == self.rank]
         self.thresh, self.dust, self.size_thr = np.float32(thresh), int(dust_thresh), int(size_thr)
         self.conn, self.with_base, self.use_graph = int(connectivity), bool(with_base), bool(graph)
+        # the exchange: "p2p" = own kernel storing the slots into the peers' symmetric memory over NVLink (multicast
+        # through the NVSwitch when available) + a signal-pad barrier; "nccl" = one all_gather_into_tensor.
+        # Decided identically on every rank before any communication (an environment variable, else the backend).
+        self.exchange = "none"
+        if self.world > 1:
+            want = os.environ.get("SYN_EXCHANGE", "p2p" if self.cuda else "nccl")
+            self.exchange = want if (want == "nccl" or self.cuda) else "nccl"
         plan, self.per_rank, self.npairs = merge_plan(self.grid, self.world)
         self.plan = torch.from_numpy(plan).to(self.device)
         self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
@@ -419,6 +427,11 @@ class VolumeJob:
         self.face_masks = [masks[i] for i in self.mine]
 
     # ---- buffers -----------------------------------------------------------------------------------
+    @property
+    def all_slots(self):
+        """The gathered slots of all chunks that the current / last step works on."""
+        return self._halves[self._half]
+
     def set_inputs(self, local_index, pred, base=None):
         """Resident inputs of own chunk #local_index (chunk self.mine[local_index]): float32 cuda tensor and,
         with_base, the int64-typed uint64 base ids.  The tensors must stay alive (and in place) while the job runs."""
@@ -440,8 +453,28 @@ class VolumeJob:
         self.slot_bytes = int(L.syn_packed_slot_bytes(self.cap_rows, self.cap_entries))
         nslots = self.per_rank * self.world
         self.my_slots = torch.zeros((self.per_rank, self.slot_bytes), dtype=torch.uint8, device=self.device)
-        self.all_slots = self.my_slots if self.world == 1 else torch.zeros(
-            (nslots, self.slot_bytes), dtype=torch.uint8, device=self.device)
+        self._halves, self._half, self._symm = None, 0, None
+        if self.world == 1:
+            self._halves = [self.my_slots]
+        elif self.exchange == "p2p":
+            # symmetric (peer-mapped) exchange buffer, two halves used alternately: a rank one step ahead never
+            # overwrites what a peer is still merging (the per-step barrier keeps ranks within one step)
+            import torch.distributed._symmetric_memory as symm_mem
+            half = nslots * self.slot_bytes
+            buf = symm_mem.empty(2 * half, dtype=torch.uint8, device=self.device)
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
+            buf.zero_()
+            self._symm = (buf, hdl, half)
+            self._halves = [buf[h * half:(h + 1) * half].view(nslots, self.slot_bytes) for h in (0, 1)]
+            mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", False) and hdl.multicast_ptr else 0
+            if os.environ.get("SYN_NO_MULTICAST"):
+                mc = 0
+            self._mc = mc
+            self._peer_ptrs = [int(p) for p in hdl.buffer_ptrs]
+            self.torch.cuda.synchronize(self.device)
+            hdl.barrier(channel=0, timeout_ms=30000)
+        else:
+            self._halves = [torch.zeros((nslots, self.slot_bytes), dtype=torch.uint8, device=self.device)]
         cap_total = self.nchunks * self.cap_rows
         self.max_edges = max(1024, self.nchunks * self.cap_entries // 2)
         nb = int(L.syn_merge_packed_workspace_bytes(self.nchunks, self.cap_rows, self.max_edges))
@@ -520,8 +553,21 @@ class VolumeJob:
             self.caps_runs[li], None, self.D._stream_ptr(self.torch)))
 
     def _gather(self):
-        if self.world > 1:
-            self.dist.all_gather_into_tensor(self.all_slots.view(-1), self.my_slots.view(-1), group=self.group)
+        """The exchange of one step: afterwards self.all_slots holds the packed slots of every chunk."""
+        if self.world == 1:
+            return
+        if self.exchange != "p2p":
+            self.dist.all_gather_into_tensor(self._halves[0].view(-1), self.my_slots.view(-1), group=self.group)
+            return
+        buf, hdl, half = self._symm
+        h = self._half = 1 - self._half
+        off = h * half + self.rank * self.per_rank * self.slot_bytes
+        peers = (ctypes.c_void_p * self.world)(*[p + off for p in self._peer_ptrs])
+        self.C.check(self.C.lib().syn_push_slots(
+            self.my_slots.data_ptr(), self.per_rank, self.slot_bytes, self.cap_rows, self.cap_entries,
+            ctypes.cast(peers, ctypes.c_void_p), self.world, (self._mc + off) if self._mc else None,
+            self.D._stream_ptr(self.torch)))
+        hdl.barrier(channel=0, timeout_ms=30000)
 
     # ---- sizing --------------------------------------------------------------------------------------
     def prepare(self):
@@ -626,12 +672,18 @@ class VolumeJob:
                     self._stage_b()
                 self.graphs = (g,)
             else:
-                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                ga = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga, stream=self.stream):
                     self._stage_a()
-                with torch.cuda.graph(gb, stream=self.stream):
-                    self._stage_b()
-                self.graphs = (ga, gb)
+                gbs = []
+                for h in range(len(self._halves)):       # stage B reads the half of the exchange buffer of its step
+                    self._half = h
+                    gb = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gb, stream=self.stream):
+                        self._stage_b()
+                    gbs.append(gb)
+                self._half = 0
+                self.graphs = (ga, gbs)
 
     # ---- running -------------------------------------------------------------------------------------
     def run(self):
@@ -656,7 +708,7 @@ class VolumeJob:
             else:
                 self.graphs[0].replay()
                 self._gather()
-                self.graphs[1].replay()
+                self.graphs[1][self._half].replay()
         cur.wait_stream(self.stream)
 
     def check(self):
@@ -901,6 +953,16 @@ class VolumeJob:
         self._sync()
         n = int(self.info.cpu()[1])
         return self.merged[:n].cpu().numpy()
+
+    def exchange_info(self):
+        """How the packed slots travel between the ranks."""
+        if self.world == 1:
+            return "none (one rank)"
+        if self.exchange != "p2p":
+            return "NCCL all_gather_into_tensor of the fixed-size slots"
+        return ("own kernel (syn_push_slots): valid part of the slots stored into the peers' symmetric memory over NVLink, "
+                + ("one multimem.st per 16 B to the NVSwitch multicast address" if self._mc else "one store per peer")
+                + ", then the symmetric-memory signal-pad barrier")
 
     def info_dict(self):
         self._sync()
