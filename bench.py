@@ -539,6 +539,11 @@ def main():
         raise SystemExit("capacities never settled")
     info0 = job.info_dict()
     counts0 = [job.counts(li) for li in range(len(job.mine))]
+    n_merged_total = info0["n_merged"]
+    if world > 1:                      # every rank holds the rows of the merged ids of ITS chunks
+        t = torch.tensor([n_merged_total], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        n_merged_total = int(t[0])
     exchange_info[0] = job.exchange_info()
     job_slot_bytes[0] = job.slot_bytes
 
@@ -644,7 +649,9 @@ def main():
                                                "chunk_begin (all owned chunks) / gather (all_gather of the packed "
                                                "slots) / merge (the id map: one cooperative kernel) / chunk_finish "
                                                "(all owned chunks, with the merged table on a second stream)",
-                       "total_ids": info0["total_ids"], "merged_segments": info0["n_merged"],
+                       "total_ids": info0["total_ids"], "merged_segments": n_merged_total,
+                       "merged_table": "sharded: every rank produces the rows of the merged ids of its own chunks"
+                       if world > 1 else "whole table on the one rank",
                        "face_edges": info0["n_edges"],
                        "slot_bytes": job_slot_bytes[0], "rank0_chunk_counts": {
                            k: counts0[0][k] for k in ("runs", "components", "kept", "pairs", "fg_voxels")},
@@ -703,7 +710,7 @@ def check_job(torch, dist, orc, job, inputs, rank, world, dev):
     whole-volume labelling (1:1 on the survivors)."""
     job_slot_bytes[0] = job.slot_bytes
     t0 = time.time()
-    merged_local = job.merged_table()
+    merged_local = job.merged_table(all_ranks=True)          # every rank holds its share: gather them
     mine = {}
     for li, ci in enumerate(job.mine):
         r, c, v, shp = job.overlaps(li)

@@ -270,7 +270,9 @@ SYN_API int syn_merge_ccs_grid(const uint32_t *faces_all, const int64_t *tables_
  *                        overflowed, 2: max_edges too small).  No host synchronisation.  With merged_out NULL only
  *                        the id map is produced (what the label write waits for) and the caller runs
  * syn_merge_ccs_table  : the merged table alone (reads the id map left in `workspace` by syn_merge_ccs_packed), e.g.
- *                        on a second stream next to syn_chunk_ccs_finish.
+ *                        on a second stream next to syn_chunk_ccs_finish.  owner_world > 1: only the rows of merged
+ *                        ids that belong to a chunk of rank owner_rank (chunk c lives on rank c % owner_world) --
+ *                        each rank then holds its share of the table; info[1] counts the rows written.
  * syn_chunk_ccs_finish : the rest of syn_chunk_ccs for a chunk started with syn_chunk_ccs_begin (same shape,
  *                        workspace, capacities, pointers): label of table row r = final_lut[final_lut_base_dev[0]
  *                        + r + 1] (final_lut NULL: r + 1), foreground label sectors, (label, base id) counts.
@@ -301,7 +303,7 @@ SYN_API int64_t syn_merge_packed_workspace_bytes(int64_t nchunks, int64_t cap_ro
 SYN_API int syn_merge_ccs_table(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
                                 const int32_t *plan_dev, int64_t nchunks, int64_t size_thr, int64_t max_edges,
                                 void *workspace, int64_t workspace_bytes, const int64_t *id_base, int64_t *merged_out,
-                                int64_t *info, void *stream);
+                                int64_t *info, int owner_rank, int owner_world, void *stream);
 SYN_API int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
                                  const int32_t *plan_dev, int64_t nchunks, int64_t npairs, int64_t size_thr,
                                  int64_t max_edges, void *workspace, int64_t workspace_bytes, int64_t *id_base_out,

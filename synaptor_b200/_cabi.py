@@ -60,7 +60,8 @@ SIGNATURES = {
                                     _i64, _vp, _i64, _i64, _vp, _vp]),
     "syn_push_slots": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
     "syn_merge_packed_workspace_bytes": (_i64, [_i64, _i64, _i64]),
-    "syn_merge_ccs_table": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "syn_merge_ccs_table": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32,
+                                   _vp]),
     "syn_merge_ccs_packed": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp,
                                     _vp]),
     "syn_merge_overlaps": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),

@@ -1068,8 +1068,9 @@ int64_t syn_merge_packed_workspace_bytes(int64_t nchunks, int64_t cap_rows, int6
 int syn_merge_ccs_table(const void *slots_all, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,
                         const int32_t *plan_dev, int64_t nchunks, int64_t size_thr, int64_t max_edges,
                         void *workspace, int64_t workspace_bytes, const int64_t *id_base, int64_t *merged_out,
-                        int64_t *info, void *stream)
+                        int64_t *info, int owner_rank, int owner_world, void *stream)
 {
+    if (owner_world < 1 || owner_rank < 0 || owner_rank >= owner_world) return fail(SYN_ERR_INVALID, "bad owner rank / world");
     int rc = merge_args_ok(slots_all, slot_bytes, cap_rows, cap_entries, plan_dev, nchunks, 0, max_edges, workspace,
                            workspace_bytes);
     if (rc != SYN_OK) return rc;
@@ -1084,7 +1085,7 @@ int syn_merge_ccs_table(const void *slots_all, int64_t slot_bytes, int64_t cap_r
     const int wide = grid_for((i64)w.cap_total + 1, 256, 4);
     k_mg_tab_init<<<wide, 256, 0, st>>>(inf, w.acc, w.scan_state, (u32)w.scan_tiles + 2);
     CK_LAUNCH();
-    k_mg_tab_acc<<<wide, 256, 0, st>>>(P, plan, base, inf, w.gmap, w.acc);
+    k_mg_tab_acc<<<wide, 256, 0, st>>>(P, plan, base, inf, w.gmap, w.acc, owner_rank, owner_world);
     CK_LAUNCH();
     {
         const i64 ntiles = ((i64)w.cap_total + 1 + SCAN_THREADS * 8 - 1) / (SCAN_THREADS * 8);
@@ -1128,7 +1129,7 @@ int syn_merge_ccs_packed(const void *slots_all, int64_t slot_bytes, int64_t cap_
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (!merged_out) return SYN_OK;            // the caller runs syn_merge_ccs_table itself (another stream)
     return syn_merge_ccs_table(slots_all, slot_bytes, cap_rows, cap_entries, plan_dev, nchunks, size_thr, max_edges,
-                               workspace, workspace_bytes, id_base_out, merged_out, info_out, stream);
+                               workspace, workspace_bytes, id_base_out, merged_out, info_out, 0, 1, stream);
 }
 
 int syn_push_slots(const void *my_slots, int64_t n_slots, int64_t slot_bytes, int64_t cap_rows, int64_t cap_entries,

@@ -561,9 +561,12 @@ __global__ void __launch_bounds__(256) k_mg_tab_init(const i64 *__restrict__ inf
     }
 }
 
+// `world` > 1: only the destinations whose id belongs to a chunk of rank `rank` (chunk c lives on rank c % world)
+// are accumulated -- every other destination keeps count 0 and is skipped by the scan, the member lists and the
+// rows: each rank produces ITS share of the merged table instead of all ranks producing all of it.
 __global__ void __launch_bounds__(256) k_mg_tab_acc(Packed P, const int *__restrict__ plan, const i64 *__restrict__ base,
                                                     const i64 *__restrict__ info, const u32 *__restrict__ gmap,
-                                                    MergeAcc2 *acc)
+                                                    MergeAcc2 *acc, int rank, int world)
 {
     __shared__ i64 s_base[MG_MAXCHUNKS + 1];
     const int nchunks = plan[0];
@@ -572,8 +575,10 @@ __global__ void __launch_bounds__(256) k_mg_tab_acc(Packed P, const int *__restr
     if (info[MG_FLAGS] & 1) return;
     const i64 total = info[MG_TOTAL];
     for (i64 gid = blockIdx.x * (i64)blockDim.x + threadIdx.x + 1; gid <= total; gid += (i64)gridDim.x * blockDim.x) {
+        const u32 d = gmap[gid];
+        if (world > 1 && mg_chunk_of(s_base, nchunks, (i64)d) % world != rank) continue;
         const i64 *r = mg_row(P, plan, s_base, nchunks, gid);
-        MergeAcc2 *a = acc + gmap[gid];
+        MergeAcc2 *a = acc + d;
         atomicAdd(&a->size, (u64)r[SYN_SEG_SIZE]);
         atomicAdd(&a->count, 1u);
 #pragma unroll

@@ -531,7 +531,8 @@ class VolumeJob:
         C.check(L.syn_merge_ccs_table(
             self.all_slots.data_ptr(), self.slot_bytes, self.cap_rows, self.cap_entries, self.plan.data_ptr(),
             self.nchunks, self.size_thr, self.max_edges, self.merge_ws.data_ptr(), self.merge_ws.numel(),
-            self.id_base.data_ptr(), self.merged.data_ptr(), self.info.data_ptr(), self.D._stream_ptr(self.torch)))
+            self.id_base.data_ptr(), self.merged.data_ptr(), self.info.data_ptr(), self.rank, self.world,
+            self.D._stream_ptr(self.torch)))
 
     def _merge(self):
         self._merge_ids()
@@ -948,11 +949,19 @@ class VolumeJob:
         self._sync()
         return self._read_counts(local_index)
 
-    def merged_table(self):
-        """[n_merged, 11] int64 numpy: id, size, centroid xyz, bbox begin xyz, bbox end xyz (ascending id)."""
+    def merged_table(self, all_ranks=False):
+        """[n, 11] int64 numpy: id, size, centroid xyz, bbox begin xyz, bbox end xyz (ascending id).  With several
+        ranks every rank produces the rows of the merged ids that belong to ITS chunks; all_ranks=True gathers the
+        shares (collective) into the whole table."""
         self._sync()
         n = int(self.info.cpu()[1])
-        return self.merged[:n].cpu().numpy()
+        part = self.merged[:n].cpu().numpy()
+        if not all_ranks or self.world == 1:
+            return part
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, part, group=self.group)
+        full = np.concatenate(parts)
+        return full[np.argsort(full[:, 0], kind="stable")]
 
     def exchange_info(self):
         """How the packed slots travel between the ranks."""

@@ -382,7 +382,8 @@ def volume_tasks(desc_chunks, base_chunks, vol_shape, chunk_shape, cc_thresh, sz
 
     Returns a VolumeResult:
       ccs            [uint32 ndarray per own chunk]  final (merged, size-thresholded) global ids, as remap_ids_task
-      merged_info    DataFrame of the merged segments (merge_ccs_task's first output; int64 index, ascending id)
+      merged_info    DataFrame of the merged segments (merge_ccs_task's first output; int64 index, ascending id);
+                     with several ranks: THIS rank's share, the merged ids that belong to its own chunks
       chunk_id_maps  [{chunk-local id: final id} per own chunk]   (merge_ccs_task's second output, own entries)
       chunk_infos    [seg-info DataFrame per own chunk]           (cc_task's third output)
       overlaps       [scipy COO per own chunk]                    overlap_task on the remapped chunk

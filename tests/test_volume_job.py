@@ -176,7 +176,8 @@ def _nccl_worker(rank, world, port, q):
         for graph in (False, True):
             job = run_job(vol, base_vol, cshape, 0.5, 10, 15, graph, world=world, rank=rank)
             out[graph] = {"labels": {ci: job.labels[li].cpu().numpy().view(np.uint32) for li, ci in enumerate(job.mine)},
-                          "merged": job.merged_table(), "maps": [job.chunk_id_map(ci) for ci in range(job.nchunks)],
+                          "merged": job.merged_table(all_ranks=True), "own_rows": len(job.merged_table()),
+                          "maps": [job.chunk_id_map(ci) for ci in range(job.nchunks)],
                           "ov": {ci: job.overlaps(li) for li, ci in enumerate(job.mine)}, "info": job.info_dict()}
         q.put(out)
     finally:
@@ -215,7 +216,7 @@ def test_volume_job_nccl_ranks():
         seen = set()
         for o in outs:
             r = o[graph]
-            assert {int(x[0]): x[1:].tolist() for x in r["merged"]} == wm
+            assert {int(x[0]): x[1:].tolist() for x in r["merged"]} == wm      # the gathered shares
             assert r["info"]["flags"] == 0
             for ci in range(len(want["chunks"])):
                 gi = want["chunks"][ci][0]
@@ -227,6 +228,7 @@ def test_volume_job_nccl_ranks():
                 assert shp == wshp and np.array_equal(rr, wr) and np.array_equal(cc, wc) and np.array_equal(vv, wv)
                 seen.add(ci)
         assert seen == set(range(len(want["chunks"])))
+        assert sum(o[graph]["own_rows"] for o in outs) == len(wm)          # every merged id on exactly one rank
 
 
 def test_volume_tasks_stream_pipelined():
