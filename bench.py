@@ -606,14 +606,15 @@ def main():
 
     # ---- reduce over ranks --------------------------------------------------------------------------
     vals = [ms_total, e2e["seconds"] if e2e else 0.0, e2e["floor_s"] if e2e else 0.0,
-            brk["chunk_begin"], brk["gather"], brk["merge"], brk["chunk_finish"], e2e["call_seconds"] if e2e else 0.0]
+            brk["chunk_begin"], brk["gather"], brk["merge"], brk["chunk_finish"], e2e["call_seconds"] if e2e else 0.0,
+            e2e["duplex_floor_s"] if e2e else 0.0]
     if world > 1:
         t = torch.tensor(vals, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         vals = [float(x) for x in t]
     ms_max, e2e_s_max, floor_s_max = vals[0], vals[1], vals[2]
     brk_max = dict(zip(brk, vals[3:7]))
-    e2e_call_s_max = vals[7]
+    e2e_call_s_max, duplex_s_max = vals[7], vals[8]
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
@@ -676,6 +677,10 @@ def main():
                            "ms_per_step": e2e_s_max * 1e3, "steps": int(e2e["n"]),
                            "h2d_floor_ms": floor_s_max * 1e3,
                            "frac_of_h2d_floor": floor_s_max / e2e_s_max if e2e_s_max else None,
+                           "h2d_d2h_floor_ms": duplex_s_max * 1e3,
+                           "frac_of_h2d_d2h_floor": duplex_s_max / e2e_s_max if e2e_s_max else None,
+                           "h2d_d2h_floor_note": "the same input copies with the label volumes (D2H) going back on a "
+                                                 "second stream at the same time, all ranks at once, max over ranks",
                            "h2d_floor_note": "bare pinned->device copy of this rank's input bytes, all ranks at once, "
                                              "max over ranks",
                            "ms_per_step_single_call": e2e_call_s_max * 1e3,
@@ -851,8 +856,24 @@ def e2e_leg(torch, dist, syn, job, inputs, rank, world, dev, args, barrier, info
             d.copy_(s, non_blocking=True)
         torch.cuda.synchronize()
         floor.append(time.perf_counter() - t0)
+    # the same with the label volumes going back at the same time (pinned, another stream): the copies of a
+    # pipelined loop share the host memory system in both directions
+    outs = [torch.empty(tuple(c.shape), dtype=torch.int32).pin_memory() for c in out.ccs]
+    dl = [torch.empty(tuple(c.shape), dtype=torch.int32, device=dev) for c in out.ccs]
+    s2 = torch.cuda.Stream()
+    duplex = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s2):
+            for (h, d) in zip(outs, dl):
+                h.copy_(d, non_blocking=True)
+        for (s, d) in zip(tp + tb, dp + db):
+            d.copy_(s, non_blocking=True)
+        torch.cuda.synchronize()
+        duplex.append(time.perf_counter() - t0)
     return {"seconds": sec, "call_seconds": sec_call, "h2d": h2d, "d2h": d2h, "n": n + 1, "floor_s": min(floor),
-            "pageable_ms": pageable_ms}
+            "duplex_floor_s": min(duplex), "pageable_ms": pageable_ms}
 
 
 if __name__ == "__main__":

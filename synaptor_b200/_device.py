@@ -507,6 +507,23 @@ class ChunkPipeline:
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             self.result = self._eager(sync=True)          # sizes the buffers (capacity retries happen here)
+            if not getattr(self, "_tight", False):
+                # capacities from what this stream of chunks actually holds (+ headroom) instead of the worst-case
+                # defaults: smaller per-run arrays and a pair table the ordering kernels walk in a fraction of the
+                # time; counts() grows them again on an overflow
+                c = self.result.counts
+                caps = (max(1 << 16, int(c["runs"] * 1.25) + 1024), max(1 << 12, int(c["kept"] * 1.25) + 256),
+                        max(1 << 12, 2 * c["pairs"] + 1024) if self.base is not None else 0)
+                old_caps = self.result.caps
+                if caps[0] < old_caps[0] or (caps[2] and caps[2] < old_caps[2]):
+                    self.result = None
+                    release_workspaces()
+                    a = self.args
+                    self.result = chunk_ccs_device(self.pred, a["thresh"], a["dust_thresh"], connectivity=a["connectivity"],
+                                                   dil_k=a["dil_k"], offset=a["offset"], base=self.base, sync=True,
+                                                   max_runs=min(caps[0], old_caps[0]), max_segs=old_caps[1],
+                                                   max_pairs=(min(caps[2], old_caps[2]) or None))
+                self._tight = True
             self._eager(sync=False)                       # warm: occupancy queries, function attributes
             self.stream.synchronize()
             g = torch.cuda.CUDAGraph()

@@ -403,6 +403,12 @@ class VolumeJob:
         self.exchange = "none"
         if self.world > 1:
             want = os.environ.get("SYN_EXCHANGE", "p2p" if self.cuda else "nccl")
+            if want == "p2p" and self.cuda:
+                # local, rank-independent facts only: every GPU of the box reaches every other one
+                n = torch.cuda.device_count()
+                ok = n >= self.world and all(torch.cuda.can_device_access_peer(a, b)
+                                             for a in range(n) for b in range(n) if a != b)
+                want = "p2p" if ok else "nccl"
             self.exchange = want if (want == "nccl" or self.cuda) else "nccl"
         plan, self.per_rank, self.npairs = merge_plan(self.grid, self.world)
         self.plan = torch.from_numpy(plan).to(self.device)
@@ -456,15 +462,11 @@ class VolumeJob:
         self._halves, self._half, self._symm = None, 0, None
         if self.world == 1:
             self._halves = [self.my_slots]
+        elif self.exchange == "p2p" and not self._symm_alloc(nslots):
+            self.exchange = "nccl"           # (agreed by all ranks inside _symm_alloc)
+            self._halves = [torch.zeros((nslots, self.slot_bytes), dtype=torch.uint8, device=self.device)]
         elif self.exchange == "p2p":
-            # symmetric (peer-mapped) exchange buffer, two halves used alternately: a rank one step ahead never
-            # overwrites what a peer is still merging (the per-step barrier keeps ranks within one step)
-            import torch.distributed._symmetric_memory as symm_mem
-            half = nslots * self.slot_bytes
-            buf = symm_mem.empty(2 * half, dtype=torch.uint8, device=self.device)
-            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
-            buf.zero_()
-            self._symm = (buf, hdl, half)
+            buf, hdl, half = self._symm
             self._halves = [buf[h * half:(h + 1) * half].view(nslots, self.slot_bytes) for h in (0, 1)]
             mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", False) and hdl.multicast_ptr else 0
             if os.environ.get("SYN_NO_MULTICAST"):
@@ -486,6 +488,31 @@ class VolumeJob:
         self.fmap = torch.zeros(cap_total + 1, dtype=torch.int32, device=self.device)
         self.info = torch.zeros(8, dtype=torch.int64, device=self.device)
         self.graphs = None
+
+    def _symm_alloc(self, nslots):
+        """Symmetric (peer-mapped) exchange buffer, two halves used alternately: a rank one step ahead never
+        overwrites what a peer is still merging (the per-step barrier keeps ranks within one step).  Returns False
+        -- on EVERY rank, by an all_reduce of the outcome -- when any rank could not set it up."""
+        torch = self.torch
+        ok, res = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            half = nslots * self.slot_bytes
+            buf = symm_mem.empty(2 * half, dtype=torch.uint8, device=self.device)
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else self.dist.group.WORLD)
+            buf.zero_()
+            res = (buf, hdl, half)
+        except Exception as e:      # noqa: BLE001 -- any failure means "use NCCL", decided collectively below
+            print(f"synaptor_b200: symmetric-memory exchange unavailable on rank {self.rank} ({type(e).__name__}: {e}); "
+                  "falling back to NCCL all_gather")
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int64, device=self.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(flag.cpu()[0]) == 0:
+            self._symm = None
+            return False
+        self._symm = res
+        return True
 
     def _alloc_chunk(self, li):
         torch, L = self.torch, self.C.lib()
@@ -615,6 +642,21 @@ class VolumeJob:
         if self.cap_rows is None or need_rows > self.cap_rows or need_ent > self.cap_entries:
             self._alloc(max(self.cap_rows or 0, int(need_rows * 1.25) + 64), max(self.cap_entries or 0,
                                                                                   int(need_ent * 1.25) + 256))
+        if self.with_base and self.cuda:
+            # one full step to learn the overlap-pair counts: the pair table (and the three kernels that walk it)
+            # are sized for 2x the pairs seen instead of the worst-case default; an overflow later grows it again
+            with self._on_stream():
+                self._stage_a()
+                self._gather()
+                self._stage_b()
+                self._sync()
+                for li in range(len(self.mine)):
+                    cnt = self._read_counts(li)
+                    if cnt["errflags"] == 0:
+                        tight = max(1 << 12, 2 * cnt["pairs"] + 1024)
+                        if tight < self.max_pairs[li]:
+                            self.max_pairs[li] = tight
+                            self._alloc_chunk(li)
         self._capture()
 
     def _read_counts(self, li):

@@ -669,3 +669,30 @@ def test_g13_merge_overlaps_device_golden(syn):
     assert run(tris, n_ids) == want
     want_t = {int(r): (int(c), int(v)) for (r, c, v) in g["tie_out"]}
     assert run([g["tie_in_a"], g["tie_in_b"]], 12) == want_t
+
+
+@pytest.mark.parametrize("name,shape,sigma,fg", [("c2", (512, 512, 512), 2.0, 0.03), ("c3", (1024, 1024, 128), 1.0, 0.10)])
+def test_full_size_bench_inputs_vs_oracle(syn, name, shape, sigma, fg):
+    """BASELINE configs 2 and 3 at their FULL size on the bench's own inputs (oracle.synth_pred seed 0, base seed
+    1000; not a tiled pattern): labels, table, overlap triples and their order bit-exact against the C oracle.
+    Config 3 is the dense case: 6.2 M runs, 577 k components, 100 k pairs."""
+    import torch
+    from synaptor_b200 import _device as D
+    pred = orc.synth_pred(shape, seed=0, sigma=sigma, fg=fg)
+    base = orc.synth_base(shape, seed=1000)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    res = D.chunk_ccs_device(torch.from_numpy(pred).to(dev), np.float32(0.5), 100,
+                             base=torch.from_numpy(base.view(np.int64)).to(dev))
+    want_ccs, _, want_info = orc.cc_task_c(pred, 0.5, 100, with_continuations=False)
+    labels = res.labels_numpy()
+    assert np.array_equal(labels, want_ccs), first_diff(labels, want_ccs)
+    table = res.table_numpy()
+    assert np.array_equal(table[:, 0], np.asarray(want_info.index, dtype=np.int64))
+    assert np.array_equal(table[:, 1:], want_info.to_numpy(dtype=np.int64).reshape(-1, 10))
+    r, c, v, sh = orc.count_overlaps_c(want_ccs, base)
+    rows, cols, vals = res.pairs_numpy()
+    assert np.array_equal(rows, r) and np.array_equal(cols.astype(np.int64), c) and np.array_equal(vals, v)
+    assert (res.counts["max_label"] + 1, res.counts["max_base"] + 1) == sh
+    assert res.counts["flagged_tiles"] == 0
+    if name == "c3":
+        assert res.counts["components"] > 500000 and res.counts["runs"] > 6000000
