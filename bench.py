@@ -446,6 +446,9 @@ def main():
     ap.add_argument("--no-check", action="store_true", help="skip the oracle parity check of the measured job")
     ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the c2 / c3 single-chunk measurements")
     ap.add_argument("--no-numa", action="store_true")
+    ap.add_argument("--inflight", type=int, default=2, choices=[1, 2],
+                    help="volumes in flight in the timed loop (2: two job instances driven alternately)")
+    ap.add_argument("--lanes", type=int, default=2, help="streams the chunk passes of one volume alternate over")
     ap.add_argument("--volume", type=int, nargs=3, default=None, help="debug: another volume shape for the job")
     ap.add_argument("--chunk", type=int, nargs=3, default=None, help="debug: another chunk shape for the job")
     args = ap.parse_args()
@@ -518,25 +521,36 @@ def main():
     # ---------------------------------------------------------------------------------------------
     # the north-star job
     # ---------------------------------------------------------------------------------------------
-    job = multi.VolumeJob(VOLUME, CHUNK, THRESH, DUST, SIZE_THR, connectivity=CONN, with_base=True, rank=rank,
-                          world=world, device=dev, graph=not args.no_graph)
-    nvox_total = int(np.prod(VOLUME))
+    # Two job instances (own workspaces, label buffers, exchange buffers and graphs; the same resident inputs) are
+    # driven alternately, so that two volumes are in flight: one volume's latency-bound kernels (labelling, merge,
+    # exchange, label writes) run next to the other's HBM-bound streaming kernels.  Every step is a complete job.
+    jobs = []
     inputs = []
     t_gen = time.time()
-    for li, ci in enumerate(job.mine):
-        beg, shp = job.chunk_rel_begin[ci], job.chunk_shape[ci]
-        p = gen_pred_chunk(torch, dev, VOLUME, beg, shp, seed=0, sigma=2.0, fg=0.03)
-        b = gen_base_chunk(torch, dev, VOLUME, beg, shp, seed=1)
-        inputs.append((p, b))
-        job.set_inputs(li, p, b)
-    torch.cuda.synchronize()
-    t_gen = time.time() - t_gen
-    for _ in range(4):
-        job.run()
-        if job.check():
-            break
-    else:
-        raise SystemExit("capacities never settled")
+    for j in range(args.inflight):
+        job = multi.VolumeJob(VOLUME, CHUNK, THRESH, DUST, SIZE_THR, connectivity=CONN, with_base=True, rank=rank,
+                              world=world, device=dev, graph=not args.no_graph, lanes=args.lanes)
+        for li, ci in enumerate(job.mine):
+            if j == 0:
+                beg, shp = job.chunk_rel_begin[ci], job.chunk_shape[ci]
+                p = gen_pred_chunk(torch, dev, VOLUME, beg, shp, seed=0, sigma=2.0, fg=0.03)
+                b = gen_base_chunk(torch, dev, VOLUME, beg, shp, seed=1)
+                inputs.append((p, b))
+            job.set_inputs(li, *inputs[li])
+        if j == 0:
+            torch.cuda.synchronize()
+            t_gen = time.time() - t_gen
+        for _ in range(4):
+            job.run()
+            if job.check():
+                break
+        else:
+            raise SystemExit("capacities never settled")
+        jobs.append(job)
+    job = jobs[0]
+    if job.exchange == "nccl" and len(jobs) > 1:
+        jobs = jobs[:1]                 # collectives of one communicator are not issued from two streams at once
+    nvox_total = int(np.prod(VOLUME))
     info0 = job.info_dict()
     counts0 = [job.counts(li) for li in range(len(job.mine))]
     n_merged_total = info0["n_merged"]
@@ -550,20 +564,33 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     sampler.wait_first_sample()
-    with torch.cuda.stream(job.stream):
-        for _ in range(2 * args.warmup):        # load already running when the timed steps start (clock samples)
-            job.run()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            job.run()
-        e1.record()
-        barrier()
+    def run_steps(n):
+        for i in range(n):
+            jobs[i % len(jobs)].run(join=False)
+        for jb in jobs:
+            jb.join()
+
+    run_steps(2 * args.warmup)                  # load already running when the timed steps start (clock samples)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    run_steps(args.steps)
+    e1.record()
+    barrier()
     ms_total = e0.elapsed_time(e1)
-    if not job.check():
-        raise SystemExit("a capacity overflowed inside the timed steps")
+    for jb in jobs:
+        if not jb.check():
+            raise SystemExit("a capacity overflowed inside the timed steps")
     launches = job.launches_per_step * args.steps
+    # one volume at a time (every step finished before the next starts), for reference
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        job.run()
+    e3.record()
+    barrier()
+    ms_single = e2.elapsed_time(e3)
 
     # ---- merge breakdown: events around the exchange and the merge kernels (plain launches, K steps) ----
     def ev():
@@ -607,19 +634,21 @@ def main():
     # ---- reduce over ranks --------------------------------------------------------------------------
     vals = [ms_total, e2e["seconds"] if e2e else 0.0, e2e["floor_s"] if e2e else 0.0,
             brk["chunk_begin"], brk["gather"], brk["merge"], brk["chunk_finish"], e2e["call_seconds"] if e2e else 0.0,
-            e2e["duplex_floor_s"] if e2e else 0.0]
+            e2e["duplex_floor_s"] if e2e else 0.0, ms_single]
     if world > 1:
         t = torch.tensor(vals, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         vals = [float(x) for x in t]
     ms_max, e2e_s_max, floor_s_max = vals[0], vals[1], vals[2]
     brk_max = dict(zip(brk, vals[3:7]))
-    e2e_call_s_max, duplex_s_max = vals[7], vals[8]
+    e2e_call_s_max, duplex_s_max, ms_single_max = vals[7], vals[8], vals[9]
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
         del inputs
         job = None
+        jobs.clear()
+        multi_release()
         torch.cuda.empty_cache()
         for name in ("c2", "c3"):
             extra[name] = bench_chunk_config(torch, dev, name, args, not args.no_check)
@@ -639,6 +668,14 @@ def main():
             "config": {"workload": WORKLOAD_C4, "volume": list(VOLUME), "chunk": list(CHUNK), "grid": list(job_grid()),
                        "chunks_per_gpu": -(-int(np.prod(job_grid())) // world),
                        "merge_ccs_in_step": True, "remap_in_step": True, "cuda_graph": not args.no_graph,
+                       "volumes_in_flight": len(jobs), "lanes": args.lanes,
+                       "in_flight_note": "the timed steps alternate over this many job instances (own buffers, same "
+                                         "inputs): a volume's chunk passes overlap the previous volume's merge, "
+                                         "exchange and label writes; within a volume the chunk passes alternate "
+                                         "over `lanes` streams.  Every step is a complete job, all inside the timed "
+                                         "region.",
+                       "ms_per_step_one_volume_at_a_time": ms_single_max / args.steps,
+                       "gvoxel_s_one_volume_at_a_time": nvox_total / (ms_single_max / args.steps * 1e-3) / 1e9,
                        "exchange": exchange_info[0],
                        "generator": "position-hash white noise -> separable Gaussian (sigma 2, wrap) -> logistic "
                                     "around the 97 % quantile, on the GPU (bench.gen_pred_chunk); base: hashed 40-bit "
@@ -700,6 +737,11 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def multi_release():
+    import synaptor_b200.proc.tasks as t
+    t._volume_jobs.clear()
 
 
 job_slot_bytes = [None]

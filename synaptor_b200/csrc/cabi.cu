@@ -479,7 +479,9 @@ int ccs_begin(CcsCall &c)
         // bulk copies into shared memory need chunk c to start at voxel 128 c (nz % 128 == 0)
         const bool tma = !no_tma && (nz % 128 == 0);
 #define SYN_STREAM(HB, FS, TB, TP, NST)                                                                            \
-    k_stream<HB, FS, TB, TP, NST><<<stream_ctas > 0 ? (int)std::min<i64>((i64)stream_ctas * sm_count(), ntiles)    \
+    k_stream<HB, FS, TB, TP, NST><<<stream_ctas > 0 ? (int)std::min<i64>((i64)std::min(stream_ctas,                \
+                                        occ_blocks(k_stream<HB, FS, TB, TP, NST>, TS_THREADS,                       \
+                                                   NST * ts_stage_bytes(TP, TB))) * sm_count(), ntiles)            \
                                                    : wave_grid(k_stream<HB, FS, TB, TP, NST>, TS_THREADS, ntiles,  \
                                                                NST * ts_stage_bytes(TP, TB)),                      \
                                    TS_THREADS, NST * ts_stage_bytes(TP, TB), st>>>(                                \

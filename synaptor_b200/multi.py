@@ -368,7 +368,7 @@ class VolumeJob:
     """
 
     def __init__(self, vol_shape, chunk_shape, thresh, dust_thresh, size_thr, connectivity=6, with_base=True,
-                 rank=None, world=None, group=None, device=None, vol_offset=(0, 0, 0), graph=True):
+                 rank=None, world=None, group=None, device=None, vol_offset=(0, 0, 0), graph=True, lanes=1):
         from . import _device as D
         from . import _cabi as C
         import torch.distributed as dist
@@ -414,6 +414,9 @@ class VolumeJob:
         self.plan = torch.from_numpy(plan).to(self.device)
         self.stream = torch.cuda.Stream(device=self.device) if self.cuda else None
         self.side = torch.cuda.Stream(device=self.device) if self.cuda else None   # merged table, next to the labels
+        self.lanes = int(lanes)
+        self.lane_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.lanes)] \
+            if self.cuda and self.lanes > 1 else []
         self.pred = [None] * len(self.mine)
         self.base = [None] * len(self.mine)
         self.labels = [torch.empty(self.chunk_shape[i], dtype=torch.int32, device=self.device) for i in self.mine]
@@ -666,9 +669,28 @@ class VolumeJob:
                                                   self.D._stream_ptr(self.torch)))
         return self.D._counts_dict(counts)
 
+    def _lanes(self):
+        """Forks the lane streams off the current stream (chunks are independent until the merge: the chunk passes
+        of neighbouring chunks go to alternating streams, so that one chunk's latency-bound labelling kernels run
+        next to another chunk's HBM-bound streaming kernel)."""
+        torch = self.torch
+        cur = torch.cuda.current_stream(self.device)
+        for ls in self.lane_streams:
+            ls.wait_stream(cur)
+        return cur
+
     def _stage_a(self):
-        for li in range(len(self.mine)):
-            self._begin(li)
+        n = len(self.mine)
+        if not self.cuda or self.lanes <= 1 or n <= 1:
+            for li in range(n):
+                self._begin(li)
+            return
+        cur = self._lanes()
+        for li in range(n):
+            with self.torch.cuda.stream(self.lane_streams[li % self.lanes]):
+                self._begin(li)
+        for ls in self.lane_streams:
+            cur.wait_stream(ls)
 
     def _on_stream(self):
         import contextlib
@@ -692,8 +714,17 @@ class VolumeJob:
         self.side.wait_stream(cur)                 # fork: the table needs nothing but the id map
         with torch.cuda.stream(self.side):
             self._merge_table()
-        for li in range(len(self.mine)):
-            self._finish(li)
+        n = len(self.mine)
+        if self.lanes <= 1 or n <= 1:
+            for li in range(n):
+                self._finish(li)
+        else:
+            self._lanes()
+            for li in range(n):
+                with torch.cuda.stream(self.lane_streams[li % self.lanes]):
+                    self._finish(li)
+            for ls in self.lane_streams:
+                cur.wait_stream(ls)
         cur.wait_stream(self.side)                 # join
 
     def _capture(self):
@@ -729,8 +760,16 @@ class VolumeJob:
                 self.graphs = (ga, gbs)
 
     # ---- running -------------------------------------------------------------------------------------
-    def run(self):
-        """Queues one step on the job's stream (ordered after the caller's current stream).  Asynchronous."""
+    def join(self):
+        """Orders the caller's current stream after everything queued on the job's stream (see run(join=False))."""
+        if self.cuda:
+            self.torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def run(self, join=True):
+        """Queues one step on the job's stream (ordered after the caller's current stream).  Asynchronous.
+        join=False leaves the caller's stream un-ordered behind the step (call join() later): two jobs driven
+        alternately then have two volumes in flight, and one volume's chunk passes overlap the other's label writes
+        and merge."""
         torch = self.torch
         if self.cap_rows is None or (self.use_graph and self.cuda and self.graphs is None):
             self.prepare()
@@ -752,7 +791,8 @@ class VolumeJob:
                 self.graphs[0].replay()
                 self._gather()
                 self.graphs[1][self._half].replay()
-        cur.wait_stream(self.stream)
+        if join:
+            cur.wait_stream(self.stream)
 
     def check(self):
         """Synchronises; True when the last step fitted every capacity.  Otherwise grows what overflowed
