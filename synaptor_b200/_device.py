@@ -6,6 +6,7 @@ staging, streams); every computation happens in libsynaptor_b200.so, reached
 through ctypes (`_cabi`).  There is no CPU fallback anywhere in this module.
 """
 import ctypes
+import os
 import threading
 from dataclasses import dataclass, field
 
@@ -72,14 +73,21 @@ def pinned_like(torch, t):
 _pinned_pool = {}
 _pinned_lock = threading.Lock()
 _PINNED_POOL_MAX = 8
+# page-locked bytes the pool may HOLD (free blocks only; blocks behind arrays the caller still references are the
+# caller's): beyond it a released block is simply freed.  SYNAPTOR_B200_PINNED_POOL_GB overrides (0 = no pooling).
+_PINNED_POOL_MAX_BYTES = int(float(os.environ.get("SYNAPTOR_B200_PINNED_POOL_GB", "16")) * (1 << 30))
+_pinned_pool_bytes = 0
 
 
 def pinned_acquire(torch, shape, dtype):
+    global _pinned_pool_bytes
     key = (tuple(int(x) for x in shape), dtype)
     with _pinned_lock:
         free = _pinned_pool.get(key)
         if free:
-            return free.pop()
+            h = free.pop()
+            _pinned_pool_bytes -= h.numel() * h.element_size()
+            return h
     return torch.empty(key[0], dtype=dtype, device="cpu", pin_memory=True)
 
 
@@ -95,11 +103,14 @@ def pinned_reserve(torch, shape, dtype, n):
 
 
 def pinned_release(host):
+    global _pinned_pool_bytes
     key = (tuple(host.shape), host.dtype)
+    nbytes = host.numel() * host.element_size()
     with _pinned_lock:
         free = _pinned_pool.setdefault(key, [])
-        if len(free) < _PINNED_POOL_MAX:
+        if len(free) < _PINNED_POOL_MAX and _pinned_pool_bytes + nbytes <= _PINNED_POOL_MAX_BYTES:
             free.append(host)
+            _pinned_pool_bytes += nbytes
 
 
 def pinned_numpy(host, view_dtype):

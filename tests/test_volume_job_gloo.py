@@ -221,6 +221,49 @@ def test_volume_job_plumbing_world2_gloo():
     assert outs[0]["runs"][1]["attempts"] >= 2
 
 
+def _worker_idle(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        vshape, cshape = (24, 20, 16), (24, 20, 16)          # ONE chunk, two ranks: rank 1 owns nothing
+        vol = orc.synth_pred(vshape, seed=5, sigma=1.5, fg=0.15)
+        job = NumpyVolumeJob(vshape, cshape, 0.5, 6, 10, with_base=False, rank=rank, world=world,
+                             device=torch.device("cpu"), graph=False)
+        for li, ci in enumerate(job.mine):
+            job.set_host_inputs(li, vol, None)
+        job.run()
+        ok = job.check()
+        q.put({"rank": rank, "ok": ok, "mine": list(job.mine), "merged": job.merged_table().copy(),
+               "labels": [job.labels[li].numpy().view(np.uint32).copy() for li in range(len(job.mine))]})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_rank_without_chunks_world2_gloo():
+    """More ranks than chunks: the idle rank still takes part in every collective and gets the merge results."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_idle, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=100) for _ in range(2)], key=lambda o: o["rank"])
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    vol = orc.synth_pred((24, 20, 16), seed=5, sigma=1.5, fg=0.15)
+    want = orc.volume_job(vol, None, (24, 20, 16), 0.5, 6, 10)
+    assert outs[0]["mine"] == [0] and outs[1]["mine"] == [] and outs[0]["ok"] and outs[1]["ok"]
+    assert np.array_equal(outs[0]["labels"][0], want["final"])
+    wm = {int(a): [int(x) for x in v] for (a, v) in want["merged"].items()}
+    for o in outs:
+        assert {int(x[0]): x[1:].tolist() for x in o["merged"]} == wm
+
+
 def test_plan_and_grid_helpers():
     grid, chunks = multi.grid_chunks((50, 40, 72), (24, 16, 32))
     assert grid == (3, 3, 3) and len(chunks) == 27
