@@ -270,3 +270,39 @@ def test_pageable_large_input_staged():
         assert np.array_equal(got[0], want[0])
         assert got[3].shape == shp and np.array_equal(got[3].row, r) and np.array_equal(got[3].col, c) \
             and np.array_equal(got[3].data, v)
+
+
+def test_volume_job_deterministic_and_lanes():
+    """Two runs of the same job, and a job whose chunk passes alternate over two streams, give identical bytes
+    (the unions, the pair table and the merge use atomics in arbitrary order; the results are canonical)."""
+    vshape, cshape = (48, 40, 128), (24, 20, 64)
+    vol = orc.synth_pred(vshape, seed=61, sigma=1.5, fg=0.12)
+    base_vol = orc.synth_base(vshape, seed=62, block=7, bg=0.1)
+    import torch
+    from synaptor_b200 import multi
+    outs = []
+    for lanes in (1, 2, 2):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        job = multi.VolumeJob(vshape, cshape, 0.5, 10, 15, with_base=True, rank=0, world=1, device=dev, graph=True,
+                              lanes=lanes)
+        keep = []
+        for li, ci in enumerate(job.mine):
+            beg, shp = job.chunk_rel_begin[ci], job.chunk_shape[ci]
+            sl = tuple(slice(b, b + s) for (b, s) in zip(beg, shp))
+            keep.append((torch.from_numpy(np.ascontiguousarray(vol[sl])).to(dev),
+                         torch.from_numpy(np.ascontiguousarray(base_vol[sl]).view(np.int64)).to(dev)))
+            job.set_inputs(li, *keep[-1])
+        for _ in range(3):
+            job.run()
+        assert job.check()
+        outs.append(([job.labels[li].cpu().numpy().copy() for li in range(len(job.mine))], job.merged_table().copy(),
+                     [tuple(np.asarray(a).copy() for a in job.overlaps(li)[:3]) for li in range(len(job.mine))]))
+    want = oracle_volume_job(vol, base_vol, cshape, 0.5, 10, 15)
+    for (labels, merged, ovs) in outs:
+        for (a, b) in zip(labels, outs[0][0]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(merged, outs[0][1])
+        for (x, y) in zip(ovs, outs[0][2]):
+            assert all(np.array_equal(p, q) for (p, q) in zip(x, y))
+    for (ci, (gi, sl, beg)) in enumerate(want["chunks"]):
+        assert np.array_equal(outs[0][0][ci].view(np.uint32), want["final"][sl])
