@@ -256,8 +256,10 @@ SYN_API int syn_merge_ccs_grid(const uint32_t *faces_all, const int64_t *tables_
  *                                          content of the reference's Continuation objects (continuation.py:15-35)
  *
  * syn_chunk_ccs_begin  : syn_chunk_ccs up to the segment table; zero-fills the label sectors without foreground,
- *                        fills the packed slot.  face_mask: bit f set = face f has a neighbour chunk and its
- *                        entries are wanted (the others stay empty).  No host synchronisation.
+ *                        fills the packed slot.  face_mask: bit f (0..5) set = face f has a neighbour chunk and its
+ *                        entries are wanted (the others stay empty); | SYN_BEGIN_SHARE_SM: the caller runs other
+ *                        chunks' kernels on other streams at the same time, so the streaming kernel leaves room
+ *                        for them on every SM.  No host synchronisation.
  * syn_merge_ccs_packed : merge_ccs_task (proc/tasks.py:72-122) over the gathered slots of ALL chunks:
  *                        id_base_out[c] = ids before chunk c in np.ndindex order (assign_ids.py:8-42; chunk c's row r
  *                        is global id id_base[c] + r + 1), edges between facing faces (merge_ccs.py:69-128),
@@ -277,6 +279,7 @@ SYN_API int syn_merge_ccs_grid(const uint32_t *faces_all, const int64_t *tables_
  *                        workspace, capacities, pointers): label of table row r = final_lut[final_lut_base_dev[0]
  *                        + r + 1] (final_lut NULL: r + 1), foreground label sectors, (label, base id) counts.
  */
+#define SYN_BEGIN_SHARE_SM 0x100
 SYN_API int64_t syn_packed_slot_bytes(int64_t cap_rows, int64_t cap_entries);
 SYN_API int syn_chunk_ccs_begin(const float *pred, int64_t nx, int64_t ny, int64_t nz, float thresh, int connectivity,
                                 int dil_k, int64_t dust_thresh, const int64_t *offset_xyz, uint32_t *labels_out,

@@ -402,6 +402,7 @@ struct CcsCall {
     cudaStream_t st;
     const u64 *ml_base;     // base segmentation of the multi-label variant (cc_task(overlap_seg=...)), else null
     bool defer;             // table-relative labels (row + 1) instead of component numbers; run labels in finish
+    bool share_sm;          // the caller runs other chunks' kernels next to this one: k_stream takes 2 CTAs per SM
     const u32 *lut;         // finish, deferred: final label = lut[lut_base[0] + row + 1] (null: row + 1)
     const i64 *lut_base;
     i64 lut_len;
@@ -474,12 +475,15 @@ int ccs_begin(CcsCall &c)
     if (sector_out) {
         const i64 ntiles = ((i64)g.nchunks + TS_CHUNKS - 1) / TS_CHUNKS;
         static const int stream_ctas = getenv("SYN_STREAM_CTAS") ? atoi(getenv("SYN_STREAM_CTAS")) : 0;   // per SM; 0 = occupancy
+        // co-running (another chunk's labelling kernels on a second stream): two resident CTAs per SM instead of three
+        // leave 100 KB of shared memory for a k_tile_ccl CTA next to them (a lone chunk loses 6 % with that)
+        const int ctas_per_sm = stream_ctas ? stream_ctas : (c.share_sm && has_base ? 2 : 0);
         static const bool no_tma = getenv("SYN_NO_TMA") != nullptr;
         static const bool all_tma = getenv("SYN_ALL_TMA") != nullptr;    // A/B: predictions by TMA on the fused path too
         // bulk copies into shared memory need chunk c to start at voxel 128 c (nz % 128 == 0)
         const bool tma = !no_tma && (nz % 128 == 0);
 #define SYN_STREAM(HB, FS, TB, TP, NST)                                                                            \
-    k_stream<HB, FS, TB, TP, NST><<<stream_ctas > 0 ? (int)std::min<i64>((i64)std::min(stream_ctas,                \
+    k_stream<HB, FS, TB, TP, NST><<<ctas_per_sm > 0 ? (int)std::min<i64>((i64)std::min(ctas_per_sm,                \
                                         occ_blocks(k_stream<HB, FS, TB, TP, NST>, TS_THREADS,                       \
                                                    NST * ts_stage_bytes(TP, TB))) * sm_count(), ntiles)            \
                                                    : wave_grid(k_stream<HB, FS, TB, TP, NST>, TS_THREADS, ntiles,  \
@@ -652,7 +656,7 @@ CcsCall make_call(const float *pred, float thresh, int connectivity, int dil_k, 
     c.base = (const u64 *)base_seg; c.prow = pair_rows; c.pcol = (u64 *)pair_cols; c.pval = (i64 *)pair_counts;
     c.max_pairs = max_pairs; c.workspace = workspace; c.ws_bytes = workspace_bytes; c.max_runs = max_runs;
     c.counts_host = (i64 *)counts_host; c.st = (cudaStream_t)stream; c.ml_base = (const u64 *)ml_base;
-    c.defer = false; c.lut = nullptr; c.lut_base = nullptr; c.lut_len = 0;
+    c.defer = false; c.share_sm = false; c.lut = nullptr; c.lut_base = nullptr; c.lut_len = 0;
     return c;
 }
 
@@ -721,6 +725,7 @@ int syn_chunk_ccs_begin(const float *pred, int64_t nx, int64_t ny, int64_t nz, f
                           base_seg, nullptr, nullptr, nullptr, max_pairs, workspace, workspace_bytes, max_runs, nullptr,
                           stream, nullptr);
     c.defer = true;
+    c.share_sm = (face_mask & SYN_BEGIN_SHARE_SM) != 0;
     int rc = ccs_setup(c, nx, ny, nz, false);
     if (rc != SYN_OK) return rc;
     rc = ccs_begin(c);
