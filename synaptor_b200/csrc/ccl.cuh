@@ -810,12 +810,15 @@ __global__ void __launch_bounds__(256) k_union_rows(const u32 *__restrict__ mask
 // straddle a tile border are left for the global pass (K3).  A tile with more
 // than TILE_RUNS runs is flagged and handled entirely by K3.
 // ===========================================================================
-constexpr int TILE_WORDS = 2048;
-constexpr int TILE_RUNS = 4096;
+#ifndef SYN_TILE_WORDS
+#define SYN_TILE_WORDS 2048
+#endif
+constexpr int TILE_WORDS = SYN_TILE_WORDS;      // (A/B builds: -DSYN_TILE_WORDS=1024; the rest scales with it)
+constexpr int TILE_RUNS = 2 * TILE_WORDS;
 constexpr int TILE_MAXTX = 16;
-constexpr int TILE_ROOTS = 512;    // tile-local components with statistics accumulated in shared memory
+constexpr int TILE_ROOTS = TILE_WORDS / 4;    // tile-local components with statistics accumulated in shared memory
 constexpr int TILE_SLOT = 10;      // u32 per root: size, sum dx, sum dy, sum z, min/max dx, dy, z
-constexpr int TILE_THREADS = 512;
+constexpr int TILE_THREADS = TILE_WORDS / 4;
 constexpr int TILE_WPT = TILE_WORDS / TILE_THREADS;   // mask words per thread (consecutive)
 // shared memory of one tile CTA (3 CTAs = 48 warps per SM; the kernel is instruction-issue bound, not
 // occupancy bound): mask words, run-start words, packed active list, parents, statistics slots, global ids of
