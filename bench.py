@@ -15,11 +15,15 @@ chunk_overlaps against the uint64 base segmentation -- synaptor/proc/tasks.py:26
 The result of the measured configuration is checked, once, outside the timed region, against the CPU oracle
 (bit-exact: final volume, merged table, id maps, overlap triples; 1:1 with whole-volume labelling).
 
-value   : Gvoxel/s, whole job, inputs resident in HBM, outputs left in HBM (CUDA events, max over ranks)
-e2e     : the same job through synaptor_b200.proc.tasks.volume_tasks with HOST chunk arrays (H2D of every chunk,
-          D2H of the final label volume + tables + overlaps, host materialisation) inside the timed region
+value   : Gvoxel/s, whole job, inputs resident in HBM, outputs left in HBM (CUDA events, max over ranks).  The K timed
+          steps keep two volumes in flight (two job instances with their own buffers, driven alternately) and the
+          chunk passes of a volume alternate over two streams; every step is a complete job and all K are inside the
+          timed region.  config.ms_per_step_one_volume_at_a_time: each step finished before the next is queued.
+e2e     : the same job through synaptor_b200.proc.tasks.volume_tasks_stream with HOST chunk arrays (H2D of every
+          chunk, D2H of the final label volume + tables + overlaps, host materialisation) inside the timed region;
+          beside it the single-call figure, pageable inputs, and the box's copy floors measured in the same run
 roofline: the dominant kernel k_stream (16 B/voxel algorithmic: 4 pred + 8 base read, 4 label write) timed with
-          CUDA events on the launching stream in an event-instrumented pass
+          CUDA events on the launching stream in an event-instrumented pass; traffic from the committed ncu capture
 """
 import argparse
 import json
