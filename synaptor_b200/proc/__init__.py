@@ -4,6 +4,7 @@ from . import seg
 from . import overlap
 from . import utils
 from . import hashing
+from . import io
 
 from . import tasks
 from .tasks import cc_task

@@ -5,8 +5,10 @@ Same file names, directory layout and CSV conventions as the reference's
 synaptor/proc/io (seginfo.py, overlap.py, idmap.py) over its local backend
 (synaptor/io/backends/local.py:47-56: `DataFrame.to_csv(index=True, header=True)`,
 `pd.read_csv(index_col=0)`), so the files written here are read by the untouched
-reference stages and vice versa.  Cloud / database back ends and the HDF5
-continuation files (h5py is not in this image) are out of scope.
+reference stages and vice versa.  The HDF5 continuation files
+(synaptor/proc/io/continuation.py:53-69, 94-118) are written and read by `h5min`, a
+minimal HDF5 emitter of our own (h5py / libhdf5 are not in this image).  Cloud /
+database back ends are out of scope.
 """
 import os
 import re
@@ -192,8 +194,7 @@ def read_dup_id_map(proc_url):
     return dict(zip(df.index, df[cn.dst_id]))
 
 
-# ---- continuation file names and the face-hash table (synaptor/proc/io/continuation.py:22-50, 207-216).  The
-#      HDF5 payload of these files is not written here (h5py is not part of this environment). ----------------
+# ---- continuation file names and the face-hash table (synaptor/proc/io/continuation.py:22-50, 207-216) ---------
 FACE_REGEXP = re.compile("f[0-2]_(hi|lo)")
 CONTIN_TABLENAME = "continuations"
 
@@ -226,12 +227,77 @@ def prep_face_hashes(face_hashes, chunk_bounds, proc_dir):
     return pd.DataFrame({cn.contin_filename: filenames, cn.facehash: hashes}), CONTIN_TABLENAME
 
 
-# ---- continuation payload.  The reference stores a face's continuations in an HDF5 file (datasets `face_axis`,
-#      `hi_face`, group `face_coords/<segid>` -> (n, 2) int64; synaptor/proc/io/continuation.py:94-118).  h5py /
-#      libhdf5 are not part of this environment, so the SAME content is written as a NumPy .npz archive under the
-#      reference's file name with the suffix `.npz` instead of `.h5`: arrays `face_axis`, `hi_face`, `segids` (m,),
-#      `counts` (m,), `face_coords` (sum counts, 2) int64 in continuation order.  The untouched reference's
-#      merge_ccs stage cannot read these files (documented in DESIGN.md); this package's own merge can. ----------
+# ---- continuation payload (synaptor/proc/io/continuation.py:53-69, 94-118): one HDF5 file per chunk face with the
+#      scalar datasets `face_axis` (int64) and `hi_face` (h5py's boolean: int8 enum FALSE / TRUE) and the group
+#      `face_coords` holding one (n, 2) int64 dataset per segment id, named by the id in decimal.  Written by h5min
+#      (same objects, same types, the file-format variant h5py's default settings produce), so the untouched
+#      reference's `_read_face_file` / `merge_ccs` stage reads them; see h5min's docstring for how that is pinned. ----
+def _write_face_file(face_continuations, fname, face=None):
+    """continuation.py:94-118 -- same arguments, same error when neither a face nor a continuation is given."""
+    from . import h5min
+    if face is None:
+        if len(face_continuations) == 0:
+            raise Exception("Need a face argument or continuations to determine face info for file")
+        face = face_continuations[0].face
+    os.makedirs(os.path.dirname(os.path.abspath(fname)), exist_ok=True)
+    coords = {}
+    for c in face_continuations:
+        name = f"{c.segid}"
+        if name in coords:          # h5py: "Unable to create dataset (name already exists)"
+            raise ValueError(f"Unable to create dataset (name already exists): {name}")
+        coords[name] = np.asarray(c.face_coords)
+    h5min.write_file(fname, {"face_axis": np.asarray(face.axis), "hi_face": np.asarray(face.hi_index),
+                             "face_coords": coords})
+
+
+def _read_face_file(fname):
+    """continuation.py:53-69 -- continuations in the order h5py's `group.keys()` yields them (link-name order)."""
+    from . import h5min
+    from ..seg.continuation import Continuation, Face
+    f = h5min.read_file(fname)
+    face = Face(f["face_axis"][()], f["hi_face"][()])
+    return [Continuation(int(segid), face, coords) for (segid, coords) in f["face_coords"].items()]
+
+
+def read_face_continuations(proc_url, chunk_bounds, face):
+    return _read_face_file(face_filename(proc_url, chunk_bounds, face))
+
+
+def read_face_filenames(filenames):
+    return list(map(_read_face_file, filenames))
+
+
+def write_face_continuations(continuations, proc_url, chunk_bounds, face):
+    _write_face_file(continuations, face_filename(proc_url, chunk_bounds, face), face)
+
+
+def write_chunk_continuations(continuations, proc_url, chunk_bounds):
+    """The six face files of a chunk ({Face: [Continuation]} as returned by cc_task); continuation.py:184-192."""
+    from ..seg.continuation import Face
+    for face in Face.all_faces():
+        _write_face_file(continuations[face], face_filename(proc_url, chunk_bounds, face), face)
+
+
+def read_chunk_continuations(proc_url, chunk_bounds):
+    """continuation.py:147-160"""
+    from ..seg.continuation import Face
+    return {face: _read_face_file(face_filename(proc_url, chunk_bounds, face)) for face in Face.all_faces()}
+
+
+def read_all_continuations(storagestr):
+    """All continuation files of a processing directory as an object array shaped like the chunk grid, each cell
+    a {Face: [Continuation]} dict, and the directory (continuation.py:219-261)."""
+    contin_dir = os.path.join(storagestr, fn.contin_dirname)
+    filenames = [os.path.join(contin_dir, f) for f in sorted(os.listdir(contin_dir)) if f.endswith(".h5")]
+    assert len(filenames) > 0, "No filenames returned"
+    chunk_to_conts = {}
+    for f in filenames:
+        chunk_to_conts.setdefault(bbox_from_fname(f).min(), {})[face_from_filename(f)] = _read_face_file(f)
+    return _grid_array(chunk_to_conts), contin_dir
+
+
+# ---- the same payload as a NumPy .npz archive (round 2's stop-gap; kept for files written by earlier versions):
+#      arrays `face_axis`, `hi_face`, `segids` (m,), `counts` (m,), `face_coords` (sum counts, 2) int64 ----------
 def npz_face_filename(proc_url, chunk_bounds, face, local=False):
     return face_filename(proc_url, chunk_bounds, face, local=local)[:-len(".h5")] + ".npz"
 
@@ -256,15 +322,3 @@ def read_face_file_npz(fname):
         ends = np.cumsum(f["counts"])
         coords = f["face_coords"]
         return [Continuation(int(s), face, coords[e - n:e]) for (s, n, e) in zip(f["segids"], f["counts"], ends)]
-
-
-def write_chunk_continuations(continuations, proc_url, chunk_bounds):
-    """The six face files of a chunk ({Face: [Continuation]} as returned by cc_task)."""
-    from ..seg.continuation import Face
-    for face in Face.all_faces():
-        write_face_file_npz(continuations[face], npz_face_filename(proc_url, chunk_bounds, face), face)
-
-
-def read_chunk_continuations(proc_url, chunk_bounds):
-    from ..seg.continuation import Face
-    return {face: read_face_file_npz(npz_face_filename(proc_url, chunk_bounds, face)) for face in Face.all_faces()}

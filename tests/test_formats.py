@@ -7,6 +7,7 @@ import os
 
 import numpy as np
 import pandas as pd
+import pytest
 import scipy.sparse as sp
 
 from util import gold
@@ -182,9 +183,10 @@ def test_g12_continuation_file_names_and_pairing():
     assert sum(len(grp) == 2 for grp in groups) == 12 and sum(len(grp) == 1 for grp in groups) == 24
 
 
-def test_continuation_files_npz_roundtrip(tmp_path):
-    """The continuation payload (reference: HDF5, proc/io/continuation.py:94-118) written as .npz under the
-    reference's names: same content back, empty faces included."""
+def test_continuation_files_roundtrip(tmp_path):
+    """The continuation payload (proc/io/continuation.py:94-118) under the reference's file names, as HDF5 written by
+    h5min: same content back in h5py's key order (link names sorted as byte strings), empty faces included; the
+    .npz stop-gap of earlier versions still reads."""
     from synaptor_b200.proc import io as taskio
     from synaptor_b200.proc.seg.continuation import Continuation, Face
     from synaptor_b200.types.bbox import BBox3d
@@ -192,11 +194,20 @@ def test_continuation_files_npz_roundtrip(tmp_path):
     conts = {f: [] for f in Face.all_faces()}
     f0 = Face(0, True)
     conts[f0] = [Continuation(7, f0, np.array([[1, 2], [1, 3]], dtype=np.int64)),
-                 Continuation(12, f0, np.array([[5, 5]], dtype=np.int64))]
+                 Continuation(12, f0, np.array([[5, 5]], dtype=np.int64)),
+                 Continuation(100, f0, np.array([[0, 0]], dtype=np.int64))]
     taskio.write_chunk_continuations(conts, str(tmp_path), bb)
-    name = taskio.npz_face_filename(str(tmp_path), bb, f0)
-    assert name.endswith("continuations/continuations_0_18_16-20_36_32_f0_hi.npz")
+    name = taskio.face_filename(str(tmp_path), bb, f0)
+    assert name.endswith("continuations/continuations_0_18_16-20_36_32_f0_hi.h5") and os.path.exists(name)
     back = taskio.read_chunk_continuations(str(tmp_path), bb)
-    assert [c.segid for c in back[f0]] == [7, 12] and back[f0][0].face.axis == 0 and back[f0][0].face.hi_index is True
-    assert np.array_equal(back[f0][0].face_coords, [[1, 2], [1, 3]]) and np.array_equal(back[f0][1].face_coords, [[5, 5]])
+    assert [c.segid for c in back[f0]] == [100, 12, 7]            # "100" < "12" < "7": what group.keys() yields
+    assert back[f0][0].face.axis == 0 and bool(back[f0][0].face.hi_index) is True and back[f0][0].face == f0
+    got = {c.segid: c.face_coords for c in back[f0]}
+    assert np.array_equal(got[7], [[1, 2], [1, 3]]) and np.array_equal(got[12], [[5, 5]]) and got[7].dtype == np.int64
     assert all(back[f] == [] for f in Face.all_faces() if not (f.axis == 0 and f.hi_index))
+    assert [c.segid for c in taskio.read_face_continuations(str(tmp_path), bb, f0)] == [100, 12, 7]
+    with pytest.raises(Exception, match="Need a face argument"):
+        taskio._write_face_file([], str(tmp_path / "x.h5"))
+    # .npz files of earlier versions
+    taskio.write_face_file_npz(conts[f0], taskio.npz_face_filename(str(tmp_path), bb, f0), f0)
+    assert [c.segid for c in taskio.read_face_file_npz(taskio.npz_face_filename(str(tmp_path), bb, f0))] == [7, 12, 100]

@@ -117,6 +117,33 @@ def test_g4_merge_golden(syn):
     assert np.array_equal(final, g["final"]), first_diff(final, g["final"])
 
 
+def test_g4_merge_through_files(syn, tmp_path):
+    """The same merge with a processing directory between the stages, as tasks_w_io.py:54-65, 112-138 runs it: chunk
+    tasks write seg-info CSVs and HDF5 continuation files, the merge task reads the directory back."""
+    g = gold("g4_merge_ccs.npz")
+    vol = g["vol"]
+    boxes = syn.chunk_bboxes(vol.shape, tuple(g["chunk_shape"].tolist()))
+    taskio = syn.proc.io
+    d = str(tmp_path)
+    for bb in boxes:
+        _, conts, info = syn.proc.tasks.cc_task(np.ascontiguousarray(vol[bb.index()]), float(g["thresh"]),
+                                                int(g["dust"]), offset=tuple(bb.min()), verbose=False)
+        taskio.write_chunk_continuations(conts, d, bb)
+        taskio.write_chunk_seg_info(info, d, bb)
+    cont_arr, _ = taskio.read_all_continuations(d)
+    info_arr, _ = taskio.read_all_chunk_seg_infos(d)
+    assert cont_arr.shape == info_arr.shape == (2, 2, 2)
+    merged, id_maps = syn.proc.tasks.merge_ccs_task(cont_arr, info_arr, int(g["size_thr"]),
+                                                    tuple(g["max_face_shape"].tolist()))
+    gold_rows = {int(i): r.astype(np.int64) for (i, r) in zip(g["merged_index"], g["merged_table"])}
+    midx, mtab = table_of(merged)
+    assert sorted(midx.tolist()) == sorted(gold_rows)
+    for (k, row) in zip(midx.tolist(), mtab):
+        assert row[0] == gold_rows[k][0] and np.array_equal(row[4:], gold_rows[k][4:])
+    for (i, gi) in enumerate(np.ndindex(2, 2, 2)):
+        assert sorted((int(a), int(b)) for (a, b) in id_maps[gi].items()) == [tuple(x) for x in g[f"id_map_{i}"].tolist()]
+
+
 def test_g9_hashed_merge_golden(syn):
     """Merge sharded by hash (tasks.py:125-180) against the executed reference: same edges, map, buckets, tables."""
     g, g4 = gold("g9_hashed_merge.npz"), gold("g4_merge_ccs.npz")
