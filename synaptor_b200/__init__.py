@@ -13,6 +13,7 @@ from . import seg_utils
 from .seg_utils import filter_segs_by_size, centers_of_mass, bounding_boxes
 
 from . import proc
+from . import io
 from .proc.seg import connected_components, dilated_components
 
 __version__ = "0.1.0"

@@ -1573,6 +1573,9 @@ __device__ __forceinline__ void stats_body(const u32 *__restrict__ lmask, const 
 
 // Merges the tile records into the per-component statistics (after the canonical ranks are known); tiles whose
 // statistics the shared-memory pass could not hold (flagged, normally none) are accumulated per piece.
+#ifndef SYN_STATS_VEC
+#define SYN_STATS_VEC 0
+#endif
 __global__ void __launch_bounds__(256) k_stats_merge(const TileRec *__restrict__ recs, const u32 *__restrict__ par,
                                                      const u32 *__restrict__ rank, CompStat *stat,
                                                      const u32 *__restrict__ lmask, const u32 *__restrict__ omask,
@@ -1633,16 +1636,35 @@ __global__ void __launch_bounds__(256) k_stats_merge(const TileRec *__restrict__
             continue;
         }
         CompStat *s = stat + c;
+#if SYN_STATS_VEC == 1
+        // box read with two vector loads before the first atomic
+        const uint4 lo = __ldcg(reinterpret_cast<const uint4 *>(&s->minx));    // minx miny minz maxx
+        const uint2 hi = __ldcg(reinterpret_cast<const uint2 *>(&s->maxy));    // maxy maxz
+#endif
         atomicAdd(&s->size, (u64)r.size);
         atomicAdd(&s->sx, r.sx);
         atomicAdd(&s->sy, r.sy);
         atomicAdd(&s->sz, r.sz);
+#if SYN_STATS_VEC == 2
+        // box read with two vector loads after the sums went out
+        const uint4 lo = __ldcg(reinterpret_cast<const uint4 *>(&s->minx));
+        const uint2 hi = __ldcg(reinterpret_cast<const uint2 *>(&s->maxy));
+#endif
+#if SYN_STATS_VEC
+        if (r.minx < lo.x) atomicMin(&s->minx, r.minx);
+        if (r.miny < lo.y) atomicMin(&s->miny, r.miny);
+        if (r.minz < lo.z) atomicMin(&s->minz, r.minz);
+        if (r.maxx > lo.w) atomicMax(&s->maxx, r.maxx);
+        if (r.maxy > hi.x) atomicMax(&s->maxy, r.maxy);
+        if (r.maxz > hi.y) atomicMax(&s->maxz, r.maxz);
+#else
         if (r.minx < ldcg_u32(&s->minx)) atomicMin(&s->minx, r.minx);
         if (r.miny < ldcg_u32(&s->miny)) atomicMin(&s->miny, r.miny);
         if (r.minz < ldcg_u32(&s->minz)) atomicMin(&s->minz, r.minz);
         if (r.maxx > ldcg_u32(&s->maxx)) atomicMax(&s->maxx, r.maxx);
         if (r.maxy > ldcg_u32(&s->maxy)) atomicMax(&s->maxy, r.maxy);
         if (r.maxz > ldcg_u32(&s->maxz)) atomicMax(&s->maxz, r.maxz);
+#endif
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_acc[0]) {

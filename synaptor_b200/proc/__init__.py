@@ -7,6 +7,7 @@ from . import hashing
 from . import io
 
 from . import tasks
+from . import tasks_w_io
 from .tasks import cc_task
 from .tasks import merge_ccs_task
 from .tasks import remap_ids_task

@@ -194,6 +194,41 @@ def read_dup_id_map(proc_url):
     return dict(zip(df.index, df[cn.dst_id]))
 
 
+def read_filtered_dup_id_map(storagestr, src_ids, chunksize=100000):
+    """The rows of the duplicate map whose source id is in `src_ids` (idmap.py:228-249; a missing file gives an
+    empty mapping with the reference's warning)."""
+    src_ids = set(src_ids)
+    mapping = dict()
+    try:
+        for subdf in pd.read_csv(os.path.join(storagestr, fn.dup_map_fname), index_col=0, chunksize=chunksize):
+            rows = subdf.loc[sorted(src_ids.intersection(subdf.index))]
+            mapping.update(dict(zip(rows.index, rows[cn.dst_id])))
+    except Exception as e:
+        print(e)
+        print("WARNING: no dup id map found, passing empty dup mapping")
+        mapping = dict()
+    return mapping
+
+
+# ---- task durations (synaptor/proc/io/timing.py:22-69).  The reference's FILE branch cannot run (timing_fname
+#      formats "{tag}" positionally, `_write_timing_file` is called without its time argument), so only the intent
+#      is mirrored: one text file `task_durations/{task_name}_{tag}` holding the seconds. ------------------------
+def timing_fname(proc_dir, task_name, timing_tag):
+    return os.path.join(proc_dir, fn.timing_dirname, f"{task_name}_{fn.timing_fmtstr.format(tag=timing_tag)}")
+
+
+def write_task_timing(time, task_name, tag, proc_url):
+    path = timing_fname(proc_url, task_name, tag)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w+") as f:
+        f.write(f"{time}")
+
+
+def read_task_timing(proc_url, task_name, tag):
+    with open(timing_fname(proc_url, task_name, tag)) as f:
+        return float(f.read().strip())
+
+
 # ---- continuation file names and the face-hash table (synaptor/proc/io/continuation.py:22-50, 207-216) ---------
 FACE_REGEXP = re.compile("f[0-2]_(hi|lo)")
 CONTIN_TABLENAME = "continuations"

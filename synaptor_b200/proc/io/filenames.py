@@ -19,3 +19,6 @@ tagged_dup_fname = "dup_id_map_{i}.df"
 overlaps_dirname = "overlaps"
 overlaps_fmtstr = "chunk_overlap_{tag}.df"
 max_overlaps_fname = "max_overlaps.df"
+
+timing_dirname = "task_durations"
+timing_fmtstr = "{tag}"

@@ -144,6 +144,56 @@ def test_g4_merge_through_files(syn, tmp_path):
         assert sorted((int(a), int(b)) for (a, b) in id_maps[gi].items()) == [tuple(x) for x in g[f"id_map_{i}"].tolist()]
 
 
+def test_tasks_w_io_local_workflow(syn, tmp_path, capsys):
+    """The five task wrappers of proc/tasks_w_io.py (mirror of synaptor/proc/tasks_w_io.py:22-143, 503-594) run as the
+    reference's workflow runs them -- cc_task per chunk, merge_ccs_task, remap_ids_task + overlap_task per chunk,
+    merge_overlaps_task -- with nothing but files between the stages (F-ordered .npy volumes, a processing
+    directory): final volume, merged table, id maps, chunk overlap matrices and max overlaps equal the executed
+    reference's (fixtures g4, g13)."""
+    import os
+    import pandas as pd
+    g, g13 = gold("g4_merge_ccs.npz"), gold("g13_merge_overlaps.npz")
+    W, taskio = syn.proc.tasks_w_io, syn.proc.io
+    d = str(tmp_path / "proc")
+    pred_p, seg_p, out_p, base_p = (str(tmp_path / n) for n in ("pred.npy", "seg.npy", "seg_final.npy", "base.npy"))
+    np.save(pred_p, np.asfortranarray(g["vol"]))              # what CloudVolume hands out is F-ordered
+    np.save(base_p, np.asfortranarray(g13["base"]))
+    shape = g["vol"].shape
+    syn.io.init_seg_volume(seg_p, vol_size=shape)
+    syn.io.init_seg_volume(out_p, vol_size=shape)
+    boxes = syn.chunk_bboxes(shape, tuple(g["chunk_shape"].tolist()))
+    for bb in boxes:
+        W.cc_task(pred_p, seg_p, d, float(g["thresh"]), int(g["dust"]), tuple(bb.min()), tuple(bb.max()), timing_tag="t")
+    assert "Running connected components" in capsys.readouterr().out
+    for (i, bb) in enumerate(boxes):
+        assert np.array_equal(syn.io.read_cloud_volume_chunk(seg_p, bb), g[f"chunk_seg_{i}"])
+    assert len(os.listdir(os.path.join(d, "continuations"))) == 6 * len(boxes)
+    W.merge_ccs_task(d, int(g["size_thr"]), tuple(g["max_face_shape"].tolist()))
+    merged = taskio.read_merged_seg_info(d)
+    gold_rows = {int(i): r.astype(np.int64) for (i, r) in zip(g["merged_index"], g["merged_table"])}
+    midx, mtab = table_of(merged)
+    assert sorted(midx.tolist()) == sorted(gold_rows)
+    for (k, row) in zip(midx.tolist(), mtab):
+        assert row[0] == gold_rows[k][0] and np.array_equal(row[4:], gold_rows[k][4:])
+    for (i, bb) in enumerate(boxes):
+        idm = taskio.read_chunk_id_map(d, bb)
+        assert sorted((int(a), int(b)) for (a, b) in idm.items()) == [tuple(x) for x in g[f"id_map_{i}"].tolist()]
+        W.remap_ids_task(seg_p, out_p, tuple(bb.min()), tuple(bb.max()), d)
+        W.overlap_task(out_p, base_p, tuple(bb.min()), tuple(bb.max()), d)
+    final = np.load(out_p)
+    assert np.array_equal(final, g["final"]), first_diff(final, g["final"])
+    for (i, bb) in enumerate(boxes):
+        m = taskio.read_chunk_overlap_mat(taskio.chunk_overlap_fname(d, bb))
+        got = sorted(zip(m.row.tolist(), m.col.tolist(), m.data.tolist()))
+        assert got == sorted(tuple(int(v) for v in t) for t in g13[f"ov_{i}"]), i
+    W.merge_overlaps_task(d)
+    mo = pd.read_csv(os.path.join(d, "max_overlaps.df"), index_col=0)
+    cn = syn.proc.colnames
+    got = sorted(zip(mo[cn.rows].tolist(), mo[cn.cols].tolist(), mo[cn.vals].tolist()))
+    assert got == sorted(zip(g13["max_row"].tolist(), g13["max_col"].tolist(), g13["max_val"].tolist()))
+    assert taskio.read_task_timing(d, "ccs", "t") > 0
+
+
 def test_g9_hashed_merge_golden(syn):
     """Merge sharded by hash (tasks.py:125-180) against the executed reference: same edges, map, buckets, tables."""
     g, g4 = gold("g9_hashed_merge.npz"), gold("g4_merge_ccs.npz")

@@ -1,0 +1,167 @@
+"""
+synaptor_b200.io (local volumes) and the small proc.io helpers the task wrappers (proc/tasks_w_io.py) need.  CPU only;
+the wrappers themselves run on the GPU (tests/test_gpu_parity.py::test_tasks_w_io_local_workflow).
+"""
+import inspect
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import synaptor_b200 as syn
+from synaptor_b200.proc import io as taskio
+
+
+def test_local_volume_chunks(tmp_path):
+    p = str(tmp_path / "seg.npy")
+    assert syn.io.init_seg_volume(p, vol_size=(10, 12, 14)) == p
+    vol = np.load(p, mmap_mode="r")
+    assert vol.dtype == np.uint32 and vol.shape == (10, 12, 14) and np.isfortran(vol) and not vol.any()
+    bb = syn.BBox3d((2, 3, 4), (6, 9, 14))
+    data = np.arange(4 * 6 * 10, dtype=np.int64).reshape(4, 6, 10)
+    syn.io.write_cloud_volume_chunk(data, p, bb)               # cast to the volume's dtype like cv[...] = data.astype
+    back = syn.io.read_cloud_volume_chunk("file://" + p, bb)
+    assert back.dtype == np.uint32 and back.flags.f_contiguous and back.flags.writeable and np.array_equal(back, data)
+    # bounded = False, fill_missing = True: the part outside the volume reads as zeros and is dropped on write
+    edge = syn.BBox3d((8, 10, 12), (12, 14, 16))
+    syn.io.write_cloud_volume_chunk(np.full((4, 4, 4), 7, dtype=np.uint32), p, edge)
+    r = syn.io.read_cloud_volume_chunk(p, edge)
+    assert r.shape == (4, 4, 4) and (r[:2, :2, :2] == 7).all() and r.sum() == 7 * 8
+    with pytest.raises(ValueError):
+        syn.io.write_cloud_volume_chunk(np.zeros((2, 2, 2), dtype=np.uint32), p, bb)
+    # C-ordered volumes and a trailing channel axis
+    q = str(tmp_path / "pred.npy")
+    np.save(q, np.arange(3 * 4 * 5, dtype=np.float32).reshape(3, 4, 5, 1))
+    c = syn.io.read_cloud_volume_chunk(q, syn.BBox3d((1, 1, 1), (3, 3, 3)))
+    assert c.shape == (2, 2, 2) and c[0, 0, 0] == 1 * 20 + 1 * 5 + 1 and c.dtype == np.float32
+
+
+def test_out_of_scope_storage_is_refused(tmp_path):
+    bb = syn.BBox3d((0, 0, 0), (1, 1, 1))
+    for name in ("gs://bucket/layer", "s3://bucket/layer", "precomputed://gs://bucket/layer"):
+        with pytest.raises(NotImplementedError):
+            syn.io.read_cloud_volume_chunk(name, bb)
+    assert syn.io.is_db_url("postgresql://u:p@host/db") and not syn.io.is_db_url(str(tmp_path))
+    W = syn.proc.tasks_w_io
+    with pytest.raises(NotImplementedError):
+        W.merge_ccs_task("postgresql://u:p@host/db", 100, (64, 64))
+    with pytest.raises(NotImplementedError):
+        W.cc_task("a.npy", "b.npy", "mysql://h/db", 0.5, 100, (0, 0, 0), (8, 8, 8))
+    with pytest.raises(FileNotFoundError):
+        syn.io.read_cloud_volume_chunk(str(tmp_path / "missing.npy"), bb)
+    with pytest.raises(NotImplementedError):
+        syn.io.read_cloud_volume_chunk(str(tmp_path / "missing.npy"), bb, mip=1)
+
+
+def test_wrapper_signatures_match_the_reference():
+    """argument names and order of synaptor/proc/tasks_w_io.py:22-25, 112, 503-506, 537, 558-561"""
+    W = syn.proc.tasks_w_io
+    want = {
+        "cc_task": ["desc_cvname", "seg_cvname", "storagestr", "cc_thresh", "sz_thresh", "chunk_begin", "chunk_end",
+                    "mip", "parallel", "storagedir", "hashmax", "timing_tag"],
+        "merge_ccs_task": ["storagestr", "size_thr", "max_face_shape", "timing_tag"],
+        "overlap_task": ["seg_cvname", "base_seg_cvname", "chunk_begin", "chunk_end", "storagedir", "mip", "seg_mip",
+                         "parallel", "timing_tag"],
+        "merge_overlaps_task": ["storagestr", "timing_tag"],
+        "remap_ids_task": ["seg_in_cvname", "seg_out_cvname", "chunk_begin", "chunk_end", "storagestr",
+                           "dup_map_storagestr", "mip", "parallel", "timing_tag"],
+    }
+    for name, args in want.items():
+        assert list(inspect.signature(getattr(W, name)).parameters) == args, name
+
+
+def test_dup_map_filter_timing_and_sorted_boxes(tmp_path, capsys):
+    d = str(tmp_path)
+    assert taskio.read_filtered_dup_id_map(d, [1, 2]) == {}                       # no file: empty map + warning
+    assert "WARNING: no dup id map found" in capsys.readouterr().out
+    taskio.write_dup_id_map({5: 2, 9: 2, 11: 3, 40: 7}, d)
+    assert taskio.read_filtered_dup_id_map(d, [9, 40, 77], chunksize=2) == {9: 2, 40: 7}
+    assert taskio.read_filtered_dup_id_map(d, []) == {}
+    taskio.write_task_timing(1.25, "ccs", "run7", d)
+    assert os.path.exists(os.path.join(d, "task_durations", "ccs_run7")) and taskio.read_task_timing(d, "ccs", "run7") == 1.25
+    boxes = syn.chunk_bboxes((20, 20, 10), (10, 10, 10))
+    for bb in reversed(boxes):
+        taskio.write_chunk_seg_info(pd.DataFrame({"size": [1]}, index=pd.Index([1], name="cleft_segid")), d, bb)
+    assert syn.io.extract_sorted_bboxes(os.path.join(d, "seg_infos")) == sorted(boxes, key=lambda b: b.min())
+
+
+def test_tasks_w_io_plumbing_with_oracle_stand_ins(tmp_path, monkeypatch, capsys):
+    """The file plumbing of proc/tasks_w_io.py on the CPU: the five device-backed `tasks.*` calls are replaced by the
+    oracle's restatements (test infrastructure), everything else -- local volumes, HDF5 continuation files, CSVs,
+    grid arrays, id maps -- is the product code.  Result against the executed reference (fixtures g4, g13).  The
+    same workflow with the real device calls: test_gpu_parity.py::test_tasks_w_io_local_workflow."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import oracle as orc
+    from util import gold, table_of
+    from synaptor_b200.proc import tasks, colnames as cn
+    from synaptor_b200.proc.seg.continuation import Continuation, Face
+    g, g13 = gold("g4_merge_ccs.npz"), gold("g13_merge_overlaps.npz")
+
+    def cc_task(desc_vol, cc_thresh, sz_thresh, offset=(0, 0, 0)):
+        assert desc_vol.flags.f_contiguous                       # the chunk arrives as CloudVolume delivers it
+        ccs, conts, info = orc.cc_task_c(np.ascontiguousarray(desc_vol), cc_thresh, sz_thresh, offset=tuple(offset))[:3]
+        conts = {Face(a, bool(h)): [Continuation(int(s), Face(a, bool(h)), np.asarray(c)) for (s, c) in lst]
+                 for ((a, h), lst) in conts.items()}
+        return ccs, conts, info
+
+    def merge_ccs_task(cont_arr, info_arr, size_thr, max_face_shape):
+        conts = np.empty(cont_arr.shape, dtype=object)
+        for idx in np.ndindex(cont_arr.shape):
+            conts[idx] = {(int(f.axis), bool(f.hi_index)): [(c.segid, np.asarray(c.face_coords)) for c in lst]
+                          for (f, lst) in cont_arr[idx].items()}
+        merged, id_maps = orc.merge_ccs_task(conts, info_arr, size_thr, max_face_shape)
+        ids = sorted(merged)
+        df = pd.DataFrame(np.array([merged[i] for i in ids], dtype=np.int64).reshape(-1, 10), columns=cn.seg_info_cols,
+                          index=pd.Index(ids, name=cn.seg_id))
+        return df, id_maps
+
+    def overlap_task(segs, base_segs):
+        import scipy.sparse as sp
+        r, c, v, shp = orc.count_overlaps_c(np.ascontiguousarray(segs), np.ascontiguousarray(base_segs))
+        return sp.coo_matrix((v, (r, c)), shape=shp)
+
+    monkeypatch.setattr(tasks, "cc_task", cc_task)
+    monkeypatch.setattr(tasks, "merge_ccs_task", merge_ccs_task)
+    monkeypatch.setattr(tasks, "overlap_task", overlap_task)
+    monkeypatch.setattr(tasks, "remap_ids_task", lambda seg, *maps, copy=False: orc.remap_ids(seg, *maps))
+
+    W, taskio = syn.proc.tasks_w_io, syn.proc.io
+    d = str(tmp_path / "proc")
+    pred_p, seg_p, out_p, base_p = (str(tmp_path / n) for n in ("pred.npy", "seg.npy", "seg_final.npy", "base.npy"))
+    np.save(pred_p, np.asfortranarray(g["vol"]))
+    np.save(base_p, np.asfortranarray(g13["base"]))
+    shape = g["vol"].shape
+    syn.io.init_seg_volume(seg_p, vol_size=shape)
+    syn.io.init_seg_volume(out_p, vol_size=shape)
+    boxes = syn.chunk_bboxes(shape, tuple(g["chunk_shape"].tolist()))
+    for bb in boxes:
+        W.cc_task(pred_p, seg_p, d, float(g["thresh"]), int(g["dust"]), tuple(bb.min()), tuple(bb.max()), timing_tag="t")
+    out = capsys.readouterr().out
+    assert "Reading network output chunk" in out and "Writing chunk_continuations complete in" in out
+    for (i, bb) in enumerate(boxes):
+        assert np.array_equal(syn.io.read_cloud_volume_chunk(seg_p, bb), g[f"chunk_seg_{i}"])
+    assert len(os.listdir(os.path.join(d, "continuations"))) == 6 * len(boxes)
+    W.merge_ccs_task(d, int(g["size_thr"]), tuple(g["max_face_shape"].tolist()), timing_tag="t")
+    merged = taskio.read_merged_seg_info(d)
+    gold_rows = {int(i): r.astype(np.int64) for (i, r) in zip(g["merged_index"], g["merged_table"])}
+    midx, mtab = table_of(merged)
+    assert sorted(midx.tolist()) == sorted(gold_rows)
+    for (k, row) in zip(midx.tolist(), mtab):
+        assert row[0] == gold_rows[k][0] and np.array_equal(row[4:], gold_rows[k][4:])
+    for (i, bb) in enumerate(boxes):
+        idm = taskio.read_chunk_id_map(d, bb)
+        assert sorted((int(a), int(b)) for (a, b) in idm.items()) == [tuple(x) for x in g[f"id_map_{i}"].tolist()]
+        W.remap_ids_task(seg_p, out_p, tuple(bb.min()), tuple(bb.max()), d)
+        W.overlap_task(out_p, base_p, tuple(bb.min()), tuple(bb.max()), d)
+    assert np.array_equal(np.load(out_p), g["final"])
+    for (i, bb) in enumerate(boxes):
+        m = taskio.read_chunk_overlap_mat(taskio.chunk_overlap_fname(d, bb))
+        assert sorted(zip(m.row.tolist(), m.col.tolist(), m.data.tolist())) == \
+            sorted(tuple(int(v) for v in t) for t in g13[f"ov_{i}"]), i
+    W.merge_overlaps_task(d, timing_tag="t")
+    mo = pd.read_csv(os.path.join(d, "max_overlaps.df"), index_col=0)
+    got = sorted(zip(mo[cn.rows].tolist(), mo[cn.cols].tolist(), mo[cn.vals].tolist()))
+    assert got == sorted(zip(g13["max_row"].tolist(), g13["max_col"].tolist(), g13["max_val"].tolist()))
+    assert all(taskio.read_task_timing(d, n, "t") >= 0 for n in ("ccs", "merge_ccs", "merge_overlap"))
