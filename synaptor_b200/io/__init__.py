@@ -28,7 +28,7 @@ def bbox_from_fname(path):
     return f(path)
 
 _REMOTE = re.compile(r"^(gs|s3|https?|precomputed|graphene|matrix|boss)://")
-_DB = re.compile(r"^(postgresql|mysql|sqlite|oracle|mssql)(\+\w+)?://")
+_DB = re.compile(r"^(postgres(ql)?|mysql|sqlite|mssql)(\+\w+)?://")
 
 
 def is_db_url(uri):
