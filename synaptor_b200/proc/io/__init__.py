@@ -294,6 +294,19 @@ def _read_face_file(fname):
     return [Continuation(int(segid), face, coords) for (segid, coords) in f["face_coords"].items()]
 
 
+def _read_legacy_file(fname):
+    """The older one-file-per-chunk layout, groups `{axis}/{high|low}/{segid}` (continuation.py:72-91):
+    {Face: [Continuation]} with an empty list for a face the file does not hold."""
+    from . import h5min
+    from ..seg.continuation import Continuation, Face
+    f = h5min.read_file(fname)
+    continuations = dict()
+    for face in Face.all_faces():
+        grp = f.get(f"{face.axis}", {}).get("high" if face.hi_index else "low", {})
+        continuations[face] = [Continuation(int(i), face, coords) for (i, coords) in grp.items()]
+    return continuations
+
+
 def read_face_continuations(proc_url, chunk_bounds, face):
     return _read_face_file(face_filename(proc_url, chunk_bounds, face))
 

@@ -211,3 +211,18 @@ def test_continuation_files_roundtrip(tmp_path):
     # .npz files of earlier versions
     taskio.write_face_file_npz(conts[f0], taskio.npz_face_filename(str(tmp_path), bb, f0), f0)
     assert [c.segid for c in taskio.read_face_file_npz(taskio.npz_face_filename(str(tmp_path), bb, f0))] == [7, 12, 100]
+
+
+def test_legacy_continuation_file(tmp_path):
+    """continuation.py:72-91: one file per chunk with groups {axis}/{high|low}/{segid}"""
+    from synaptor_b200.proc import io as taskio
+    from synaptor_b200.proc.io import h5min
+    from synaptor_b200.proc.seg.continuation import Face
+    p = str(tmp_path / "legacy.h5")
+    h5min.write_file(p, {"0": {"high": {"4": np.array([[1, 2]], dtype=np.int64), "15": np.array([[3, 3], [3, 4]], dtype=np.int64)}},
+                         "2": {"low": {"9": np.array([[0, 0]], dtype=np.int64)}, "high": {}}})
+    c = taskio._read_legacy_file(p)
+    assert set(c) == set(Face.all_faces())
+    assert [(x.segid, x.face_coords.tolist()) for x in c[Face(0, True)]] == [(15, [[3, 3], [3, 4]]), (4, [[1, 2]])]
+    assert [(x.segid, x.face_coords.tolist()) for x in c[Face(2, False)]] == [(9, [[0, 0]])]
+    assert c[Face(2, True)] == [] and c[Face(1, True)] == [] and c[Face(0, False)] == []

@@ -165,3 +165,53 @@ def test_tasks_w_io_plumbing_with_oracle_stand_ins(tmp_path, monkeypatch, capsys
     got = sorted(zip(mo[cn.rows].tolist(), mo[cn.cols].tolist(), mo[cn.vals].tolist()))
     assert got == sorted(zip(g13["max_row"].tolist(), g13["max_col"].tolist(), g13["max_val"].tolist()))
     assert all(taskio.read_task_timing(d, n, "t") >= 0 for n in ("ccs", "merge_ccs", "merge_overlap"))
+
+
+def test_reference_merge_stage_reads_our_chunk_outputs(tmp_path):
+    """SURVEY section 8 row F3, end to end at the level of the reference's code: the UNMODIFIED reference's
+    `tasks_w_io.merge_ccs_task` (tasks_w_io.py:112-143, file branch) run on a processing directory written by THIS
+    package's chunk-task writers -- seg-info CSVs and HDF5 continuation files -- gives the executed reference's own
+    merged table and chunk id maps (fixture g4).  The one stand-in: `h5py`, absent from this image, is the three-call
+    shim of tests/test_h5min.py on top of h5min (the file bytes themselves are pinned there)."""
+    import importlib
+    import io as _io
+    import sys
+    import types
+    import warnings
+    from contextlib import redirect_stdout
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import oracle as orc, refshim
+    if refshim.available() is None:
+        pytest.skip("no reference copy (baseline/_ref or /root/reference)")
+    from test_h5min import _ShimFile
+    from util import gold
+    from synaptor_b200.proc.seg.continuation import Continuation, Face
+    refshim.load()
+    rc = importlib.import_module("synaptor.proc.io.continuation")
+    ref_w_io = importlib.import_module("synaptor.proc.tasks_w_io")
+    g = gold("g4_merge_ccs.npz")
+    vol = g["vol"]
+    boxes = syn.chunk_bboxes(vol.shape, tuple(g["chunk_shape"].tolist()))
+    d = str(tmp_path)
+    for bb in boxes:        # chunk outputs: the oracle stands in for the device call, the WRITERS are the product's
+        _, conts, info = orc.cc_task_c(np.ascontiguousarray(vol[bb.index()]), float(g["thresh"]), int(g["dust"]),
+                                       offset=tuple(bb.min()))[:3]
+        conts = {Face(a, bool(h)): [Continuation(int(s), Face(a, bool(h)), np.asarray(c)) for (s, c) in lst]
+                 for ((a, h), lst) in conts.items()}
+        taskio.write_chunk_continuations(conts, d, bb)
+        taskio.write_chunk_seg_info(info, d, bb)
+    old, rc.h5py = rc.h5py, types.SimpleNamespace(File=_ShimFile)
+    try:
+        with redirect_stdout(_io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_w_io.merge_ccs_task(d, int(g["size_thr"]), tuple(g["max_face_shape"].tolist()))
+    finally:
+        rc.h5py = old
+    merged = taskio.read_merged_seg_info(d)              # written by the reference
+    gold_rows = {int(i): r.astype(np.int64) for (i, r) in zip(g["merged_index"], g["merged_table"])}
+    assert sorted(int(i) for i in merged.index) == sorted(gold_rows)
+    for (k, row) in zip(merged.index, merged.to_numpy(dtype=np.int64)):
+        assert np.array_equal(row, gold_rows[int(k)]), k
+    for (i, bb) in enumerate(boxes):
+        idm = taskio.read_chunk_id_map(d, bb)
+        assert sorted((int(a), int(b)) for (a, b) in idm.items()) == [tuple(x) for x in g[f"id_map_{i}"].tolist()]
