@@ -27,7 +27,6 @@ roofline: the dominant kernel k_stream (16 B/voxel algorithmic: 4 pred + 8 base 
 """
 import argparse
 import json
-import math
 import os
 import statistics
 import subprocess
