@@ -232,3 +232,38 @@ def test_reference_reader_and_writer_code_on_our_files(tmp_path):
         assert open(theirs, "rb").read() == open(ours, "rb").read()
     finally:
         rc.h5py = old
+
+
+def test_random_trees_roundtrip(tmp_path):
+    """property test: random nested groups / names / dtypes / shapes survive write -> strict read"""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from hypothesis.extra import numpy as hnp
+
+    names = st.text(alphabet=st.characters(min_codepoint=33, max_codepoint=126, blacklist_characters="/"), min_size=1, max_size=20)
+    dtypes = st.sampled_from([np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64,
+                              np.float32, np.float64, np.bool_])
+    arrays = dtypes.flatmap(lambda dt: hnp.arrays(dt, hnp.array_shapes(min_dims=0, max_dims=3, min_side=0, max_side=5),
+                                                  elements=hnp.from_dtype(np.dtype(dt), allow_nan=False)))
+    trees = st.recursive(st.dictionaries(names, arrays, max_size=12),
+                         lambda children: st.dictionaries(names, st.one_of(arrays, children), max_size=6), max_leaves=40)
+    counter = [0]
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(trees)
+    def run(tree):
+        counter[0] += 1
+        p = str(tmp_path / f"t{counter[0]}.h5")
+        h5min.write_file(p, tree)
+        back = h5min.read_file(p)
+
+        def same(a, b):
+            if isinstance(a, dict):
+                assert isinstance(b, dict) and list(b) == sorted(a, key=lambda s: s.encode("utf-8"))
+                for k in a:
+                    same(a[k], b[k])
+            else:
+                a = np.asarray(a)
+                assert b.dtype == a.dtype and b.shape == a.shape and np.array_equal(a, b)
+        same(tree, back)
+
+    run()
