@@ -215,3 +215,15 @@ def test_reference_merge_stage_reads_our_chunk_outputs(tmp_path):
     for (i, bb) in enumerate(boxes):
         idm = taskio.read_chunk_id_map(d, bb)
         assert sorted((int(a), int(b)) for (a, b) in idm.items()) == [tuple(x) for x in g[f"id_map_{i}"].tolist()]
+
+
+def test_cc_task_wrapper_skips_a_completed_chunk(tmp_path, monkeypatch, capsys):
+    """tasks_w_io.py:31-46: a chunk with a unique-id file is not run again (no volume is touched, no duration written)"""
+    from synaptor_b200.proc import tasks
+    d = str(tmp_path)
+    bb = syn.BBox3d((0, 0, 0), (8, 8, 8))
+    taskio.write_chunk_unique_ids({1: 11, 2: 12}, d, bb)
+    monkeypatch.setattr(tasks, "cc_task", lambda *a, **k: (_ for _ in ()).throw(AssertionError("must not run")))
+    syn.proc.tasks_w_io.cc_task("missing_pred.npy", "missing_seg.npy", d, 0.5, 10, (0, 0, 0), (8, 8, 8), timing_tag="x")
+    assert "Task already completed." in capsys.readouterr().out
+    assert not os.path.exists(os.path.join(d, "task_durations"))
