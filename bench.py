@@ -535,6 +535,8 @@ def main():
         sk = float(r["stage_ms"]["stream"])
         ach = BYTES_PER_VOXEL * nvox / (sk * 1e-3) / 1e9
         traffic, tsrc = stream_traffic(shape)
+        if args.config == "c3":        # the committed capture of this shape is of the job's chunk (fg 3 %), not this input
+            traffic, tsrc = None, None
         line = {"metric": METRIC, "value": r["gvoxel_s_two_chunks_in_flight"], "unit": "Gvoxel/s", "n_gpus": 1,
                 "steps": 2 * args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step_two_chunks_in_flight"],
                 "higher_is_better": True, "scaling": "weak",
@@ -548,6 +550,9 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": "k_stream<base,scan,tma>", "achieved": ach, "peak": peak,
                              "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": tsrc,
                              "peak_source": peak_src, "algorithmic_bytes_per_voxel": BYTES_PER_VOXEL, "kernel_ms": sk,
+                             "note": "algorithmic bytes count the whole 4 B/voxel label write for this kernel although it "
+                                     "writes only the sectors without foreground (k_sector_labels writes the others): on a "
+                                     "dense input `frac` can exceed 1; `pipeline` is the whole step",
                              "pipeline": {"bytes_per_voxel": BYTES_PER_VOXEL, "achieved": r["pipeline_gb_s"],
                                           "frac": r["pipeline_frac_of_measured_peak"],
                                           "frac_of_8TBs_nominal": r["pipeline_frac_of_8TBs_nominal"]},
