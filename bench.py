@@ -594,6 +594,7 @@ def main():
     job = jobs[0]
     if job.exchange == "nccl" and len(jobs) > 1:
         jobs = jobs[:1]                 # collectives of one communicator are not issued from two streams at once
+    n_in_flight = len(jobs)            # job instances the timed steps alternate over (reported below)
     nvox_total = int(np.prod(VOLUME))
     info0 = job.info_dict()
     counts0 = [job.counts(li) for li in range(len(job.mine))]
@@ -712,7 +713,7 @@ def main():
             "config": {"workload": WORKLOAD_C4, "volume": list(VOLUME), "chunk": list(CHUNK), "grid": list(job_grid()),
                        "chunks_per_gpu": -(-int(np.prod(job_grid())) // world),
                        "merge_ccs_in_step": True, "remap_in_step": True, "cuda_graph": not args.no_graph,
-                       "volumes_in_flight": len(jobs), "lanes": args.lanes,
+                       "volumes_in_flight": n_in_flight, "lanes": args.lanes,
                        "in_flight_note": "the timed steps alternate over this many job instances (own buffers, same "
                                          "inputs): a volume's chunk passes overlap the previous volume's merge, "
                                          "exchange and label writes; within a volume the chunk passes alternate "
