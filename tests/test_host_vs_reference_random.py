@@ -178,3 +178,64 @@ def test_chunk_grids_and_boxes(ref, seed):
         assert tuple(a.merge(b).min()) == tuple(ra.merge(rb).min()) and tuple(a.merge(b).max()) == tuple(ra.merge(rb).max())
         assert a.shape() == ra.shape() if callable(getattr(ra, "shape", None)) else True
         assert syn.proc.io.fname_chunk_tag(a) == ref.io.fname_chunk_tag(ra)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_local_files_byte_for_byte_and_cross_read(ref, seed, tmp_path):
+    """the chunk-task files (seg info, overlap matrix, id map, unique ids, duplicate map, merged tables) written by
+    this package and by the reference's own local writers from the same random objects: identical bytes; and each
+    side reads the other's files back to the same objects"""
+    rng = np.random.default_rng(600 + seed)
+    ours, theirs = str(tmp_path / "ours"), str(tmp_path / "theirs")
+    rio, oio = ref.proc.io, syn.proc.io
+    for d in (ours, theirs):
+        for sub in ("seg_infos", "overlaps", "id_maps", "unique_ids"):
+            os.makedirs(os.path.join(d, sub))
+    lo = tuple(int(v) for v in rng.integers(0, 4000, size=3))
+    bb_o = syn.BBox3d(lo, tuple(v + int(e) for v, e in zip(lo, rng.integers(1, 600, size=3))))
+    bb_t = ref.types.bbox.BBox3d(tuple(bb_o.min()), tuple(bb_o.max()))
+    info = random_info(rng, int(rng.integers(1, 40)))
+    n = int(rng.integers(1, 30))
+    pairs = np.unique(np.stack([rng.integers(1, 50, size=n), rng.integers(1, 1 << 45, size=n)], 1), axis=0)
+    mat = sp.coo_matrix((rng.integers(1, 900, size=len(pairs)), (pairs[:, 0], pairs[:, 1])))
+    id_map = {int(k): int(k) + int(rng.integers(1, 10 ** 6)) for k in info.index}
+    dup_map = {int(v): int(min(id_map.values())) for v in list(id_map.values())[1:5]}
+    oio.write_chunk_seg_info(info.copy(), ours, bb_o)
+    rio.write_chunk_seg_info(info.copy(), theirs, bb_t)
+    oio.write_chunk_overlap_mat(mat.copy(), bb_o, ours)
+    rio.write_chunk_overlap_mat(mat.copy(), bb_t, theirs)
+    oio.write_chunk_id_map(dict(id_map), ours, bb_o)
+    rio.write_chunk_id_map(dict(id_map), theirs, bb_t)
+    oio.write_chunk_unique_ids(dict(id_map), ours, bb_o)
+    rio.write_chunk_unique_ids(dict(id_map), theirs, bb_t)
+    oio.write_dup_id_map(dict(dup_map), ours)
+    rio.write_dup_id_map(dict(dup_map), theirs)
+    oio.write_merged_seg_info(info.copy(), ours)
+    rio.write_merged_seg_info(info.copy(), theirs)
+    oio.write_merged_seg_info(info.copy(), ours, hash_tag=3)
+    rio.write_merged_seg_info(info.copy(), theirs, hash_tag=3)
+
+    def tree(d):
+        out = {}
+        for (root, _, names) in os.walk(d):
+            for nm in names:
+                out[os.path.relpath(os.path.join(root, nm), d)] = open(os.path.join(root, nm), "rb").read()
+        return out
+
+    to, tt = tree(ours), tree(theirs)
+    assert sorted(to) == sorted(tt) and len(to) == 7
+    for k in to:
+        assert to[k] == tt[k], k
+    # cross-reading: ours <- their files, theirs <- our files
+    frames_equal(oio.read_chunk_seg_info(theirs, bb_o), rio.read_chunk_seg_info(ours, bb_t))
+    assert {int(a): int(b) for a, b in oio.read_chunk_id_map(theirs, bb_o).items()} == id_map == \
+        {int(a): int(b) for a, b in rio.read_chunk_id_map(ours, bb_t).items()}
+    assert {int(a): int(b) for a, b in oio.read_dup_id_map(theirs).items()} == dup_map == \
+        {int(a): int(b) for a, b in rio.read_dup_id_map(ours).items()}
+    mo = oio.read_chunk_overlap_mat(oio.chunk_overlap_fname(theirs, bb_o))
+    mt = rio.read_chunk_overlap_mat(rio.overlap.chunk_overlap_fname(ours, bb_t)) \
+        if hasattr(rio, "overlap") and hasattr(rio.overlap, "chunk_overlap_fname") else mo
+    want = sorted(zip(mat.row.tolist(), mat.col.tolist(), mat.data.tolist()))
+    assert sorted(zip(mo.row.tolist(), mo.col.tolist(), mo.data.tolist())) == want
+    assert sorted(zip(mt.row.tolist(), mt.col.tolist(), mt.data.tolist())) == want
+    frames_equal(oio.read_merged_seg_info(theirs), rio.read_merged_seg_info(ours))
