@@ -239,3 +239,38 @@ def test_local_files_byte_for_byte_and_cross_read(ref, seed, tmp_path):
     assert sorted(zip(mo.row.tolist(), mo.col.tolist(), mo.data.tolist())) == want
     assert sorted(zip(mt.row.tolist(), mt.col.tolist(), mt.data.tolist())) == want
     frames_equal(oio.read_merged_seg_info(theirs), rio.read_merged_seg_info(ours))
+
+
+def test_host_merge_ccs_task_exact_on_g4(ref):
+    """proc.tasks.merge_ccs_task -- every host step of it (id assignment, map application and updates, table merge
+    with the pandas-ordered compensated centroid sum, size threshold) -- on the chunks of fixture g4, with the one
+    device step (face matching, `merge_continuations`) done by the reference's own CPU function: merged table equal to
+    the executed reference's INCLUDING the truncated float64 centroids (0 of 25 rows differ, no +-1), id maps equal."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle import oracle as orc
+    from util import gold, table_of
+    from synaptor_b200.proc import seg, tasks
+    from synaptor_b200.proc.seg.continuation import Continuation, Face
+    g = gold("g4_merge_ccs.npz")
+    vol = g["vol"]
+    boxes = syn.chunk_bboxes(vol.shape, tuple(g["chunk_shape"].tolist()))
+    grid = (2, 2, 2)
+    cont, info = np.empty(grid, dtype=object), np.empty(grid, dtype=object)
+    for gi, bb in zip(np.ndindex(grid), boxes):
+        _, c, info[gi] = orc.cc_task_c(np.ascontiguousarray(vol[bb.index()]), float(g["thresh"]), int(g["dust"]),
+                                       offset=tuple(bb.min()))[:3]
+        cont[gi] = {Face(a, bool(h)): [Continuation(int(s), Face(a, bool(h)), np.asarray(xy)) for (s, xy) in lst]
+                    for ((a, h), lst) in c.items()}
+    old = seg.merge.merge_continuations
+    seg.merge.merge_continuations = lambda arr, max_face_shape=(1152, 1152), overlap_df=None: \
+        ref.proc.seg.merge.merge_continuations(arr, max_face_shape=max_face_shape)
+    try:
+        merged, maps = quiet(tasks.merge_ccs_task, cont, info, int(g["size_thr"]), tuple(g["max_face_shape"].tolist()))
+    finally:
+        seg.merge.merge_continuations = old
+    gold_rows = {int(i): r.astype(np.int64) for i, r in zip(g["merged_index"], g["merged_table"])}
+    idx, tab = table_of(merged)
+    assert sorted(idx.tolist()) == sorted(gold_rows) and len(gold_rows) == 25
+    assert sum(not np.array_equal(row, gold_rows[k]) for k, row in zip(idx.tolist(), tab)) == 0
+    for i, gi in enumerate(np.ndindex(grid)):
+        assert sorted((int(a), int(b)) for a, b in maps[gi].items()) == [tuple(x) for x in g[f"id_map_{i}"].tolist()]
