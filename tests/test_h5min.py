@@ -267,3 +267,21 @@ def test_random_trees_roundtrip(tmp_path):
         same(tree, back)
 
     run()
+
+
+def test_face_file_bytes_do_not_drift(tmp_path):
+    """tests/golden/h5min_face_file_sample.h5 is a face file written by this module when it was validated (three
+    continuations on the high z face); the writer must keep producing exactly these bytes"""
+    from synaptor_b200.proc import io as taskio
+    from synaptor_b200.proc.seg.continuation import Continuation, Face
+    f = Face(2, True)
+    conts = [Continuation(7, f, np.array([[1, 2], [1, 3]], dtype=np.int64)),
+             Continuation(12, f, np.array([[5, 5]], dtype=np.int64)),
+             Continuation(100, f, np.array([[0, 0], [9, 9], [10, 9]], dtype=np.int64))]
+    p = str(tmp_path / "continuations_0_0_0-8_8_8_f2_hi.h5")
+    taskio._write_face_file(conts, p, f)
+    assert open(p, "rb").read() == open(os.path.join(GOLD, "h5min_face_file_sample.h5"), "rb").read()
+    back = taskio._read_face_file(os.path.join(GOLD, "h5min_face_file_sample.h5"))
+    assert [(c.segid, c.face_coords.tolist()) for c in back] == \
+        [(100, [[0, 0], [9, 9], [10, 9]]), (12, [[5, 5]]), (7, [[1, 2], [1, 3]])]
+    assert back[0].face == f
